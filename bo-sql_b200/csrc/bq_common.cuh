@@ -1,0 +1,175 @@
+// bq_common.cuh — shared device/host helpers for the sm_100a kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "bosql_b200.h"
+
+#if defined(__CUDACC__)
+#define BQ_HD __host__ __device__ __forceinline__
+#define BQ_D __device__ __forceinline__
+#else
+#define BQ_HD inline
+#define BQ_D inline
+#endif
+
+#define BQ_CUDA(expr)                                                                             \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) {                                                                  \
+            throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " + \
+                                     __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")");   \
+        }                                                                                         \
+    } while (0)
+
+namespace bq {
+
+constexpr int kBlock = 256;          // threads per CTA of the streaming kernels
+constexpr int kRowsPerThread = 4;    // one 128-bit load of a 4-byte column, two of an 8-byte column
+constexpr int kTileRows = kBlock * kRowsPerThread;
+
+// ---- physical kinds = type ordinals of include/bosql_b200.h -------------------------------------
+BQ_HD int width_of(int type) { return (type == BQ_INT64 || type == BQ_DOUBLE) ? 8 : 4; }
+
+// Order-preserving int64 key of a double: IEEE '<' on non-NaN values == '<' on keys.
+// -0.0 is folded onto +0.0 first (IEEE compares them equal); NaNs land outside [key(-inf), key(+inf)].
+BQ_HD int64_t f64_key_from_bits(uint64_t b) {
+    if (b == 0x8000000000000000ULL) b = 0;
+    int64_t s = static_cast<int64_t>(b);
+    return s ^ ((s >> 63) & 0x7FFFFFFFFFFFFFFFLL);
+}
+BQ_HD uint64_t f64_bits_from_key(int64_t k) {
+    return static_cast<uint64_t>(k ^ ((k >> 63) & 0x7FFFFFFFFFFFFFFFLL));
+}
+
+// ---- counter-based hash (splitmix64 finaliser): value(row) = f(seed, stream, row) ---------------
+BQ_HD uint64_t mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ULL;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+BQ_HD uint64_t row_hash(uint64_t seed, uint64_t stream, uint64_t row) {
+    return mix64(mix64(seed ^ (stream * 0xD6E8FEB86659FD93ULL)) + row);
+}
+
+// hash used by the open-addressing tables (the reference's hash is not observable)
+BQ_HD uint64_t key_hash(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xFF51AFD7ED558CCDULL;
+    k ^= k >> 33;
+    k *= 0xC4CEB9FE1A85EC53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+#if defined(__CUDACC__)
+// ---- streaming loads: 128-bit, read-only path, no L1 allocation (each byte is read once) --------
+BQ_D int4 ldg_stream(const int4* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// Widen one element of `kind` at row i to its 8-byte slot value (what BQ_OP_COL pushes).
+BQ_D int64_t load_raw(const void* base, int kind, size_t i) {
+    switch (kind) {
+        case BQ_INT64:
+        case BQ_DOUBLE: return __ldg(reinterpret_cast<const long long*>(base) + i);
+        case BQ_STRING: return static_cast<int64_t>(__ldg(reinterpret_cast<const unsigned*>(base) + i));
+        default: return static_cast<int64_t>(__ldg(reinterpret_cast<const int*>(base) + i));
+    }
+}
+// The integer key on which ranges are tested.
+BQ_D int64_t key_of(int64_t raw, int kind) {
+    return kind == BQ_DOUBLE ? f64_key_from_bits(static_cast<uint64_t>(raw)) : raw;
+}
+// datum_as_double (src/exec/operator.cpp:280-292)
+BQ_D double as_double(int64_t raw, int kind) {
+    return kind == BQ_DOUBLE ? __longlong_as_double(raw) : static_cast<double>(raw);
+}
+
+BQ_D double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+BQ_D unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+#endif
+
+// ---- host-side objects behind the opaque handles ------------------------------------------------
+}  // namespace bq
+
+struct bq_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    // small reusable device scratch (partials, tickets, error flags)
+    void* scratch = nullptr;
+    size_t scratch_bytes = 0;
+    void* pinned = nullptr;      // small pinned staging for scalar results
+    size_t pinned_bytes = 0;
+};
+
+struct bq_col {
+    int type = BQ_INT64;
+    size_t n = 0;
+    void* ptr = nullptr;
+    bool owns = true;
+    bool has_minmax = false;
+    int64_t min_key = 0, max_key = 0;
+    size_t ndv = 0;
+};
+
+struct bq_rel {
+    std::vector<bq_col*> cols;
+    size_t rows = 0;
+};
+
+struct bq_join {
+    int kind = BQ_JOIN_HASH;
+    int64_t key_min = 0, key_max = 0;     // BITMAP / DIRECT domain
+    unsigned* bitmap = nullptr;           // BITMAP: bit (key-key_min)
+    size_t bitmap_words = 0;
+    unsigned* direct = nullptr;           // DIRECT: build row id + 1 at [key-key_min], 0 = absent
+    long long* h_keys = nullptr;          // HASH: open addressing, linear probing
+    unsigned* h_rows = nullptr;           //       build row id + 1, 0 = empty slot
+    uint64_t h_mask = 0;
+    size_t build_rows = 0;                // rows inserted
+    size_t bytes = 0;
+};
+
+namespace bq {
+
+void set_error(const std::string& msg);
+bq_col* new_col(bq_ctx* ctx, int type, size_t n);
+void free_col(bq_col* c);
+void* scratch(bq_ctx* ctx, size_t bytes);     // device scratch, valid until the next call that asks for more
+void* pinned(bq_ctx* ctx, size_t bytes);
+int grid_for(bq_ctx* ctx, size_t rows, int blocks_per_sm);
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        set_error(e.what());
+        return 1;
+    }
+}
+
+}  // namespace bq

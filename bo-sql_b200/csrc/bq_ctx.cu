@@ -1,0 +1,286 @@
+// bq_ctx.cu — context, device-resident columns and relations (the storage/ side of the hot path).
+//
+// Replaces, on the device, what the reference keeps in std::vector<T> inside ColumnVector<T>
+// (include/types.h:134-145) and Table (include/storage/table.h:20-30).  A column is one contiguous
+// HBM allocation (cudaMalloc: 256-byte aligned, so every 128-bit load in the scan kernels is aligned).
+#include "bq_common.cuh"
+
+#include <cstring>
+
+namespace bq {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+
+bq_col* new_col(bq_ctx* ctx, int type, size_t n) {
+    (void)ctx;
+    if (type < 0 || type > 3) throw std::runtime_error("Unknown column type");
+    auto* c = new bq_col();
+    c->type = type;
+    c->n = n;
+    size_t bytes = n * width_of(type);
+    // pad to a whole 16-byte vector so tail vector loads never leave the allocation
+    size_t alloc = ((bytes + 255) / 256) * 256 + 256;
+    try {
+        BQ_CUDA(cudaMalloc(&c->ptr, alloc));
+    } catch (...) {
+        delete c;
+        throw;
+    }
+    return c;
+}
+
+void free_col(bq_col* c) {
+    if (!c) return;
+    if (c->owns && c->ptr) cudaFree(c->ptr);
+    delete c;
+}
+
+void* scratch(bq_ctx* ctx, size_t bytes) {
+    if (bytes > ctx->scratch_bytes) {
+        if (ctx->scratch) {
+            BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+            cudaFree(ctx->scratch);
+            ctx->scratch = nullptr;
+        }
+        size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
+        BQ_CUDA(cudaMalloc(&ctx->scratch, want));
+        ctx->scratch_bytes = want;
+    }
+    return ctx->scratch;
+}
+
+void* pinned(bq_ctx* ctx, size_t bytes) {
+    if (bytes > ctx->pinned_bytes) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        size_t want = bytes < 4096 ? 4096 : bytes;
+        BQ_CUDA(cudaMallocHost(&ctx->pinned, want));
+        ctx->pinned_bytes = want;
+    }
+    return ctx->pinned;
+}
+
+// Persistent-style grids: a multiple of the SM count, capped by the work available.
+int grid_for(bq_ctx* ctx, size_t rows, int blocks_per_sm) {
+    size_t tiles = (rows + kTileRows - 1) / kTileRows;
+    size_t want = static_cast<size_t>(ctx->sm_count) * blocks_per_sm;
+    if (tiles < want) want = tiles;
+    if (want < 1) want = 1;
+    return static_cast<int>(want);
+}
+
+// ---- min/max of a column's integer key (cached in the handle) -----------------------------------
+__global__ void __launch_bounds__(kBlock) k_minmax(const void* __restrict__ base, int kind, size_t n,
+                                                   long long* __restrict__ out /* [min,max] */) {
+    long long lo = INT64_MAX, hi = INT64_MIN;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        long long k = key_of(load_raw(base, kind, i), kind);
+        lo = k < lo ? k : lo;
+        hi = k > hi ? k : hi;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        long long l2 = __shfl_xor_sync(0xffffffffu, lo, o);
+        long long h2 = __shfl_xor_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo;
+        hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, lo);
+        atomicMax(out + 1, hi);
+    }
+}
+
+}  // namespace bq
+
+using namespace bq;
+
+extern "C" {
+
+const char* bq_last_error(void) { return g_error.c_str(); }
+
+int bq_ctx_create(int device, bq_ctx** out) {
+    return guarded([&] {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        if (e != cudaSuccess || n == 0)
+            throw std::runtime_error(std::string("no CUDA device: the bo-sql B200 hot path has no CPU fallback (") +
+                                     cudaGetErrorString(e) + ")");
+        if (device < 0 || device >= n) throw std::runtime_error("bad device ordinal");
+        BQ_CUDA(cudaSetDevice(device));
+        auto* ctx = new bq_ctx();
+        ctx->device = device;
+        cudaDeviceProp prop;
+        BQ_CUDA(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount;
+        BQ_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        ctx->stream = ctx->own_stream;
+        *out = ctx;
+    });
+}
+
+void bq_ctx_destroy(bq_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+}
+
+int bq_ctx_set_stream(bq_ctx* ctx, void* s) {
+    return guarded([&] {
+        BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        ctx->stream = s ? static_cast<cudaStream_t>(s) : ctx->own_stream;
+    });
+}
+
+int bq_ctx_sync(bq_ctx* ctx) {
+    return guarded([&] { BQ_CUDA(cudaStreamSynchronize(ctx->stream)); });
+}
+
+int bq_ctx_info(bq_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes) {
+    return guarded([&] {
+        BQ_CUDA(cudaSetDevice(ctx->device));
+        if (sm_count) *sm_count = ctx->sm_count;
+        size_t f = 0, t = 0;
+        BQ_CUDA(cudaMemGetInfo(&f, &t));
+        if (free_bytes) *free_bytes = f;
+        if (total_bytes) *total_bytes = t;
+    });
+}
+
+uint64_t bq_ctx_launches(bq_ctx* ctx) { return ctx->launches; }
+
+int bq_col_alloc(bq_ctx* ctx, int type, size_t n, bq_col** out) {
+    return guarded([&] { *out = new_col(ctx, type, n); });
+}
+
+int bq_col_upload(bq_ctx* ctx, int type, const void* host, size_t n, bq_col** out) {
+    return guarded([&] {
+        bq_col* c = new_col(ctx, type, n);
+        if (n) {
+            cudaError_t e = cudaMemcpyAsync(c->ptr, host, n * width_of(type), cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) {
+                free_col(c);
+                throw std::runtime_error(std::string("upload failed: ") + cudaGetErrorString(e));
+            }
+        }
+        *out = c;
+    });
+}
+
+int bq_col_write(bq_ctx* ctx, bq_col* col, size_t offset, const void* host, size_t n) {
+    return guarded([&] {
+        if (offset + n > col->n) throw std::runtime_error("bq_col_write out of range");
+        size_t w = width_of(col->type);
+        BQ_CUDA(cudaMemcpyAsync(static_cast<char*>(col->ptr) + offset * w, host, n * w, cudaMemcpyHostToDevice,
+                                ctx->stream));
+        col->has_minmax = false;
+    });
+}
+
+int bq_col_read(bq_ctx* ctx, const bq_col* col, size_t offset, size_t n, void* host) {
+    return guarded([&] {
+        if (offset + n > col->n) throw std::runtime_error("bq_col_read out of range");
+        if (!n) return;
+        size_t w = width_of(col->type);
+        BQ_CUDA(cudaMemcpyAsync(host, static_cast<const char*>(col->ptr) + offset * w, n * w, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+        BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+void bq_col_free(bq_ctx* ctx, bq_col* col) {
+    if (!col) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    free_col(col);
+}
+
+size_t bq_col_size(const bq_col* col) { return col->n; }
+int bq_col_type(const bq_col* col) { return col->type; }
+void* bq_col_ptr(const bq_col* col) { return col->ptr; }
+
+int bq_col_set_stats(bq_col* col, int64_t min_key, int64_t max_key, size_t ndv) {
+    col->has_minmax = true;
+    col->min_key = min_key;
+    col->max_key = max_key;
+    col->ndv = ndv;
+    return 0;
+}
+
+int bq_col_minmax(bq_ctx* ctx, bq_col* col, int64_t* min_key, int64_t* max_key) {
+    return guarded([&] {
+        if (!col->has_minmax) {
+            if (col->n == 0) {
+                col->min_key = 0;
+                col->max_key = -1;
+            } else {
+                auto* d = static_cast<long long*>(scratch(ctx, 16));
+                auto* h = static_cast<long long*>(pinned(ctx, 16));
+                h[0] = INT64_MAX;
+                h[1] = INT64_MIN;
+                BQ_CUDA(cudaMemcpyAsync(d, h, 16, cudaMemcpyHostToDevice, ctx->stream));
+                int grid = grid_for(ctx, col->n, 8);
+                k_minmax<<<grid, kBlock, 0, ctx->stream>>>(col->ptr, col->type, col->n, d);
+                ctx->launches++;
+                BQ_CUDA(cudaGetLastError());
+                BQ_CUDA(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+                BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+                col->min_key = h[0];
+                col->max_key = h[1];
+            }
+            col->has_minmax = true;
+        }
+        if (min_key) *min_key = col->min_key;
+        if (max_key) *max_key = col->max_key;
+    });
+}
+
+int64_t bq_f64_key(double v) {
+    uint64_t b;
+    std::memcpy(&b, &v, 8);
+    return f64_key_from_bits(b);
+}
+double bq_f64_from_key(int64_t k) {
+    uint64_t b = f64_bits_from_key(k);
+    double v;
+    std::memcpy(&v, &b, 8);
+    return v;
+}
+
+int bq_host_alloc(size_t bytes, void** out) {
+    return guarded([&] { BQ_CUDA(cudaMallocHost(out, bytes ? bytes : 1)); });
+}
+void bq_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int bq_rel_create(bq_ctx* ctx, bq_col* const* cols, int n_cols, bq_rel** out) {
+    (void)ctx;
+    return guarded([&] {
+        auto* r = new bq_rel();
+        for (int i = 0; i < n_cols; ++i) {
+            if (i && cols[i]->n != cols[0]->n) {
+                delete r;
+                throw std::runtime_error("relation columns differ in length");
+            }
+            r->cols.push_back(cols[i]);
+        }
+        r->rows = n_cols ? cols[0]->n : 0;
+        *out = r;
+    });
+}
+size_t bq_rel_rows(const bq_rel* rel) { return rel->rows; }
+int bq_rel_cols(const bq_rel* rel) { return static_cast<int>(rel->cols.size()); }
+bq_col* bq_rel_col(const bq_rel* rel, int i) { return rel->cols.at(i); }
+void bq_rel_free(bq_ctx* ctx, bq_rel* rel) {
+    if (!rel) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    for (auto* c : rel->cols) free_col(c);
+    delete rel;
+}
+
+}  // extern "C"

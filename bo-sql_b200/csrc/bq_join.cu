@@ -1,0 +1,362 @@
+// bq_join.cu — hash-join build and the materialising probe.
+//
+// HashJoin::open drains the right child into unordered_map<Key, vector<row_id>> plus a copy of every
+// build row (src/exec/operator.cpp:739-762, ~250 B per build row).  Here the build side stays where it is
+// (device columns) and the table holds only what a probe needs, chosen from catalog statistics
+// (include/catalog/catalog.h:16-21: min/max/ndv, row_count):
+//   BITMAP  unique dense key, no build column read downstream: one bit per key of [min,max]
+//           (Q2: 250 M orders -> 31 MB, resident in the 126 MB L2 for the whole probe)
+//   DIRECT  unique dense key: uint32 build row id per key of [min,max]
+//   HASH    anything else: open addressing in HBM, linear probing, capacity 2x rows (power of two),
+//           slot = (key, build row id+1) claimed with atomicCAS; duplicate keys occupy separate slots.
+// Build-side predicate ranges are applied before insertion (filter push-down below an inner join keeps
+// the joined row set of the reference, which filters above the join, src/logical/planner.cpp:110-117).
+//
+// The fused probe lives in bq_scan.cu; this file also has the materialising probe that HashJoin::next
+// needs when its rows are consumed as rows: count matches per probe row, exclusive scan, fill pairs in
+// probe order with each row's matches in build insertion order (src/exec/operator.cpp:802-816).
+#include "bq_common.cuh"
+#include "bq_internal.cuh"
+
+namespace bq {
+
+struct BuildParams {
+    const void* key;
+    int key_kind;
+    DSlot s[3];
+    const long long* mask;
+    size_t row_begin, row_end;
+    long long key_min;
+    unsigned long long domain;
+    unsigned* bitmap;
+    unsigned* direct;
+    long long* h_keys;
+    unsigned* h_rows;
+    unsigned long long h_mask;
+    unsigned long long* n_inserted;
+    int* flags;   // 1 = duplicate key seen (BITMAP/DIRECT), 2 = key outside [min,max], 4 = table full
+};
+
+BQ_D bool canon_join_key(long long& k, int kind) {
+    if (kind == BQ_DOUBLE) {
+        if (k == INT64_MIN) k = 0;                                             // -0.0 == 0.0 (KeyEqual, src/exec/operator.cpp:657)
+        if ((k & 0x7FFFFFFFFFFFFFFFLL) > 0x7FF0000000000000LL) return false;   // NaN never equals anything
+    }
+    return true;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(kBlock) k_join_build(const __grid_constant__ BuildParams p) {
+    unsigned long long local = 0;
+    const size_t n = p.row_end - p.row_begin;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = p.row_begin + t;
+        bool ok = true;
+#pragma unroll
+        for (int s = 0; s < 3; ++s)
+            if (p.s[s].ptr) ok = ok && slot_pass(p.s[s], load_raw(p.s[s].ptr, p.s[s].kind, i));
+        if (p.mask && __ldg(p.mask + i) == 0) ok = false;
+        if (!ok) continue;
+        long long k = load_raw(p.key, p.key_kind, i);
+        if (!canon_join_key(k, p.key_kind)) continue;
+        if (KIND == BQ_JOIN_BITMAP) {
+            unsigned long long idx = static_cast<unsigned long long>(k - p.key_min);
+            if (idx >= p.domain) { atomicOr(p.flags, 2); continue; }
+            unsigned bit = 1u << (idx & 31);
+            unsigned old = atomicOr(p.bitmap + (idx >> 5), bit);
+            if (old & bit) atomicOr(p.flags, 1);
+            local++;
+        } else if (KIND == BQ_JOIN_DIRECT) {
+            unsigned long long idx = static_cast<unsigned long long>(k - p.key_min);
+            if (idx >= p.domain) { atomicOr(p.flags, 2); continue; }
+            unsigned old = atomicCAS(p.direct + idx, 0u, static_cast<unsigned>(i) + 1u);
+            if (old) atomicOr(p.flags, 1);
+            local++;
+        } else {
+            unsigned long long h = key_hash(static_cast<uint64_t>(k)) & p.h_mask;
+            bool placed = false;
+            for (unsigned long long probes = 0; probes <= p.h_mask; ++probes) {
+                unsigned old = atomicCAS(p.h_rows + h, 0u, static_cast<unsigned>(i) + 1u);
+                if (old == 0u) {
+                    p.h_keys[h] = k;
+                    placed = true;
+                    break;
+                }
+                h = (h + 1) & p.h_mask;
+            }
+            if (!placed) atomicOr(p.flags, 4);
+            local++;
+        }
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(p.n_inserted, local);
+}
+
+// ---- materialising probe ---------------------------------------------------------------------------
+struct ProbeParams {
+    const void* key;
+    int key_kind;
+    const unsigned* rowids;   // optional probe row subset (in order)
+    size_t row_begin;
+    size_t n;                 // probe items
+    int jkind;
+    long long key_min;
+    unsigned long long domain;
+    const unsigned* bitmap;
+    const unsigned* direct;
+    const long long* h_keys;
+    const unsigned* h_rows;
+    unsigned long long h_mask;
+};
+
+BQ_D unsigned probe_matches(const ProbeParams& p, long long k, unsigned* out, unsigned cap_out) {
+    // returns the number of matches; writes up to cap_out build row ids to `out` when out != nullptr
+    if (!canon_join_key(k, p.key_kind)) return 0;
+    if (p.jkind == BQ_JOIN_DIRECT) {
+        unsigned long long idx = static_cast<unsigned long long>(k - p.key_min);
+        if (idx >= p.domain) return 0;
+        unsigned e = __ldg(p.direct + idx);
+        if (!e) return 0;
+        if (out && cap_out) out[0] = e - 1;
+        return 1;
+    }
+    unsigned m = 0;
+    unsigned long long h = key_hash(static_cast<uint64_t>(k)) & p.h_mask;
+    for (unsigned long long probes = 0; probes <= p.h_mask; ++probes) {
+        unsigned e = __ldg(p.h_rows + h);
+        if (!e) break;
+        if (__ldg(p.h_keys + h) == k) {
+            if (out && m < cap_out) out[m] = e - 1;
+            ++m;
+        }
+        h = (h + 1) & p.h_mask;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(kBlock) k_probe_count(const __grid_constant__ ProbeParams p, unsigned* __restrict__ counts) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= p.n) return;
+    size_t i = p.rowids ? p.rowids[t] : p.row_begin + t;
+    counts[t] = probe_matches(p, load_raw(p.key, p.key_kind, i), nullptr, 0);
+}
+
+__global__ void __launch_bounds__(kBlock) k_probe_fill(const __grid_constant__ ProbeParams p,
+                                                       const unsigned* __restrict__ counts,
+                                                       const unsigned long long* __restrict__ offsets,
+                                                       unsigned* __restrict__ out_probe, unsigned* __restrict__ out_build) {
+    size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (t >= p.n) return;
+    unsigned m = counts[t];
+    if (!m) return;
+    size_t i = p.rowids ? p.rowids[t] : p.row_begin + t;
+    unsigned* dst = out_build + offsets[t];
+    probe_matches(p, load_raw(p.key, p.key_kind, i), dst, m);
+    // build insertion order == ascending build row id (the build side is inserted in scan order)
+    for (unsigned a = 1; a < m; ++a) {
+        unsigned v = dst[a];
+        unsigned b = a;
+        while (b > 0 && dst[b - 1] > v) {
+            dst[b] = dst[b - 1];
+            --b;
+        }
+        dst[b] = v;
+    }
+    unsigned* pr = out_probe + offsets[t];
+    for (unsigned a = 0; a < m; ++a) pr[a] = static_cast<unsigned>(i);
+}
+
+static size_t next_pow2(size_t v) {
+    size_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+static void free_tables(bq_join* j) {
+    if (j->bitmap) cudaFree(j->bitmap);
+    if (j->direct) cudaFree(j->direct);
+    if (j->h_keys) cudaFree(j->h_keys);
+    if (j->h_rows) cudaFree(j->h_rows);
+    j->bitmap = j->direct = j->h_rows = nullptr;
+    j->h_keys = nullptr;
+}
+
+// Builds one table kind; returns the kernel's flag word.
+static int build_kind(bq_ctx* ctx, const bq_join_spec* spec, int kind, bq_join* j) {
+    BuildParams p{};
+    p.key = spec->key->ptr;
+    p.key_kind = spec->key->type;
+    for (int s = 0; s < 3; ++s) {
+        if (spec->pred[s].from_build) throw std::runtime_error("bq_join_build: slots are build-side columns already");
+        p.s[s] = make_dslot(spec->pred[s], spec->row_end, "pred");
+    }
+    if (spec->mask) {
+        if (spec->mask->type != BQ_INT64 || spec->mask->n < spec->row_end) throw std::runtime_error("mask must be an INT64 column covering the row range");
+        p.mask = static_cast<const long long*>(spec->mask->ptr);
+    }
+    p.row_begin = spec->row_begin;
+    p.row_end = spec->row_end;
+    const size_t n = spec->row_end - spec->row_begin;
+    free_tables(j);
+    j->kind = kind;
+    j->bytes = 0;
+    if (kind == BQ_JOIN_BITMAP || kind == BQ_JOIN_DIRECT) {
+        j->key_min = spec->key_min;
+        j->key_max = spec->key_max;
+        p.key_min = spec->key_min;
+        p.domain = static_cast<unsigned long long>(spec->key_max - spec->key_min) + 1ULL;
+        if (kind == BQ_JOIN_BITMAP) {
+            j->bitmap_words = (p.domain + 31) / 32;
+            j->bytes = j->bitmap_words * 4;
+            BQ_CUDA(cudaMalloc(&j->bitmap, j->bytes + 4));
+            BQ_CUDA(cudaMemsetAsync(j->bitmap, 0, j->bytes + 4, ctx->stream));
+            p.bitmap = j->bitmap;
+        } else {
+            j->bytes = p.domain * 4;
+            BQ_CUDA(cudaMalloc(&j->direct, j->bytes + 4));
+            BQ_CUDA(cudaMemsetAsync(j->direct, 0, j->bytes + 4, ctx->stream));
+            p.direct = j->direct;
+        }
+    } else {
+        size_t cap = next_pow2(n * 2 < 1024 ? 1024 : n * 2);
+        j->h_mask = cap - 1;
+        j->bytes = cap * 12;
+        BQ_CUDA(cudaMalloc(&j->h_keys, cap * 8));
+        BQ_CUDA(cudaMalloc(&j->h_rows, cap * 4));
+        BQ_CUDA(cudaMemsetAsync(j->h_rows, 0, cap * 4, ctx->stream));
+        p.h_keys = j->h_keys;
+        p.h_rows = j->h_rows;
+        p.h_mask = j->h_mask;
+    }
+    auto* d = static_cast<unsigned long long*>(scratch(ctx, 16));
+    BQ_CUDA(cudaMemsetAsync(d, 0, 16, ctx->stream));
+    p.n_inserted = d;
+    p.flags = reinterpret_cast<int*>(d + 1);
+    if (n) {
+        int grid = grid_for(ctx, n, 8);
+        if (kind == BQ_JOIN_BITMAP) k_join_build<BQ_JOIN_BITMAP><<<grid, kBlock, 0, ctx->stream>>>(p);
+        else if (kind == BQ_JOIN_DIRECT) k_join_build<BQ_JOIN_DIRECT><<<grid, kBlock, 0, ctx->stream>>>(p);
+        else k_join_build<BQ_JOIN_HASH><<<grid, kBlock, 0, ctx->stream>>>(p);
+        ctx->launches++;
+        BQ_CUDA(cudaGetLastError());
+    }
+    auto* h = static_cast<unsigned long long*>(pinned(ctx, 16));
+    BQ_CUDA(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    j->build_rows = static_cast<size_t>(h[0]);
+    return static_cast<int>(h[1] & 0xFFFFFFFFull);
+}
+
+}  // namespace bq
+
+using namespace bq;
+
+extern "C" {
+
+int bq_join_build(bq_ctx* ctx, const bq_join_spec* spec, bq_join** out) {
+    return guarded([&] {
+        if (!spec->key) throw std::runtime_error("join build needs a key column");
+        if (spec->row_end < spec->row_begin || spec->row_end > spec->key->n) throw std::runtime_error("bad build row range");
+        if (spec->row_end > 0xFFFFFFFEull) throw std::runtime_error("row ids are 32-bit: at most 2^32-1 build rows");
+        auto* j = new bq_join();
+        try {
+            int kind = spec->kind;
+            const size_t n = spec->row_end - spec->row_begin;
+            if (kind == BQ_JOIN_AUTO) {
+                kind = BQ_JOIN_HASH;
+                bool int_key = spec->key->type != BQ_DOUBLE;
+                if (int_key && spec->key_max >= spec->key_min) {
+                    unsigned long long dom = static_cast<unsigned long long>(spec->key_max - spec->key_min) + 1ULL;
+                    // dense enough that a direct-address table beats 12 B/row of hash slots
+                    if (dom <= (1ULL << 32) && dom <= 8ULL * (n ? n : 1) + 1024) kind = spec->need_rows ? BQ_JOIN_DIRECT : BQ_JOIN_BITMAP;
+                }
+            }
+            int flags = build_kind(ctx, spec, kind, j);
+            if (kind != BQ_JOIN_HASH && (flags & 3)) {
+                // duplicate keys (or stale catalog bounds): a bitmap / direct table cannot represent them
+                flags = build_kind(ctx, spec, BQ_JOIN_HASH, j);
+            }
+            if (flags & 4) throw std::runtime_error("join table overflow");
+            *out = j;
+        } catch (...) {
+            free_tables(j);
+            delete j;
+            throw;
+        }
+    });
+}
+
+void bq_join_free(bq_ctx* ctx, bq_join* j) {
+    if (!j) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    free_tables(j);
+    delete j;
+}
+
+int bq_join_kind(const bq_join* j) { return j->kind; }
+size_t bq_join_bytes(const bq_join* j) { return j->bytes; }
+void* bq_join_bitmap_ptr(const bq_join* j, size_t* n_words) {
+    if (n_words) *n_words = j->bitmap_words;
+    return j->bitmap;
+}
+
+int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const bq_col* probe_rowids,
+                  size_t row_begin, size_t row_end, bq_col** out_probe_rows, bq_col** out_build_rows) {
+    return guarded([&] {
+        if (j->kind == BQ_JOIN_BITMAP) throw std::runtime_error("a bitmap join cannot materialise build rows");
+        if (probe_rowids && probe_rowids->type != BQ_STRING) throw std::runtime_error("row ids must be a uint32 column");
+        if (!probe_rowids && (row_end < row_begin || row_end > probe_key->n)) throw std::runtime_error("bad probe row range");
+        ProbeParams p{};
+        p.key = probe_key->ptr;
+        p.key_kind = probe_key->type;
+        p.rowids = probe_rowids ? static_cast<const unsigned*>(probe_rowids->ptr) : nullptr;
+        p.row_begin = row_begin;
+        p.n = probe_rowids ? probe_rowids->n : row_end - row_begin;
+        p.jkind = j->kind;
+        p.key_min = j->key_min;
+        p.domain = static_cast<unsigned long long>(j->key_max - j->key_min) + 1ULL;
+        p.bitmap = j->bitmap;
+        p.direct = j->direct;
+        p.h_keys = j->h_keys;
+        p.h_rows = j->h_rows;
+        p.h_mask = j->h_mask;
+        bq_col *op = nullptr, *ob = nullptr;
+        unsigned* counts = nullptr;
+        unsigned long long* offsets = nullptr;
+        try {
+            size_t total = 0;
+            if (p.n) {
+                BQ_CUDA(cudaMalloc(&counts, p.n * 4));
+                BQ_CUDA(cudaMalloc(&offsets, p.n * 8));
+                unsigned blocks = static_cast<unsigned>((p.n + kBlock - 1) / kBlock);
+                k_probe_count<<<blocks, kBlock, 0, ctx->stream>>>(p, counts);
+                ctx->launches++;
+                BQ_CUDA(cudaGetLastError());
+                total = exclusive_scan_u32(ctx, counts, p.n, offsets);
+                if (total > 0xFFFFFFFFull) throw std::runtime_error("join result exceeds 2^32 rows");
+            }
+            op = new_col(ctx, BQ_STRING, total);
+            ob = new_col(ctx, BQ_STRING, total);
+            if (total) {
+                unsigned blocks = static_cast<unsigned>((p.n + kBlock - 1) / kBlock);
+                k_probe_fill<<<blocks, kBlock, 0, ctx->stream>>>(p, counts, offsets, static_cast<unsigned*>(op->ptr),
+                                                               static_cast<unsigned*>(ob->ptr));
+                ctx->launches++;
+                BQ_CUDA(cudaGetLastError());
+            }
+            BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (counts) cudaFree(counts);
+            if (offsets) cudaFree(offsets);
+            *out_probe_rows = op;
+            *out_build_rows = ob;
+        } catch (...) {
+            if (counts) cudaFree(counts);
+            if (offsets) cudaFree(offsets);
+            free_col(op);
+            free_col(ob);
+            throw;
+        }
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,920 @@
+// bq_scan.cu — the fused hot path: scan -> selection -> [join probe] -> aggregate in ONE kernel.
+//
+// Replaces the per-row loops of ColumnarScan::next (src/exec/operator.cpp:345-384), Selection::next
+// (:403-429, evaluate_predicate per row), HashJoin::next's probe (:764-837) and HashAggregate::next's
+// accumulate phase (:984-1014) for pipelines whose predicate is a conjunction of `column OP literal`
+// ranges (anything else arrives pre-evaluated as `mask`).  Nothing is materialised between operators.
+//
+// Memory behaviour (HBM-bound, the only roofline that applies to this path):
+//  * every referenced column is read exactly once with coalesced vector loads on the read-only,
+//    no-L1-allocate path: a warp owns a 128-row chunk; lane t holds rows {2t,2t+1,64+2t,65+2t}, so an
+//    8-byte column is two fully coalesced 128-bit loads per lane and a 4-byte column two 64-bit loads;
+//  * all loads of a chunk are issued before the first use (memory-level parallelism), the grid is a
+//    multiple of the SM count and warps walk chunks grid-stride, so neighbouring warps stream
+//    neighbouring DRAM pages;
+//  * aggregation state: registers + shuffle (global aggregate), a per-CTA shared-memory table merged
+//    once per CTA (dense low-cardinality GROUP BY: Q1), L2-resident global arrays with red.add
+//    (dense medium cardinality: Q2's sku), or an open-addressing table in HBM (atomicCAS claim +
+//    red.add; sized from catalog NDV).
+//  * the slot layout is a template parameter for the shapes of the configurations (loads, widening and
+//    range tests fold to straight-line code); any other shape runs the same source with run-time flags.
+//
+// Exactness: COUNT is an integer; SUM accumulates in double like AggState::sum
+// (include/exec/operator.hpp:149-152) — exact for integer arguments while |sum| <= 2^53 (H1), within
+// 1e-12 relative for DOUBLE arguments whose order of addition differs (H2).  `a*b` is rounded before it
+// is added (H12): every FP op below is an explicit __d*_rn intrinsic, which is never contracted to FMA.
+#include "bq_common.cuh"
+#include "bq_internal.cuh"
+
+#include <cstring>
+
+namespace bq {
+
+enum { S_KEY = 0, S_A = 1, S_B = 2, S_P0 = 3, S_P1 = 4, S_P2 = 5, S_JK = 6, N_SLOTS = 7 };
+enum { G_NONE = 0, G_SMEM = 1, G_DENSE = 2, G_HASH = 3 };
+
+constexpr long long kEmptyKey = INT64_MIN;   // empty marker of the group table (a real INT64_MIN key uses the spare slot)
+constexpr uint32_t kGenericShape = 0xFFFFFFFFu;
+
+struct DVExpr {
+    int op, b_is_imm, imm_is_f, swap;
+    long long imm_i;
+    double imm_f;
+};
+
+struct ScanParams {
+    DSlot s[N_SLOTS];
+    unsigned present;          // bit per slot
+    int nv;
+    DVExpr v[2];
+    size_t row_begin, row_end; // all rows
+    size_t vec_begin;          // first row of the vector region (multiple of 4)
+    size_t n_chunks;           // 128-row chunks in the vector region
+    const long long* mask;     // optional 0/1 per row
+    // group state
+    long long key_min;
+    unsigned long long key_domain;     // G_SMEM / G_DENSE: number of slots
+    double* g_sum0;
+    double* g_sum1;
+    unsigned long long* g_cnt;
+    long long* h_keys;                 // G_HASH: capacity+1 entries
+    unsigned long long h_mask;
+    // join
+    int jmode;
+    long long jk_min;
+    unsigned long long jk_domain;
+    const unsigned* j_bitmap;
+    const unsigned* j_direct;
+    const long long* jh_keys;
+    const unsigned* jh_rows;
+    unsigned long long jh_mask;
+    // G_NONE partials: [grid] x {cnt, sum0, sum1}
+    unsigned long long* part_cnt;
+    double* part_sum;                  // [grid][2]
+    unsigned* ticket;
+    int* err;                          // 1 = integer division by zero, 2 = group table full
+};
+
+// ---- compile-time / run-time slot description ---------------------------------------------------
+// SHAPE packs 4 bits per slot: 0 = absent, else 1+kind; bit 3 = value comes from the build side.
+constexpr uint32_t shape_bits(int slot, int kind, bool from_build) {
+    return static_cast<uint32_t>((1 + kind) | (from_build ? 8 : 0)) << (4 * slot);
+}
+template <uint32_t SHAPE>
+struct Shape {
+    static constexpr bool generic = (SHAPE == kGenericShape);
+    BQ_D static bool present(const ScanParams& p, int s) {
+        if (generic) return (p.present >> s) & 1u;
+        return ((SHAPE >> (4 * s)) & 7u) != 0;
+    }
+    BQ_D static int kind(const ScanParams& p, int s) {
+        if (generic) return p.s[s].kind;
+        return static_cast<int>((SHAPE >> (4 * s)) & 7u) - 1;
+    }
+    BQ_D static bool from_build(const ScanParams& p, int s) {
+        if (generic) return p.s[s].from_build != 0;
+        return ((SHAPE >> (4 * s)) & 8u) != 0;
+    }
+    BQ_D static bool streamed(const ScanParams& p, int s) { return present(p, s) && !from_build(p, s); }
+};
+
+// ---- loads ---------------------------------------------------------------------------------------
+BQ_D int2 ldg_stream2(const int2* p) {
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.s32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+BQ_D long long pack64(int lo, int hi) {
+    return static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(hi)) << 32) |
+                                  static_cast<unsigned>(lo));
+}
+// rows {base+2t, base+2t+1, base+64+2t, base+65+2t} of one column widened to 8-byte slot values
+BQ_D void load_quad(const void* ptr, int kind, size_t base, int lane, long long (&raw)[4]) {
+    if (kind == BQ_INT64 || kind == BQ_DOUBLE) {
+        const int4* q = reinterpret_cast<const int4*>(static_cast<const char*>(ptr) + (base + 2 * lane) * 8);
+        int4 a = ldg_stream(q);
+        int4 b = ldg_stream(q + 32);
+        raw[0] = pack64(a.x, a.y);
+        raw[1] = pack64(a.z, a.w);
+        raw[2] = pack64(b.x, b.y);
+        raw[3] = pack64(b.z, b.w);
+    } else {
+        const int2* q = reinterpret_cast<const int2*>(static_cast<const char*>(ptr) + (base + 2 * lane) * 4);
+        int2 a = ldg_stream2(q);
+        int2 b = ldg_stream2(q + 32);
+        if (kind == BQ_STRING) {
+            raw[0] = static_cast<unsigned>(a.x);
+            raw[1] = static_cast<unsigned>(a.y);
+            raw[2] = static_cast<unsigned>(b.x);
+            raw[3] = static_cast<unsigned>(b.y);
+        } else {
+            raw[0] = a.x;
+            raw[1] = a.y;
+            raw[2] = b.x;
+            raw[3] = b.y;
+        }
+    }
+}
+
+// ---- aggregate argument: numeric_binary + datum_as_double ---------------------------------------
+BQ_D double eval_vexpr(const DVExpr& e, long long a, int ka, long long b, int kb, int* err) {
+    if (e.op == BQ_V_A) return as_double(a, ka);
+    if (e.op == BQ_V_B) return as_double(b, kb);
+    long long r = b;
+    int kr = kb;
+    if (e.b_is_imm) {
+        r = e.imm_is_f ? __double_as_longlong(e.imm_f) : e.imm_i;
+        kr = e.imm_is_f ? BQ_DOUBLE : BQ_INT64;
+    }
+    long long l = a;
+    int kl = ka;
+    if (e.swap) {
+        long long t = l; l = r; r = t;
+        int kt = kl; kl = kr; kr = kt;
+    }
+    if (kl == BQ_DOUBLE || kr == BQ_DOUBLE) {       // src/exec/expression.cpp:34-44
+        double x = as_double(l, kl), y = as_double(r, kr);
+        switch (e.op) {
+            case BQ_V_MUL: return __dmul_rn(x, y);
+            case BQ_V_ADD: return __dadd_rn(x, y);
+            case BQ_V_SUB: return __dsub_rn(x, y);
+            default: return y == 0.0 ? __longlong_as_double(0x7FF0000000000000LL) : __ddiv_rn(x, y);
+        }
+    }
+    long long z = 0;                                // src/exec/expression.cpp:45-56 (wraps like int64_t)
+    switch (e.op) {
+        case BQ_V_MUL: z = static_cast<long long>(static_cast<unsigned long long>(l) * static_cast<unsigned long long>(r)); break;
+        case BQ_V_ADD: z = static_cast<long long>(static_cast<unsigned long long>(l) + static_cast<unsigned long long>(r)); break;
+        case BQ_V_SUB: z = static_cast<long long>(static_cast<unsigned long long>(l) - static_cast<unsigned long long>(r)); break;
+        default:
+            if (r == 0) { *err = 1; z = 0; }
+            else if (l == INT64_MIN && r == -1) z = INT64_MIN;
+            else z = l / r;
+    }
+    return static_cast<double>(z);
+}
+
+// ---- group table claim (open addressing, linear probing) ----------------------------------------
+BQ_D unsigned long long group_slot(long long* h_keys, unsigned long long h_mask, int* err, long long key) {
+    if (key == kEmptyKey) return h_mask + 1;        // spare slot for the one key that equals the marker
+    unsigned long long h = key_hash(static_cast<uint64_t>(key)) & h_mask;
+    for (unsigned long long probes = 0; probes <= h_mask; ++probes) {
+        long long cur = *reinterpret_cast<volatile long long*>(h_keys + h);
+        if (cur == key) return h;
+        if (cur == kEmptyKey) {
+            long long prev = static_cast<long long>(atomicCAS(reinterpret_cast<unsigned long long*>(h_keys + h),
+                                                              static_cast<unsigned long long>(kEmptyKey),
+                                                              static_cast<unsigned long long>(key)));
+            if (prev == kEmptyKey || prev == key) return h;
+        }
+        h = (h + 1) & h_mask;
+    }
+    *err = 2;
+    return h_mask + 1;
+}
+
+template <uint32_t SHAPE, int GMODE>
+struct RowSink {
+    using Sh = Shape<SHAPE>;
+    const ScanParams& p;
+    double* s_sum0;
+    double* s_sum1;
+    unsigned* s_cnt;
+    unsigned long long cnt = 0;
+    double sum0 = 0.0, sum1 = 0.0;
+    int err = 0;
+
+    BQ_D RowSink(const ScanParams& pp, double* a, double* b, unsigned* c) : p(pp), s_sum0(a), s_sum1(b), s_cnt(c) {}
+
+    // one qualifying (probe row, build row) pair
+    BQ_D void add(long long key_raw, long long a, long long b) {
+        const int ka = Sh::present(p, S_A) ? Sh::kind(p, S_A) : BQ_INT64;
+        const int kb = Sh::present(p, S_B) ? Sh::kind(p, S_B) : BQ_INT64;
+        double v0 = 0.0, v1 = 0.0;
+        if (p.nv > 0) v0 = eval_vexpr(p.v[0], a, ka, b, kb, &err);
+        if (p.nv > 1) v1 = eval_vexpr(p.v[1], a, ka, b, kb, &err);
+        if (GMODE == G_NONE) {
+            cnt += 1;
+            sum0 = __dadd_rn(sum0, v0);
+            sum1 = __dadd_rn(sum1, v1);
+        } else if (GMODE == G_SMEM) {
+            unsigned long long idx = static_cast<unsigned long long>(key_raw - p.key_min);
+            if (idx < p.key_domain) {
+                atomicAdd(s_cnt + idx, 1u);
+                if (p.nv > 0) atomicAdd(s_sum0 + idx, v0);
+                if (p.nv > 1) atomicAdd(s_sum1 + idx, v1);
+            }
+        } else if (GMODE == G_DENSE) {
+            unsigned long long idx = static_cast<unsigned long long>(key_raw - p.key_min);
+            if (idx < p.key_domain) {
+                atomicAdd(p.g_cnt + idx, 1ULL);
+                if (p.nv > 0) atomicAdd(p.g_sum0 + idx, v0);
+                if (p.nv > 1) atomicAdd(p.g_sum1 + idx, v1);
+            }
+        } else {
+            long long k = key_raw;
+            if (Sh::kind(p, S_KEY) == BQ_DOUBLE && k == INT64_MIN) k = 0;   // -0.0 groups with +0.0
+            unsigned long long idx = group_slot(p.h_keys, p.h_mask, p.err, k);
+            atomicAdd(p.g_cnt + idx, 1ULL);
+            if (p.nv > 0) atomicAdd(p.g_sum0 + idx, v0);
+            if (p.nv > 1) atomicAdd(p.g_sum1 + idx, v1);
+        }
+    }
+
+    // a probe row that passed every streamed range: resolve the join, then add each match
+    BQ_D void row(long long key_raw, long long a, long long b, long long jk) {
+        if (p.jmode == 0) {
+            add(key_raw, a, b);
+            return;
+        }
+        if (Sh::kind(p, S_JK) == BQ_DOUBLE) {
+            if (jk == INT64_MIN) jk = 0;                                         // -0.0 == 0.0 (KeyEqual, :657)
+            if ((jk & 0x7FFFFFFFFFFFFFFFLL) > 0x7FF0000000000000LL) return;      // NaN never matches
+        }
+        if (p.jmode == BQ_JOIN_BITMAP) {
+            unsigned long long idx = static_cast<unsigned long long>(jk - p.jk_min);
+            if (idx < p.jk_domain && ((__ldg(p.j_bitmap + (idx >> 5)) >> (idx & 31)) & 1u)) add(key_raw, a, b);
+            return;
+        }
+        if (p.jmode == BQ_JOIN_DIRECT) {
+            unsigned long long idx = static_cast<unsigned long long>(jk - p.jk_min);
+            if (idx >= p.jk_domain) return;
+            unsigned e = __ldg(p.j_direct + idx);
+            if (e) build_add(key_raw, a, b, e - 1);
+            return;
+        }
+        unsigned long long h = key_hash(static_cast<uint64_t>(jk)) & p.jh_mask;
+        for (unsigned long long probes = 0; probes <= p.jh_mask; ++probes) {
+            unsigned e = __ldg(p.jh_rows + h);
+            if (!e) return;
+            if (__ldg(p.jh_keys + h) == jk) build_add(key_raw, a, b, e - 1);
+            h = (h + 1) & p.jh_mask;
+        }
+    }
+
+    BQ_D void build_add(long long key_raw, long long a, long long b, unsigned brow) {
+        if (Sh::present(p, S_KEY) && Sh::from_build(p, S_KEY)) key_raw = load_raw(p.s[S_KEY].ptr, Sh::kind(p, S_KEY), brow);
+        if (Sh::present(p, S_A) && Sh::from_build(p, S_A)) a = load_raw(p.s[S_A].ptr, Sh::kind(p, S_A), brow);
+        if (Sh::present(p, S_B) && Sh::from_build(p, S_B)) b = load_raw(p.s[S_B].ptr, Sh::kind(p, S_B), brow);
+        add(key_raw, a, b);
+    }
+};
+
+template <uint32_t SHAPE, int GMODE>
+__global__ void __launch_bounds__(kBlock) k_scan(const __grid_constant__ ScanParams p) {
+    using Sh = Shape<SHAPE>;
+    extern __shared__ double smem_dyn[];
+    __shared__ double red_sum[kBlock / 32][2];
+    __shared__ unsigned long long red_cnt[kBlock / 32];
+    __shared__ int red_err;
+    __shared__ bool is_last;
+
+    double* s_sum0 = nullptr;
+    double* s_sum1 = nullptr;
+    unsigned* s_cnt = nullptr;
+    if (GMODE == G_SMEM) {
+        s_sum0 = smem_dyn;
+        s_sum1 = smem_dyn + p.key_domain;
+        s_cnt = reinterpret_cast<unsigned*>(smem_dyn + 2 * p.key_domain);
+        for (unsigned long long i = threadIdx.x; i < p.key_domain; i += blockDim.x) {
+            s_sum0[i] = 0.0;
+            s_sum1[i] = 0.0;
+            s_cnt[i] = 0u;
+        }
+    }
+    if (threadIdx.x == 0) red_err = 0;
+    __syncthreads();
+
+    RowSink<SHAPE, GMODE> sink(p, s_sum0, s_sum1, s_cnt);
+    const int lane = threadIdx.x & 31;
+    const size_t warps_total = static_cast<size_t>(gridDim.x) * (kBlock / 32);
+    const size_t warp_global = static_cast<size_t>(blockIdx.x) * (kBlock / 32) + (threadIdx.x >> 5);
+
+    // ---- vector region: whole 128-row chunks -----------------------------------------------------
+    for (size_t c = warp_global; c < p.n_chunks; c += warps_total) {
+        const size_t base = p.vec_begin + c * 128;
+        long long raw[N_SLOTS][4];
+        long long mk[4] = {1, 1, 1, 1};
+        // phase 1: issue every load of the chunk
+#pragma unroll
+        for (int s = 0; s < N_SLOTS; ++s) {
+            if (Sh::streamed(p, s)) load_quad(p.s[s].ptr, Sh::kind(p, s), base, lane, raw[s]);
+        }
+        if (p.mask) load_quad(p.mask, BQ_INT64, base, lane, mk);
+        // phase 2: range tests
+        unsigned pass = 0xFu;
+#pragma unroll
+        for (int s = 0; s < N_SLOTS; ++s) {
+            if (Sh::streamed(p, s) && p.s[s].nr > 0) {
+                const int kind = Sh::kind(p, s);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    long long k = key_of(raw[s][r], kind);
+                    bool ok = in_range(k, p.s[s].lo0, p.s[s].hi0, p.s[s].neg0);
+                    if (p.s[s].nr > 1) ok = ok && in_range(k, p.s[s].lo1, p.s[s].hi1, p.s[s].neg1);
+                    if (!ok) pass &= ~(1u << r);
+                }
+            }
+        }
+        if (p.mask) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (mk[r] == 0) pass &= ~(1u << r);
+        }
+        // phase 3: aggregate the survivors
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (pass & (1u << r)) {
+                long long kr = Sh::streamed(p, S_KEY) ? raw[S_KEY][r] : 0;
+                long long a = Sh::streamed(p, S_A) ? raw[S_A][r] : 0;
+                long long b = Sh::streamed(p, S_B) ? raw[S_B][r] : 0;
+                long long jk = Sh::streamed(p, S_JK) ? raw[S_JK][r] : 0;
+                sink.row(kr, a, b, jk);
+            }
+        }
+    }
+
+    // ---- head and tail rows (fewer than 4 + 128): one row per thread, CTA 0 -----------------------
+    if (blockIdx.x == 0) {
+        const size_t vec_end = p.vec_begin + p.n_chunks * 128;
+        const size_t n_head = p.vec_begin - p.row_begin;
+        const size_t n_tail = p.row_end - vec_end;
+        for (size_t t = threadIdx.x; t < n_head + n_tail; t += blockDim.x) {
+            const size_t i = t < n_head ? p.row_begin + t : vec_end + (t - n_head);
+            bool ok = true;
+            long long val[N_SLOTS];
+#pragma unroll
+            for (int s = 0; s < N_SLOTS; ++s) {
+                val[s] = 0;
+                if (Sh::streamed(p, s)) {
+                    val[s] = load_raw(p.s[s].ptr, Sh::kind(p, s), i);
+                    ok = ok && slot_pass(p.s[s], val[s]);
+                }
+            }
+            if (p.mask && __ldg(p.mask + i) == 0) ok = false;
+            if (ok) sink.row(val[S_KEY], val[S_A], val[S_B], val[S_JK]);
+        }
+    }
+
+    // ---- epilogue ----------------------------------------------------------------------------------
+    if (sink.err) atomicOr(&red_err, sink.err);
+    if (GMODE == G_NONE) {
+        unsigned long long c = warp_sum(sink.cnt);
+        double s0 = warp_sum(sink.sum0), s1 = warp_sum(sink.sum1);
+        if (lane == 0) {
+            red_cnt[threadIdx.x >> 5] = c;
+            red_sum[threadIdx.x >> 5][0] = s0;
+            red_sum[threadIdx.x >> 5][1] = s1;
+        }
+    }
+    __syncthreads();
+    if (GMODE == G_SMEM) {
+        // merge the CTA's table into the global one: one red per touched group per CTA
+        for (unsigned long long i = threadIdx.x; i < p.key_domain; i += blockDim.x) {
+            unsigned c = s_cnt[i];
+            if (c) {
+                atomicAdd(p.g_cnt + i, static_cast<unsigned long long>(c));
+                if (p.nv > 0) atomicAdd(p.g_sum0 + i, s_sum0[i]);
+                if (p.nv > 1) atomicAdd(p.g_sum1 + i, s_sum1[i]);
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        if (red_err) atomicOr(p.err, red_err);
+        if (GMODE == G_NONE) {
+            unsigned long long c = 0;
+            double s0 = 0.0, s1 = 0.0;
+            for (int w = 0; w < kBlock / 32; ++w) {     // fixed order: deterministic per grid size
+                c += red_cnt[w];
+                s0 = __dadd_rn(s0, red_sum[w][0]);
+                s1 = __dadd_rn(s1, red_sum[w][1]);
+            }
+            p.part_cnt[blockIdx.x] = c;
+            p.part_sum[2 * blockIdx.x] = s0;
+            p.part_sum[2 * blockIdx.x + 1] = s1;
+            __threadfence();
+            unsigned t = atomicAdd(p.ticket, 1u);
+            is_last = (t == gridDim.x - 1);
+        }
+    }
+    if (GMODE == G_NONE) {
+        __syncthreads();
+        if (is_last && threadIdx.x == 0) {
+            // the last CTA folds the per-CTA partials in CTA order into slot 0 of the global state
+            unsigned long long c = 0;
+            double s0 = 0.0, s1 = 0.0;
+            for (unsigned b = 0; b < gridDim.x; ++b) {
+                c += *reinterpret_cast<volatile unsigned long long*>(p.part_cnt + b);
+                s0 = __dadd_rn(s0, *reinterpret_cast<volatile double*>(p.part_sum + 2 * b));
+                s1 = __dadd_rn(s1, *reinterpret_cast<volatile double*>(p.part_sum + 2 * b + 1));
+            }
+            p.g_cnt[0] = c;
+            p.g_sum0[0] = s0;
+            p.g_sum1[0] = s1;
+            *p.ticket = 0;
+        }
+    }
+}
+
+// ---- emit: presence bits over the state, then one thread per surviving group ---------------------
+__global__ void __launch_bounds__(kBlock) k_presence_bits(const unsigned long long* __restrict__ cnt, size_t n,
+                                                          unsigned* __restrict__ bits) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    bool on = i < n && cnt[i] != 0ULL;
+    unsigned b = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0 && (i >> 5) < (n + 31) / 32) bits[i >> 5] = b;
+}
+
+struct EmitParams {
+    const unsigned* rowids;
+    size_t n;
+    int gmode;
+    int key_type;
+    long long key_min;
+    const long long* h_keys;
+    const unsigned long long* cnt;
+    const double* sum0;
+    const double* sum1;
+    void* out_key;
+    int n_out;
+    int func[BQ_MAX_AGG_OUT];
+    int v[BQ_MAX_AGG_OUT];
+    int as_int[BQ_MAX_AGG_OUT];
+    void* out[BQ_MAX_AGG_OUT];
+};
+
+__global__ void __launch_bounds__(kBlock) k_emit(const __grid_constant__ EmitParams p) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= p.n) return;
+    size_t g = p.rowids ? p.rowids[i] : i;
+    if (p.out_key) {
+        long long k = (p.gmode == G_HASH) ? p.h_keys[g] : p.key_min + static_cast<long long>(g);
+        switch (p.key_type) {
+            case BQ_INT64:
+            case BQ_DOUBLE: static_cast<long long*>(p.out_key)[i] = k; break;
+            case BQ_STRING: static_cast<unsigned*>(p.out_key)[i] = static_cast<unsigned>(k); break;
+            default: static_cast<int*>(p.out_key)[i] = static_cast<int>(k); break;
+        }
+    }
+    unsigned long long c = p.cnt[g];
+    for (int o = 0; o < p.n_out; ++o) {
+        double s = p.v[o] == 0 ? p.sum0[g] : p.sum1[g];
+        if (p.func[o] == BQ_AGG_COUNT) {
+            static_cast<long long*>(p.out[o])[i] = static_cast<long long>(c);
+        } else if (p.func[o] == BQ_AGG_SUM) {
+            if (p.as_int[o]) static_cast<long long*>(p.out[o])[i] = static_cast<long long>(s);   // :1044
+            else static_cast<double*>(p.out[o])[i] = s;
+        } else {
+            static_cast<double*>(p.out[o])[i] = c == 0 ? 0.0 : __ddiv_rn(s, static_cast<double>(c));   // :1047
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) k_fill_keys(long long* __restrict__ keys, size_t n, long long v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) keys[i] = v;
+}
+
+// ---- shape registry -------------------------------------------------------------------------------
+using ScanKernel = void (*)(const ScanParams);
+struct ShapeEntry {
+    uint32_t shape;
+    int gmode;
+    ScanKernel fn;
+};
+#define BQ_SHAPE(shape, gmode) {shape, gmode, k_scan<shape, gmode>}
+
+// Q1: status (STRING range) AND order_date (DATE32 ranges, also the group key), SUM(total DOUBLE)
+constexpr uint32_t kShapeQ1 = shape_bits(S_KEY, BQ_DATE32, false) | shape_bits(S_A, BQ_DOUBLE, false) |
+                              shape_bits(S_P0, BQ_STRING, false);
+// filter sweep: predicate column of each type, SUM(v DOUBLE) [+ SUM(w INT64)]
+constexpr uint32_t kShapeF_I64 = shape_bits(S_A, BQ_DOUBLE, false) | shape_bits(S_P0, BQ_INT64, false);
+constexpr uint32_t kShapeF_F64 = shape_bits(S_A, BQ_DOUBLE, false) | shape_bits(S_P0, BQ_DOUBLE, false);
+constexpr uint32_t kShapeF_STR = shape_bits(S_A, BQ_DOUBLE, false) | shape_bits(S_P0, BQ_STRING, false);
+constexpr uint32_t kShapeF_DATE = shape_bits(S_A, BQ_DOUBLE, false) | shape_bits(S_P0, BQ_DATE32, false);
+constexpr uint32_t kShapeF2_I64 = kShapeF_I64 | shape_bits(S_B, BQ_INT64, false);
+constexpr uint32_t kShapeF2_F64 = kShapeF_F64 | shape_bits(S_B, BQ_INT64, false);
+constexpr uint32_t kShapeF2_STR = kShapeF_STR | shape_bits(S_B, BQ_INT64, false);
+constexpr uint32_t kShapeF2_DATE = kShapeF_DATE | shape_bits(S_B, BQ_INT64, false);
+// predicate on the summed column itself
+constexpr uint32_t kShapeA_F64 = shape_bits(S_A, BQ_DOUBLE, false);
+// Q2: probe l.order_id, GROUP BY l.sku (INT64 or STRING), SUM(l.qty INT64 * l.price DOUBLE)
+constexpr uint32_t kShapeQ2 = shape_bits(S_KEY, BQ_INT64, false) | shape_bits(S_A, BQ_INT64, false) |
+                              shape_bits(S_B, BQ_DOUBLE, false) | shape_bits(S_JK, BQ_INT64, false);
+constexpr uint32_t kShapeQ2S = shape_bits(S_KEY, BQ_STRING, false) | shape_bits(S_A, BQ_INT64, false) |
+                               shape_bits(S_B, BQ_DOUBLE, false) | shape_bits(S_JK, BQ_INT64, false);
+// high-cardinality GROUP BY k (INT64) SUM/COUNT/AVG(v DOUBLE)
+constexpr uint32_t kShapeGB = shape_bits(S_KEY, BQ_INT64, false) | shape_bits(S_A, BQ_DOUBLE, false);
+// skewed join: probe p.k, SUM(p.v * b.w) with b.w from the build side
+constexpr uint32_t kShapeJ5 = shape_bits(S_A, BQ_DOUBLE, false) | shape_bits(S_B, BQ_DOUBLE, true) |
+                              shape_bits(S_JK, BQ_INT64, false);
+
+static const ShapeEntry kShapes[] = {
+    BQ_SHAPE(kShapeQ1, G_SMEM),      BQ_SHAPE(kShapeQ1, G_DENSE),
+    BQ_SHAPE(kShapeF_I64, G_NONE),   BQ_SHAPE(kShapeF_F64, G_NONE),  BQ_SHAPE(kShapeF_STR, G_NONE),
+    BQ_SHAPE(kShapeF_DATE, G_NONE),  BQ_SHAPE(kShapeF2_I64, G_NONE), BQ_SHAPE(kShapeF2_F64, G_NONE),
+    BQ_SHAPE(kShapeF2_STR, G_NONE),  BQ_SHAPE(kShapeF2_DATE, G_NONE), BQ_SHAPE(kShapeA_F64, G_NONE),
+    BQ_SHAPE(kShapeQ2, G_DENSE),     BQ_SHAPE(kShapeQ2, G_HASH),     BQ_SHAPE(kShapeQ2S, G_DENSE),
+    BQ_SHAPE(kShapeQ2S, G_SMEM),     BQ_SHAPE(kShapeGB, G_HASH),     BQ_SHAPE(kShapeGB, G_DENSE),
+    BQ_SHAPE(kShapeJ5, G_NONE),
+    // any other slot layout: same source, run-time flags
+    BQ_SHAPE(kGenericShape, G_NONE), BQ_SHAPE(kGenericShape, G_SMEM), BQ_SHAPE(kGenericShape, G_DENSE),
+    BQ_SHAPE(kGenericShape, G_HASH),
+};
+
+static ScanKernel pick_kernel(uint32_t shape, int gmode, bool* specialised) {
+    for (const auto& e : kShapes)
+        if (e.shape == shape && e.gmode == gmode) {
+            *specialised = true;
+            return e.fn;
+        }
+    for (const auto& e : kShapes)
+        if (e.shape == kGenericShape && e.gmode == gmode) {
+            *specialised = false;
+            return e.fn;
+        }
+    throw std::runtime_error("no scan kernel for group mode");
+}
+
+DSlot make_dslot(const bq_slot& s, size_t need_rows, const char* what) {
+    DSlot d{};
+    if (!s.col) return d;
+    if (!s.from_build && s.col->n < need_rows)
+        throw std::runtime_error(std::string("column bound to slot '") + what + "' is shorter than the scanned row range");
+    if (s.n_ranges < 0 || s.n_ranges > 2) throw std::runtime_error("a slot carries at most two ranges");
+    d.ptr = s.col->ptr;
+    d.kind = s.col->type;
+    d.nr = s.n_ranges;
+    d.lo0 = s.r[0].lo; d.hi0 = s.r[0].hi; d.neg0 = s.r[0].neg;
+    d.lo1 = s.r[1].lo; d.hi1 = s.r[1].hi; d.neg1 = s.r[1].neg;
+    d.from_build = s.from_build;
+    return d;
+}
+
+static size_t next_pow2(size_t v) {
+    size_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+struct AggState {
+    int gmode = G_NONE;
+    size_t slots = 1;              // entries of cnt/sum arrays
+    int key_type = BQ_INT64;
+    bool has_key = false;
+    long long key_min = 0;
+    unsigned long long* cnt = nullptr;
+    double* sum0 = nullptr;
+    double* sum1 = nullptr;
+    long long* h_keys = nullptr;
+    void* block = nullptr;         // one allocation behind the arrays
+
+    ~AggState() {
+        if (block) cudaFree(block);
+    }
+};
+
+// Runs the fused kernel for `spec`, leaving the aggregate state on the device.
+static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st) {
+    if (spec->row_end < spec->row_begin) throw std::runtime_error("bad row range");
+    if (spec->row_end > 0xFFFFFFFFull) throw std::runtime_error("row ids are 32-bit: at most 2^32 rows per scan");
+    ScanParams p{};
+    const bq_slot* slots[N_SLOTS] = {&spec->key, &spec->a, &spec->b, &spec->pred[0], &spec->pred[1], &spec->pred[2], &spec->jkey};
+    static const char* names[N_SLOTS] = {"key", "a", "b", "pred0", "pred1", "pred2", "jkey"};
+    uint32_t shape = 0;
+    for (int s = 0; s < N_SLOTS; ++s) {
+        p.s[s] = make_dslot(*slots[s], spec->row_end, names[s]);
+        if (slots[s]->col) {
+            p.present |= 1u << s;
+            shape |= shape_bits(s, p.s[s].kind, p.s[s].from_build != 0);
+            if (p.s[s].from_build && p.s[s].nr) throw std::runtime_error("build-side predicates belong in bq_join_build");
+            if (p.s[s].from_build && !spec->join) throw std::runtime_error("from_build slot without a join");
+        }
+    }
+    if (spec->n_v < 0 || spec->n_v > 2) throw std::runtime_error("at most two aggregate arguments");
+    p.nv = spec->n_v;
+    for (int i = 0; i < spec->n_v; ++i) {
+        const bq_vexpr& e = spec->v[i];
+        if (e.op < BQ_V_A || e.op > BQ_V_DIV) throw std::runtime_error("bad aggregate argument op");
+        bool needs_a = e.op != BQ_V_B;
+        bool needs_b = e.op == BQ_V_B || (e.op >= BQ_V_MUL && !e.b_is_imm);
+        if (needs_a && !spec->a.col) throw std::runtime_error("aggregate argument reads slot a, which is empty");
+        if (needs_b && !spec->b.col) throw std::runtime_error("aggregate argument reads slot b, which is empty");
+        p.v[i] = DVExpr{e.op, e.b_is_imm, e.imm_is_f, e.swap, e.imm_i, e.imm_f};
+    }
+    p.row_begin = spec->row_begin;
+    p.row_end = spec->row_end;
+    p.vec_begin = ((spec->row_begin + 3) / 4) * 4;
+    if (p.vec_begin > p.row_end) p.vec_begin = p.row_end;
+    p.n_chunks = (p.row_end - p.vec_begin) / 128;
+    if (spec->mask) {
+        if (spec->mask->type != BQ_INT64 || spec->mask->n < spec->row_end) throw std::runtime_error("mask must be an INT64 column covering the row range");
+        p.mask = static_cast<const long long*>(spec->mask->ptr);
+    }
+
+    // ---- join ----
+    if (spec->join) {
+        const bq_join* j = spec->join;
+        if (!spec->jkey.col) throw std::runtime_error("join without a probe key slot");
+        p.jmode = j->kind;
+        p.jk_min = j->key_min;
+        p.jk_domain = static_cast<unsigned long long>(j->key_max - j->key_min) + 1ULL;
+        p.j_bitmap = j->bitmap;
+        p.j_direct = j->direct;
+        p.jh_keys = j->h_keys;
+        p.jh_rows = j->h_rows;
+        p.jh_mask = j->h_mask;
+        if (j->kind == BQ_JOIN_BITMAP)
+            for (int s = 0; s < N_SLOTS; ++s)
+                if (p.s[s].from_build) throw std::runtime_error("a bitmap join carries no build columns");
+    } else if (spec->jkey.col) {
+        throw std::runtime_error("probe key slot without a join");
+    }
+
+    // ---- group state ----
+    st.has_key = spec->group_mode != BQ_GROUP_NONE;
+    size_t smem = 0;
+    if (spec->group_mode == BQ_GROUP_NONE) {
+        st.gmode = G_NONE;
+        st.slots = 1;
+    } else {
+        if (!spec->key.col) throw std::runtime_error("GROUP BY without a key slot");
+        st.key_type = spec->key.col->type;
+        if (spec->group_mode == BQ_GROUP_DENSE) {
+            if (st.key_type == BQ_DOUBLE) throw std::runtime_error("dense grouping needs an integer key");
+            if (spec->key_max < spec->key_min) throw std::runtime_error("dense grouping needs key_min <= key_max");
+            unsigned long long dom = static_cast<unsigned long long>(spec->key_max - spec->key_min) + 1ULL;
+            if (dom > (1ULL << 31)) throw std::runtime_error("dense domain too large");
+            st.slots = dom;
+            st.key_min = spec->key_min;
+            size_t need = dom * (2 * sizeof(double) + sizeof(unsigned));
+            if (need <= 48 * 1024) {
+                st.gmode = G_SMEM;
+                smem = need;
+            } else {
+                st.gmode = G_DENSE;
+            }
+        } else {
+            st.gmode = G_HASH;
+            size_t hint = spec->ndv_hint ? spec->ndv_hint : (spec->row_end - spec->row_begin);
+            size_t cap = next_pow2(hint * 2 < 1024 ? 1024 : hint * 2);
+            st.slots = cap + 1;
+            p.h_mask = cap - 1;
+        }
+    }
+    p.key_min = st.key_min;
+    p.key_domain = (st.gmode == G_SMEM || st.gmode == G_DENSE) ? st.slots : 0;
+
+    bool specialised = false;
+    ScanKernel fn = pick_kernel(shape, st.gmode, &specialised);
+    size_t rows = spec->row_end - spec->row_begin;
+    int blocks_per_sm = 4;
+    if (smem > 24 * 1024) blocks_per_sm = 2;
+    int grid = grid_for(ctx, rows, blocks_per_sm);
+
+    // one allocation: cnt | sum0 | sum1 | keys | part_cnt | part_sum | ticket | err
+    size_t n = st.slots;
+    size_t off_cnt = 0, off_s0 = off_cnt + n * 8, off_s1 = off_s0 + n * 8, off_keys = off_s1 + n * 8;
+    size_t off_pc = off_keys + (st.gmode == G_HASH ? n * 8 : 0);
+    size_t off_ps = off_pc + static_cast<size_t>(grid) * 8, off_tk = off_ps + static_cast<size_t>(grid) * 16;
+    size_t total = off_tk + 16;
+    BQ_CUDA(cudaMalloc(&st.block, total));
+    char* base = static_cast<char*>(st.block);
+    st.cnt = reinterpret_cast<unsigned long long*>(base + off_cnt);
+    st.sum0 = reinterpret_cast<double*>(base + off_s0);
+    st.sum1 = reinterpret_cast<double*>(base + off_s1);
+    st.h_keys = st.gmode == G_HASH ? reinterpret_cast<long long*>(base + off_keys) : nullptr;
+    // zero everything (0 bits == 0.0 and count 0), then mark hash keys empty
+    BQ_CUDA(cudaMemsetAsync(st.block, 0, total, ctx->stream));
+    if (st.gmode == G_HASH) {
+        k_fill_keys<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(st.h_keys, n, kEmptyKey);
+        ctx->launches++;
+    }
+    p.g_cnt = st.cnt;
+    p.g_sum0 = st.sum0;
+    p.g_sum1 = st.sum1;
+    p.h_keys = st.h_keys;
+    p.part_cnt = reinterpret_cast<unsigned long long*>(base + off_pc);
+    p.part_sum = reinterpret_cast<double*>(base + off_ps);
+    p.ticket = reinterpret_cast<unsigned*>(base + off_tk);
+    p.err = reinterpret_cast<int*>(base + off_tk + 8);
+
+    if (rows > 0 || st.gmode == G_NONE) {
+        if (smem > 0) BQ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        fn<<<grid, kBlock, smem, ctx->stream>>>(p);
+        ctx->launches++;
+        BQ_CUDA(cudaGetLastError());
+    }
+    // error flag (division by zero / table overflow) comes back with the first host-visible read
+    auto* h = static_cast<int*>(pinned(ctx, 8));
+    BQ_CUDA(cudaMemcpyAsync(h, p.err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (*h & 1) throw std::runtime_error("Division by zero");          // src/exec/expression.cpp:52
+    if (*h & 2) throw std::runtime_error("group table overflow: ndv_hint too small");
+}
+
+// Turns the device state into a relation. partial = [key] count sum0 sum1, else [key] + outs.
+static bq_rel* emit_state(bq_ctx* ctx, AggState& st, const bq_agg_out* outs, int n_out, bool partial) {
+    bq_col* rowids = nullptr;
+    size_t n_groups = 0;
+    {
+        size_t n_words = (st.slots + 31) / 32;
+        unsigned* bits = nullptr;
+        BQ_CUDA(cudaMalloc(&bits, n_words * 4 + 4));
+        try {
+            size_t blocks = (st.slots + kBlock - 1) / kBlock;
+            k_presence_bits<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(st.cnt, st.slots, bits);
+            ctx->launches++;
+            BQ_CUDA(cudaGetLastError());
+            n_groups = compact_bits(ctx, bits, st.slots, 0, &rowids);
+        } catch (...) {
+            cudaFree(bits);
+            throw;
+        }
+        cudaFree(bits);
+    }
+    std::vector<bq_col*> cols;
+    try {
+        EmitParams e{};
+        e.rowids = static_cast<const unsigned*>(rowids->ptr);
+        e.n = n_groups;
+        e.gmode = st.gmode;
+        e.key_type = st.key_type;
+        e.key_min = st.key_min;
+        e.h_keys = st.h_keys;
+        e.cnt = st.cnt;
+        e.sum0 = st.sum0;
+        e.sum1 = st.sum1;
+        if (st.has_key) {
+            cols.push_back(new_col(ctx, st.key_type, n_groups));
+            e.out_key = cols.back()->ptr;
+        }
+        bq_agg_out pouts[3] = {{BQ_AGG_COUNT, 0, 0, 0}, {BQ_AGG_SUM, 0, 0, 0}, {BQ_AGG_SUM, 1, 0, 0}};
+        if (partial) {
+            outs = pouts;
+            n_out = 3;
+        }
+        if (n_out < 0 || n_out > BQ_MAX_AGG_OUT) throw std::runtime_error("too many aggregate outputs");
+        e.n_out = n_out;
+        for (int o = 0; o < n_out; ++o) {
+            int type = BQ_DOUBLE;
+            if (outs[o].func == BQ_AGG_COUNT) type = BQ_INT64;
+            else if (outs[o].func == BQ_AGG_SUM) type = outs[o].as_int ? BQ_INT64 : BQ_DOUBLE;
+            else if (outs[o].func != BQ_AGG_AVG) throw std::runtime_error("unknown aggregate function");
+            if (outs[o].v < 0 || outs[o].v > 1) throw std::runtime_error("bad aggregate argument index");
+            cols.push_back(new_col(ctx, type, n_groups));
+            e.func[o] = outs[o].func;
+            e.v[o] = outs[o].v;
+            e.as_int[o] = outs[o].as_int;
+            e.out[o] = cols.back()->ptr;
+        }
+        if (n_groups) {
+            k_emit<<<(unsigned)((n_groups + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(e);
+            ctx->launches++;
+            BQ_CUDA(cudaGetLastError());
+        }
+        BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        free_col(rowids);
+        auto* rel = new bq_rel();
+        rel->cols = cols;
+        rel->rows = n_groups;
+        return rel;
+    } catch (...) {
+        free_col(rowids);
+        for (auto* c : cols) free_col(c);
+        throw;
+    }
+}
+
+// ---- merging partial states (multi-GPU) -----------------------------------------------------------
+struct MergeParams {
+    const void* key;
+    int key_type;
+    const long long* cnt;
+    const double* s0;
+    const double* s1;
+    size_t n;
+    int has_key;
+    long long* h_keys;
+    unsigned long long h_mask;
+    unsigned long long* g_cnt;
+    double* g_sum0;
+    double* g_sum1;
+    int* err;
+};
+
+__global__ void __launch_bounds__(kBlock) k_merge_partial(const __grid_constant__ MergeParams m) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= m.n) return;
+    unsigned long long idx = 0;
+    if (m.has_key) {
+        long long k = load_raw(m.key, m.key_type, i);
+        if (m.key_type == BQ_DOUBLE && k == INT64_MIN) k = 0;
+        idx = group_slot(m.h_keys, m.h_mask, m.err, k);
+    }
+    atomicAdd(m.g_cnt + idx, static_cast<unsigned long long>(m.cnt[i]));
+    atomicAdd(m.g_sum0 + idx, m.s0[i]);
+    atomicAdd(m.g_sum1 + idx, m.s1[i]);
+}
+
+}  // namespace bq
+
+using namespace bq;
+
+extern "C" {
+
+int bq_scan_aggregate(bq_ctx* ctx, const bq_scan_spec* spec, bq_rel** out) {
+    return guarded([&] {
+        AggState st;
+        run_scan(ctx, spec, st);
+        *out = emit_state(ctx, st, spec->out, spec->n_out, false);
+    });
+}
+
+int bq_scan_partial(bq_ctx* ctx, const bq_scan_spec* spec, bq_rel** out) {
+    return guarded([&] {
+        AggState st;
+        run_scan(ctx, spec, st);
+        *out = emit_state(ctx, st, nullptr, 0, true);
+    });
+}
+
+int bq_agg_finish(bq_ctx* ctx, const bq_rel* const* parts, int n_parts, int has_key, int key_type,
+                  const bq_agg_out* outs, int n_out, bq_rel** out) {
+    return guarded([&] {
+        size_t total = 0;
+        const int ncols = has_key ? 4 : 3;
+        for (int i = 0; i < n_parts; ++i) {
+            if (static_cast<int>(parts[i]->cols.size()) != ncols) throw std::runtime_error("partial relation has the wrong arity");
+            total += parts[i]->rows;
+        }
+        AggState st;
+        st.has_key = has_key != 0;
+        st.key_type = key_type;
+        st.gmode = has_key ? G_HASH : G_NONE;
+        size_t cap = next_pow2(total * 2 < 1024 ? 1024 : total * 2);
+        st.slots = has_key ? cap + 1 : 1;
+        size_t n = st.slots;
+        size_t bytes = n * 8 * 4 + 16;
+        BQ_CUDA(cudaMalloc(&st.block, bytes));
+        char* base = static_cast<char*>(st.block);
+        st.cnt = reinterpret_cast<unsigned long long*>(base);
+        st.sum0 = reinterpret_cast<double*>(base + n * 8);
+        st.sum1 = reinterpret_cast<double*>(base + n * 16);
+        st.h_keys = has_key ? reinterpret_cast<long long*>(base + n * 24) : nullptr;
+        int* err = reinterpret_cast<int*>(base + n * 32);
+        BQ_CUDA(cudaMemsetAsync(st.block, 0, bytes, ctx->stream));
+        if (has_key) {
+            k_fill_keys<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(st.h_keys, n, kEmptyKey);
+            ctx->launches++;
+        }
+        // parts are folded one launch after another, i.e. in index order per group
+        for (int i = 0; i < n_parts; ++i) {
+            const bq_rel* r = parts[i];
+            if (!r->rows) continue;
+            MergeParams m{};
+            int c = 0;
+            if (has_key) {
+                m.key = r->cols[c]->ptr;
+                m.key_type = r->cols[c]->type;
+                ++c;
+            }
+            m.cnt = static_cast<const long long*>(r->cols[c]->ptr);
+            m.s0 = static_cast<const double*>(r->cols[c + 1]->ptr);
+            m.s1 = static_cast<const double*>(r->cols[c + 2]->ptr);
+            m.n = r->rows;
+            m.has_key = has_key;
+            m.h_keys = st.h_keys;
+            m.h_mask = cap - 1;
+            m.g_cnt = st.cnt;
+            m.g_sum0 = st.sum0;
+            m.g_sum1 = st.sum1;
+            m.err = err;
+            k_merge_partial<<<(unsigned)((r->rows + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(m);
+            ctx->launches++;
+            BQ_CUDA(cudaGetLastError());
+        }
+        *out = emit_state(ctx, st, outs, n_out, false);
+    });
+}
+
+}  // extern "C"

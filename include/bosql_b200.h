@@ -1,0 +1,255 @@
+/* bosql_b200.h — C ABI of the B200-native bo-sql operator hot path (kernel layer).
+ *
+ * This is the drop-in boundary: plain pointers, sizes and opaque handles, no C++ or torch types.
+ * The C++ operator mirror in bo-sql_b200/host/ (same class names and constructor signatures as the
+ * reference's include/exec/operator.hpp:17-218) is the only product caller; tests and bench.py bind
+ * the same symbols through ctypes.  Each entry point names the reference code it replaces
+ * (paths relative to the reference repository).
+ *
+ * Conventions
+ *  - every function returns 0 on success; on failure it returns nonzero and bq_last_error() holds the
+ *    message (the C++ wrapper rethrows it as std::runtime_error, the reference's only error channel,
+ *    SURVEY.md section 5).
+ *  - type ordinals equal the reference's TypeId (include/types.h:17): INT64, DOUBLE, STRING, DATE32.
+ *    Physical widths: 8, 8, 4 (uint32 dictionary id), 4 (int32 YYYYMMDD)  (include/types.h:11-14).
+ *  - all kernels run on the context's stream (bq_ctx_set_stream); nothing synchronises the device
+ *    unless it returns host-visible data.
+ *  - there is NO CPU fallback anywhere behind this header: without a CUDA device bq_ctx_create fails.
+ */
+#ifndef BOSQL_B200_H
+#define BOSQL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bq_ctx bq_ctx;   /* one per process per GPU */
+typedef struct bq_col bq_col;   /* device-resident column: the HBM mirror of ColumnVector<T> (include/types.h:134-145) */
+typedef struct bq_rel bq_rel;   /* device-resident relation: equal-length columns (an operator's whole output) */
+typedef struct bq_join bq_join; /* built join table (HashJoin::open, src/exec/operator.cpp:739-762) */
+
+enum { BQ_INT64 = 0, BQ_DOUBLE = 1, BQ_STRING = 2, BQ_DATE32 = 3 };
+
+/* ---- context ------------------------------------------------------------------------------- */
+int bq_ctx_create(int device, bq_ctx** out);
+void bq_ctx_destroy(bq_ctx* ctx);
+int bq_ctx_set_stream(bq_ctx* ctx, void* cuda_stream);    /* cudaStream_t; NULL = the context's own stream */
+int bq_ctx_sync(bq_ctx* ctx);
+int bq_ctx_info(bq_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t bq_ctx_launches(bq_ctx* ctx);
+const char* bq_last_error(void);
+
+/* ---- columns: storage/ becomes device resident ------------------------------------------------ */
+int bq_col_alloc(bq_ctx* ctx, int type, size_t n, bq_col** out);
+/* synchronous upload of a host ColumnVector<T>::data (pageable or pinned) */
+int bq_col_upload(bq_ctx* ctx, int type, const void* host, size_t n, bq_col** out);
+/* asynchronous H2D into an existing column (host should be pinned); ordered on the context stream */
+int bq_col_write(bq_ctx* ctx, bq_col* col, size_t offset, const void* host, size_t n);
+/* synchronous D2H of rows [offset, offset+n) */
+int bq_col_read(bq_ctx* ctx, const bq_col* col, size_t offset, size_t n, void* host);
+void bq_col_free(bq_ctx* ctx, bq_col* col);
+size_t bq_col_size(const bq_col* col);
+int bq_col_type(const bq_col* col);
+void* bq_col_ptr(const bq_col* col);                       /* raw device pointer */
+/* Catalog statistics (include/catalog/catalog.h:16-21): min/max on the column's integer key
+ * (for DOUBLE: the order-preserving key of the value, see bq_f64_key) and NDV; used to size tables. */
+int bq_col_set_stats(bq_col* col, int64_t min_key, int64_t max_key, size_t ndv);
+/* min/max computed on the device and cached when the catalog gave none */
+int bq_col_minmax(bq_ctx* ctx, bq_col* col, int64_t* min_key, int64_t* max_key);
+/* order-preserving int64 key of a double (so that every predicate is an integer range test) */
+int64_t bq_f64_key(double v);
+double bq_f64_from_key(int64_t k);
+
+/* pinned host memory for paging results / staging uploads */
+int bq_host_alloc(size_t bytes, void** out);
+void bq_host_free(void* p);
+
+/* ---- deterministic synthetic columns ---------------------------------------------
+ * value(row) = f(seed, stream, global_row) with a counter-based hash, so any slice can be regenerated
+ * on the host (oracle/datagen.py restates the same arithmetic in numpy). */
+enum {
+    BQ_GEN_SEQ = 0,        /* lo + global_row                                   (unique dense keys)      */
+    BQ_GEN_UNIFORM = 1,    /* lo + hash % (hi-lo+1)                             (ints, ids)              */
+    BQ_GEN_UNIFORM_DIV = 2,/* (double)(lo + hash % (hi-lo+1)) / div             (DOUBLE, k/div)          */
+    BQ_GEN_DATE = 3,       /* base_year*10000 + 100*m + d, m in 1..12, d in 1..28, uniform over years    */
+    BQ_GEN_TABLE = 4,      /* inverse-CDF lookup: smallest i with cdf[i] > hash>>11 (53-bit), value lo+i */
+    BQ_GEN_HASHED = 5      /* lo + mix(hash % (hi-lo+1)) % modulus: sparse keys drawn from hi-lo+1 ids   */
+};
+typedef struct bq_gen_spec {
+    int dist;
+    uint64_t seed;
+    uint64_t stream;       /* column id */
+    int64_t lo, hi;
+    double div;            /* BQ_GEN_UNIFORM_DIV */
+    int32_t base_year;     /* BQ_GEN_DATE */
+    int32_t n_years;       /* BQ_GEN_DATE */
+    const uint64_t* cdf;   /* BQ_GEN_TABLE: HOST pointer to n_cdf ascending 53-bit thresholds */
+    size_t n_cdf;
+    uint64_t modulus;      /* BQ_GEN_HASHED */
+} bq_gen_spec;
+int bq_col_generate(bq_ctx* ctx, bq_col* col, const bq_gen_spec* spec, uint64_t global_row0);
+
+/* ---- typed expression programs: exec/expression.cpp compiled once per plan ----------------------
+ * A postfix program over 8-byte slots; every operand type is resolved on the host (so the device never
+ * dispatches on a Datum tag) while keeping evaluate_internal's semantics (src/exec/expression.cpp:153-206):
+ * INT64-left comparisons truncate a DOUBLE right operand (:64), DOUBLE / 0 = +inf (:41), AND/OR evaluate
+ * both sides (:176-198).  INT64 / 0 raises the reference's "Division by zero" (:52) as an error. */
+enum {
+    BQ_OP_COL = 0,     /* push column `arg` widened to 8 bytes (u32 zero-extended, i32 sign-extended) */
+    BQ_OP_IMM_I = 1, BQ_OP_IMM_F = 2,
+    BQ_OP_I2F = 3,     /* top: int64 -> double                      */
+    BQ_OP_I2F_2 = 4,   /* second from top: int64 -> double          */
+    BQ_OP_F2I = 5,     /* top: static_cast<int64_t>(double)         */
+    BQ_OP_SX32 = 6,    /* top: keep the low 32 bits, sign-extended (DATE32-left comparison, :93-94) */
+    BQ_OP_ZX32 = 7,    /* top: keep the low 32 bits, zero-extended (STRING-left comparison, :107-108) */
+    BQ_OP_ADD_I = 8, BQ_OP_SUB_I = 9, BQ_OP_MUL_I = 10, BQ_OP_DIV_I = 11,
+    BQ_OP_ADD_F = 12, BQ_OP_SUB_F = 13, BQ_OP_MUL_F = 14, BQ_OP_DIV_F = 15,
+    BQ_OP_EQ_I = 16, BQ_OP_NE_I = 17, BQ_OP_LT_I = 18, BQ_OP_LE_I = 19, BQ_OP_GT_I = 20, BQ_OP_GE_I = 21,
+    BQ_OP_EQ_F = 22, BQ_OP_NE_F = 23, BQ_OP_LT_F = 24, BQ_OP_LE_F = 25, BQ_OP_GT_F = 26, BQ_OP_GE_F = 27,
+    BQ_OP_TRUTHY_I = 28, /* top: int -> 0/1   (is_truthy, :10-22)  */
+    BQ_OP_TRUTHY_F = 29, /* top: double != 0.0 -> 0/1               */
+    BQ_OP_TRUTHY_I_2 = 30, BQ_OP_TRUTHY_F_2 = 31, /* same on the second from top */
+    BQ_OP_AND = 32, BQ_OP_OR = 33                  /* on 0/1 ints */
+};
+typedef struct bq_insn {
+    int32_t op;
+    int32_t arg;
+    union { int64_t i; double f; } imm;
+} bq_insn;
+#define BQ_MAX_PROGRAM 64
+#define BQ_MAX_PROGRAM_COLS 8
+/* Evaluate a program over rows [row_begin,row_end) of `cols`; the result column has `out_type`
+ * (INT64 takes the slot as int64, DOUBLE as double, STRING/DATE32 its low 32 bits).
+ * Replaces Project::next's per-row evaluate_expr (src/exec/operator.cpp:498-555). */
+int bq_eval(bq_ctx* ctx, const bq_insn* prog, int n_insn, const bq_col* const* cols, int n_cols,
+            size_t row_begin, size_t row_end, int out_type, bq_col** out);
+
+/* ---- fused scan -> selection -> [join probe] -> aggregate ------------------------------------------
+ * One kernel replaces ColumnarScan::next + Selection::next + HashJoin::next + HashAggregate::next's
+ * accumulate phase (src/exec/operator.cpp:345, 403, 764, 984-1014) for the pipeline shapes of the
+ * configurations.  Columns are bound to fixed slots so every value lives in a register:
+ *   key   group key column                       a, b   aggregate argument columns
+ *   pred  up to 3 predicate-only columns         jkey   probe-side join key
+ * Each slot carries up to two integer ranges on the column's order-preserving key: a row passes a range
+ * iff (lo <= key && key <= hi) != neg.  Every `col OP literal` conjunct of the reference's predicate
+ * language reduces to such a range with compare_values' semantics (src/exec/expression.cpp:60-120);
+ * the host compiler (bo-sql_b200/host/expr_compile.cpp) does the reduction, anything else arrives as `mask`. */
+typedef struct bq_range { int64_t lo, hi; int32_t neg; int32_t pad; } bq_range;
+typedef struct bq_slot {
+    const bq_col* col;     /* NULL = slot unused */
+    int32_t n_ranges;
+    int32_t from_build;    /* 1: read the value from the join's build side at the matched row */
+    bq_range r[2];
+} bq_slot;
+/* aggregate argument: datum_as_double(A) / datum_as_double(B) (src/exec/operator.cpp:280-292) or
+ * numeric_binary(A, B|imm) (src/exec/expression.cpp:31-58) followed by datum_as_double */
+enum { BQ_V_NONE = 0, BQ_V_A = 1, BQ_V_B = 2, BQ_V_MUL = 3, BQ_V_ADD = 4, BQ_V_SUB = 5, BQ_V_DIV = 6 };
+typedef struct bq_vexpr {
+    int32_t op;
+    int32_t b_is_imm;      /* right operand is imm (its type: imm_is_f) instead of slot b */
+    int32_t imm_is_f;
+    int32_t swap;          /* evaluate (B|imm) OP A instead of A OP (B|imm) */
+    int64_t imm_i;
+    double imm_f;
+} bq_vexpr;
+enum { BQ_GROUP_NONE = 0, BQ_GROUP_DENSE = 1, BQ_GROUP_HASH = 2 };
+enum { BQ_AGG_COUNT = 0, BQ_AGG_SUM = 1, BQ_AGG_AVG = 2 };
+typedef struct bq_agg_out {
+    int32_t func;          /* BQ_AGG_*                                                     */
+    int32_t v;             /* which value expression (0/1); ignored for COUNT               */
+    int32_t as_int;        /* SUM of a non-DOUBLE argument: static_cast<int64_t>(sum) (src/exec/operator.cpp:1044) */
+    int32_t pad;
+} bq_agg_out;
+#define BQ_MAX_AGG_OUT 8
+typedef struct bq_scan_spec {
+    bq_slot key, a, b, pred[3], jkey;
+    size_t row_begin, row_end;
+    const bq_col* mask;      /* optional INT64 0/1 column from bq_eval: predicate parts no range expresses */
+    int32_t n_v;
+    bq_vexpr v[2];
+    int32_t group_mode;      /* BQ_GROUP_* ; DENSE needs key_min/key_max (catalog stats)    */
+    int64_t key_min, key_max;
+    size_t ndv_hint;         /* HASH: table capacity = next pow2 >= 2*ndv_hint               */
+    const bq_join* join;     /* optional: inner-join probe on jkey                          */
+    int32_t n_out;
+    bq_agg_out out[BQ_MAX_AGG_OUT];
+} bq_scan_spec;
+/* Result relation: [key] then one column per out[] — HashAggregate's emit layout (src/exec/operator.cpp:1016-1062).
+ * Rows = groups that received at least one row (none at all for a global aggregate over zero rows, :990-993).
+ * Emit order: ascending key (DENSE) / table order (HASH); the reference's order is unordered_map iteration order
+ * and carries no meaning. */
+int bq_scan_aggregate(bq_ctx* ctx, const bq_scan_spec* spec, bq_rel** out);
+
+/* Partial aggregate state for multi-GPU merges: same pipeline, but instead of finished outputs the relation
+ * holds [key] count sum0 sum1 (INT64, DOUBLE, DOUBLE), to be combined across ranks and finished by bq_agg_finish. */
+int bq_scan_partial(bq_ctx* ctx, const bq_scan_spec* spec, bq_rel** out);
+/* Merge `n_parts` partial relations (equal keys combined, parts added in index order) and emit final outputs. */
+int bq_agg_finish(bq_ctx* ctx, const bq_rel* const* parts, int n_parts, int has_key, int key_type,
+                  const bq_agg_out* outs, int n_out, bq_rel** out);
+
+/* ---- selection vectors: Selection::next + copy_selected (src/exec/operator.cpp:403-429, 11-49) ------
+ * Rows of [row_begin,row_end) passing all slot ranges (and mask), in scan order, as a STRING-typed (uint32)
+ * column of row ids — warp ballot/popc compaction, stable. */
+typedef struct bq_select_spec {
+    bq_slot pred[4];
+    const bq_col* mask;
+    size_t row_begin, row_end;
+} bq_select_spec;
+int bq_select(bq_ctx* ctx, const bq_select_spec* spec, bq_col** out_rowids);
+/* out[i] = col[rowids[i]] */
+int bq_gather(bq_ctx* ctx, const bq_col* col, const bq_col* rowids, bq_col** out);
+/* out = col[begin:end) (copy_range, src/exec/operator.cpp:51-82) */
+int bq_slice(bq_ctx* ctx, const bq_col* col, size_t begin, size_t end, bq_col** out);
+
+/* ---- hash join ---------------------------------------------------------------------------------------
+ * Build on the right child (HashJoin::open, src/exec/operator.cpp:739-762).  The table kind comes from catalog
+ * statistics: BITMAP when the key is unique and dense and no build column is read downstream (semi-join),
+ * DIRECT (row id array indexed by key-min) when unique and dense, HASH (open addressing, linear probing,
+ * duplicate keys kept) otherwise.  Rows failing the build-side ranges / mask are not inserted — the
+ * reference evaluates such predicates above the join (src/logical/planner.cpp:110-117); for an inner join the
+ * row set is the same. */
+enum { BQ_JOIN_AUTO = 0, BQ_JOIN_BITMAP = 1, BQ_JOIN_DIRECT = 2, BQ_JOIN_HASH = 3 };
+typedef struct bq_join_spec {
+    const bq_col* key;
+    bq_slot pred[3];
+    const bq_col* mask;
+    size_t row_begin, row_end;
+    int32_t kind;            /* BQ_JOIN_* */
+    int32_t need_rows;       /* build columns are read downstream (rules out BITMAP) */
+    int32_t unique;          /* catalog: ndv == row_count */
+    int32_t pad;
+    int64_t key_min, key_max;/* catalog min/max of the key */
+} bq_join_spec;
+int bq_join_build(bq_ctx* ctx, const bq_join_spec* spec, bq_join** out);
+void bq_join_free(bq_ctx* ctx, bq_join* j);
+int bq_join_kind(const bq_join* j);
+size_t bq_join_bytes(const bq_join* j);
+/* BITMAP joins: raw words, so ranks can exchange/OR partial bitmaps (multi-GPU broadcast join) */
+void* bq_join_bitmap_ptr(const bq_join* j, size_t* n_words);
+/* Materialising probe (HashJoin::next, src/exec/operator.cpp:764-837): all (probe row, build row) pairs in probe
+ * order, matches of one probe row in build insertion order. `probe_rowids` (optional) restricts/ordering the probe rows. */
+int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const bq_col* probe_rowids,
+                  size_t row_begin, size_t row_end, bq_col** out_probe_rows, bq_col** out_build_rows);
+
+/* ---- OrderBy / Limit (src/exec/operator.cpp:1097-1151, 561-620) ---------------------------------------
+ * Stable LSD radix sort of the relation by up to 4 key columns (asc/desc each); limit >= 0 keeps the first
+ * `limit` rows (top-k when the relation is large).  Ties keep input order (the reference's std::sort leaves
+ * them unspecified). */
+int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int* key_cols, const int* asc,
+                int64_t limit, bq_rel** out);
+
+/* ---- relations -------------------------------------------------------------------------------------- */
+int bq_rel_create(bq_ctx* ctx, bq_col* const* cols, int n_cols, bq_rel** out); /* takes ownership of cols */
+size_t bq_rel_rows(const bq_rel* rel);
+int bq_rel_cols(const bq_rel* rel);
+bq_col* bq_rel_col(const bq_rel* rel, int i);     /* borrowed */
+void bq_rel_free(bq_ctx* ctx, bq_rel* rel);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOSQL_B200_H */

@@ -1,0 +1,102 @@
+"""Quick wall-clock probe of the fused kernels at full size (not the bench; used while developing)."""
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from __graft_entry__ import load_package  # noqa: E402
+from oracle import datagen  # noqa: E402
+from tests.parity import q1_kernel_spec  # noqa: E402
+
+bq = load_package()
+n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000_000
+ctx = bq.Context(0)
+print("sm, free, total:", ctx.info())
+
+
+def gen(schema, n, seed):
+    out = {}
+    for i, (name, typ, spec) in enumerate(schema):
+        t0 = time.perf_counter()
+        out[name] = ctx.alloc(typ, n).generate(seed=seed, stream=i, **spec)
+        ctx.sync()
+        print(f"  gen {name}: {time.perf_counter() - t0:.3f}s")
+    return out
+
+
+def timeit(fn, reps=5):
+    fn()
+    ts = []
+    for _ in range(reps):
+        ctx.sync()
+        t0 = time.perf_counter()
+        fn()
+        ctx.sync()
+        ts.append(time.perf_counter() - t0)
+    return min(ts), sorted(ts)[len(ts) // 2]
+
+
+res = {}
+o = gen(datagen.orders_schema(n), n, 1)
+spec = q1_kernel_spec(bq, o["status"], o["order_date"], o["total"], n, 0, 20240101, 20240131, 20240101, 20241228)
+best, med = timeit(lambda: ctx.scan_aggregate(spec).free())
+res["q1"] = dict(rows=n, best_ms=best * 1e3, med_ms=med * 1e3, gbs=16 * n / best / 1e9, grows=n / best / 1e9)
+print("Q1", res["q1"])
+
+# filter sweep on the same table: SUM(total) WHERE order_id < T
+for sel in (0.01, 0.5, 0.99):
+    s = bq.ScanSpec()
+    s.a = bq.make_slot(o["total"])
+    s.pred[0] = bq.make_slot(o["order_id"], [(-(1 << 63), int(n * sel), 0)])
+    s.row_begin, s.row_end = 0, n
+    s.n_v = 1
+    s.v[0] = bq.VExpr(op=bq.V_A)
+    s.n_out = 2
+    s.out[0] = bq.AggOut(func=bq.AGG_COUNT)
+    s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
+    best, med = timeit(lambda: ctx.scan_aggregate(s).free())
+    res[f"filter_i64_{sel}"] = dict(best_ms=best * 1e3, gbs=16 * n / best / 1e9)
+    print("filter", sel, res[f"filter_i64_{sel}"])
+del o
+
+# Q2: lineitem(n) x orders(n/4)
+no = n // 4
+od = gen(datagen.orders_schema(no, prefix="o.")[:2], no, 2)
+li = gen(datagen.lineitem_schema(no), n, 3)
+t0 = time.perf_counter()
+j = ctx.join_build(od["o.order_id"], preds=[bq.make_slot(od["o.status"], [(0, 0, 0)])], unique=True, key_min=1, key_max=no)
+ctx.sync()
+print("join build", time.perf_counter() - t0, "kind", j.kind, "bytes", j.bytes)
+s = bq.ScanSpec()
+s.key = bq.make_slot(li["l.sku"])
+s.a = bq.make_slot(li["l.qty"])
+s.b = bq.make_slot(li["l.price"])
+s.jkey = bq.make_slot(li["l.order_id"])
+s.join = j.h
+s.row_begin, s.row_end = 0, n
+s.n_v = 1
+s.v[0] = bq.VExpr(op=bq.V_MUL)
+s.group_mode = bq.GROUP_DENSE
+s.key_min, s.key_max = 0, 99999
+s.n_out = 1
+s.out[0] = bq.AggOut(func=bq.AGG_SUM, v=0)
+best, med = timeit(lambda: ctx.scan_aggregate(s).free())
+res["q2_probe"] = dict(best_ms=best * 1e3, gbs=32 * n / best / 1e9)
+print("Q2 probe", res["q2_probe"])
+
+
+def q2_all():
+    jj = ctx.join_build(od["o.order_id"], preds=[bq.make_slot(od["o.status"], [(0, 0, 0)])], unique=True, key_min=1, key_max=no)
+    s.join = jj.h
+    rel = ctx.scan_aggregate(s)
+    top = ctx.rel_sort(rel, [1], [0], limit=20)
+    top.free(); rel.free(); jj.free()
+
+
+best, med = timeit(q2_all)
+res["q2"] = dict(best_ms=best * 1e3, gbs=(32 * n + 12 * no) / best / 1e9, mrows=(n + no) / best / 1e6)
+print("Q2 all", res["q2"])
+os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+json.dump(res, open(os.path.join(ROOT, "gpurun_out", "perf_probe.json"), "w"), indent=1)

@@ -1,0 +1,455 @@
+"""Kernel-layer parity on the GPU: every call goes through the C ABI of include/bosql_b200.h.
+
+Oracles: oracle/datagen.py (generator restatement), the compiled reference executor (oracle/_ref, through SQL on the
+same arrays) and plain numpy restatements of the operator being tested.
+"""
+import numpy as np
+import pytest
+
+from oracle import datagen
+from tests.parity import DATE32, DOUBLE, INT64, STRING, assert_close, assert_same_rows, q1_kernel_spec
+
+pytestmark = pytest.mark.gpu
+
+
+# ---- generator -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("schema_fn,n", [(lambda: datagen.orders_schema(1000), 10007),
+                                          (lambda: datagen.lineitem_schema(1000), 4099),
+                                          (lambda: datagen.sweep_schema(), 5003)])
+def test_generator_matches_numpy(bq, ctx, schema_fn, n):
+    schema = schema_fn()
+    for row0 in (0, 123456789):
+        host = datagen.host_table(schema, n, seed=42, row0=row0)
+        for i, (name, typ, spec) in enumerate(schema):
+            col = ctx.alloc(typ, n).generate(seed=42, stream=i, row0=row0, **spec)
+            got = col.to_numpy()
+            assert got.dtype == host[i][2].dtype
+            assert np.array_equal(got, host[i][2]), f"{name} differs at row0={row0}"
+
+
+def test_generator_table_and_hashed(bq, ctx):
+    n = 20011
+    cdf = datagen.zipf_cdf(1000, 1.1)
+    col = ctx.alloc(INT64, n).generate(dist=bq.GEN_TABLE, seed=5, stream=3, lo=1, cdf=cdf)
+    want = datagen.generate(INT64, n, datagen.GEN_TABLE, 5, 3, lo=1, cdf=cdf)
+    assert np.array_equal(col.to_numpy(), want)
+    col = ctx.alloc(INT64, n).generate(dist=bq.GEN_HASHED, seed=5, stream=4, lo=0, hi=9999, modulus=1 << 61)
+    want = datagen.generate(INT64, n, datagen.GEN_HASHED, 5, 4, lo=0, hi=9999, modulus=1 << 61)
+    assert np.array_equal(col.to_numpy(), want)
+    assert len(np.unique(want)) <= 10000
+
+
+def test_minmax_and_f64_key(bq, ctx):
+    rng = np.random.default_rng(1)
+    a = rng.normal(size=10001) * 1e6
+    col = ctx.upload(DOUBLE, a)
+    lo, hi = col.minmax()
+    assert lo == bq.f64_key(a.min()) and hi == bq.f64_key(a.max())
+    keys = np.array([bq.f64_key(x) for x in a[:500]])
+    assert np.array_equal(np.argsort(keys, kind="stable"), np.argsort(a[:500], kind="stable"))
+    assert bq.f64_key(-0.0) == bq.f64_key(0.0) == 0
+    b = rng.integers(-10**12, 10**12, size=7777)
+    assert ctx.upload(INT64, b).minmax() == (b.min(), b.max())
+
+
+# ---- fused filter + global aggregate (configuration 2) ----------------------------------------------
+def _sweep_cols(ctx, n, seed):
+    host = {name: arr for name, _t, arr in datagen.host_table(datagen.sweep_schema(), n, seed)}
+    types = {name: t for name, t, _ in datagen.sweep_schema()}
+    dev = {name: ctx.upload(types[name], arr) for name, arr in host.items()}
+    return host, dev
+
+
+def _range_for(bq, op, lit, is_f):
+    """compare_values (src/exec/expression.cpp:60-120) reduced to a key range, as the host compiler does."""
+    k = bq.f64_key(lit) if is_f else int(lit)
+    lo_all, hi_all = -(1 << 63), (1 << 63) - 1
+    if is_f:
+        lo_all, hi_all = bq.f64_key(-np.inf), bq.f64_key(np.inf)
+    return {"<": (lo_all, k - 1, 0), "<=": (lo_all, k, 0), ">": (k + 1, hi_all, 0), ">=": (k, hi_all, 0),
+            "=": (k, k, 0), "!=": (k, k, 1)}[op]
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 127, 131, 1024, 100003])
+def test_filter_agg_sizes(bq, ctx, n):
+    host, dev = _sweep_cols(ctx, n, seed=11)
+    s = bq.ScanSpec()
+    s.a = bq.make_slot(dev["v"])
+    s.b = bq.make_slot(dev["w"])
+    s.pred[0] = bq.make_slot(dev["c_i64"], [_range_for(bq, "<", 500000, False)])
+    s.row_begin, s.row_end = 0, n
+    s.n_v = 2
+    s.v[0] = bq.VExpr(op=bq.V_A)
+    s.v[1] = bq.VExpr(op=bq.V_B)
+    s.group_mode = bq.GROUP_NONE
+    s.n_out = 4
+    s.out[0] = bq.AggOut(func=bq.AGG_COUNT)
+    s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
+    s.out[2] = bq.AggOut(func=bq.AGG_SUM, v=1, as_int=1)
+    s.out[3] = bq.AggOut(func=bq.AGG_AVG, v=0)
+    got = ctx.scan_aggregate(s).to_numpy()
+    m = host["c_i64"] < 500000
+    if m.sum() == 0:
+        assert all(len(c) == 0 for c in got)       # zero qualifying rows -> zero output rows (H5)
+        return
+    assert got[0][0] == m.sum()
+    assert_close(got[1], [host["v"][m].sum()], "SUM(v)")
+    assert got[2][0] == host["w"][m].sum()
+    assert_close(got[3], [host["v"][m].sum() / m.sum()], "AVG(v)")
+
+
+@pytest.mark.parametrize("pred,op,lit", [
+    ("c_i64", "<", 10000), ("c_i64", ">=", 990000), ("c_i64", "=", 697221), ("c_i64", "!=", 5),
+    ("c_f64", "<", 5000.0), ("c_f64", ">", 9899.995), ("c_f64", "<=", 1146.09), ("c_f64", "!=", 1146.09),
+    ("c_str", "=", 7), ("c_str", "!=", 7),
+    ("c_date", ">=", 20200101), ("c_date", "<", 20150201), ("c_date", "=", 20170925),
+])
+def test_filter_agg_predicate_types(bq, ctx, pred, op, lit):
+    n = 300007
+    host, dev = _sweep_cols(ctx, n, seed=7)
+    is_f = pred == "c_f64"
+    s = bq.ScanSpec()
+    s.a = bq.make_slot(dev["v"])
+    s.pred[0] = bq.make_slot(dev[pred], [_range_for(bq, op, lit, is_f)])
+    s.row_begin, s.row_end = 0, n
+    s.n_v = 1
+    s.v[0] = bq.VExpr(op=bq.V_A)
+    s.n_out = 2
+    s.out[0] = bq.AggOut(func=bq.AGG_COUNT)
+    s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
+    got = ctx.scan_aggregate(s).to_numpy()
+    x = host[pred]
+    m = {"<": x < lit, "<=": x <= lit, ">": x > lit, ">=": x >= lit, "=": x == lit, "!=": x != lit}[op]
+    assert m.sum() > 0
+    assert got[0][0] == m.sum()
+    assert_close(got[1], [host["v"][m].sum()], "SUM(v)")
+
+
+def test_filter_agg_vs_reference_sql(bq, ctx, ref):
+    n = 50021
+    host, dev = _sweep_cols(ctx, n, seed=3)
+    eng = ref.RefEngine()
+    eng.add_table("t", [(name, t, host[name]) for name, t, _ in datagen.sweep_schema()])
+    r = eng.query("SELECT COUNT(*), SUM(v), SUM(w), AVG(v) FROM t WHERE c_date >= 20180101 AND c_date <= 20191231 AND c_str != 3")
+    s = bq.ScanSpec()
+    s.a = bq.make_slot(dev["v"])
+    s.b = bq.make_slot(dev["w"])
+    s.pred[0] = bq.make_slot(dev["c_date"], [(20180101, 20191231, 0)])
+    s.pred[1] = bq.make_slot(dev["c_str"], [(3, 3, 1)])
+    s.row_begin, s.row_end = 0, n
+    s.n_v = 2
+    s.v[0] = bq.VExpr(op=bq.V_A)
+    s.v[1] = bq.VExpr(op=bq.V_B)
+    s.n_out = 4
+    s.out[0] = bq.AggOut(func=bq.AGG_COUNT)
+    s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
+    s.out[2] = bq.AggOut(func=bq.AGG_SUM, v=1, as_int=1)
+    s.out[3] = bq.AggOut(func=bq.AGG_AVG, v=0)
+    got = ctx.scan_aggregate(s).to_numpy()
+    assert_same_rows(got, r.cols, what="filter+agg vs reference")
+
+
+def test_filter_agg_subrange_and_mask(bq, ctx):
+    n = 70001
+    host, dev = _sweep_cols(ctx, n, seed=5)
+    mask_h = (host["c_str"] % 3 == 0).astype(np.int64)
+    mask = ctx.upload(INT64, mask_h)
+    for rb, re in [(1, n), (5, 69999), (130, 131), (4, 4), (1000, 50000)]:
+        s = bq.ScanSpec()
+        s.a = bq.make_slot(dev["v"], [_range_for(bq, ">", 100.0, True)])
+        s.mask = mask.h
+        s.row_begin, s.row_end = rb, re
+        s.n_v = 1
+        s.v[0] = bq.VExpr(op=bq.V_MUL, b_is_imm=1, imm_is_f=0, imm_i=3)
+        s.n_out = 2
+        s.out[0] = bq.AggOut(func=bq.AGG_COUNT)
+        s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
+        got = ctx.scan_aggregate(s).to_numpy()
+        v = host["v"][rb:re]
+        m = (v > 100.0) & (mask_h[rb:re] != 0)
+        if m.sum() == 0:
+            assert len(got[0]) == 0
+            continue
+        assert got[0][0] == m.sum()
+        assert_close(got[1], [(v[m] * 3.0).sum()], f"SUM(v*3) [{rb},{re})")
+
+
+# ---- Q1 shape: dense GROUP BY in shared memory -------------------------------------------------------
+@pytest.mark.parametrize("n", [1000, 250_003])
+def test_q1_kernel_vs_reference(bq, ctx, ref, n):
+    tab = datagen.host_table(datagen.orders_schema(n), n, seed=2024)
+    cols = {name: arr for name, _t, arr in tab}
+    eng = ref.RefEngine()
+    d = eng.new_dict(datagen.STATUS_DICT)
+    eng.add_table("orders", tab, d)
+    r = eng.query("SELECT order_date, SUM(total) AS revenue FROM orders WHERE status = 'COMPLETE' AND "
+                  "order_date >= 20240101 AND order_date <= 20240131 GROUP BY order_date ORDER BY order_date")
+    status = ctx.upload(STRING, cols["status"])
+    date = ctx.upload(DATE32, cols["order_date"])
+    total = ctx.upload(DOUBLE, cols["total"])
+    lo, hi = date.minmax()
+    spec = q1_kernel_spec(bq, status, date, total, n, 0, 20240101, 20240131, lo, hi)
+    rel = ctx.scan_aggregate(spec)
+    got = ctx.rel_sort(rel, [0], [1]).to_numpy()
+    assert_same_rows(got, r.cols, ordered_by=[(0, True)], what="Q1")
+
+
+def test_group_dense_global_and_hash_agree(bq, ctx):
+    """The same GROUP BY through the three table kinds (smem / dense global / hash) gives the same rows."""
+    n = 400_009
+    rng = np.random.default_rng(9)
+    key = rng.integers(-50, 20000, size=n).astype(np.int64)
+    val = rng.integers(1, 1000, size=n).astype(np.float64) / 8.0      # dyadic: sums are exact in any order
+    kc, vc = ctx.upload(INT64, key), ctx.upload(DOUBLE, val)
+    uk, inv = np.unique(key, return_inverse=True)
+    want = [uk, np.bincount(inv).astype(np.int64), np.bincount(inv, weights=val), np.bincount(inv, weights=val) / np.bincount(inv)]
+    for mode, kmin, kmax in [(bq.GROUP_DENSE, -50, 19999), (bq.GROUP_HASH, 0, -1)]:
+        s = bq.ScanSpec()
+        s.key = bq.make_slot(kc)
+        s.a = bq.make_slot(vc)
+        s.row_begin, s.row_end = 0, n
+        s.n_v = 1
+        s.v[0] = bq.VExpr(op=bq.V_A)
+        s.group_mode = mode
+        s.key_min, s.key_max = kmin, kmax
+        s.ndv_hint = 20050
+        s.n_out = 3
+        s.out[0] = bq.AggOut(func=bq.AGG_COUNT)
+        s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
+        s.out[2] = bq.AggOut(func=bq.AGG_AVG, v=0)
+        got = ctx.scan_aggregate(s).to_numpy()
+        assert_same_rows(got, want, what=f"group mode {mode}")
+        assert np.array_equal(np.sort(got[0]), uk)
+        g = dict(zip(got[0].tolist(), got[2].tolist()))
+        assert all(g[k] == w for k, w in zip(uk.tolist(), want[2].tolist())), "dyadic sums must be bit-exact"
+    # small domain -> shared-memory tables
+    key2 = (key % 300).astype(np.int64)
+    kc2 = ctx.upload(INT64, key2)
+    s = bq.ScanSpec()
+    s.key = bq.make_slot(kc2)
+    s.a = bq.make_slot(vc)
+    s.row_begin, s.row_end = 0, n
+    s.n_v = 1
+    s.v[0] = bq.VExpr(op=bq.V_A)
+    s.group_mode = bq.GROUP_DENSE
+    s.key_min, s.key_max = 0, 299
+    s.n_out = 2
+    s.out[0] = bq.AggOut(func=bq.AGG_COUNT)
+    s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
+    got = ctx.scan_aggregate(s).to_numpy()
+    uk2, inv2 = np.unique(key2, return_inverse=True)
+    assert np.array_equal(got[0], uk2)
+    assert np.array_equal(got[1], np.bincount(inv2))
+    assert np.array_equal(got[2], np.bincount(inv2, weights=val))
+
+
+def test_group_hash_special_keys(bq, ctx):
+    key = np.array([np.iinfo(np.int64).min, 5, np.iinfo(np.int64).min, np.iinfo(np.int64).max, 5, 0], dtype=np.int64)
+    val = np.array([1.0, 2.0, 3.0, 4.0, 5.0, 6.0])
+    s = bq.ScanSpec()
+    s.key = bq.make_slot(ctx.upload(INT64, key))
+    s.a = bq.make_slot(ctx.upload(DOUBLE, val))
+    s.row_begin, s.row_end = 0, len(key)
+    s.n_v = 1
+    s.v[0] = bq.VExpr(op=bq.V_A)
+    s.group_mode = bq.GROUP_HASH
+    s.n_out = 1
+    s.out[0] = bq.AggOut(func=bq.AGG_SUM, v=0)
+    # keep the uploaded columns alive through the call
+    kc, vc = ctx.upload(INT64, key), ctx.upload(DOUBLE, val)
+    s.key, s.a = bq.make_slot(kc), bq.make_slot(vc)
+    got = ctx.scan_aggregate(s).to_numpy()
+    want = [np.array([np.iinfo(np.int64).min, 0, 5, np.iinfo(np.int64).max], dtype=np.int64), np.array([4.0, 6.0, 7.0, 4.0])]
+    assert_same_rows(got, want)
+
+
+# ---- selection vectors, gather, slice ------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 31, 32, 33, 8191, 100_001])
+def test_select_gather(bq, ctx, n):
+    host, dev = _sweep_cols(ctx, n, seed=21)
+    ids = ctx.select([bq.make_slot(dev["c_i64"], [_range_for(bq, "<", 300000, False)]),
+                      bq.make_slot(dev["c_str"], [(10, 60, 0)])], row_begin=0, row_end=n)
+    m = (host["c_i64"] < 300000) & (host["c_str"] >= 10) & (host["c_str"] <= 60)
+    want_ids = np.nonzero(m)[0].astype(np.uint32)
+    assert np.array_equal(ids.to_numpy(), want_ids)       # stable: scan order
+    for name in ("v", "c_date", "w", "c_str"):
+        assert np.array_equal(ctx.gather(dev[name], ids).to_numpy(), host[name][m])
+    if n > 40:
+        assert np.array_equal(ctx.slice(dev["w"], 7, n - 3).to_numpy(), host["w"][7:n - 3])
+        sub = ctx.select([bq.make_slot(dev["c_i64"], [_range_for(bq, "<", 300000, False)])], row_begin=33, row_end=n - 5)
+        want = (np.nonzero(host["c_i64"][33:n - 5] < 300000)[0] + 33).astype(np.uint32)
+        assert np.array_equal(sub.to_numpy(), want)
+
+
+# ---- joins -----------------------------------------------------------------------------------------
+def test_join_kinds_and_probe(bq, ctx):
+    rng = np.random.default_rng(3)
+    nb, npb = 5000, 40_003
+    bkey = rng.permutation(np.arange(100, 100 + nb)).astype(np.int64)          # unique, dense
+    pkey = rng.integers(0, 100 + nb + 200, size=npb).astype(np.int64)
+    bk, pk = ctx.upload(INT64, bkey), ctx.upload(INT64, pkey)
+    pos = {k: i for i, k in enumerate(bkey.tolist())}
+    want_p = np.array([i for i, k in enumerate(pkey.tolist()) if k in pos], dtype=np.uint32)
+    want_b = np.array([pos[k] for k in pkey.tolist() if k in pos], dtype=np.uint32)
+    for kind, expect in [(bq.JOIN_AUTO, bq.JOIN_DIRECT), (bq.JOIN_DIRECT, bq.JOIN_DIRECT), (bq.JOIN_HASH, bq.JOIN_HASH)]:
+        j = ctx.join_build(bk, kind=kind, need_rows=True, unique=True, key_min=100, key_max=100 + nb - 1)
+        assert j.kind == expect
+        p, b = ctx.join_probe(j, pk)
+        assert np.array_equal(p.to_numpy(), want_p) and np.array_equal(b.to_numpy(), want_b)
+    j = ctx.join_build(bk, kind=bq.JOIN_AUTO, need_rows=False, unique=True, key_min=100, key_max=100 + nb - 1)
+    assert j.kind == bq.JOIN_BITMAP and j.bytes <= (nb // 8) + 8
+
+
+def test_join_duplicates_insertion_order(bq, ctx):
+    rng = np.random.default_rng(4)
+    bkey = rng.integers(0, 50, size=400).astype(np.int64)         # heavy duplicates
+    pkey = rng.integers(-5, 60, size=3001).astype(np.int64)
+    bk, pk = ctx.upload(INT64, bkey), ctx.upload(INT64, pkey)
+    j = ctx.join_build(bk, kind=bq.JOIN_AUTO, need_rows=True, key_min=0, key_max=49)    # duplicates force HASH
+    assert j.kind == bq.JOIN_HASH
+    p, b = ctx.join_probe(j, pk)
+    wp, wb = [], []
+    for i, k in enumerate(pkey.tolist()):
+        for r in np.nonzero(bkey == k)[0].tolist():        # build insertion order (src/exec/operator.cpp:802-816)
+            wp.append(i)
+            wb.append(r)
+    assert np.array_equal(p.to_numpy(), np.array(wp, dtype=np.uint32))
+    assert np.array_equal(b.to_numpy(), np.array(wb, dtype=np.uint32))
+
+
+@pytest.mark.parametrize("sku_type", [INT64, STRING])
+def test_q2_kernel_vs_reference(bq, ctx, ref, sku_type):
+    n_orders, n_line, n_sku = 20_000, 150_007, 500
+    orders = datagen.host_table(datagen.orders_schema(n_orders, prefix="o."), n_orders, seed=1)
+    line = datagen.host_table(datagen.lineitem_schema(n_orders, n_sku, sku_type=sku_type), n_line, seed=2)
+    eng = ref.RefEngine()
+    d = eng.new_dict(datagen.STATUS_DICT + [f"sku{i}" for i in range(n_sku)] if sku_type == STRING else datagen.STATUS_DICT)
+    eng.add_table("orders", orders, d)
+    eng.add_table("lineitem", line, d)
+    r = eng.query("SELECT l.sku, SUM(l.qty * l.price) AS rev FROM lineitem l JOIN orders o ON l.order_id = o.order_id "
+                  "WHERE o.status = 'COMPLETE' GROUP BY l.sku ORDER BY rev DESC LIMIT 20")
+    o = {name: ctx.upload(t, a) for name, t, a in orders}
+    l = {name: ctx.upload(t, a) for name, t, a in line}
+    j = ctx.join_build(o["o.order_id"], preds=[bq.make_slot(o["o.status"], [(0, 0, 0)])], unique=True,
+                       key_min=1, key_max=n_orders)
+    assert j.kind == bq.JOIN_BITMAP
+    s = bq.ScanSpec()
+    s.key = bq.make_slot(l["l.sku"])
+    s.a = bq.make_slot(l["l.qty"])
+    s.b = bq.make_slot(l["l.price"])
+    s.jkey = bq.make_slot(l["l.order_id"])
+    s.join = j.h
+    s.row_begin, s.row_end = 0, n_line
+    s.n_v = 1
+    s.v[0] = bq.VExpr(op=bq.V_MUL)
+    s.group_mode = bq.GROUP_DENSE
+    s.key_min, s.key_max = 0, n_sku - 1
+    s.n_out = 1
+    s.out[0] = bq.AggOut(func=bq.AGG_SUM, v=0)
+    rel = ctx.scan_aggregate(s)
+    top = ctx.rel_sort(rel, [1], [0], limit=20).to_numpy()
+    assert_same_rows(top, r.cols, ordered_by=[(1, False)], what="Q2")
+    # the same join through DIRECT and HASH tables, status read from the build side is not needed: same result
+    for kind in (bq.JOIN_DIRECT, bq.JOIN_HASH):
+        j2 = ctx.join_build(o["o.order_id"], preds=[bq.make_slot(o["o.status"], [(0, 0, 0)])], kind=kind, need_rows=True,
+                            unique=True, key_min=1, key_max=n_orders)
+        s.join = j2.h
+        top2 = ctx.rel_sort(ctx.scan_aggregate(s), [1], [0], limit=20).to_numpy()
+        assert_same_rows(top2, r.cols, ordered_by=[(1, False)], what=f"Q2 join kind {kind}")
+
+
+def test_join_payload_from_build_side(bq, ctx):
+    """SUM(p.v * b.w) with b.w read from the matched build row (configuration 5's shape)."""
+    rng = np.random.default_rng(6)
+    nb, npb = 3000, 50_001
+    bkey = np.arange(1, nb + 1, dtype=np.int64)
+    bw = rng.integers(1, 64, size=nb).astype(np.float64) / 4.0
+    pkey = rng.integers(1, nb + 500, size=npb).astype(np.int64)
+    pv = rng.integers(1, 64, size=npb).astype(np.float64) / 4.0
+    bk, bwc, pk, pvc = ctx.upload(INT64, bkey), ctx.upload(DOUBLE, bw), ctx.upload(INT64, pkey), ctx.upload(DOUBLE, pv)
+    m = pkey <= nb
+    want_cnt, want_sum = m.sum(), (pv[m] * bw[pkey[m] - 1]).sum()
+    for kind in (bq.JOIN_DIRECT, bq.JOIN_HASH):
+        j = ctx.join_build(bk, kind=kind, need_rows=True, unique=True, key_min=1, key_max=nb)
+        s = bq.ScanSpec()
+        s.a = bq.make_slot(pvc)
+        s.b = bq.make_slot(bwc, from_build=True)
+        s.jkey = bq.make_slot(pk)
+        s.join = j.h
+        s.row_begin, s.row_end = 0, npb
+        s.n_v = 1
+        s.v[0] = bq.VExpr(op=bq.V_MUL)
+        s.n_out = 2
+        s.out[0] = bq.AggOut(func=bq.AGG_COUNT)
+        s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
+        got = ctx.scan_aggregate(s).to_numpy()
+        assert got[0][0] == want_cnt and got[1][0] == want_sum       # dyadic values: exact
+
+
+# ---- sort / limit --------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [0, 1, 2, 500, 4096, 4097, 300_001])
+def test_sort_multi_key(bq, ctx, n):
+    rng = np.random.default_rng(n + 1)
+    a = rng.integers(-5, 5, size=n).astype(np.int64)
+    b = (rng.integers(-1000, 1000, size=n) / 7.0).astype(np.float64)
+    c = rng.integers(0, 2**32 - 1, size=n, dtype=np.uint64).astype(np.uint32)
+    d = np.arange(n, dtype=np.int32)
+    rel = ctx.rel_create([ctx.upload(INT64, a), ctx.upload(DOUBLE, b), ctx.upload(STRING, c), ctx.upload(DATE32, d)])
+    got = ctx.rel_sort(rel, [0, 1], [0, 1]).to_numpy()       # a DESC, b ASC ; ties keep input order
+    order = np.lexsort((d, b, -a))
+    for g, w in zip(got, (a, b, c, d)):
+        assert np.array_equal(g, w[order])
+    got = ctx.rel_sort(rel, [2], [1], limit=10).to_numpy()
+    order = np.argsort(c, kind="stable")[:10]
+    for g, w in zip(got, (a, b, c, d)):
+        assert np.array_equal(g, w[order])
+
+
+# ---- expression programs -----------------------------------------------------------------------------
+def test_eval_programs(bq, ctx):
+    n = 10_007
+    rng = np.random.default_rng(8)
+    x = rng.integers(-1000, 1000, size=n).astype(np.int64)
+    y = (rng.integers(-1000, 1000, size=n) / 4.0).astype(np.float64)
+    dte = rng.integers(20200101, 20201231, size=n).astype(np.int32)
+    xc, yc, dc = ctx.upload(INT64, x), ctx.upload(DOUBLE, y), ctx.upload(DATE32, dte)
+    # (x * 2 + 1)  int arithmetic
+    got = ctx.eval([("COL", 0, 0), ("IMM_I", 0, 2), ("MUL_I", 0, 0), ("IMM_I", 0, 1), ("ADD_I", 0, 0)], [xc], 0, n, INT64).to_numpy()
+    assert np.array_equal(got, x * 2 + 1)
+    # x * y -> double(x) * y
+    got = ctx.eval([("COL", 0, 0), ("COL", 1, 0), ("I2F_2", 0, 0), ("MUL_F", 0, 0)], [xc, yc], 0, n, DOUBLE).to_numpy()
+    assert np.array_equal(got, x.astype(np.float64) * y)
+    # x < y : INT64-left compare truncates the double right operand (H6)
+    got = ctx.eval([("COL", 0, 0), ("COL", 1, 0), ("F2I", 0, 0), ("LT_I", 0, 0)], [xc, yc], 0, n, INT64).to_numpy()
+    assert np.array_equal(got, (x < np.trunc(y).astype(np.int64)).astype(np.int64))
+    # y / 0 = +inf regardless of sign (H10)
+    got = ctx.eval([("COL", 0, 0), ("IMM_F", 0, 0.0), ("DIV_F", 0, 0)], [yc], 0, n, DOUBLE).to_numpy()
+    assert np.all(np.isposinf(got))
+    # (x > 0 OR y < 0.0) AND date >= 20200601
+    prog = [("COL", 0, 0), ("IMM_I", 0, 0), ("GT_I", 0, 0), ("COL", 1, 0), ("IMM_F", 0, 0.0), ("LT_F", 0, 0), ("OR", 0, 0),
+            ("COL", 2, 0), ("IMM_I", 0, 20200601), ("SX32", 0, 0), ("GE_I", 0, 0), ("AND", 0, 0)]
+    got = ctx.eval(prog, [xc, yc, dc], 0, n, INT64).to_numpy()
+    assert np.array_equal(got, (((x > 0) | (y < 0.0)) & (dte >= 20200601)).astype(np.int64))
+    # integer division by zero raises the reference's message (H10)
+    with pytest.raises(bq.BqError, match="Division by zero"):
+        ctx.eval([("COL", 0, 0), ("IMM_I", 0, 0), ("DIV_I", 0, 0)], [xc], 0, n, INT64)
+    # malformed programs are rejected on the host
+    with pytest.raises(bq.BqError):
+        ctx.eval([("ADD_I", 0, 0)], [xc], 0, n, INT64)
+
+
+def test_partial_merge(bq, ctx):
+    """Two row-range partials merged == one scan (the multi-GPU merge path, run on one device)."""
+    n = 120_001
+    tab = datagen.host_table(datagen.orders_schema(n), n, seed=77)
+    cols = {name: arr for name, _t, arr in tab}
+    status, date, total = ctx.upload(STRING, cols["status"]), ctx.upload(DATE32, cols["order_date"]), ctx.upload(DOUBLE, cols["total"])
+    full = q1_kernel_spec(bq, status, date, total, n, 0, 20240101, 20241231, 20240101, 20241228)
+    want = ctx.scan_aggregate(full).to_numpy()
+    parts = []
+    for rb, re in [(0, 50_001), (50_001, n)]:
+        sp = q1_kernel_spec(bq, status, date, total, n, 0, 20240101, 20241231, 20240101, 20241228)
+        sp.row_begin, sp.row_end = rb, re
+        parts.append(ctx.scan_aggregate(sp, partial=True))
+    got = ctx.agg_finish(parts, True, DATE32, [bq.AggOut(func=bq.AGG_SUM, v=0)]).to_numpy()
+    assert_same_rows(got, want, what="merged partials")
