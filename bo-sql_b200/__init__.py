@@ -29,6 +29,8 @@ TYPE_NAMES = {INT64: "INT64", DOUBLE: "DOUBLE", STRING: "STRING", DATE32: "DATE3
 
 GEN_SEQ, GEN_UNIFORM, GEN_UNIFORM_DIV, GEN_DATE, GEN_TABLE, GEN_HASHED = range(6)
 V_NONE, V_A, V_B, V_MUL, V_ADD, V_SUB, V_DIV = range(7)
+L_A, L_B, L_IMM = range(3)      # left operand of a binary aggregate argument
+R_B, R_A, R_IMM = range(3)      # right operand (zero values = A op B)
 GROUP_NONE, GROUP_DENSE, GROUP_HASH = range(3)
 AGG_COUNT, AGG_SUM, AGG_AVG = range(3)
 JOIN_AUTO, JOIN_BITMAP, JOIN_DIRECT, JOIN_HASH = range(4)
@@ -60,7 +62,7 @@ class Slot(C.Structure):
 
 
 class VExpr(C.Structure):
-    _fields_ = [("op", C.c_int32), ("b_is_imm", C.c_int32), ("imm_is_f", C.c_int32), ("swap", C.c_int32),
+    _fields_ = [("op", C.c_int32), ("l_src", C.c_int32), ("r_src", C.c_int32), ("imm_is_f", C.c_int32),
                 ("imm_i", C.c_int64), ("imm_f", C.c_double)]
 
 
@@ -126,6 +128,7 @@ def kernel_lib():
         "bq_col_type": ([vp], C.c_int),
         "bq_col_ptr": ([vp], vp),
         "bq_col_set_stats": ([vp, i64, i64, sz], C.c_int),
+        "bq_col_invalidate_stats": ([vp], None),
         "bq_col_minmax": ([vp, vp, P(i64), P(i64)], C.c_int),
         "bq_f64_key": ([C.c_double], i64),
         "bq_f64_from_key": ([i64], C.c_double),
@@ -151,6 +154,7 @@ def kernel_lib():
         "bq_rel_cols": ([vp], C.c_int),
         "bq_rel_col": ([vp, C.c_int], vp),
         "bq_rel_free": ([vp, vp], None),
+        "bq_rel_release": ([vp, P(vp)], None),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)          # AttributeError here = the library does not export what the header declares
@@ -443,3 +447,16 @@ class Context:
         h = C.c_void_p()
         _check(self.L.bq_rel_sort(self.h, rel.h, len(key_cols), k, a, limit, C.byref(h)))
         return Relation(self, h)
+
+
+def wrap_context(handle) -> "Context":
+    """A non-owning Context over an existing bq_ctx (e.g. the operator layer's: engine.exec_lib().bqx_context())."""
+    c = Context.__new__(Context)
+    c.L = kernel_lib()
+    c.h = C.c_void_p(handle)
+    c.device = -1
+    c.close = lambda: None
+    return c
+
+
+from .engine import PARSE_BETWEEN, PARSE_DECIMALS, Engine, exec_lib  # noqa: E402,F401

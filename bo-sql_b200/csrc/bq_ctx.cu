@@ -211,6 +211,8 @@ int bq_col_set_stats(bq_col* col, int64_t min_key, int64_t max_key, size_t ndv) 
     return 0;
 }
 
+void bq_col_invalidate_stats(bq_col* col) { col->has_minmax = false; }
+
 int bq_col_minmax(bq_ctx* ctx, bq_col* col, int64_t* min_key, int64_t* max_key) {
     return guarded([&] {
         if (!col->has_minmax) {
@@ -280,6 +282,12 @@ void bq_rel_free(bq_ctx* ctx, bq_rel* rel) {
     if (!rel) return;
     if (ctx) cudaStreamSynchronize(ctx->stream);
     for (auto* c : rel->cols) free_col(c);
+    delete rel;
+}
+
+void bq_rel_release(bq_rel* rel, bq_col** out_cols) {
+    if (!rel) return;
+    for (size_t i = 0; i < rel->cols.size(); ++i) out_cols[i] = rel->cols[i];
     delete rel;
 }
 

@@ -37,7 +37,7 @@ constexpr long long kEmptyKey = INT64_MIN;   // empty marker of the group table 
 constexpr uint32_t kGenericShape = 0xFFFFFFFFu;
 
 struct DVExpr {
-    int op, b_is_imm, imm_is_f, swap;
+    int op, l_src, r_src, imm_is_f;
     long long imm_i;
     double imm_f;
 };
@@ -72,7 +72,7 @@ struct ScanParams {
     unsigned long long* part_cnt;
     double* part_sum;                  // [grid][2]
     unsigned* ticket;
-    int* err;                          // 1 = integer division by zero, 2 = group table full
+    int* err;                          // 1 = integer division by zero, 2 = group table full, 4 = key outside dense domain
 };
 
 // ---- compile-time / run-time slot description ---------------------------------------------------
@@ -140,18 +140,14 @@ BQ_D void load_quad(const void* ptr, int kind, size_t base, int lane, long long 
 BQ_D double eval_vexpr(const DVExpr& e, long long a, int ka, long long b, int kb, int* err) {
     if (e.op == BQ_V_A) return as_double(a, ka);
     if (e.op == BQ_V_B) return as_double(b, kb);
-    long long r = b;
-    int kr = kb;
-    if (e.b_is_imm) {
-        r = e.imm_is_f ? __double_as_longlong(e.imm_f) : e.imm_i;
-        kr = e.imm_is_f ? BQ_DOUBLE : BQ_INT64;
-    }
-    long long l = a;
-    int kl = ka;
-    if (e.swap) {
-        long long t = l; l = r; r = t;
-        int kt = kl; kl = kr; kr = kt;
-    }
+    const long long imm = e.imm_is_f ? __double_as_longlong(e.imm_f) : e.imm_i;
+    const int kimm = e.imm_is_f ? BQ_DOUBLE : BQ_INT64;
+    long long l = a, r = b;
+    int kl = ka, kr = kb;
+    if (e.l_src == BQ_L_B) { l = b; kl = kb; }
+    else if (e.l_src == BQ_L_IMM) { l = imm; kl = kimm; }
+    if (e.r_src == BQ_R_A) { r = a; kr = ka; }
+    else if (e.r_src == BQ_R_IMM) { r = imm; kr = kimm; }
     if (kl == BQ_DOUBLE || kr == BQ_DOUBLE) {       // src/exec/expression.cpp:34-44
         double x = as_double(l, kl), y = as_double(r, kr);
         switch (e.op) {
@@ -223,6 +219,8 @@ struct RowSink {
                 atomicAdd(s_cnt + idx, 1u);
                 if (p.nv > 0) atomicAdd(s_sum0 + idx, v0);
                 if (p.nv > 1) atomicAdd(s_sum1 + idx, v1);
+            } else {
+                err |= 4;       // key outside the catalog's [min,max]: stale statistics, the host re-plans
             }
         } else if (GMODE == G_DENSE) {
             unsigned long long idx = static_cast<unsigned long long>(key_raw - p.key_min);
@@ -230,6 +228,8 @@ struct RowSink {
                 atomicAdd(p.g_cnt + idx, 1ULL);
                 if (p.nv > 0) atomicAdd(p.g_sum0 + idx, v0);
                 if (p.nv > 1) atomicAdd(p.g_sum1 + idx, v1);
+            } else {
+                err |= 4;
             }
         } else {
             long long k = key_raw;
@@ -615,11 +615,14 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st) {
     for (int i = 0; i < spec->n_v; ++i) {
         const bq_vexpr& e = spec->v[i];
         if (e.op < BQ_V_A || e.op > BQ_V_DIV) throw std::runtime_error("bad aggregate argument op");
-        bool needs_a = e.op != BQ_V_B;
-        bool needs_b = e.op == BQ_V_B || (e.op >= BQ_V_MUL && !e.b_is_imm);
+        const bool binary = e.op >= BQ_V_MUL;
+        if (binary && (e.l_src < BQ_L_A || e.l_src > BQ_L_IMM || e.r_src < BQ_R_B || e.r_src > BQ_R_IMM))
+            throw std::runtime_error("bad aggregate argument operand source");
+        bool needs_a = e.op == BQ_V_A || (binary && (e.l_src == BQ_L_A || e.r_src == BQ_R_A));
+        bool needs_b = e.op == BQ_V_B || (binary && (e.l_src == BQ_L_B || e.r_src == BQ_R_B));
         if (needs_a && !spec->a.col) throw std::runtime_error("aggregate argument reads slot a, which is empty");
         if (needs_b && !spec->b.col) throw std::runtime_error("aggregate argument reads slot b, which is empty");
-        p.v[i] = DVExpr{e.op, e.b_is_imm, e.imm_is_f, e.swap, e.imm_i, e.imm_f};
+        p.v[i] = DVExpr{e.op, e.l_src, e.r_src, e.imm_is_f, e.imm_i, e.imm_f};
     }
     p.row_begin = spec->row_begin;
     p.row_end = spec->row_end;
@@ -730,6 +733,7 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st) {
     BQ_CUDA(cudaStreamSynchronize(ctx->stream));
     if (*h & 1) throw std::runtime_error("Division by zero");          // src/exec/expression.cpp:52
     if (*h & 2) throw std::runtime_error("group table overflow: ndv_hint too small");
+    if (*h & 4) throw std::runtime_error("group key outside [key_min,key_max]: stale statistics");
 }
 
 // Turns the device state into a relation. partial = [key] count sum0 sum1, else [key] + outs.

@@ -1,0 +1,249 @@
+// capi.cpp — include/bosql_b200_exec.h over the C++ operator layer.
+#include <chrono>
+#include <cstring>
+#include <typeinfo>
+
+#include "bosql_b200_exec.h"
+#include "bosql_operator.hpp"
+#include "gpu_device.hpp"
+
+using namespace bosql;
+
+struct bqx_dict {
+    std::shared_ptr<Dictionary> dict = std::make_shared<Dictionary>();
+};
+struct bqx_table {
+    Table table;
+    std::vector<ColumnMeta> metas;
+    size_t rows = 0;
+};
+struct bqx_catalog {
+    Catalog catalog;
+};
+struct bqx_plan {
+    std::unique_ptr<LogicalOp> logical;
+    std::unique_ptr<Operator> root;
+    ExecBatch batch;
+    std::string kind;
+};
+struct bqx_result {
+    std::vector<std::vector<unsigned char>> cols;
+    size_t rows = 0;
+    double seconds = 0.0;
+};
+
+namespace {
+
+thread_local std::string g_err;
+
+template <typename F>
+int guarded(F&& f) {
+    try {
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+template <typename T>
+std::unique_ptr<Column> host_column(const void* data, size_t n) {
+    const T* p = static_cast<const T*>(data);
+    return std::make_unique<ColumnVector<T>>(std::vector<T>(p, p + n));
+}
+
+ParseOptions parse_options(unsigned flags) {
+    ParseOptions o;
+    o.between = flags & 1u;
+    o.decimal_literals = flags & 2u;
+    return o;
+}
+
+const char* kind_of(const Operator* op) {
+    if (dynamic_cast<const ColumnarScan*>(op)) return "ColumnarScan";
+    if (dynamic_cast<const Selection*>(op)) return "Selection";
+    if (dynamic_cast<const Project*>(op)) return "Project";
+    if (dynamic_cast<const HashJoin*>(op)) return "HashJoin";
+    if (dynamic_cast<const HashAggregate*>(op)) return "HashAggregate";
+    if (dynamic_cast<const OrderBy*>(op)) return "OrderBy";
+    if (dynamic_cast<const Limit*>(op)) return "Limit";
+    return "Operator";
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* bqx_last_error(void) { return g_err.c_str(); }
+
+int bqx_init(int device) {
+    return guarded([&] { gpu::init_context(device); });
+}
+
+bq_ctx* bqx_context(void) {
+    try {
+        return gpu::context();
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+bqx_dict* bqx_dict_create(void) { return new bqx_dict(); }
+void bqx_dict_destroy(bqx_dict* d) { delete d; }
+uint32_t bqx_dict_get_or_add(bqx_dict* d, const char* s) { return d->dict->get_or_add(s); }
+size_t bqx_dict_size(const bqx_dict* d) { return d->dict->strings.size(); }
+const char* bqx_dict_get(const bqx_dict* d, uint32_t id) {
+    return id < d->dict->strings.size() ? d->dict->strings[id].c_str() : nullptr;
+}
+
+bqx_catalog* bqx_catalog_create(void) { return new bqx_catalog(); }
+void bqx_catalog_destroy(bqx_catalog* c) { delete c; }
+
+bqx_table* bqx_table_create(const char* name, bqx_dict* dict) {
+    auto* t = new bqx_table();
+    t->table.name = name;
+    t->table.dict = dict ? dict->dict : std::make_shared<Dictionary>();
+    return t;
+}
+
+int bqx_table_add_column(bqx_table* t, const char* name, int type, const void* data, size_t n) {
+    return guarded([&] {
+        if (!t->table.columns.empty() && n != t->rows) throw std::runtime_error("column length mismatch");
+        std::unique_ptr<Column> col;
+        switch (static_cast<TypeId>(type)) {
+            case TypeId::INT64: col = host_column<int64_t>(data, n); break;
+            case TypeId::DOUBLE: col = host_column<double>(data, n); break;
+            case TypeId::STRING: col = host_column<uint32_t>(data, n); break;
+            case TypeId::DATE32: col = host_column<int32_t>(data, n); break;
+            default: throw std::runtime_error("Unknown column type");
+        }
+        t->table.columns.push_back({name, std::move(col)});
+        t->metas.emplace_back(name, static_cast<TypeId>(type));
+        t->rows = n;
+    });
+}
+
+int bqx_table_add_device_column(bqx_table* t, const char* name, bq_col* col, int take_ownership) {
+    return guarded([&] {
+        const size_t n = bq_col_size(col);
+        if (!t->table.columns.empty() && n != t->rows) throw std::runtime_error("column length mismatch");
+        const TypeId type = static_cast<TypeId>(bq_col_type(col));
+        t->table.columns.push_back({name, std::make_unique<DeviceColumn>(type, col, n, take_ownership != 0)});
+        t->metas.emplace_back(name, type);
+        t->rows = n;
+    });
+}
+
+int bqx_table_set_stats(bqx_table* t, const char* column, int64_t min_i, int64_t max_i, double min_f, double max_f, size_t ndv) {
+    return guarded([&] {
+        for (auto& m : t->metas)
+            if (m.name == column) {
+                m.stats.ndv = ndv;
+                m.stats.min_f64 = min_f;
+                m.stats.max_f64 = max_f;
+                if (m.type == TypeId::DATE32) {
+                    m.stats.min_date = static_cast<Date32>(min_i);
+                    m.stats.max_date = static_cast<Date32>(max_i);
+                } else {
+                    m.stats.min_i64 = min_i;
+                    m.stats.max_i64 = max_i;
+                }
+                return;
+            }
+        throw std::runtime_error(std::string("Column not found: ") + column);
+    });
+}
+
+int bqx_catalog_register(bqx_catalog* c, bqx_table* tp) {
+    return guarded([&] {
+        std::unique_ptr<bqx_table> t(tp);
+        TableMeta meta(t->table.name, std::move(t->metas), t->rows);
+        c->catalog.register_table(std::move(t->table), std::move(meta));
+    });
+}
+
+int bqx_plan_create(bqx_catalog* c, const char* sql, unsigned parse_flags, bqx_plan** out) {
+    return guarded([&] {
+        SelectStmt stmt = parse_sql(sql, parse_options(parse_flags));
+        auto p = std::make_unique<bqx_plan>();
+        LogicalPlanner planner;
+        p->logical = planner.build_logical_plan(stmt);
+        p->root = build_physical_plan(p->logical.get(), c->catalog);
+        p->kind = kind_of(p->root.get());
+        *out = p.release();
+    });
+}
+
+void bqx_plan_destroy(bqx_plan* p) { delete p; }
+size_t bqx_plan_columns(const bqx_plan* p) { return p->root->output_names().size(); }
+const char* bqx_plan_column_name(const bqx_plan* p, size_t i) { return p->root->output_names().at(i).c_str(); }
+int bqx_plan_column_type(const bqx_plan* p, size_t i) { return static_cast<int>(p->root->output_types().at(i)); }
+int bqx_plan_has_dict(const bqx_plan* p) { return p->root->dictionary() != nullptr; }
+const char* bqx_plan_dict_get(const bqx_plan* p, uint32_t id) {
+    Dictionary* d = p->root->dictionary();
+    return (d && id < d->strings.size()) ? d->strings[id].c_str() : nullptr;
+}
+const char* bqx_plan_root_kind(const bqx_plan* p) { return p->kind.c_str(); }
+
+int bqx_plan_open(bqx_plan* p) {
+    return guarded([&] { p->root->open(); });
+}
+
+int bqx_plan_next(bqx_plan* p, const void** col_data, size_t n_cols, size_t* rows, int* end_of_stream) {
+    return guarded([&] {
+        if (!p->root->next(p->batch)) {
+            *rows = 0;
+            *end_of_stream = 1;
+            return;
+        }
+        *end_of_stream = 0;
+        *rows = p->batch.length;
+        for (size_t i = 0; i < n_cols && i < p->batch.columns.size(); ++i) col_data[i] = p->batch.columns[i].data;
+    });
+}
+
+int bqx_plan_close(bqx_plan* p) {
+    return guarded([&] { p->root->close(); });
+}
+
+int bqx_plan_run(bqx_plan* p, bqx_result** out) {
+    return guarded([&] {
+        auto res = std::make_unique<bqx_result>();
+        const auto& types = p->root->output_types();
+        res->cols.resize(types.size());
+        auto t0 = std::chrono::steady_clock::now();
+        p->root->open();
+        ExecBatch batch;
+        while (p->root->next(batch)) {
+            for (size_t j = 0; j < batch.columns.size() && j < res->cols.size(); ++j) {
+                const auto& s = batch.columns[j];
+                const auto* b = static_cast<const unsigned char*>(s.data);
+                res->cols[j].insert(res->cols[j].end(), b, b + type_width(s.type) * batch.length);
+            }
+            res->rows += batch.length;
+        }
+        p->root->close();
+        res->seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        *out = res.release();
+    });
+}
+
+size_t bqx_result_rows(const bqx_result* r) { return r->rows; }
+size_t bqx_result_cols(const bqx_result* r) { return r->cols.size(); }
+double bqx_result_seconds(const bqx_result* r) { return r->seconds; }
+const void* bqx_result_data(const bqx_result* r, size_t i) { return r->cols.at(i).data(); }
+void bqx_result_free(bqx_result* r) { delete r; }
+
+int bqx_explain(const char* sql, unsigned parse_flags, char* out, size_t cap) {
+    return guarded([&] {
+        SelectStmt stmt = parse_sql(sql, parse_options(parse_flags));
+        LogicalPlanner planner;
+        std::string s = planner.build_logical_plan(stmt)->to_string();
+        std::strncpy(out, s.c_str(), cap - 1);
+        out[cap - 1] = 0;
+    });
+}
+
+}  // extern "C"

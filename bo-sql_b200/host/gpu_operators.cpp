@@ -1,0 +1,640 @@
+// gpu_operators.cpp — the seven physical operators of the reference (src/exec/operator.cpp) as GPU plan nodes.
+//
+// Constructors validate and name/type their output exactly like the reference's (cited per constructor), because
+// callers observe output_names()/output_types()/dictionary() and the thrown messages.  Execution differs
+// completely: nothing loops over rows on the host.  A blocking operator asks its child to describe() itself;
+// scan / selection / join chains fold into one Pipeline that gpu_plan.cpp runs as a single fused kernel.  Children
+// that cannot be described (an aggregate under a sort, a projection ...) are materialised as device relations and
+// the same kernels run over those.  next() pages the finished device relation out in <= 4096-row batches.
+#include <algorithm>
+#include <cctype>
+#include <cstring>
+
+#include "bosql_operator.hpp"
+#include "gpu_plan.hpp"
+
+namespace bosql {
+
+using gpu::check;
+using gpu::context;
+using gpu::DeviceRelation;
+using gpu::DeviceRelationPtr;
+using gpu::DevColPtr;
+using gpu::PipeCol;
+using gpu::Pipeline;
+
+ExprBindings make_bindings(const std::vector<std::string>& names, const std::vector<TypeId>& types, Dictionary* dictionary) {
+    ExprBindings b;
+    b.column_names = &names;
+    b.column_types = &types;
+    b.dictionary = dictionary;
+    for (size_t i = 0; i < names.size(); ++i) b.name_to_index[names[i]] = i;
+    return b;
+}
+
+namespace {
+
+constexpr size_t kBatchRows = 4096;    // include/exec/operator.hpp:34 and src/exec/operator.cpp:765,1020,1129
+
+std::string upper(std::string s) {
+    std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return static_cast<char>(std::toupper(c)); });
+    return s;
+}
+
+// infer_type, src/exec/operator.cpp:84-146 (declared output type of a projection / aggregate argument)
+TypeId infer_type(const Expr* e, const ExprBindings& b) {
+    switch (e->type) {
+        case ExprType::COLUMN_REF: {
+            auto it = b.name_to_index.find(e->str_val);
+            if (it == b.name_to_index.end()) throw std::runtime_error("Unknown column: " + e->str_val);
+            return (*b.column_types)[it->second];
+        }
+        case ExprType::LITERAL_INT: return TypeId::INT64;
+        case ExprType::LITERAL_DOUBLE: return TypeId::DOUBLE;
+        case ExprType::LITERAL_STRING: return TypeId::STRING;
+        case ExprType::BINARY_OP:
+            if (e->op >= BinaryOp::ADD && e->op <= BinaryOp::DIV) {
+                TypeId l = infer_type(e->left.get(), b), r = infer_type(e->right.get(), b);
+                return (l == TypeId::DOUBLE || r == TypeId::DOUBLE) ? TypeId::DOUBLE : TypeId::INT64;
+            }
+            return TypeId::INT64;
+        case ExprType::FUNC_CALL: {
+            if (e->func_name.empty()) throw std::runtime_error("Function call unsupported in projection");
+            std::string f = upper(e->func_name);
+            if (f == "COUNT") return TypeId::INT64;
+            TypeId arg = TypeId::INT64;
+            if (!e->args.empty()) arg = infer_type(e->args[0].get(), b);
+            if (f == "SUM") return arg == TypeId::DOUBLE ? TypeId::DOUBLE : TypeId::INT64;
+            if (f == "AVG") return TypeId::DOUBLE;
+            throw std::runtime_error("Function call unsupported in projection");
+        }
+    }
+    throw std::runtime_error("Cannot infer expression type");
+}
+
+std::vector<PipeCol> pipe_cols(const std::vector<std::string>& names, const std::vector<TypeId>& types, const DeviceRelation& rel) {
+    std::vector<PipeCol> out(names.size());
+    for (size_t i = 0; i < names.size(); ++i) {
+        out[i].name = names[i];
+        out[i].type = types[i];
+        out[i].dev = rel.cols.at(i);
+    }
+    return out;
+}
+
+gpu::KeyStats stats_from_meta(const ColumnMeta& m, size_t table_rows) {
+    gpu::KeyStats s;
+    const ColumnStats& c = m.stats;
+    s.ndv = c.ndv;
+    s.table_rows = table_rows;
+    switch (m.type) {
+        case TypeId::INT64: s.min_key = c.min_i64; s.max_key = c.max_i64; break;
+        case TypeId::DOUBLE: s.min_key = gpu::f64_key(c.min_f64); s.max_key = gpu::f64_key(c.max_f64); break;
+        case TypeId::DATE32: s.min_key = c.min_date; s.max_key = c.max_date; break;
+        case TypeId::STRING: s.min_key = 0; s.max_key = c.ndv ? static_cast<int64_t>(c.ndv) - 1 : -1; break;
+    }
+    // hand-built metas (tests/test_execution.cpp:31-36) leave every statistic zero: that means "unknown".
+    // STRING min/max are never recorded by the loader, and ids may come from a shared dictionary: measure them.
+    s.known = m.type != TypeId::STRING && (s.max_key > s.min_key || (c.ndv == 1 && s.max_key == s.min_key));
+    return s;
+}
+
+template <typename T>
+std::shared_ptr<void> download(const DevColPtr& col, size_t rows) {
+    auto v = std::make_shared<std::vector<T>>(rows);
+    if (rows) check(bq_col_read(context(), col->h, 0, rows, v->data()));
+    return std::shared_ptr<void>(v, v->data());
+}
+
+}  // namespace
+
+// ---- result paging -----------------------------------------------------------------------------------------
+void Operator::reset_paging() {
+    result_.reset();
+    host_cols_.clear();
+    emit_offset_ = 0;
+    paged_ = false;
+}
+
+bool Operator::page_out(ExecBatch& out) {
+    if (!paged_) {
+        result_ = device_result();
+        host_cols_.clear();
+        for (size_t c = 0; c < result_->cols.size(); ++c) {
+            switch (types_[c]) {
+                case TypeId::INT64: host_cols_.push_back(download<int64_t>(result_->cols[c], result_->rows)); break;
+                case TypeId::DOUBLE: host_cols_.push_back(download<double>(result_->cols[c], result_->rows)); break;
+                case TypeId::STRING: host_cols_.push_back(download<uint32_t>(result_->cols[c], result_->rows)); break;
+                case TypeId::DATE32: host_cols_.push_back(download<int32_t>(result_->cols[c], result_->rows)); break;
+            }
+        }
+        emit_offset_ = 0;
+        paged_ = true;
+    }
+    if (emit_offset_ >= result_->rows) return false;      // never an empty batch with `true`
+    const size_t take = std::min(kBatchRows, result_->rows - emit_offset_);
+    out.clear();
+    for (size_t c = 0; c < host_cols_.size(); ++c) {
+        const char* base = static_cast<const char*>(host_cols_[c].get()) + emit_offset_ * type_width(types_[c]);
+        out.columns.push_back({base, types_[c], take, host_cols_[c]});
+    }
+    out.length = take;
+    emit_offset_ += take;
+    return true;
+}
+
+// ---- ColumnarScan (src/exec/operator.cpp:321-386) -------------------------------------------------------------
+ColumnarScan::ColumnarScan(Table* t, std::vector<size_t> idx, size_t batch)
+    : table(t), indices(std::move(idx)), offset(0), batch_size(batch) {
+    if (!table) throw std::runtime_error("Scan table is null");
+    if (indices.empty())
+        for (size_t i = 0; i < table->columns.size(); ++i) indices.push_back(i);      // empty list = all columns (:326-331)
+    for (size_t i : indices) {
+        names_.push_back(table->columns[i].name);
+        types_.push_back(table->columns[i].data->type());
+    }
+    dict_ = table->dict.get();
+}
+
+void ColumnarScan::open() {
+    offset = 0;
+    reset_paging();
+}
+
+bool ColumnarScan::next(ExecBatch& out) {
+    if (indices.empty()) return false;
+    bool host_backed = true;
+    for (size_t i : indices) host_backed = host_backed && table->columns[i].data->host_data() != nullptr;
+    if (!host_backed) return page_out(out);        // device-only table: page rows out of HBM
+    // host-backed table: zero-copy slices of ColumnVector<T>::data, as the reference (:345-384)
+    const size_t rows = table->columns[indices[0]].data->size();
+    if (offset >= rows) return false;
+    const size_t take = std::min(batch_size, rows - offset);
+    out.clear();
+    for (size_t i : indices) {
+        const Column& c = *table->columns[i].data;
+        const char* base = static_cast<const char*>(c.host_data()) + offset * type_width(c.type());
+        out.columns.push_back({base, c.type(), take, {}});
+    }
+    out.length = take;
+    offset += take;
+    return true;
+}
+
+void ColumnarScan::close() {}
+
+DeviceRelationPtr ColumnarScan::device_result() {
+    auto rel = std::make_shared<DeviceRelation>();
+    for (size_t i : indices) rel->cols.push_back(gpu::mirror_of(*table->columns[i].data));
+    rel->rows = indices.empty() ? 0 : table->columns[indices[0]].data->size();
+    return rel;
+}
+
+bool ColumnarScan::describe(Pipeline& p) {
+    DeviceRelationPtr rel = device_result();
+    p = Pipeline{};
+    p.rows = rel->rows;
+    p.dict = dict_;
+    for (size_t k = 0; k < indices.size(); ++k) {
+        PipeCol c;
+        c.name = names_[k];
+        c.type = types_[k];
+        c.dev = rel->cols[k];
+        if (meta_)
+            for (const ColumnMeta& m : meta_->columns)
+                if (m.name == c.name && m.type == c.type) c.stats = stats_from_meta(m, meta_->row_count);
+        p.cols.push_back(std::move(c));
+    }
+    return true;
+}
+
+// ---- Selection (src/exec/operator.cpp:388-433) -------------------------------------------------------------------
+Selection::Selection(std::unique_ptr<Operator> c, std::unique_ptr<Expr> pred) : child(std::move(c)), predicate(std::move(pred)) {
+    if (!child) throw std::runtime_error("Selection child is null");
+    names_ = child->output_names();
+    types_ = child->output_types();
+    dict_ = child->dictionary();
+    bindings = make_bindings(names_, types_, dict_);
+}
+
+void Selection::open() {
+    child->open();
+    reset_paging();
+}
+bool Selection::next(ExecBatch& out) { return page_out(out); }
+void Selection::close() { child->close(); }
+
+bool Selection::describe(Pipeline& p) {
+    if (!child->describe(p)) return false;
+    if (predicate) gpu::split_conjuncts(predicate.get(), dict_, p.conjuncts);
+    return true;
+}
+
+DeviceRelationPtr Selection::device_result() {
+    DeviceRelationPtr in = child->device_result();
+    if (!predicate) return in;                       // null predicate = pass-through (:406-409)
+    std::vector<gpu::Conjunct> conj;
+    gpu::split_conjuncts(predicate.get(), dict_, conj);
+    std::vector<const gpu::Conjunct*> ptrs;
+    for (const auto& c : conj) ptrs.push_back(&c);
+    return gpu::run_selection(pipe_cols(names_, types_, *in), in->rows, ptrs);
+}
+
+// ---- Project (src/exec/operator.cpp:435-559) ------------------------------------------------------------------------
+Project::Project(std::unique_ptr<Operator> c, std::vector<std::unique_ptr<Expr>> exprs, std::vector<std::string> alias_list)
+    : child(std::move(c)), expressions(std::move(exprs)), aliases(std::move(alias_list)) {
+    if (!child) throw std::runtime_error("Project child is null");
+    input_names = child->output_names();
+    input_types = child->output_types();
+    dict_ = child->dictionary();
+    bindings = make_bindings(input_names, input_types, dict_);
+    direct_indices.assign(expressions.size(), -1);
+    for (size_t i = 0; i < expressions.size(); ++i) {
+        const Expr* e = expressions[i].get();
+        types_.push_back(infer_type(e, bindings));
+        const bool has_alias = i < aliases.size() && !aliases[i].empty();
+        names_.push_back(has_alias ? aliases[i] : (e->type == ExprType::COLUMN_REF ? e->str_val : "expr"));
+        if (e->type == ExprType::COLUMN_REF) {
+            auto it = bindings.name_to_index.find(e->str_val);
+            if (it != bindings.name_to_index.end()) direct_indices[i] = static_cast<int>(it->second);
+            continue;
+        }
+        // an expression that the child already computed under that name (aggregate outputs), :468-490
+        const std::string candidate = has_alias ? aliases[i] : e->to_string();
+        auto it = std::find(input_names.begin(), input_names.end(), candidate);
+        if (it != input_names.end()) {
+            direct_indices[i] = static_cast<int>(it - input_names.begin());
+        } else if (e->type == ExprType::FUNC_CALL) {
+            const std::string want = upper(candidate);
+            for (size_t k = 0; k < input_names.size(); ++k)
+                if (upper(input_names[k]) == want) {
+                    direct_indices[i] = static_cast<int>(k);
+                    break;
+                }
+        }
+    }
+}
+
+void Project::open() {
+    child->open();
+    reset_paging();
+}
+bool Project::next(ExecBatch& out) { return page_out(out); }
+void Project::close() { child->close(); }
+
+DeviceRelationPtr Project::device_result() {
+    DeviceRelationPtr in = child->device_result();
+    auto out = std::make_shared<DeviceRelation>();
+    out->rows = in->rows;
+    std::vector<PipeCol> cols = pipe_cols(input_names, input_types, *in);
+    for (size_t i = 0; i < expressions.size(); ++i) {
+        if (direct_indices[i] >= 0) {
+            out->cols.push_back(in->cols[direct_indices[i]]);
+            continue;
+        }
+        if (in->rows == 0) {                 // no row is ever evaluated, so nothing can throw (:505-551)
+            bq_col* h = nullptr;
+            check(bq_col_alloc(context(), static_cast<int>(types_[i]), 0, &h));
+            out->cols.push_back(gpu::adopt(h));
+            continue;
+        }
+        // evaluate_expr per row; the declared type equals the value's static type for every well-typed
+        // expression, so the coercions of :512-551 are identities
+        out->cols.push_back(gpu::eval_to_column(expressions[i].get(), cols, in->rows, dict_, types_[i], false));
+    }
+    return out;
+}
+
+// ---- Limit (src/exec/operator.cpp:561-620) -----------------------------------------------------------------------------
+Limit::Limit(std::unique_ptr<Operator> c, int64_t n) : child(std::move(c)), limit(n) {
+    if (!child) throw std::runtime_error("Limit child is null");
+    names_ = child->output_names();
+    types_ = child->output_types();
+    dict_ = child->dictionary();
+}
+
+void Limit::open() {
+    child->open();
+    reset_paging();
+}
+bool Limit::next(ExecBatch& out) { return page_out(out); }
+void Limit::close() { child->close(); }
+
+DeviceRelationPtr Limit::device_result() {
+    const int64_t want = limit < 0 ? 0 : limit;
+    if (auto* ob = dynamic_cast<OrderBy*>(child.get())) return ob->sorted_prefix(want);      // top-k
+    DeviceRelationPtr in = child->device_result();
+    if (static_cast<uint64_t>(want) >= in->rows) return in;
+    auto out = std::make_shared<DeviceRelation>();
+    out->rows = static_cast<size_t>(want);
+    for (auto& c : in->cols) {
+        bq_col* h = nullptr;
+        check(bq_slice(context(), c->h, 0, out->rows, &h));      // copy_range, :51-82
+        out->cols.push_back(gpu::adopt(h));
+    }
+    return out;
+}
+
+// ---- HashJoin (src/exec/operator.cpp:671-858) ------------------------------------------------------------------------------
+HashJoin::HashJoin(std::unique_ptr<Operator> left, std::unique_ptr<Operator> right, std::vector<std::string> left_keys,
+                   std::vector<std::string> right_keys, std::unique_ptr<Expr> residual)
+    : left_child(std::move(left)), right_child(std::move(right)), left_key_names(std::move(left_keys)),
+      right_key_names(std::move(right_keys)), residual_filter(std::move(residual)) {
+    if (!left_child || !right_child) throw std::runtime_error("Join operands cannot be null");
+    left_names = left_child->output_names();
+    left_types = left_child->output_types();
+    right_names = right_child->output_names();
+    right_types = right_child->output_types();
+    names_ = left_names;
+    names_.insert(names_.end(), right_names.begin(), right_names.end());
+    types_ = left_types;
+    types_.insert(types_.end(), right_types.begin(), right_types.end());
+
+    // dictionary choice: left if the left side has a STRING column, else right (:694-704)
+    Dictionary* ld = left_child->dictionary();
+    Dictionary* rd = right_child->dictionary();
+    auto has_string = [](const std::vector<TypeId>& t) { return std::find(t.begin(), t.end(), TypeId::STRING) != t.end(); };
+    if (has_string(left_types) && ld) dict_ = ld;
+    else if (has_string(right_types) && rd) dict_ = rd;
+    else dict_ = ld ? ld : rd;
+
+    auto resolve = [](const std::vector<std::string>& keys, const std::vector<std::string>& cols) {
+        std::vector<size_t> out;
+        for (const auto& k : keys) {
+            auto it = std::find(cols.begin(), cols.end(), k);
+            if (it == cols.end()) throw std::runtime_error("Join key not found: " + k);
+            out.push_back(static_cast<size_t>(it - cols.begin()));
+        }
+        return out;
+    };
+    left_key_indices = resolve(left_key_names, left_names);
+    right_key_indices = resolve(right_key_names, right_names);
+    if (left_key_indices.size() != right_key_indices.size()) throw std::runtime_error("Join key cardinality mismatch");
+    for (size_t i : left_key_indices) left_key_types.push_back(left_types[i]);
+    for (size_t i : right_key_indices) right_key_types.push_back(right_types[i]);
+}
+
+void HashJoin::open() {
+    right_child->open();      // the reference drains the build side here (:748-759); ours is built lazily on the device
+    right_child->close();
+    left_child->open();
+    reset_paging();
+}
+bool HashJoin::next(ExecBatch& out) { return page_out(out); }
+void HashJoin::close() { left_child->close(); }
+
+bool HashJoin::describe(Pipeline& p) {
+    if (left_key_indices.size() > 1) return false;
+    Pipeline l, r;
+    if (!left_child->describe(l) || !right_child->describe(r)) return false;
+    if (l.joined || r.joined) return false;
+    p = Pipeline{};
+    p.rows = l.rows;
+    p.build_rows = r.rows;
+    p.joined = true;
+    p.dict = dict_;
+    for (auto& c : l.cols) {
+        c.side = 0;
+        p.cols.push_back(std::move(c));
+    }
+    const size_t n_left = p.cols.size();
+    for (auto& c : r.cols) {
+        c.side = 1;
+        p.cols.push_back(std::move(c));
+    }
+    if (left_key_indices.empty()) {
+        p.cross_join = true;       // every row matches every row
+    } else {
+        p.probe_key = static_cast<int>(left_key_indices[0]);
+        p.build_key = static_cast<int>(n_left + right_key_indices[0]);
+    }
+    // predicates sitting under the join stay bound to their side: they only name that side's columns, but a name
+    // that also exists on the other side would rebind after the merge, so such plans are not fused
+    auto names_clash = [&]() {
+        for (size_t i = 0; i < n_left; ++i)
+            for (size_t j = n_left; j < p.cols.size(); ++j)
+                if (p.cols[i].name == p.cols[j].name) return true;
+        return false;
+    };
+    if ((!l.conjuncts.empty() || !r.conjuncts.empty()) && names_clash()) return false;
+    for (auto& c : l.conjuncts) p.conjuncts.push_back(std::move(c));
+    for (auto& c : r.conjuncts) p.conjuncts.push_back(std::move(c));
+    return true;
+}
+
+DeviceRelationPtr HashJoin::device_result() {
+    DeviceRelationPtr l = left_child->device_result();
+    DeviceRelationPtr r = right_child->device_result();
+    bq_ctx* ctx = context();
+    DevColPtr probe_rows, build_rows;
+    if (l->rows == 0 || r->rows == 0) return gpu::empty_relation(types_);
+    if (left_key_indices.empty()) {
+        // cross product in probe order: pair i = (i / n_right, i % n_right)
+        const uint64_t total = static_cast<uint64_t>(l->rows) * r->rows;
+        if (total > 0xFFFFFFFFull) throw std::runtime_error("join result exceeds 2^32 rows");
+        bq_col* iota = nullptr;
+        check(bq_col_alloc(ctx, BQ_INT64, total, &iota));
+        DevColPtr idx = gpu::adopt(iota);
+        bq_gen_spec g{};
+        g.dist = BQ_GEN_SEQ;
+        check(bq_col_generate(ctx, idx->h, &g, 0));
+        const int64_t nr = static_cast<int64_t>(r->rows);
+        bq_insn q[3] = {{BQ_OP_COL, 0, {0}}, {BQ_OP_IMM_I, 0, {nr}}, {BQ_OP_DIV_I, 0, {0}}};
+        bq_insn m[7] = {{BQ_OP_COL, 0, {0}}, {BQ_OP_COL, 0, {0}}, {BQ_OP_IMM_I, 0, {nr}}, {BQ_OP_DIV_I, 0, {0}},
+                        {BQ_OP_IMM_I, 0, {nr}}, {BQ_OP_MUL_I, 0, {0}}, {BQ_OP_SUB_I, 0, {0}}};
+        const bq_col* cols[1] = {idx->h};
+        bq_col *pr = nullptr, *br = nullptr;
+        check(bq_eval(ctx, q, 3, cols, 1, 0, total, BQ_STRING, &pr));
+        probe_rows = gpu::adopt(pr);
+        check(bq_eval(ctx, m, 7, cols, 1, 0, total, BQ_STRING, &br));
+        build_rows = gpu::adopt(br);
+    } else {
+        if (left_key_indices.size() > 1) throw std::runtime_error("multi-column join keys are not supported on the GPU path");
+        if (left_key_types[0] != right_key_types[0]) return gpu::empty_relation(types_);   // KeyEqual (:652)
+        DevColPtr bk = r->cols[right_key_indices[0]];
+        DevColPtr pk = l->cols[left_key_indices[0]];
+        bq_join_spec js{};
+        js.key = bk->h;
+        js.row_begin = 0;
+        js.row_end = r->rows;
+        js.need_rows = 1;
+        js.kind = BQ_JOIN_HASH;
+        if (right_key_types[0] != TypeId::DOUBLE) {
+            int64_t lo = 0, hi = -1;
+            check(bq_col_minmax(ctx, bk->h, &lo, &hi));
+            js.kind = BQ_JOIN_AUTO;
+            js.key_min = lo;
+            js.key_max = hi;
+        }
+        bq_join* j = nullptr;
+        check(bq_join_build(ctx, &js, &j));
+        bq_col *pr = nullptr, *br = nullptr;
+        int rc = bq_join_probe(ctx, j, pk->h, nullptr, 0, l->rows, &pr, &br);
+        bq_join_free(ctx, j);
+        check(rc);
+        probe_rows = gpu::adopt(pr);
+        build_rows = gpu::adopt(br);
+    }
+    auto out = std::make_shared<DeviceRelation>();
+    out->rows = probe_rows->rows();
+    for (auto& c : l->cols) {
+        bq_col* g = nullptr;
+        check(bq_gather(ctx, c->h, probe_rows->h, &g));
+        out->cols.push_back(gpu::adopt(g));
+    }
+    for (auto& c : r->cols) {
+        bq_col* g = nullptr;
+        check(bq_gather(ctx, c->h, build_rows->h, &g));
+        out->cols.push_back(gpu::adopt(g));
+    }
+    return out;
+}
+
+// ---- HashAggregate (src/exec/operator.cpp:907-1074) ------------------------------------------------------------------------
+HashAggregate::HashAggregate(std::unique_ptr<Operator> child_op, std::vector<std::unique_ptr<Expr>> group_exprs_in,
+                             std::vector<AggregateSpec> aggregates_in)
+    : child(std::move(child_op)), group_exprs(std::move(group_exprs_in)), aggregates(std::move(aggregates_in)) {
+    if (!child) throw std::runtime_error("HashAggregate child is null");
+    dict_ = child->dictionary();
+    child_bindings = make_bindings(child->output_names(), child->output_types(), dict_);
+    for (size_t i = 0; i < group_exprs.size(); ++i) {
+        TypeId t = infer_type(group_exprs[i].get(), child_bindings);
+        group_types.push_back(t);
+        names_.push_back(group_exprs[i]->type == ExprType::COLUMN_REF ? group_exprs[i]->str_val : "group" + std::to_string(i + 1));
+        types_.push_back(t);
+    }
+    for (const auto& a : aggregates) {
+        TypeId arg = TypeId::INT64;
+        if (a.arg && a.func_name != "COUNT") arg = infer_type(a.arg.get(), child_bindings);
+        TypeId res = TypeId::INT64;                        // COUNT, and any unknown function (:940-947)
+        if (a.func_name == "SUM") res = arg == TypeId::DOUBLE ? TypeId::DOUBLE : TypeId::INT64;
+        else if (a.func_name == "AVG") res = TypeId::DOUBLE;
+        agg_arg_types.push_back(arg);
+        agg_types.push_back(res);
+        names_.push_back(!a.alias.empty() ? a.alias : a.func_name + "(" + (a.arg ? a.arg->to_string() : std::string("*")) + ")");
+        types_.push_back(res);
+    }
+}
+
+void HashAggregate::open() {
+    child_consumed = false;
+    child->open();
+    reset_paging();
+}
+
+bool HashAggregate::next(ExecBatch& out) {
+    bool more = page_out(out);
+    if (!child_consumed) {
+        child->close();
+        child_consumed = true;
+    }
+    return more;
+}
+
+void HashAggregate::close() {
+    if (!child_consumed) {
+        child->close();
+        child_consumed = true;
+    }
+    reset_paging();
+}
+
+DeviceRelationPtr HashAggregate::device_result() {
+    gpu::AggRequest req;
+    req.group_exprs = &group_exprs;
+    req.group_types = group_types;
+    req.dict = dict_;
+    for (size_t i = 0; i < aggregates.size(); ++i) {
+        const auto& a = aggregates[i];
+        if (a.func_name != "COUNT" && a.func_name != "SUM" && a.func_name != "AVG")
+            throw std::runtime_error("unsupported aggregate function: " + a.func_name);
+        req.aggs.push_back({a.func_name, a.arg.get(), agg_types[i]});
+    }
+    Pipeline p;
+    if (child->describe(p)) {
+        if (DeviceRelationPtr r = gpu::run_aggregate(p, req)) return r;
+    }
+    // not a fusable chain (or it mixes both join sides in one predicate): materialise the child, then the same kernels
+    DeviceRelationPtr in = child->device_result();
+    Pipeline plain;
+    plain.rows = in->rows;
+    plain.dict = dict_;
+    plain.cols = pipe_cols(child->output_names(), child->output_types(), *in);
+    DeviceRelationPtr r = gpu::run_aggregate(plain, req);
+    if (!r) throw std::runtime_error("internal: aggregate over a materialised relation was not planned");
+    return r;
+}
+
+// ---- OrderBy (src/exec/operator.cpp:1076-1161) -----------------------------------------------------------------------------
+OrderBy::OrderBy(std::unique_ptr<Operator> child_op, std::vector<SortKey> sort_keys_in)
+    : child(std::move(child_op)), sort_keys(std::move(sort_keys_in)) {
+    if (!child) throw std::runtime_error("OrderBy child is null");
+    names_ = child->output_names();
+    types_ = child->output_types();
+    dict_ = child->dictionary();
+    bindings = make_bindings(names_, types_, dict_);
+}
+
+void OrderBy::open() {
+    child_consumed = false;
+    child->open();
+    reset_paging();
+}
+
+bool OrderBy::next(ExecBatch& out) {
+    bool more = page_out(out);
+    if (!child_consumed) {
+        child->close();
+        child_consumed = true;
+    }
+    return more;
+}
+
+void OrderBy::close() {
+    if (!child_consumed) {
+        child->close();
+        child_consumed = true;
+    }
+    reset_paging();
+}
+
+DeviceRelationPtr OrderBy::device_result() { return sorted_prefix(-1); }
+
+DeviceRelationPtr OrderBy::sorted_prefix(int64_t limit) {
+    DeviceRelationPtr in = child->device_result();
+    if (in->rows == 0 || limit == 0) return gpu::empty_relation(types_);
+    if (sort_keys.size() > 4) throw std::runtime_error("more than 4 ORDER BY keys are not supported on the GPU path");
+    bq_ctx* ctx = context();
+    std::vector<PipeCol> cols = pipe_cols(names_, types_, *in);
+    // sort columns: plain column references sort the column itself; anything else is evaluated first (:1105-1107)
+    std::vector<DevColPtr> rel_cols = in->cols;
+    std::vector<int> key_cols, asc;
+    for (const auto& k : sort_keys) {
+        int idx = -1;
+        if (k.expr->type == ExprType::COLUMN_REF) {
+            auto it = bindings.name_to_index.find(k.expr->str_val);
+            if (it == bindings.name_to_index.end()) throw std::runtime_error("Unknown column: " + k.expr->str_val);
+            idx = static_cast<int>(it->second);
+        } else {
+            TypeId t = gpu::value_type(k.expr.get(), gpu::lookup_for(cols));
+            rel_cols.push_back(gpu::eval_to_column(k.expr.get(), cols, in->rows, dict_, t, false));
+            idx = static_cast<int>(rel_cols.size()) - 1;
+        }
+        key_cols.push_back(idx);
+        asc.push_back(k.asc ? 1 : 0);
+    }
+    std::vector<bq_col*> hs;
+    for (auto& c : rel_cols) hs.push_back(c->h);
+    bq_rel* shell = nullptr;
+    check(bq_rel_create(ctx, hs.data(), static_cast<int>(hs.size()), &shell));
+    bq_rel* sorted = nullptr;
+    int rc = bq_rel_sort(ctx, shell, static_cast<int>(key_cols.size()), key_cols.data(), asc.data(), limit, &sorted);
+    std::vector<bq_col*> back(hs.size());
+    bq_rel_release(shell, back.data());       // the inputs stay owned by their DevCols
+    check(rc);
+    DeviceRelationPtr out = gpu::relation_from(sorted);
+    out->cols.resize(in->cols.size());        // drop evaluated sort keys
+    return out;
+}
+
+}  // namespace bosql

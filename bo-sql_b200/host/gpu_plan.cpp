@@ -1,0 +1,649 @@
+// gpu_plan.cpp — the host side of the fused pipelines: slot assignment, join-table choice from catalog statistics,
+// grouping strategy, and the calls into include/bosql_b200.h.
+//
+// What the reference does per row at run time (HashAggregate::next, src/exec/operator.cpp:984-1014;
+// Selection::next :403-429; HashJoin::open/next :739-837) is decided here once per query.
+#include "gpu_plan.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+
+namespace bosql::gpu {
+
+ColumnLookup lookup_for(const std::vector<PipeCol>& cols) {
+    const std::vector<PipeCol>* c = &cols;
+    ColumnLookup l;
+    // the reference's name->index map is filled in column order, so the LAST duplicate name wins
+    l.index_of = [c](const std::string& name) {
+        for (int i = static_cast<int>(c->size()) - 1; i >= 0; --i)
+            if ((*c)[i].name == name) return i;
+        return -1;
+    };
+    l.type_of = [c](int i) { return (*c)[i].type; };
+    return l;
+}
+
+ColumnLookup lookup_for(const std::vector<std::string>& names, const std::vector<TypeId>& types) {
+    const auto* n = &names;
+    const auto* t = &types;
+    ColumnLookup l;
+    l.index_of = [n](const std::string& name) {
+        for (int i = static_cast<int>(n->size()) - 1; i >= 0; --i)
+            if ((*n)[i] == name) return i;
+        return -1;
+    };
+    l.type_of = [t](int i) { return (*t)[i]; };
+    return l;
+}
+
+DeviceRelationPtr empty_relation(const std::vector<TypeId>& types) {
+    auto rel = std::make_shared<DeviceRelation>();
+    for (TypeId t : types) {
+        bq_col* h = nullptr;
+        check(bq_col_alloc(context(), static_cast<int>(t), 0, &h));
+        rel->cols.push_back(adopt(h));
+    }
+    rel->rows = 0;
+    return rel;
+}
+
+void resolve_stats(PipeCol& col, bool force_device) {
+    if (col.stats.known && !force_device) return;
+    int64_t lo = 0, hi = -1;
+    if (force_device) bq_col_invalidate_stats(col.dev->h);
+    check(bq_col_minmax(context(), col.dev->h, &lo, &hi));
+    col.stats.known = true;
+    col.stats.min_key = lo;
+    col.stats.max_key = hi;
+}
+
+DevColPtr eval_to_column(const Expr* e, const std::vector<PipeCol>& cols, size_t rows, Dictionary* dict, TypeId out_type,
+                         bool as_predicate) {
+    Program prog = compile(e, lookup_for(cols), dict, as_predicate);
+    std::vector<const bq_col*> cs;
+    for (int idx : prog.columns) cs.push_back(cols[idx].dev->h);
+    bq_col* out = nullptr;
+    const bq_col* none = nullptr;
+    check(bq_eval(context(), prog.code.data(), static_cast<int>(prog.code.size()), cs.empty() ? &none : cs.data(),
+                  static_cast<int>(cs.size()), 0, rows, static_cast<int>(out_type), &out));
+    return adopt(out);
+}
+
+// Runs a hand-assembled program (no Expr typing rules: used for packing several integer keys into one).
+static DevColPtr eval_program(const std::vector<bq_insn>& code, const std::vector<DevColPtr>& cols, size_t rows, TypeId out_type) {
+    std::vector<const bq_col*> cs;
+    for (const auto& c : cols) cs.push_back(c->h);
+    bq_col* out = nullptr;
+    check(bq_eval(context(), code.data(), static_cast<int>(code.size()), cs.data(), static_cast<int>(cs.size()), 0, rows,
+                  static_cast<int>(out_type), &out));
+    return adopt(out);
+}
+static bq_insn insn(int op, int arg = 0, int64_t imm = 0) {
+    bq_insn in{};
+    in.op = op;
+    in.arg = arg;
+    in.imm.i = imm;
+    return in;
+}
+
+bq_slot make_slot(const DevColPtr& col, const std::vector<bq_range>& ranges, bool from_build) {
+    bq_slot s{};
+    s.col = col ? col->h : nullptr;
+    s.n_ranges = static_cast<int32_t>(ranges.size());
+    s.from_build = from_build ? 1 : 0;
+    for (size_t i = 0; i < ranges.size() && i < 2; ++i) s.r[i] = ranges[i];
+    return s;
+}
+
+namespace {
+
+// Intersect all positive ranges into one; keep negated ranges as they are.
+std::vector<bq_range> normalise(const std::vector<bq_range>& in) {
+    bool have_pos = false;
+    bq_range pos{};
+    std::vector<bq_range> out;
+    for (const auto& r : in) {
+        if (r.neg) {
+            out.push_back(r);
+        } else if (!have_pos) {
+            pos = r;
+            have_pos = true;
+        } else {
+            pos.lo = std::max(pos.lo, r.lo);
+            pos.hi = std::min(pos.hi, r.hi);
+        }
+    }
+    if (have_pos) out.insert(out.begin(), pos);
+    return out;
+}
+
+std::unique_ptr<Expr> and_of(const std::vector<const Expr*>& es) {
+    std::unique_ptr<Expr> acc;
+    for (const Expr* e : es) {
+        if (!acc) {
+            acc = e->clone();
+            continue;
+        }
+        auto n = std::make_unique<Expr>();
+        n->type = ExprType::BINARY_OP;
+        n->op = BinaryOp::AND;
+        n->left = std::move(acc);
+        n->right = e->clone();
+        acc = std::move(n);
+    }
+    return acc;
+}
+
+}  // namespace
+
+SlotPlan plan_slots(const std::vector<const Conjunct*>& conjuncts, const std::vector<PipeCol>& cols, size_t rows,
+                    const std::vector<int>& role_cols, int n_pred_slots) {
+    SlotPlan plan;
+    plan.role_ranges.resize(role_cols.size());
+    const ColumnLookup look = lookup_for(cols);
+
+    struct PerCol {
+        std::vector<bq_range> ranges;
+        std::vector<const Conjunct*> sources;
+    };
+    std::map<int, PerCol> by_col;
+    std::vector<const Conjunct*> leftovers;
+    for (const Conjunct* c : conjuncts) {
+        ColumnRange cr;
+        if (to_range(c->expr.get(), look, c->dict, cr)) {
+            by_col[cr.column].ranges.push_back(cr.range);
+            by_col[cr.column].sources.push_back(c);
+        } else {
+            leftovers.push_back(c);
+        }
+    }
+    for (auto& [col, pc] : by_col) {
+        std::vector<bq_range> norm = normalise(pc.ranges);
+        bool placed = false;
+        if (norm.size() <= 2) {
+            for (size_t r = 0; r < role_cols.size() && !placed; ++r) {
+                // the same device column may sit in a role slot under another index (e.g. a name bound twice)
+                if (role_cols[r] >= 0 && cols[role_cols[r]].dev->h == cols[col].dev->h && plan.role_ranges[r].empty()) {
+                    plan.role_ranges[r] = norm;
+                    placed = true;
+                }
+            }
+            if (!placed && static_cast<int>(plan.pred.size()) < n_pred_slots) {
+                plan.pred.push_back({col, norm});
+                placed = true;
+            }
+        }
+        if (!placed) leftovers.insert(leftovers.end(), pc.sources.begin(), pc.sources.end());
+    }
+    if (!leftovers.empty()) {
+        // one program: c1 AND c2 AND ...  (every conjunct still evaluated for every row, H11)
+        std::vector<const Expr*> es;
+        Dictionary* dict = nullptr;
+        for (const Conjunct* c : leftovers) {
+            es.push_back(c->expr.get());
+            if (c->dict) dict = c->dict;
+        }
+        auto all = and_of(es);
+        plan.mask = eval_to_column(all.get(), cols, rows, dict, TypeId::INT64, true);
+    }
+    return plan;
+}
+
+DeviceRelationPtr run_selection(const std::vector<PipeCol>& cols, size_t rows, const std::vector<const Conjunct*>& conjuncts) {
+    auto out = std::make_shared<DeviceRelation>();
+    if (rows == 0) {
+        std::vector<TypeId> types;
+        for (const auto& c : cols) types.push_back(c.type);
+        return empty_relation(types);
+    }
+    SlotPlan plan = plan_slots(conjuncts, cols, rows, {}, 4);
+    bq_select_spec spec{};
+    for (size_t i = 0; i < plan.pred.size(); ++i) spec.pred[i] = make_slot(cols[plan.pred[i].first].dev, plan.pred[i].second);
+    spec.mask = plan.mask ? plan.mask->h : nullptr;
+    spec.row_begin = 0;
+    spec.row_end = rows;
+    bq_col* ids = nullptr;
+    check(bq_select(context(), &spec, &ids));
+    DevColPtr rowids = adopt(ids);
+    out->rows = rowids->rows();
+    for (const auto& c : cols) {
+        bq_col* g = nullptr;
+        check(bq_gather(context(), c.dev->h, rowids->h, &g));
+        out->cols.push_back(adopt(g));
+    }
+    return out;
+}
+
+// ---- aggregate ------------------------------------------------------------------------------------------
+namespace {
+
+bool is_int_literal(const Expr* e) { return e->type == ExprType::LITERAL_INT; }
+bool is_arith_op(BinaryOp op) { return op == BinaryOp::ADD || op == BinaryOp::SUB || op == BinaryOp::MUL || op == BinaryOp::DIV; }
+
+int vop_of(BinaryOp op) {
+    switch (op) {
+        case BinaryOp::MUL: return BQ_V_MUL;
+        case BinaryOp::ADD: return BQ_V_ADD;
+        case BinaryOp::SUB: return BQ_V_SUB;
+        default: return BQ_V_DIV;
+    }
+}
+
+// One aggregate argument in the fused kernel's vocabulary: a column, or left OP right where each operand is a
+// numeric column or an integer literal.
+struct ValueForm {
+    bool unary = true;
+    int op = BQ_V_A;                // BQ_V_MUL.. when binary
+    int col_l = -1, col_r = -1;     // pipeline column of each operand (-1 = immediate / unused)
+    int64_t imm = 0;
+    TypeId type = TypeId::INT64;    // static type of the argument (decides SUM's result type)
+};
+
+bool numeric_col(const std::vector<PipeCol>& cols, int idx) {
+    return cols[idx].type == TypeId::INT64 || cols[idx].type == TypeId::DOUBLE;
+}
+
+// false = needs a derived column (evaluated by bq_eval first)
+bool simple_value_form(const Expr* arg, const std::vector<PipeCol>& cols, const ColumnLookup& look, ValueForm& out) {
+    if (arg->type == ExprType::COLUMN_REF) {
+        int idx = look.index_of(arg->str_val);
+        if (idx < 0) throw std::runtime_error("Unknown column: " + arg->str_val);
+        out.unary = true;
+        out.col_l = idx;
+        out.type = cols[idx].type;
+        return true;
+    }
+    if (arg->type != ExprType::BINARY_OP || !is_arith_op(arg->op)) return false;
+    auto col_of = [&](const Expr* e) {
+        if (e->type != ExprType::COLUMN_REF) return -1;
+        int idx = look.index_of(e->str_val);
+        if (idx < 0) throw std::runtime_error("Unknown column: " + e->str_val);
+        return numeric_col(cols, idx) ? idx : -1;
+    };
+    const Expr* l = arg->left.get();
+    const Expr* r = arg->right.get();
+    const int lc = col_of(l), rc = col_of(r);
+    const bool l_ok = lc >= 0 || is_int_literal(l), r_ok = rc >= 0 || is_int_literal(r);
+    if (!l_ok || !r_ok || (lc < 0 && rc < 0)) return false;
+    out.unary = false;
+    out.op = vop_of(arg->op);
+    out.col_l = lc;
+    out.col_r = rc;
+    out.imm = lc < 0 ? l->i64_val : (rc < 0 ? r->i64_val : 0);
+    const bool fp = (lc >= 0 && cols[lc].type == TypeId::DOUBLE) || (rc >= 0 && cols[rc].type == TypeId::DOUBLE);
+    out.type = fp ? TypeId::DOUBLE : TypeId::INT64;
+    return true;
+}
+
+struct Domain {
+    int64_t lo = 0, hi = -1;
+    uint64_t size() const { return hi < lo ? 0 : static_cast<uint64_t>(hi - lo) + 1; }
+};
+
+}  // namespace
+
+DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
+    bq_ctx* ctx = context();
+    std::vector<TypeId> out_types = req.group_types;
+    for (const auto& a : req.aggs) out_types.push_back(a.result_type);
+
+    // zero input rows -> zero output rows, even for a global aggregate (src/exec/operator.cpp:990-993, H5)
+    if (p.rows == 0 || (p.joined && p.build_rows == 0)) return empty_relation(out_types);
+    if (p.cross_join) return nullptr;
+
+    ColumnLookup look = lookup_for(p.cols);
+
+    // ---- split predicates by the side they read ---------------------------------------------------------
+    std::vector<const Conjunct*> probe_conj, build_conj;
+    for (const Conjunct& c : p.conjuncts) {
+        std::vector<int> refs;
+        referenced(c.expr.get(), look, refs);
+        bool any_probe = false, any_build = false;
+        for (int r : refs) (p.cols[r].side ? any_build : any_probe) = true;
+        if (any_probe && any_build) return nullptr;        // compares columns of both sides: materialise the join
+        (any_build ? build_conj : probe_conj).push_back(&c);
+    }
+
+    // the columns a derived expression may read: everything on the probe side (same length, streamed)
+    auto all_on_probe = [&](const Expr* e) {
+        std::vector<int> refs;
+        referenced(e, look, refs);
+        for (int r : refs)
+            if (p.cols[r].side) return false;
+        return true;
+    };
+
+    // ---- group key -----------------------------------------------------------------------------------------
+    const auto& gexprs = *req.group_exprs;
+    int key_col = -1;
+    std::vector<Domain> packed_domains;      // multi-column keys packed into one int64
+    std::vector<uint64_t> packed_strides;
+    if (gexprs.size() == 1 && gexprs[0]->type == ExprType::COLUMN_REF) {
+        key_col = look.index_of(gexprs[0]->str_val);
+        if (key_col < 0) throw std::runtime_error("Unknown column: " + gexprs[0]->str_val);
+    } else if (gexprs.size() == 1) {
+        if (!all_on_probe(gexprs[0].get())) return nullptr;
+        PipeCol derived;
+        derived.name = "\x01group1";
+        derived.type = req.group_types[0];
+        derived.dev = eval_to_column(gexprs[0].get(), p.cols, p.rows, req.dict, derived.type, false);
+        p.cols.push_back(std::move(derived));
+        key_col = static_cast<int>(p.cols.size()) - 1;
+        look = lookup_for(p.cols);
+    } else if (gexprs.size() > 1) {
+        // GROUP BY a, b, ...: pack (a-min_a, b-min_b, ...) into one integer, most significant first
+        uint64_t total = 1;
+        std::vector<int> key_cols;
+        for (const auto& g : gexprs) {
+            if (g->type != ExprType::COLUMN_REF) throw std::runtime_error("GROUP BY over several expressions is not supported on the GPU path");
+            int idx = look.index_of(g->str_val);
+            if (idx < 0) throw std::runtime_error("Unknown column: " + g->str_val);
+            if (p.cols[idx].type == TypeId::DOUBLE) throw std::runtime_error("GROUP BY over several keys needs integer-typed keys on the GPU path");
+            if (p.cols[idx].side) return nullptr;
+            key_cols.push_back(idx);
+            resolve_stats(p.cols[idx]);
+            Domain d{p.cols[idx].stats.min_key, p.cols[idx].stats.max_key};
+            if (d.size() == 0) d = Domain{0, 0};
+            if (total > (1ULL << 62) / d.size()) throw std::runtime_error("GROUP BY key domain too large to pack");
+            total *= d.size();
+            packed_domains.push_back(d);
+        }
+        if (key_cols.size() > BQ_MAX_PROGRAM_COLS) throw std::runtime_error("too many GROUP BY keys");
+        std::vector<bq_insn> code;
+        std::vector<DevColPtr> kcols;
+        uint64_t stride = total;
+        for (size_t i = 0; i < key_cols.size(); ++i) {
+            stride /= packed_domains[i].size();
+            packed_strides.push_back(stride);
+            kcols.push_back(p.cols[key_cols[i]].dev);
+            code.push_back(insn(BQ_OP_COL, static_cast<int>(i)));
+            code.push_back(insn(BQ_OP_IMM_I, 0, packed_domains[i].lo));
+            code.push_back(insn(BQ_OP_SUB_I));
+            code.push_back(insn(BQ_OP_IMM_I, 0, static_cast<int64_t>(stride)));
+            code.push_back(insn(BQ_OP_MUL_I));
+            if (i) code.push_back(insn(BQ_OP_ADD_I));
+        }
+        PipeCol derived;
+        derived.name = "\x01packed";
+        derived.type = TypeId::INT64;
+        derived.dev = eval_program(code, kcols, p.rows, TypeId::INT64);
+        derived.stats.known = true;
+        derived.stats.min_key = 0;
+        derived.stats.max_key = static_cast<int64_t>(total - 1);
+        p.cols.push_back(std::move(derived));
+        key_col = static_cast<int>(p.cols.size()) - 1;
+        look = lookup_for(p.cols);
+    }
+
+    // ---- aggregate arguments -----------------------------------------------------------------------------------
+    struct Value {
+        std::string text;
+        ValueForm form;
+    };
+    std::vector<Value> values;                 // distinct arguments
+    std::vector<int> agg_value(req.aggs.size(), -1);
+    for (size_t i = 0; i < req.aggs.size(); ++i) {
+        const auto& a = req.aggs[i];
+        if (a.func == "COUNT") continue;
+        if (a.func != "SUM" && a.func != "AVG") throw std::runtime_error("unsupported aggregate function: " + a.func);
+        std::string text = a.arg->to_string();
+        int found = -1;
+        for (size_t v = 0; v < values.size(); ++v)
+            if (values[v].text == text) found = static_cast<int>(v);
+        if (found < 0) {
+            Value val;
+            val.text = text;
+            if (!simple_value_form(a.arg, p.cols, look, val.form)) {
+                if (!all_on_probe(a.arg)) return nullptr;
+                PipeCol derived;
+                derived.name = "\x01value" + std::to_string(values.size());
+                derived.type = value_type(a.arg, look);
+                derived.dev = eval_to_column(a.arg, p.cols, p.rows, req.dict, derived.type, false);
+                p.cols.push_back(std::move(derived));
+                look = lookup_for(p.cols);
+                val.form = ValueForm{};
+                val.form.col_l = static_cast<int>(p.cols.size()) - 1;
+                val.form.type = p.cols.back().type;
+            }
+            values.push_back(std::move(val));
+            found = static_cast<int>(values.size()) - 1;
+        }
+        agg_value[i] = found;
+    }
+
+    // ---- passes: each holds <= 2 arguments over <= 2 columns ---------------------------------------------------
+    struct Pass {
+        int col_a = -1, col_b = -1;
+        std::vector<int> vals;     // indices into values
+    };
+    std::vector<Pass> passes;
+    for (size_t v = 0; v < values.size(); ++v) {
+        const ValueForm& f = values[v].form;
+        bool placed = false;
+        for (Pass& ps : passes) {
+            if (ps.vals.size() >= 2) continue;
+            // try to fit f's columns into the pass's (A, B)
+            int a = ps.col_a, b = ps.col_b;
+            auto add = [&](int c) {
+                if (c < 0 || c == a || c == b) return true;
+                if (a < 0) { a = c; return true; }
+                if (b < 0) { b = c; return true; }
+                return false;
+            };
+            if (add(f.col_l) && add(f.col_r)) {
+                ps.col_a = a;
+                ps.col_b = b;
+                ps.vals.push_back(static_cast<int>(v));
+                placed = true;
+                break;
+            }
+        }
+        if (!placed) {
+            Pass ps;
+            ps.col_a = f.col_l >= 0 ? f.col_l : f.col_r;
+            ps.col_b = (f.col_r >= 0 && f.col_r != ps.col_a) ? f.col_r : -1;
+            ps.vals.push_back(static_cast<int>(v));
+            passes.push_back(ps);
+        }
+    }
+    if (passes.empty()) passes.push_back(Pass{});      // COUNT only
+
+    // ---- join build ------------------------------------------------------------------------------------------------
+    bq_join* join = nullptr;
+    struct JoinGuard {
+        bq_join*& j;
+        ~JoinGuard() { if (j) bq_join_free(nullptr, j); }
+    } join_guard{join};
+    if (p.joined) {
+        PipeCol& bk = p.cols[p.build_key];
+        const PipeCol& pk = p.cols[p.probe_key];
+        if (bk.type != pk.type) return empty_relation(out_types);     // KeyEqual: different TypeId never match (:652)
+        bool need_rows = key_col >= 0 && p.cols[key_col].side;
+        for (const auto& v : values)
+            for (int c : {v.form.col_l, v.form.col_r})
+                if (c >= 0 && p.cols[c].side) need_rows = true;
+        // build-side columns as a column set of their own (length build_rows)
+        std::vector<PipeCol> bcols;
+        std::vector<int> bmap(p.cols.size(), -1);
+        for (size_t i = 0; i < p.cols.size(); ++i)
+            if (p.cols[i].side) {
+                bmap[i] = static_cast<int>(bcols.size());
+                bcols.push_back(p.cols[i]);
+            }
+        SlotPlan bplan = plan_slots(build_conj, bcols, p.build_rows, {}, 3);
+        bq_join_spec js{};
+        js.key = bk.dev->h;
+        for (size_t i = 0; i < bplan.pred.size(); ++i) js.pred[i] = make_slot(bcols[bplan.pred[i].first].dev, bplan.pred[i].second);
+        js.mask = bplan.mask ? bplan.mask->h : nullptr;
+        js.row_begin = 0;
+        js.row_end = p.build_rows;
+        js.kind = BQ_JOIN_AUTO;
+        js.need_rows = need_rows ? 1 : 0;
+        if (bk.type != TypeId::DOUBLE) {
+            resolve_stats(bk);
+            js.key_min = bk.stats.min_key;
+            js.key_max = bk.stats.max_key;
+            js.unique = (bk.stats.ndv && bk.stats.ndv == p.build_rows) ? 1 : 0;
+        } else {
+            js.kind = BQ_JOIN_HASH;
+        }
+        check(bq_join_build(ctx, &js, &join));
+    }
+
+    // ---- run the passes ---------------------------------------------------------------------------------------------------
+    std::vector<DeviceRelationPtr> pass_results;
+    std::vector<std::vector<size_t>> pass_aggs;      // which aggregates each pass produced, in column order
+    for (const Pass& ps : passes) {
+        std::vector<int> roles = {key_col, ps.col_a, ps.col_b, p.joined ? p.probe_key : -1};
+        // ranges may only ride on streamed (probe-side) role columns
+        std::vector<int> range_roles = roles;
+        for (int& r : range_roles)
+            if (r >= 0 && p.cols[r].side) r = -1;
+        SlotPlan plan = plan_slots(probe_conj, p.cols, p.rows, range_roles, 3);
+
+        bq_scan_spec s{};
+        auto slot_for = [&](int role_index) {
+            int c = roles[role_index];
+            if (c < 0) return bq_slot{};
+            return make_slot(p.cols[c].dev, plan.role_ranges[role_index], p.cols[c].side != 0);
+        };
+        s.key = slot_for(0);
+        s.a = slot_for(1);
+        s.b = slot_for(2);
+        s.jkey = slot_for(3);
+        for (size_t i = 0; i < plan.pred.size(); ++i) s.pred[i] = make_slot(p.cols[plan.pred[i].first].dev, plan.pred[i].second);
+        s.mask = plan.mask ? plan.mask->h : nullptr;
+        s.row_begin = 0;
+        s.row_end = p.rows;
+        s.join = join;
+        s.n_v = static_cast<int32_t>(ps.vals.size());
+        for (size_t k = 0; k < ps.vals.size(); ++k) {
+            const ValueForm& f = values[ps.vals[k]].form;
+            bq_vexpr ve{};
+            if (f.unary) {
+                ve.op = f.col_l == ps.col_a ? BQ_V_A : BQ_V_B;
+            } else {
+                ve.op = f.op;
+                ve.l_src = f.col_l < 0 ? BQ_L_IMM : (f.col_l == ps.col_a ? BQ_L_A : BQ_L_B);
+                ve.r_src = f.col_r < 0 ? BQ_R_IMM : (f.col_r == ps.col_a ? BQ_R_A : BQ_R_B);
+                ve.imm_i = f.imm;
+            }
+            s.v[k] = ve;
+        }
+        // outputs of this pass
+        std::vector<size_t> agg_index;
+        for (size_t i = 0; i < req.aggs.size(); ++i) {
+            const auto& a = req.aggs[i];
+            int vpos = -1;
+            if (a.func != "COUNT") {
+                for (size_t k = 0; k < ps.vals.size(); ++k)
+                    if (ps.vals[k] == agg_value[i]) vpos = static_cast<int>(k);
+                if (vpos < 0) continue;
+            } else if (&ps != &passes.front()) {
+                continue;                                  // COUNT comes out of the first pass
+            }
+            if (s.n_out >= BQ_MAX_AGG_OUT) throw std::runtime_error("too many aggregates in one query");
+            bq_agg_out o{};
+            o.func = a.func == "COUNT" ? BQ_AGG_COUNT : (a.func == "SUM" ? BQ_AGG_SUM : BQ_AGG_AVG);
+            o.v = vpos < 0 ? 0 : vpos;
+            o.as_int = (a.func == "SUM" && a.result_type != TypeId::DOUBLE) ? 1 : 0;
+            s.out[s.n_out++] = o;
+            agg_index.push_back(i);
+        }
+
+        // grouping strategy from statistics
+        auto choose_group = [&](bool force_device_stats) {
+            if (key_col < 0) {
+                s.group_mode = BQ_GROUP_NONE;
+                return;
+            }
+            PipeCol& kc = p.cols[key_col];
+            if (kc.type == TypeId::DOUBLE) {
+                s.group_mode = BQ_GROUP_HASH;
+                s.ndv_hint = kc.stats.ndv ? kc.stats.ndv : 0;
+                return;
+            }
+            resolve_stats(kc, force_device_stats);
+            Domain d{kc.stats.min_key, kc.stats.max_key};
+            const uint64_t est_rows = p.rows;
+            if (d.size() > 0 && d.size() <= (1ULL << 26) && d.size() <= 4 * est_rows + 4096) {
+                s.group_mode = BQ_GROUP_DENSE;
+                s.key_min = d.lo;
+                s.key_max = d.hi;
+            } else {
+                s.group_mode = BQ_GROUP_HASH;
+                uint64_t hint = kc.stats.ndv ? kc.stats.ndv : std::min<uint64_t>(est_rows, d.size() ? d.size() : est_rows);
+                s.ndv_hint = static_cast<size_t>(hint);
+            }
+        };
+        choose_group(false);
+        bq_rel* rel = nullptr;
+        int rc = bq_scan_aggregate(ctx, &s, &rel);
+        if (rc && std::strstr(bq_last_error(), "stale statistics")) {
+            choose_group(true);                 // the catalog's min/max were wrong: measure and retry
+            rc = bq_scan_aggregate(ctx, &s, &rel);
+        }
+        check(rc);
+        DeviceRelationPtr r = relation_from(rel);
+        // with several passes over a keyed aggregate, bring every pass into key order so rows line up
+        if (passes.size() > 1 && key_col >= 0 && r->rows > 1) {
+            std::vector<bq_col*> hs;
+            for (auto& c : r->cols) hs.push_back(c->h);
+            bq_rel* shell = nullptr;
+            // a non-owning shell around r's columns
+            check(bq_rel_create(ctx, hs.data(), static_cast<int>(hs.size()), &shell));
+            int kc0 = 0, asc = 1;
+            bq_rel* sorted = nullptr;
+            int rc2 = bq_rel_sort(ctx, shell, 1, &kc0, &asc, -1, &sorted);
+            std::vector<bq_col*> back(hs.size());
+            bq_rel_release(shell, back.data());
+            check(rc2);
+            r = relation_from(sorted);
+        }
+        pass_results.push_back(r);
+        pass_aggs.push_back(agg_index);
+    }
+
+    // ---- stitch: [keys] then aggregates in declaration order ----------------------------------------------------
+    auto out = std::make_shared<DeviceRelation>();
+    out->rows = pass_results.front()->rows;
+    for (auto& pr : pass_results)
+        if (pr->rows != out->rows) throw std::runtime_error("internal: aggregate passes disagree on the group count");
+    const int key_cols_in_rel = key_col >= 0 ? 1 : 0;
+    std::vector<DevColPtr> agg_cols(req.aggs.size());
+    for (size_t pi = 0; pi < pass_results.size(); ++pi)
+        for (size_t k = 0; k < pass_aggs[pi].size(); ++k) agg_cols[pass_aggs[pi][k]] = pass_results[pi]->cols[key_cols_in_rel + k];
+    if (key_col >= 0) {
+        DevColPtr key = pass_results.front()->cols[0];
+        if (packed_domains.empty()) {
+            out->cols.push_back(key);
+        } else {
+            // unpack the combined key: k_i = (packed / stride_i) % size_i + min_i, with q % s = q - (q / s) * s
+            for (size_t i = 0; i < packed_domains.size(); ++i) {
+                const int64_t st = static_cast<int64_t>(packed_strides[i]);
+                const int64_t size = static_cast<int64_t>(packed_domains[i].size());
+                if (out->rows == 0) {
+                    bq_col* h = nullptr;
+                    check(bq_col_alloc(ctx, static_cast<int>(req.group_types[i]), 0, &h));
+                    out->cols.push_back(adopt(h));
+                    continue;
+                }
+                std::vector<bq_insn> code = {
+                    insn(BQ_OP_COL, 0), insn(BQ_OP_IMM_I, 0, st), insn(BQ_OP_DIV_I),                       // q
+                    insn(BQ_OP_COL, 0), insn(BQ_OP_IMM_I, 0, st), insn(BQ_OP_DIV_I),                       // q
+                    insn(BQ_OP_IMM_I, 0, size), insn(BQ_OP_DIV_I), insn(BQ_OP_IMM_I, 0, size), insn(BQ_OP_MUL_I),
+                    insn(BQ_OP_SUB_I),                                                                        // q % size
+                    insn(BQ_OP_IMM_I, 0, packed_domains[i].lo), insn(BQ_OP_ADD_I)};
+                out->cols.push_back(eval_program(code, {key}, out->rows, req.group_types[i]));
+            }
+        }
+    }
+    for (size_t i = 0; i < req.aggs.size(); ++i) {
+        if (!agg_cols[i]) throw std::runtime_error("internal: aggregate output missing");
+        out->cols.push_back(agg_cols[i]);
+    }
+    return out;
+}
+
+}  // namespace bosql::gpu

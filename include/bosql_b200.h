@@ -58,6 +58,7 @@ void* bq_col_ptr(const bq_col* col);                       /* raw device pointer
 /* Catalog statistics (include/catalog/catalog.h:16-21): min/max on the column's integer key
  * (for DOUBLE: the order-preserving key of the value, see bq_f64_key) and NDV; used to size tables. */
 int bq_col_set_stats(bq_col* col, int64_t min_key, int64_t max_key, size_t ndv);
+void bq_col_invalidate_stats(bq_col* col);
 /* min/max computed on the device and cached when the catalog gave none */
 int bq_col_minmax(bq_ctx* ctx, bq_col* col, int64_t* min_key, int64_t* max_key);
 /* order-preserving int64 key of a double (so that every predicate is an integer range test) */
@@ -148,11 +149,14 @@ typedef struct bq_slot {
 /* aggregate argument: datum_as_double(A) / datum_as_double(B) (src/exec/operator.cpp:280-292) or
  * numeric_binary(A, B|imm) (src/exec/expression.cpp:31-58) followed by datum_as_double */
 enum { BQ_V_NONE = 0, BQ_V_A = 1, BQ_V_B = 2, BQ_V_MUL = 3, BQ_V_ADD = 4, BQ_V_SUB = 5, BQ_V_DIV = 6 };
+/* operand sources of a binary argument; the zero value of both fields means `A op B` */
+enum { BQ_L_A = 0, BQ_L_B = 1, BQ_L_IMM = 2 };
+enum { BQ_R_B = 0, BQ_R_A = 1, BQ_R_IMM = 2 };
 typedef struct bq_vexpr {
-    int32_t op;
-    int32_t b_is_imm;      /* right operand is imm (its type: imm_is_f) instead of slot b */
-    int32_t imm_is_f;
-    int32_t swap;          /* evaluate (B|imm) OP A instead of A OP (B|imm) */
+    int32_t op;            /* BQ_V_A / BQ_V_B: the slot's value; BQ_V_MUL..DIV: left OP right */
+    int32_t l_src;         /* BQ_L_* */
+    int32_t r_src;         /* BQ_R_* */
+    int32_t imm_is_f;      /* type of the immediate operand: 0 INT64 (imm_i), 1 DOUBLE (imm_f) */
     int64_t imm_i;
     double imm_f;
 } bq_vexpr;
@@ -248,6 +252,8 @@ size_t bq_rel_rows(const bq_rel* rel);
 int bq_rel_cols(const bq_rel* rel);
 bq_col* bq_rel_col(const bq_rel* rel, int i);     /* borrowed */
 void bq_rel_free(bq_ctx* ctx, bq_rel* rel);
+/* hand the columns (bq_rel_cols of them) back to the caller and destroy the shell without freeing them */
+void bq_rel_release(bq_rel* rel, bq_col** out_cols);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,89 @@
+/* bosql_b200_exec.h — C ABI of the operator layer (libbosql_b200_exec.so).
+ *
+ * The reference is a C++ program; its "plugin interface" for the hot path is the Operator class family of
+ * include/exec/operator.hpp:17-218, constructed only by build_physical_plan (src/exec/physical_planner.cpp:9)
+ * and consumed only through open()/next()/close() (src/exec/execution.cpp:14-59).  The C++ mirror of that
+ * interface lives in bo-sql_b200/host/bosql_operator.hpp.  This header exposes the same life cycle to non-C++
+ * callers (pytest, bench.py): build tables from typed arrays, plan a SQL string exactly as
+ * execute_select_sql does (src/cli/main.cpp:40-57: parse_sql -> build_logical_plan -> build_physical_plan),
+ * then open / next / close, or run to completion into typed result columns.
+ *
+ * Status convention: 0 = ok, nonzero = error with the message in bqx_last_error() (the reference's only error
+ * channel is std::runtime_error).  Handles are opaque.  Nothing here falls back to the CPU.
+ */
+#ifndef BOSQL_B200_EXEC_H
+#define BOSQL_B200_EXEC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "bosql_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bqx_dict bqx_dict;         /* shared_ptr<Dictionary>   (include/storage/dictionary.h:11) */
+typedef struct bqx_table bqx_table;       /* a Table under construction (include/storage/table.h:20)    */
+typedef struct bqx_catalog bqx_catalog;   /* Catalog                  (include/catalog/catalog.h:46)    */
+typedef struct bqx_plan bqx_plan;         /* root Operator of a physical plan                           */
+typedef struct bqx_result bqx_result;     /* drained output of a plan: typed host columns               */
+
+const char* bqx_last_error(void);
+/* Select the GPU of this process (one process per GPU). Optional: default $BOSQL_DEVICE, $LOCAL_RANK, 0. */
+int bqx_init(int device);
+/* The kernel-layer context of this process (for callers that mix both layers, e.g. bench.py's generator). */
+bq_ctx* bqx_context(void);
+
+bqx_dict* bqx_dict_create(void);
+void bqx_dict_destroy(bqx_dict* d);
+uint32_t bqx_dict_get_or_add(bqx_dict* d, const char* s);      /* src/storage/dictionary.cpp:5 */
+size_t bqx_dict_size(const bqx_dict* d);
+const char* bqx_dict_get(const bqx_dict* d, uint32_t id);
+
+bqx_catalog* bqx_catalog_create(void);
+void bqx_catalog_destroy(bqx_catalog* c);
+
+/* dict may be NULL (fresh dictionary) or shared between tables (tests/test_execution.cpp:116-123). */
+bqx_table* bqx_table_create(const char* name, bqx_dict* dict);
+/* host column: copied into a ColumnVector<T>; uploaded to HBM on first use by an operator */
+int bqx_table_add_column(bqx_table* t, const char* name, int type, const void* data, size_t n);
+/* device-resident column (synthetic tables generated in HBM); take_ownership: the table frees it */
+int bqx_table_add_device_column(bqx_table* t, const char* name, bq_col* col, int take_ownership);
+/* catalog statistics of a column (ColumnStats, include/catalog/catalog.h:16-21); integers for INT64/DATE32,
+ * doubles for DOUBLE; ndv = 0 when unknown */
+int bqx_table_set_stats(bqx_table* t, const char* column, int64_t min_i, int64_t max_i, double min_f, double max_f, size_t ndv);
+/* Catalog::register_table (src/catalog/catalog.cpp:5); consumes the table handle */
+int bqx_catalog_register(bqx_catalog* c, bqx_table* t);
+
+/* extensions of the SQL front end, off by default: bit 0 BETWEEN, bit 1 decimal literals */
+int bqx_plan_create(bqx_catalog* c, const char* sql, unsigned parse_flags, bqx_plan** out);
+void bqx_plan_destroy(bqx_plan* p);
+size_t bqx_plan_columns(const bqx_plan* p);
+const char* bqx_plan_column_name(const bqx_plan* p, size_t i);   /* Operator::output_names() */
+int bqx_plan_column_type(const bqx_plan* p, size_t i);           /* Operator::output_types() */
+int bqx_plan_has_dict(const bqx_plan* p);                        /* Operator::dictionary() != nullptr */
+const char* bqx_plan_dict_get(const bqx_plan* p, uint32_t id);
+const char* bqx_plan_root_kind(const bqx_plan* p);               /* class name of the root operator */
+
+/* Operator::open / next / close.  next fills up to n_cols column pointers valid until the following call on this
+ * plan and sets *rows (0 and return value 1 = end of stream; a batch never has 0 rows). */
+int bqx_plan_open(bqx_plan* p);
+int bqx_plan_next(bqx_plan* p, const void** col_data, size_t n_cols, size_t* rows, int* end_of_stream);
+int bqx_plan_close(bqx_plan* p);
+
+/* open .. next* .. close into typed columns; seconds = host wall time of that interval */
+int bqx_plan_run(bqx_plan* p, bqx_result** out);
+size_t bqx_result_rows(const bqx_result* r);
+size_t bqx_result_cols(const bqx_result* r);
+double bqx_result_seconds(const bqx_result* r);
+const void* bqx_result_data(const bqx_result* r, size_t i);
+void bqx_result_free(bqx_result* r);
+
+/* LogicalOp::to_string of the planned statement (plan-shape tests, tests/test_logical.cpp of the reference) */
+int bqx_explain(const char* sql, unsigned parse_flags, char* out, size_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BOSQL_B200_EXEC_H */

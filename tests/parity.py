@@ -67,13 +67,13 @@ def assert_same_rows(got_cols, want_cols, ordered_by=None, what=""):
                 assert_close(got_cols[i], want_cols[i], f"{what}: sort key column {i}")
             else:
                 assert np.array_equal(got_cols[i], want_cols[i]), f"{what}: sort key column {i} differs"
-    # ... and the rows are the same multiset
-    if exact:
-        g2, w2 = _sort_rows(got_cols, exact), _sort_rows(want_cols, exact)
-    else:
-        og = np.lexsort([c for c in reversed(got_cols)])
-        ow = np.lexsort([c for c in reversed(want_cols)])
-        g2, w2 = [c[og] for c in got_cols], [c[ow] for c in want_cols]
+    # ... and the rows are the same multiset: canonical order = exact columns first, then the DOUBLE columns
+    # (group keys of type DOUBLE are bit-exact; DOUBLE aggregates only break ties among otherwise equal rows)
+    floats = [i for i in range(len(want_cols)) if i not in exact]
+    def canon(cols):
+        order = np.lexsort([cols[i] for i in reversed(exact + floats)])
+        return [c[order] for c in cols]
+    g2, w2 = canon(got_cols), canon(want_cols)
     for i, (g, w) in enumerate(zip(g2, w2)):
         if _is_float(w):
             assert_close(g, w, f"{what}: column {i}")

@@ -160,7 +160,7 @@ def test_filter_agg_subrange_and_mask(bq, ctx):
         s.mask = mask.h
         s.row_begin, s.row_end = rb, re
         s.n_v = 1
-        s.v[0] = bq.VExpr(op=bq.V_MUL, b_is_imm=1, imm_is_f=0, imm_i=3)
+        s.v[0] = bq.VExpr(op=bq.V_MUL, l_src=bq.L_A, r_src=bq.R_IMM, imm_i=3)
         s.n_out = 2
         s.out[0] = bq.AggOut(func=bq.AGG_COUNT)
         s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
