@@ -118,6 +118,9 @@ def kernel_lib():
         "bq_ctx_sync": ([vp], C.c_int),
         "bq_ctx_info": ([vp, P(C.c_int), P(sz), P(sz)], C.c_int),
         "bq_ctx_launches": ([vp], C.c_uint64),
+        "bq_ctx_profile": ([vp, C.c_int], C.c_int),
+        "bq_ctx_profile_read": ([vp, P(C.c_uint64), P(C.c_double)], C.c_int),
+        "bq_col_wrap": ([vp, C.c_int, vp, sz, P(vp)], C.c_int),
         "bq_last_error": ([], C.c_char_p),
         "bq_col_alloc": ([vp, C.c_int, sz, P(vp)], C.c_int),
         "bq_col_upload": ([vp, C.c_int, vp, sz, P(vp)], C.c_int),
@@ -338,6 +341,21 @@ class Context:
     @property
     def launches(self):
         return self.L.bq_ctx_launches(self.h)
+
+    def profile(self, enable: bool):
+        _check(self.L.bq_ctx_profile(self.h, int(enable)))
+
+    def profile_read(self):
+        """(launches, total_ms) of the fused scan kernel since the last read."""
+        n, ms = C.c_uint64(), C.c_double()
+        _check(self.L.bq_ctx_profile_read(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def wrap(self, typ, device_ptr, n) -> Column:
+        """A non-owning Column over device memory managed elsewhere (e.g. a torch tensor)."""
+        h = C.c_void_p()
+        _check(self.L.bq_col_wrap(self.h, typ, C.c_void_p(device_ptr), n, C.byref(h)))
+        return Column(self, h)
 
     # ---- columns
     def alloc(self, typ, n) -> Column:

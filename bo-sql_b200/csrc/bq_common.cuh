@@ -122,9 +122,12 @@ struct bq_ctx {
     size_t scratch_bytes = 0;
     void* pinned = nullptr;      // small pinned staging for scalar results
     size_t pinned_bytes = 0;
+    bool profile = false;        // bracket the fused scan kernel with events (bench.py roofline)
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profile_events;
 };
 
 struct bq_col {
+    bq_ctx* ctx = nullptr;       // owner (frees go back to its stream-ordered pool while it is alive)
     int type = BQ_INT64;
     size_t n = 0;
     void* ptr = nullptr;
@@ -140,6 +143,7 @@ struct bq_rel {
 };
 
 struct bq_join {
+    bq_ctx* ctx = nullptr;
     int kind = BQ_JOIN_HASH;
     int64_t key_min = 0, key_max = 0;     // BITMAP / DIRECT domain
     unsigned* bitmap = nullptr;           // BITMAP: bit (key-key_min)
@@ -157,6 +161,19 @@ namespace bq {
 void set_error(const std::string& msg);
 bq_col* new_col(bq_ctx* ctx, int type, size_t n);
 void free_col(bq_col* c);
+// Stream-ordered device memory (cudaMallocAsync on the context's stream, pool never trimmed): allocation and
+// release cost microseconds and never synchronise the device, unlike cudaMalloc/cudaFree.
+void* dev_alloc(bq_ctx* ctx, size_t bytes);
+void dev_free(bq_ctx* ctx, void* p);          // ctx may be dead or null: falls back to cudaFree
+struct DevBuf {
+    bq_ctx* ctx;
+    void* p = nullptr;
+    DevBuf(bq_ctx* c, size_t bytes) : ctx(c), p(dev_alloc(c, bytes)) {}
+    ~DevBuf() { dev_free(ctx, p); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+};
 void* scratch(bq_ctx* ctx, size_t bytes);     // device scratch, valid until the next call that asks for more
 void* pinned(bq_ctx* ctx, size_t bytes);
 int grid_for(bq_ctx* ctx, size_t rows, int blocks_per_sm);

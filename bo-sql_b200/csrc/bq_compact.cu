@@ -97,25 +97,34 @@ __global__ void __launch_bounds__(kBlock) k_bits_expand(const unsigned* __restri
 }
 
 // rowids of the set bits of `bits` (n_bits candidates), ascending. Returns the count (host sync).
-size_t compact_bits(bq_ctx* ctx, const unsigned* bits, size_t n_bits, unsigned base_index, bq_col** out_rowids) {
+size_t compact_bits(bq_ctx* ctx, const unsigned* bits, size_t n_bits, unsigned base_index, bq_col** out_rowids,
+                    const int* dev_flag, int* host_flag) {
     size_t n_words = (n_bits + 31) / 32;
     if (n_words == 0) {
         *out_rowids = new_col(ctx, BQ_STRING, 0);
+        if (dev_flag && host_flag) {
+            auto* h = static_cast<int*>(pinned(ctx, 16));
+            BQ_CUDA(cudaMemcpyAsync(h, dev_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+            *host_flag = *h;
+        }
         return 0;
     }
     size_t n_blocks = (n_words + kBlock - 1) / kBlock;
-    unsigned long long* sums = nullptr;
-    BQ_CUDA(cudaMalloc(&sums, (n_blocks + 1) * sizeof(unsigned long long)));
+    DevBuf sums_buf(ctx, (n_blocks + 1) * sizeof(unsigned long long));
+    auto* sums = sums_buf.as<unsigned long long>();
     bq_col* ids = nullptr;
     try {
         k_bits_block_count<<<(unsigned)n_blocks, kBlock, 0, ctx->stream>>>(bits, n_words, sums);
         k_scan_block_sums<<<1, 1024, 0, ctx->stream>>>(sums, n_blocks, sums + n_blocks);
         ctx->launches += 2;
         BQ_CUDA(cudaGetLastError());
-        auto* h = static_cast<unsigned long long*>(pinned(ctx, 8));
+        auto* h = static_cast<unsigned long long*>(pinned(ctx, 16));
         BQ_CUDA(cudaMemcpyAsync(h, sums + n_blocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
-        BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (dev_flag) BQ_CUDA(cudaMemcpyAsync(h + 1, dev_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        BQ_CUDA(cudaStreamSynchronize(ctx->stream));      // the one host round trip: output size (+ the error word)
         size_t total = static_cast<size_t>(*h);
+        if (dev_flag && host_flag) *host_flag = static_cast<int>(h[1] & 0xFFFFFFFFull);
         ids = new_col(ctx, BQ_STRING, total);
         if (total) {
             k_bits_expand<<<(unsigned)n_blocks, kBlock, 0, ctx->stream>>>(bits, n_words, sums,
@@ -123,12 +132,9 @@ size_t compact_bits(bq_ctx* ctx, const unsigned* bits, size_t n_bits, unsigned b
             ctx->launches++;
             BQ_CUDA(cudaGetLastError());
         }
-        BQ_CUDA(cudaStreamSynchronize(ctx->stream));
-        cudaFree(sums);
         *out_rowids = ids;
         return total;
     } catch (...) {
-        cudaFree(sums);
         free_col(ids);
         throw;
     }
@@ -175,9 +181,9 @@ __global__ void __launch_bounds__(kBlock) k_u32_block_scan(const unsigned* __res
 size_t exclusive_scan_u32(bq_ctx* ctx, const unsigned* counts, size_t n, unsigned long long* offsets) {
     if (n == 0) return 0;
     size_t n_blocks = (n + kBlock - 1) / kBlock;
-    unsigned long long* sums = nullptr;
-    BQ_CUDA(cudaMalloc(&sums, (n_blocks + 1) * sizeof(unsigned long long)));
-    try {
+    DevBuf sums_buf(ctx, (n_blocks + 1) * sizeof(unsigned long long));
+    auto* sums = sums_buf.as<unsigned long long>();
+    {
         k_u32_block_sum<<<(unsigned)n_blocks, kBlock, 0, ctx->stream>>>(counts, n, sums);
         k_scan_block_sums<<<1, 1024, 0, ctx->stream>>>(sums, n_blocks, sums + n_blocks);
         k_u32_block_scan<<<(unsigned)n_blocks, kBlock, 0, ctx->stream>>>(counts, n, sums, offsets);
@@ -186,12 +192,7 @@ size_t exclusive_scan_u32(bq_ctx* ctx, const unsigned* counts, size_t n, unsigne
         auto* h = static_cast<unsigned long long*>(pinned(ctx, 8));
         BQ_CUDA(cudaMemcpyAsync(h, sums + n_blocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
         BQ_CUDA(cudaStreamSynchronize(ctx->stream));
-        size_t total = static_cast<size_t>(*h);
-        cudaFree(sums);
-        return total;
-    } catch (...) {
-        cudaFree(sums);
-        throw;
+        return static_cast<size_t>(*h);
     }
 }
 

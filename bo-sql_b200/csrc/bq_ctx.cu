@@ -6,23 +6,44 @@
 #include "bq_common.cuh"
 
 #include <cstring>
+#include <mutex>
+#include <set>
 
 namespace bq {
 
 static thread_local std::string g_error;
 void set_error(const std::string& msg) { g_error = msg; }
 
+static std::mutex g_live_mu;
+static std::set<bq_ctx*> g_live;
+static bool is_live(bq_ctx* ctx) {
+    std::lock_guard<std::mutex> lk(g_live_mu);
+    return ctx && g_live.count(ctx);
+}
+
+void* dev_alloc(bq_ctx* ctx, size_t bytes) {
+    void* p = nullptr;
+    BQ_CUDA(cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream));
+    return p;
+}
+
+void dev_free(bq_ctx* ctx, void* p) {
+    if (!p) return;
+    if (is_live(ctx)) cudaFreeAsync(p, ctx->stream);
+    else cudaFree(p);
+}
+
 bq_col* new_col(bq_ctx* ctx, int type, size_t n) {
-    (void)ctx;
     if (type < 0 || type > 3) throw std::runtime_error("Unknown column type");
     auto* c = new bq_col();
+    c->ctx = ctx;
     c->type = type;
     c->n = n;
     size_t bytes = n * width_of(type);
     // pad to a whole 16-byte vector so tail vector loads never leave the allocation
     size_t alloc = ((bytes + 255) / 256) * 256 + 256;
     try {
-        BQ_CUDA(cudaMalloc(&c->ptr, alloc));
+        c->ptr = dev_alloc(ctx, alloc);
     } catch (...) {
         delete c;
         throw;
@@ -32,19 +53,18 @@ bq_col* new_col(bq_ctx* ctx, int type, size_t n) {
 
 void free_col(bq_col* c) {
     if (!c) return;
-    if (c->owns && c->ptr) cudaFree(c->ptr);
+    if (c->owns && c->ptr) dev_free(c->ctx, c->ptr);
     delete c;
 }
 
 void* scratch(bq_ctx* ctx, size_t bytes) {
     if (bytes > ctx->scratch_bytes) {
         if (ctx->scratch) {
-            BQ_CUDA(cudaStreamSynchronize(ctx->stream));
-            cudaFree(ctx->scratch);
+            dev_free(ctx, ctx->scratch);
             ctx->scratch = nullptr;
         }
         size_t want = bytes < (1u << 20) ? (1u << 20) : bytes;
-        BQ_CUDA(cudaMalloc(&ctx->scratch, want));
+        ctx->scratch = dev_alloc(ctx, want);
         ctx->scratch_bytes = want;
     }
     return ctx->scratch;
@@ -115,6 +135,15 @@ int bq_ctx_create(int device, bq_ctx** out) {
         ctx->sm_count = prop.multiProcessorCount;
         BQ_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         ctx->stream = ctx->own_stream;
+        // keep freed blocks in the pool: a query's temporaries are reused by the next query without driver calls
+        cudaMemPool_t pool;
+        BQ_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        BQ_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        {
+            std::lock_guard<std::mutex> lk(g_live_mu);
+            g_live.insert(ctx);
+        }
         *out = ctx;
     });
 }
@@ -123,6 +152,10 @@ void bq_ctx_destroy(bq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    {
+        std::lock_guard<std::mutex> lk(g_live_mu);
+        g_live.erase(ctx);
+    }
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -152,6 +185,41 @@ int bq_ctx_info(bq_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_by
 }
 
 uint64_t bq_ctx_launches(bq_ctx* ctx) { return ctx->launches; }
+
+int bq_ctx_profile(bq_ctx* ctx, int enable) {
+    ctx->profile = enable != 0;
+    return 0;
+}
+
+int bq_ctx_profile_read(bq_ctx* ctx, uint64_t* launches, double* total_ms) {
+    return guarded([&] {
+        BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        double total = 0.0;
+        for (auto& pr : ctx->profile_events) {
+            float ms = 0.f;
+            BQ_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+            total += ms;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        if (launches) *launches = ctx->profile_events.size();
+        if (total_ms) *total_ms = total;
+        ctx->profile_events.clear();
+    });
+}
+
+int bq_col_wrap(bq_ctx* ctx, int type, void* device_ptr, size_t n, bq_col** out) {
+    return guarded([&] {
+        if (type < 0 || type > 3) throw std::runtime_error("Unknown column type");
+        auto* c = new bq_col();
+        c->ctx = ctx;
+        c->type = type;
+        c->n = n;
+        c->ptr = device_ptr;
+        c->owns = false;
+        *out = c;
+    });
+}
 
 int bq_col_alloc(bq_ctx* ctx, int type, size_t n, bq_col** out) {
     return guarded([&] { *out = new_col(ctx, type, n); });
@@ -194,8 +262,7 @@ int bq_col_read(bq_ctx* ctx, const bq_col* col, size_t offset, size_t n, void* h
 }
 
 void bq_col_free(bq_ctx* ctx, bq_col* col) {
-    if (!col) return;
-    if (ctx) cudaStreamSynchronize(ctx->stream);
+    (void)ctx;          // the column remembers its owner; release is stream-ordered, no synchronisation
     free_col(col);
 }
 
@@ -279,8 +346,8 @@ size_t bq_rel_rows(const bq_rel* rel) { return rel->rows; }
 int bq_rel_cols(const bq_rel* rel) { return static_cast<int>(rel->cols.size()); }
 bq_col* bq_rel_col(const bq_rel* rel, int i) { return rel->cols.at(i); }
 void bq_rel_free(bq_ctx* ctx, bq_rel* rel) {
+    (void)ctx;
     if (!rel) return;
-    if (ctx) cudaStreamSynchronize(ctx->stream);
     for (auto* c : rel->cols) free_col(c);
     delete rel;
 }

@@ -99,7 +99,7 @@ extern "C" int bq_col_generate(bq_ctx* ctx, bq_col* col, const bq_gen_spec* s, u
         uint64_t* d_cdf = nullptr;
         if (s->dist == BQ_GEN_TABLE) {
             if (!s->cdf || !s->n_cdf) throw std::runtime_error("BQ_GEN_TABLE needs a cdf");
-            BQ_CUDA(cudaMalloc(&d_cdf, s->n_cdf * 8));
+            d_cdf = static_cast<uint64_t*>(dev_alloc(ctx, s->n_cdf * 8));
             BQ_CUDA(cudaMemcpyAsync(d_cdf, s->cdf, s->n_cdf * 8, cudaMemcpyHostToDevice, ctx->stream));
             p.cdf = d_cdf;
             p.n_cdf = s->n_cdf;
@@ -110,10 +110,7 @@ extern "C" int bq_col_generate(bq_ctx* ctx, bq_col* col, const bq_gen_spec* s, u
             ctx->launches++;
             BQ_CUDA(cudaGetLastError());
         }
-        if (d_cdf) {
-            BQ_CUDA(cudaStreamSynchronize(ctx->stream));
-            cudaFree(d_cdf);
-        }
+        if (d_cdf) dev_free(ctx, d_cdf);
         col->has_minmax = false;
     });
 }

@@ -173,10 +173,10 @@ static size_t next_pow2(size_t v) {
 }
 
 static void free_tables(bq_join* j) {
-    if (j->bitmap) cudaFree(j->bitmap);
-    if (j->direct) cudaFree(j->direct);
-    if (j->h_keys) cudaFree(j->h_keys);
-    if (j->h_rows) cudaFree(j->h_rows);
+    dev_free(j->ctx, j->bitmap);
+    dev_free(j->ctx, j->direct);
+    dev_free(j->ctx, j->h_keys);
+    dev_free(j->ctx, j->h_rows);
     j->bitmap = j->direct = j->h_rows = nullptr;
     j->h_keys = nullptr;
 }
@@ -208,12 +208,12 @@ static int build_kind(bq_ctx* ctx, const bq_join_spec* spec, int kind, bq_join* 
         if (kind == BQ_JOIN_BITMAP) {
             j->bitmap_words = (p.domain + 31) / 32;
             j->bytes = j->bitmap_words * 4;
-            BQ_CUDA(cudaMalloc(&j->bitmap, j->bytes + 4));
+            j->bitmap = static_cast<unsigned*>(dev_alloc(ctx, j->bytes + 4));
             BQ_CUDA(cudaMemsetAsync(j->bitmap, 0, j->bytes + 4, ctx->stream));
             p.bitmap = j->bitmap;
         } else {
             j->bytes = p.domain * 4;
-            BQ_CUDA(cudaMalloc(&j->direct, j->bytes + 4));
+            j->direct = static_cast<unsigned*>(dev_alloc(ctx, j->bytes + 4));
             BQ_CUDA(cudaMemsetAsync(j->direct, 0, j->bytes + 4, ctx->stream));
             p.direct = j->direct;
         }
@@ -221,8 +221,8 @@ static int build_kind(bq_ctx* ctx, const bq_join_spec* spec, int kind, bq_join* 
         size_t cap = next_pow2(n * 2 < 1024 ? 1024 : n * 2);
         j->h_mask = cap - 1;
         j->bytes = cap * 12;
-        BQ_CUDA(cudaMalloc(&j->h_keys, cap * 8));
-        BQ_CUDA(cudaMalloc(&j->h_rows, cap * 4));
+        j->h_keys = static_cast<long long*>(dev_alloc(ctx, cap * 8));
+        j->h_rows = static_cast<unsigned*>(dev_alloc(ctx, cap * 4));
         BQ_CUDA(cudaMemsetAsync(j->h_rows, 0, cap * 4, ctx->stream));
         p.h_keys = j->h_keys;
         p.h_rows = j->h_rows;
@@ -259,6 +259,7 @@ int bq_join_build(bq_ctx* ctx, const bq_join_spec* spec, bq_join** out) {
         if (spec->row_end < spec->row_begin || spec->row_end > spec->key->n) throw std::runtime_error("bad build row range");
         if (spec->row_end > 0xFFFFFFFEull) throw std::runtime_error("row ids are 32-bit: at most 2^32-1 build rows");
         auto* j = new bq_join();
+        j->ctx = ctx;
         try {
             int kind = spec->kind;
             const size_t n = spec->row_end - spec->row_begin;
@@ -287,8 +288,8 @@ int bq_join_build(bq_ctx* ctx, const bq_join_spec* spec, bq_join** out) {
 }
 
 void bq_join_free(bq_ctx* ctx, bq_join* j) {
+    (void)ctx;
     if (!j) return;
-    if (ctx) cudaStreamSynchronize(ctx->stream);
     free_tables(j);
     delete j;
 }
@@ -326,8 +327,8 @@ int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const 
         try {
             size_t total = 0;
             if (p.n) {
-                BQ_CUDA(cudaMalloc(&counts, p.n * 4));
-                BQ_CUDA(cudaMalloc(&offsets, p.n * 8));
+                counts = static_cast<unsigned*>(dev_alloc(ctx, p.n * 4));
+                offsets = static_cast<unsigned long long*>(dev_alloc(ctx, p.n * 8));
                 unsigned blocks = static_cast<unsigned>((p.n + kBlock - 1) / kBlock);
                 k_probe_count<<<blocks, kBlock, 0, ctx->stream>>>(p, counts);
                 ctx->launches++;
@@ -344,14 +345,13 @@ int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const 
                 ctx->launches++;
                 BQ_CUDA(cudaGetLastError());
             }
-            BQ_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (counts) cudaFree(counts);
-            if (offsets) cudaFree(offsets);
+            dev_free(ctx, counts);
+            dev_free(ctx, offsets);
             *out_probe_rows = op;
             *out_build_rows = ob;
         } catch (...) {
-            if (counts) cudaFree(counts);
-            if (offsets) cudaFree(offsets);
+            dev_free(ctx, counts);
+            dev_free(ctx, offsets);
             free_col(op);
             free_col(ob);
             throw;

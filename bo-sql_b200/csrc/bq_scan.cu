@@ -587,10 +587,10 @@ struct AggState {
     double* sum1 = nullptr;
     long long* h_keys = nullptr;
     void* block = nullptr;         // one allocation behind the arrays
+    int* err = nullptr;            // device error word (division by zero, table overflow, stale statistics)
+    bq_ctx* ctx = nullptr;
 
-    ~AggState() {
-        if (block) cudaFree(block);
-    }
+    ~AggState() { dev_free(ctx, block); }
 };
 
 // Runs the fused kernel for `spec`, leaving the aggregate state on the device.
@@ -700,7 +700,8 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st) {
     size_t off_pc = off_keys + (st.gmode == G_HASH ? n * 8 : 0);
     size_t off_ps = off_pc + static_cast<size_t>(grid) * 8, off_tk = off_ps + static_cast<size_t>(grid) * 16;
     size_t total = off_tk + 16;
-    BQ_CUDA(cudaMalloc(&st.block, total));
+    st.ctx = ctx;
+    st.block = dev_alloc(ctx, total);
     char* base = static_cast<char*>(st.block);
     st.cnt = reinterpret_cast<unsigned long long*>(base + off_cnt);
     st.sum0 = reinterpret_cast<double*>(base + off_s0);
@@ -720,20 +721,32 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st) {
     p.part_sum = reinterpret_cast<double*>(base + off_ps);
     p.ticket = reinterpret_cast<unsigned*>(base + off_tk);
     p.err = reinterpret_cast<int*>(base + off_tk + 8);
+    st.err = p.err;
 
     if (rows > 0 || st.gmode == G_NONE) {
         if (smem > 0) BQ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (ctx->profile) {
+            BQ_CUDA(cudaEventCreate(&ev0));
+            BQ_CUDA(cudaEventCreate(&ev1));
+            BQ_CUDA(cudaEventRecord(ev0, ctx->stream));
+        }
         fn<<<grid, kBlock, smem, ctx->stream>>>(p);
+        if (ctx->profile) {
+            BQ_CUDA(cudaEventRecord(ev1, ctx->stream));
+            ctx->profile_events.emplace_back(ev0, ev1);
+        }
         ctx->launches++;
         BQ_CUDA(cudaGetLastError());
     }
-    // error flag (division by zero / table overflow) comes back with the first host-visible read
-    auto* h = static_cast<int*>(pinned(ctx, 8));
-    BQ_CUDA(cudaMemcpyAsync(h, p.err, 4, cudaMemcpyDeviceToHost, ctx->stream));
-    BQ_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (*h & 1) throw std::runtime_error("Division by zero");          // src/exec/expression.cpp:52
-    if (*h & 2) throw std::runtime_error("group table overflow: ndv_hint too small");
-    if (*h & 4) throw std::runtime_error("group key outside [key_min,key_max]: stale statistics");
+    // the error word (division by zero / table overflow / stale statistics) is read back together with the group
+    // count in emit_state: one host round trip per aggregate
+}
+
+static void check_scan_flags(int flags) {
+    if (flags & 1) throw std::runtime_error("Division by zero");          // src/exec/expression.cpp:52
+    if (flags & 2) throw std::runtime_error("group table overflow: ndv_hint too small");
+    if (flags & 4) throw std::runtime_error("group key outside [key_min,key_max]: stale statistics");
 }
 
 // Turns the device state into a relation. partial = [key] count sum0 sum1, else [key] + outs.
@@ -742,19 +755,18 @@ static bq_rel* emit_state(bq_ctx* ctx, AggState& st, const bq_agg_out* outs, int
     size_t n_groups = 0;
     {
         size_t n_words = (st.slots + 31) / 32;
-        unsigned* bits = nullptr;
-        BQ_CUDA(cudaMalloc(&bits, n_words * 4 + 4));
-        try {
-            size_t blocks = (st.slots + kBlock - 1) / kBlock;
-            k_presence_bits<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(st.cnt, st.slots, bits);
-            ctx->launches++;
-            BQ_CUDA(cudaGetLastError());
-            n_groups = compact_bits(ctx, bits, st.slots, 0, &rowids);
-        } catch (...) {
-            cudaFree(bits);
-            throw;
+        DevBuf bits_buf(ctx, n_words * 4 + 4);
+        auto* bits = bits_buf.as<unsigned>();
+        size_t blocks = (st.slots + kBlock - 1) / kBlock;
+        k_presence_bits<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(st.cnt, st.slots, bits);
+        ctx->launches++;
+        BQ_CUDA(cudaGetLastError());
+        int flags = 0;
+        n_groups = compact_bits(ctx, bits, st.slots, 0, &rowids, st.err, &flags);
+        if (flags) {
+            free_col(rowids);
+            check_scan_flags(flags);
         }
-        cudaFree(bits);
     }
     std::vector<bq_col*> cols;
     try {
@@ -796,7 +808,6 @@ static bq_rel* emit_state(bq_ctx* ctx, AggState& st, const bq_agg_out* outs, int
             ctx->launches++;
             BQ_CUDA(cudaGetLastError());
         }
-        BQ_CUDA(cudaStreamSynchronize(ctx->stream));
         free_col(rowids);
         auto* rel = new bq_rel();
         rel->cols = cols;
@@ -879,13 +890,15 @@ int bq_agg_finish(bq_ctx* ctx, const bq_rel* const* parts, int n_parts, int has_
         st.slots = has_key ? cap + 1 : 1;
         size_t n = st.slots;
         size_t bytes = n * 8 * 4 + 16;
-        BQ_CUDA(cudaMalloc(&st.block, bytes));
+        st.ctx = ctx;
+        st.block = dev_alloc(ctx, bytes);
         char* base = static_cast<char*>(st.block);
         st.cnt = reinterpret_cast<unsigned long long*>(base);
         st.sum0 = reinterpret_cast<double*>(base + n * 8);
         st.sum1 = reinterpret_cast<double*>(base + n * 16);
         st.h_keys = has_key ? reinterpret_cast<long long*>(base + n * 24) : nullptr;
         int* err = reinterpret_cast<int*>(base + n * 32);
+        st.err = err;
         BQ_CUDA(cudaMemsetAsync(st.block, 0, bytes, ctx->stream));
         if (has_key) {
             k_fill_keys<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(st.h_keys, n, kEmptyKey);

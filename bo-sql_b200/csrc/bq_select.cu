@@ -67,18 +67,12 @@ int bq_select(bq_ctx* ctx, const bq_select_spec* spec, bq_col** out_rowids) {
             return;
         }
         size_t n_words = (n + 31) / 32;
-        unsigned* bits = nullptr;
-        BQ_CUDA(cudaMalloc(&bits, n_words * 4 + 4));
-        try {
-            k_pred_bits<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(p, bits);
-            ctx->launches++;
-            BQ_CUDA(cudaGetLastError());
-            compact_bits(ctx, bits, n, static_cast<unsigned>(spec->row_begin), out_rowids);
-        } catch (...) {
-            cudaFree(bits);
-            throw;
-        }
-        cudaFree(bits);
+        DevBuf bits_buf(ctx, n_words * 4 + 4);
+        auto* bits = bits_buf.as<unsigned>();
+        k_pred_bits<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(p, bits);
+        ctx->launches++;
+        BQ_CUDA(cudaGetLastError());
+        compact_bits(ctx, bits, n, static_cast<unsigned>(spec->row_begin), out_rowids);
     });
 }
 

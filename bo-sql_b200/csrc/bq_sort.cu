@@ -55,6 +55,42 @@ __global__ void __launch_bounds__(kBlock) k_rank_sort(const unsigned long long* 
     perm[rank] = static_cast<unsigned>(i);
 }
 
+// ---- top-k (ORDER BY ... LIMIT k over a large input) ----------------------------------------------
+// Each 4096-row tile rank-sorts itself and keeps its first k rows; the survivors (k per tile, in tile order, so
+// ties still resolve by input position) are reduced again until one tile remains.  The reference sorts everything
+// and lets Limit copy a prefix (src/exec/operator.cpp:1115, :579-613).
+constexpr int kTopkTile = 4096;
+
+__global__ void __launch_bounds__(kBlock) k_tile_topk(const unsigned long long* __restrict__ keys, int n_keys, size_t n,
+                                                      unsigned k, unsigned* __restrict__ cand /* positions, k per tile */) {
+    const size_t tile = blockIdx.y;
+    const size_t t0 = tile * kTopkTile;
+    const size_t tn = (n - t0) < (size_t)kTopkTile ? (n - t0) : (size_t)kTopkTile;
+    const size_t li = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (li >= tn) return;
+    const size_t i = t0 + li;
+    unsigned long long mine[4];
+    for (int q = 0; q < n_keys; ++q) mine[q] = keys[q * n + i];
+    unsigned rank = 0;
+    for (size_t lj = 0; lj < tn; ++lj) {
+        const size_t j = t0 + lj;
+        int cmp = 0;
+        for (int q = 0; q < n_keys && cmp == 0; ++q) {
+            unsigned long long o = __ldg(keys + q * n + j);
+            cmp = o < mine[q] ? -1 : (o > mine[q] ? 1 : 0);
+        }
+        if (cmp < 0 || (cmp == 0 && lj < li)) ++rank;
+    }
+    if (rank < k) cand[tile * k + rank] = static_cast<unsigned>(i);
+}
+
+// out[i] = src[idx[i]] (src == nullptr: identity)
+__global__ void __launch_bounds__(kBlock) k_compose(const unsigned* __restrict__ src, const unsigned* __restrict__ idx, size_t n,
+                                                    unsigned* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = src ? src[idx[i]] : idx[i];
+}
+
 // ---- radix sort passes ---------------------------------------------------------------------------
 constexpr int kRadixRounds = 8;
 constexpr int kRadixTile = kBlock * kRadixRounds;
@@ -122,14 +158,6 @@ __global__ void __launch_bounds__(kBlock) k_radix_scatter(const unsigned long lo
     }
 }
 
-struct DevBuf {
-    void* p = nullptr;
-    explicit DevBuf(size_t bytes) { BQ_CUDA(cudaMalloc(&p, bytes ? bytes : 16)); }
-    ~DevBuf() { if (p) cudaFree(p); }
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-};
-
 // Stable sort of (keys, vals) by keys ascending; result left in keys/vals (buffers may swap).
 static void radix_sort_pairs(bq_ctx* ctx, unsigned long long*& keys, unsigned*& vals, unsigned long long*& keys_alt,
                              unsigned*& vals_alt, size_t n) {
@@ -142,7 +170,7 @@ static void radix_sort_pairs(bq_ctx* ctx, unsigned long long*& keys, unsigned*& 
     BQ_CUDA(cudaStreamSynchronize(ctx->stream));
     const unsigned long long diff = *h;
     const unsigned n_blocks = static_cast<unsigned>((n + kRadixTile - 1) / kRadixTile);
-    DevBuf hist(256 * (size_t)n_blocks * 4), offs(256 * (size_t)n_blocks * 8);
+    DevBuf hist(ctx, 256 * (size_t)n_blocks * 4), offs(ctx, 256 * (size_t)n_blocks * 8);
     for (int byte = 0; byte < 8; ++byte) {
         if (((diff >> (8 * byte)) & 0xFFull) == 0) continue;
         const int shift = 8 * byte;
@@ -179,14 +207,14 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
             if (n == 0 || m == 0) {
                 for (int c = 0; c < nc; ++c) cols.push_back(new_col(ctx, rel->cols[c]->type, 0));
             } else {
-                DevBuf permA(n * 4), permB(n * 4);
+                DevBuf permA(ctx, n * 4), permB(ctx, n * 4);
                 auto* perm = static_cast<unsigned*>(permA.p);
                 auto* perm_alt = static_cast<unsigned*>(permB.p);
                 if (n_keys == 0) {
                     k_iota<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(perm, n);
                     ctx->launches++;
                 } else if (n <= 4096) {
-                    DevBuf keys(static_cast<size_t>(n_keys) * n * 8);
+                    DevBuf keys(ctx, static_cast<size_t>(n_keys) * n * 8);
                     for (int k = 0; k < n_keys; ++k) {
                         const bq_col* c = rel->cols[key_cols[k]];
                         k_make_keys<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(
@@ -197,9 +225,43 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
                         static_cast<unsigned long long*>(keys.p), n_keys, n, perm);
                     ctx->launches++;
                     BQ_CUDA(cudaGetLastError());
-                    BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+                } else if (m <= 256 && n <= 65535ull * kTopkTile) {
+                    // top-k: tiles keep their first m rows until one tile is left
+                    const size_t max_cand = ((n + kTopkTile - 1) / kTopkTile) * m;
+                    DevBuf keys(ctx, static_cast<size_t>(n_keys) * n * 8), candB(ctx, max_cand * 4), idsA(ctx, max_cand * 4), idsB(ctx, max_cand * 4);
+                    auto* kbuf = static_cast<unsigned long long*>(keys.p);
+                    auto* cand = static_cast<unsigned*>(candB.p);
+                    unsigned* ids = nullptr;                    // current survivors (global row ids); nullptr = all rows
+                    auto* ids_next = static_cast<unsigned*>(idsA.p);
+                    auto* ids_other = static_cast<unsigned*>(idsB.p);
+                    size_t cur = n;
+                    while (true) {
+                        for (int k = 0; k < n_keys; ++k) {
+                            const bq_col* c = rel->cols[key_cols[k]];
+                            k_make_keys<<<grid_for(ctx, cur, 8), kBlock, 0, ctx->stream>>>(c->ptr, c->type, asc[k], ids, cur, kbuf + k * cur);
+                            ctx->launches++;
+                        }
+                        if (cur <= (size_t)kTopkTile) {
+                            k_rank_sort<<<(unsigned)((cur + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(kbuf, n_keys, cur, cand);
+                            const size_t take = m < cur ? m : cur;
+                            k_compose<<<grid_for(ctx, take, 8), kBlock, 0, ctx->stream>>>(ids, cand, take, perm);
+                            ctx->launches += 2;
+                            BQ_CUDA(cudaGetLastError());
+                            break;
+                        }
+                        const size_t tiles = (cur + kTopkTile - 1) / kTopkTile;
+                        k_tile_topk<<<dim3(kTopkTile / kBlock, (unsigned)tiles), kBlock, 0, ctx->stream>>>(kbuf, n_keys, cur, (unsigned)m, cand);
+                        const size_t last = cur - (tiles - 1) * kTopkTile;
+                        const size_t next = (tiles - 1) * m + (m < last ? m : last);
+                        k_compose<<<grid_for(ctx, next, 8), kBlock, 0, ctx->stream>>>(ids, cand, next, ids_next);
+                        ctx->launches += 2;
+                        BQ_CUDA(cudaGetLastError());
+                        ids = ids_next;
+                        std::swap(ids_next, ids_other);
+                        cur = next;
+                    }
                 } else {
-                    DevBuf keysA(n * 8), keysB(n * 8);
+                    DevBuf keysA(ctx, n * 8), keysB(ctx, n * 8);
                     auto* keys = static_cast<unsigned long long*>(keysA.p);
                     auto* keys_alt = static_cast<unsigned long long*>(keysB.p);
                     k_iota<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(perm, n);
@@ -211,10 +273,10 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
                         BQ_CUDA(cudaGetLastError());
                         radix_sort_pairs(ctx, keys, perm, keys_alt, perm_alt, n);
                     }
-                    BQ_CUDA(cudaStreamSynchronize(ctx->stream));
                 }
                 // gather the first m rows of every column
                 bq_col ids;
+                ids.ctx = ctx;
                 ids.type = BQ_STRING;
                 ids.n = m;
                 ids.ptr = perm;
@@ -224,7 +286,6 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
                     if (bq_gather(ctx, rel->cols[c], &ids, &o)) throw std::runtime_error(bq_last_error());
                     cols.push_back(o);
                 }
-                BQ_CUDA(cudaStreamSynchronize(ctx->stream));
             }
             auto* r = new bq_rel();
             r->cols = cols;

@@ -42,6 +42,8 @@ def exec_lib():
         "bqx_catalog_destroy": ([vp], None),
         "bqx_table_create": ([cp, vp], vp),
         "bqx_table_add_column": ([vp, cp, C.c_int, vp, sz], C.c_int),
+        "bqx_table_add_borrowed_column": ([vp, cp, C.c_int, vp, sz], C.c_int),
+        "bqx_catalog_evict_device": ([vp, cp], C.c_int),
         "bqx_table_add_device_column": ([vp, cp, vp, C.c_int], C.c_int),
         "bqx_table_set_stats": ([vp, cp, C.c_int64, C.c_int64, C.c_double, C.c_double, sz], C.c_int),
         "bqx_catalog_register": ([vp, vp], C.c_int),
@@ -214,6 +216,8 @@ class Engine:
             if hasattr(data, "h") and hasattr(data, "ctx"):        # device-resident column, kept alive by the caller
                 self._keep.append(data)
                 _check(self.L.bqx_table_add_device_column(t, cname.encode(), data.h, 0))
+            elif isinstance(data, tuple):                          # (host pointer, rows): caller-owned (pinned) memory
+                _check(self.L.bqx_table_add_borrowed_column(t, cname.encode(), typ, C.c_void_p(data[0]), data[1]))
             else:
                 a = np.ascontiguousarray(data, dtype=NP_DTYPES[typ])
                 _check(self.L.bqx_table_add_column(t, cname.encode(), typ, a.ctypes.data_as(C.c_void_p), a.size))
@@ -222,6 +226,10 @@ class Engine:
             _check(self.L.bqx_table_set_stats(t, cname.encode(), 0 if is_f else int(lo), 0 if is_f else int(hi),
                                               float(lo) if is_f else 0.0, float(hi) if is_f else 0.0, int(ndv)))
         _check(self.L.bqx_catalog_register(self.cat, t))
+
+    def evict_device(self, table: str):
+        """Drop the HBM mirrors of `table`'s host columns (they are uploaded again by the next query)."""
+        _check(self.L.bqx_catalog_evict_device(self.cat, table.encode()))
 
     def plan(self, sql: str, parse_flags=0) -> Plan:
         h = C.c_void_p()

@@ -114,6 +114,18 @@ struct ColumnVector : public Column {
     void append(const T& v) { data.push_back(v); }
 };
 
+// A host column over memory the caller owns (e.g. pinned buffers): no copy into a std::vector, and uploads run at
+// full PCIe speed.  The caller keeps the memory alive and unchanged while the table is registered.
+struct BorrowedColumn : public Column {
+    TypeId type_id;
+    const void* ptr;
+    size_t rows;
+    BorrowedColumn(TypeId t, const void* p, size_t n) : type_id(t), ptr(p), rows(n) {}
+    TypeId type() const override { return type_id; }
+    size_t size() const override { return rows; }
+    const void* host_data() const override { return ptr; }
+};
+
 // A column that exists only on the device (synthetic 1 B-row tables never touch host memory).
 struct DeviceColumn : public Column {
     TypeId type_id;

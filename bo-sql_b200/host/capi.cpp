@@ -125,6 +125,16 @@ int bqx_table_add_column(bqx_table* t, const char* name, int type, const void* d
     });
 }
 
+int bqx_table_add_borrowed_column(bqx_table* t, const char* name, int type, const void* data, size_t n) {
+    return guarded([&] {
+        if (!t->table.columns.empty() && n != t->rows) throw std::runtime_error("column length mismatch");
+        if (type < 0 || type > 3) throw std::runtime_error("Unknown column type");
+        t->table.columns.push_back({name, std::make_unique<BorrowedColumn>(static_cast<TypeId>(type), data, n)});
+        t->metas.emplace_back(name, static_cast<TypeId>(type));
+        t->rows = n;
+    });
+}
+
 int bqx_table_add_device_column(bqx_table* t, const char* name, bq_col* col, int take_ownership) {
     return guarded([&] {
         const size_t n = bq_col_size(col);
@@ -161,6 +171,15 @@ int bqx_catalog_register(bqx_catalog* c, bqx_table* tp) {
         std::unique_ptr<bqx_table> t(tp);
         TableMeta meta(t->table.name, std::move(t->metas), t->rows);
         c->catalog.register_table(std::move(t->table), std::move(meta));
+    });
+}
+
+int bqx_catalog_evict_device(bqx_catalog* c, const char* table) {
+    return guarded([&] {
+        OptionalRef<const Table> t = c->catalog.get_table_data(table);
+        if (!t.has_value()) throw std::runtime_error(std::string("Table not found: ") + table);
+        for (const auto& col : t->columns)
+            if (col.data->host_data()) col.data->device.reset();
     });
 }
 

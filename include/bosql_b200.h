@@ -41,6 +41,11 @@ int bq_ctx_sync(bq_ctx* ctx);
 int bq_ctx_info(bq_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 uint64_t bq_ctx_launches(bq_ctx* ctx);
+/* Kernel timing for the roofline: while enabled, every launch of the fused scan kernel (bq_scan.cu k_scan) is
+ * bracketed by CUDA events on the context's stream.  bq_ctx_profile_read synchronises, returns the number of
+ * bracketed launches and their summed duration, and clears the record. */
+int bq_ctx_profile(bq_ctx* ctx, int enable);
+int bq_ctx_profile_read(bq_ctx* ctx, uint64_t* launches, double* total_ms);
 const char* bq_last_error(void);
 
 /* ---- columns: storage/ becomes device resident ------------------------------------------------ */
@@ -52,6 +57,8 @@ int bq_col_write(bq_ctx* ctx, bq_col* col, size_t offset, const void* host, size
 /* synchronous D2H of rows [offset, offset+n) */
 int bq_col_read(bq_ctx* ctx, const bq_col* col, size_t offset, size_t n, void* host);
 void bq_col_free(bq_ctx* ctx, bq_col* col);
+/* non-owning column over device memory the caller manages (e.g. a buffer filled by an NCCL collective) */
+int bq_col_wrap(bq_ctx* ctx, int type, void* device_ptr, size_t n, bq_col** out);
 size_t bq_col_size(const bq_col* col);
 int bq_col_type(const bq_col* col);
 void* bq_col_ptr(const bq_col* col);                       /* raw device pointer */

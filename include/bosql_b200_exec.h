@@ -48,6 +48,8 @@ void bqx_catalog_destroy(bqx_catalog* c);
 bqx_table* bqx_table_create(const char* name, bqx_dict* dict);
 /* host column: copied into a ColumnVector<T>; uploaded to HBM on first use by an operator */
 int bqx_table_add_column(bqx_table* t, const char* name, int type, const void* data, size_t n);
+/* host column over caller-owned memory (e.g. pinned, bq_host_alloc): not copied; must outlive the catalog */
+int bqx_table_add_borrowed_column(bqx_table* t, const char* name, int type, const void* data, size_t n);
 /* device-resident column (synthetic tables generated in HBM); take_ownership: the table frees it */
 int bqx_table_add_device_column(bqx_table* t, const char* name, bq_col* col, int take_ownership);
 /* catalog statistics of a column (ColumnStats, include/catalog/catalog.h:16-21); integers for INT64/DATE32,
@@ -55,6 +57,10 @@ int bqx_table_add_device_column(bqx_table* t, const char* name, bq_col* col, int
 int bqx_table_set_stats(bqx_table* t, const char* column, int64_t min_i, int64_t max_i, double min_f, double max_f, size_t ndv);
 /* Catalog::register_table (src/catalog/catalog.cpp:5); consumes the table handle */
 int bqx_catalog_register(bqx_catalog* c, bqx_table* t);
+
+/* Drop the HBM mirrors of a registered table's host columns: the next query uploads them again (bench.py's
+ * end-to-end leg pays the host->device copy inside every timed step this way). */
+int bqx_catalog_evict_device(bqx_catalog* c, const char* table);
 
 /* extensions of the SQL front end, off by default: bit 0 BETWEEN, bit 1 decimal literals */
 int bqx_plan_create(bqx_catalog* c, const char* sql, unsigned parse_flags, bqx_plan** out);
