@@ -72,6 +72,7 @@ struct ScanParams {
     unsigned long long* part_cnt;
     double* part_sum;                  // [grid][2]
     unsigned* ticket;
+    int staged;                        // 1: qualifying rows are staged per warp and aggregated 32 at a time
     int* err;                          // 1 = integer division by zero, 2 = group table full, 4 = key outside dense domain
 };
 
@@ -202,13 +203,19 @@ struct RowSink {
 
     BQ_D RowSink(const ScanParams& pp, double* a, double* b, unsigned* c) : p(pp), s_sum0(a), s_sum1(b), s_cnt(c) {}
 
-    // one qualifying (probe row, build row) pair
-    BQ_D void add(long long key_raw, long long a, long long b) {
+    BQ_D void values(long long a, long long b, double& v0, double& v1) {
         const int ka = Sh::present(p, S_A) ? Sh::kind(p, S_A) : BQ_INT64;
         const int kb = Sh::present(p, S_B) ? Sh::kind(p, S_B) : BQ_INT64;
-        double v0 = 0.0, v1 = 0.0;
+        v0 = 0.0;
+        v1 = 0.0;
         if (p.nv > 0) v0 = eval_vexpr(p.v[0], a, ka, b, kb, &err);
         if (p.nv > 1) v1 = eval_vexpr(p.v[1], a, ka, b, kb, &err);
+    }
+
+    // one qualifying (probe row, build row) pair
+    BQ_D void add(long long key_raw, long long a, long long b) {
+        double v0, v1;
+        values(a, b, v0, v1);
         if (GMODE == G_NONE) {
             cnt += 1;
             sum0 = __dadd_rn(sum0, v0);
@@ -241,27 +248,42 @@ struct RowSink {
         }
     }
 
-    // a probe row that passed every streamed range: resolve the join, then add each match
-    BQ_D void row(long long key_raw, long long a, long long b, long long jk) {
-        if (p.jmode == 0) {
-            add(key_raw, a, b);
-            return;
-        }
+    // branch-free accumulation for the global aggregate: a failed row adds +0.0 and 0
+    BQ_D void add_masked(bool pass, long long a, long long b) {
+        double v0, v1;
+        values(a, b, v0, v1);
+        cnt += pass ? 1ULL : 0ULL;
+        sum0 = __dadd_rn(sum0, pass ? v0 : 0.0);
+        sum1 = __dadd_rn(sum1, pass ? v1 : 0.0);
+    }
+
+    BQ_D void build_add(long long key_raw, long long a, long long b, unsigned brow) {
+        if (Sh::present(p, S_KEY) && Sh::from_build(p, S_KEY)) key_raw = load_raw(p.s[S_KEY].ptr, Sh::kind(p, S_KEY), brow);
+        if (Sh::present(p, S_A) && Sh::from_build(p, S_A)) a = load_raw(p.s[S_A].ptr, Sh::kind(p, S_A), brow);
+        if (Sh::present(p, S_B) && Sh::from_build(p, S_B)) b = load_raw(p.s[S_B].ptr, Sh::kind(p, S_B), brow);
+        add(key_raw, a, b);
+    }
+
+    // bitmap / direct-address probe: true = the row joins (brow = matched build row for DIRECT)
+    BQ_D bool probe_dense(long long jk, unsigned& brow) {
+        brow = 0;
         if (Sh::kind(p, S_JK) == BQ_DOUBLE) {
             if (jk == INT64_MIN) jk = 0;                                         // -0.0 == 0.0 (KeyEqual, :657)
-            if ((jk & 0x7FFFFFFFFFFFFFFFLL) > 0x7FF0000000000000LL) return;      // NaN never matches
+            if ((jk & 0x7FFFFFFFFFFFFFFFLL) > 0x7FF0000000000000LL) return false;   // NaN never matches
         }
-        if (p.jmode == BQ_JOIN_BITMAP) {
-            unsigned long long idx = static_cast<unsigned long long>(jk - p.jk_min);
-            if (idx < p.jk_domain && ((__ldg(p.j_bitmap + (idx >> 5)) >> (idx & 31)) & 1u)) add(key_raw, a, b);
-            return;
-        }
-        if (p.jmode == BQ_JOIN_DIRECT) {
-            unsigned long long idx = static_cast<unsigned long long>(jk - p.jk_min);
-            if (idx >= p.jk_domain) return;
-            unsigned e = __ldg(p.j_direct + idx);
-            if (e) build_add(key_raw, a, b, e - 1);
-            return;
+        unsigned long long idx = static_cast<unsigned long long>(jk - p.jk_min);
+        if (idx >= p.jk_domain) return false;
+        if (p.jmode == BQ_JOIN_BITMAP) return (__ldg(p.j_bitmap + (idx >> 5)) >> (idx & 31)) & 1u;
+        unsigned e = __ldg(p.j_direct + idx);
+        brow = e - 1;
+        return e != 0;
+    }
+
+    // hash probe: every matching build row contributes (duplicate build keys, src/exec/operator.cpp:802-816)
+    BQ_D void probe_hash(long long key_raw, long long a, long long b, long long jk) {
+        if (Sh::kind(p, S_JK) == BQ_DOUBLE) {
+            if (jk == INT64_MIN) jk = 0;
+            if ((jk & 0x7FFFFFFFFFFFFFFFLL) > 0x7FF0000000000000LL) return;
         }
         unsigned long long h = key_hash(static_cast<uint64_t>(jk)) & p.jh_mask;
         for (unsigned long long probes = 0; probes <= p.jh_mask; ++probes) {
@@ -272,22 +294,67 @@ struct RowSink {
         }
     }
 
-    BQ_D void build_add(long long key_raw, long long a, long long b, unsigned brow) {
-        if (Sh::present(p, S_KEY) && Sh::from_build(p, S_KEY)) key_raw = load_raw(p.s[S_KEY].ptr, Sh::kind(p, S_KEY), brow);
-        if (Sh::present(p, S_A) && Sh::from_build(p, S_A)) a = load_raw(p.s[S_A].ptr, Sh::kind(p, S_A), brow);
-        if (Sh::present(p, S_B) && Sh::from_build(p, S_B)) b = load_raw(p.s[S_B].ptr, Sh::kind(p, S_B), brow);
-        add(key_raw, a, b);
+    // a row that passed every streamed range (scalar head/tail path and staged flushes)
+    BQ_D void row(long long key_raw, long long a, long long b, long long jk) {
+        if (p.jmode == 0) {
+            add(key_raw, a, b);
+        } else if (p.jmode == BQ_JOIN_HASH) {
+            probe_hash(key_raw, a, b, jk);
+        } else {
+            unsigned brow;
+            if (probe_dense(jk, brow)) build_add(key_raw, a, b, brow);
+        }
     }
 };
 
-template <uint32_t SHAPE, int GMODE>
-__global__ void __launch_bounds__(kBlock) k_scan(const __grid_constant__ ScanParams p) {
+// One range test on a streamed value.  Ranges reaching the device are never empty (the host resolves those), so
+// lo <= k <= hi is the single unsigned compare (k - lo) <= (hi - lo); 4-byte kinds compare in 32 bits.
+struct RangeRegs {
+    unsigned long long lo0, span0, lo1, span1;
+    bool neg0, neg1;
+    int nr;
+};
+BQ_D RangeRegs range_regs(const DSlot& s) {
+    RangeRegs r;
+    r.nr = s.nr;
+    r.lo0 = static_cast<unsigned long long>(s.lo0);
+    r.span0 = static_cast<unsigned long long>(s.hi0) - static_cast<unsigned long long>(s.lo0);
+    r.lo1 = static_cast<unsigned long long>(s.lo1);
+    r.span1 = static_cast<unsigned long long>(s.hi1) - static_cast<unsigned long long>(s.lo1);
+    r.neg0 = s.neg0 != 0;
+    r.neg1 = s.neg1 != 0;
+    return r;
+}
+BQ_D bool range_pass(const RangeRegs& r, long long raw, int kind) {
+    bool ok;
+    if (kind == BQ_STRING || kind == BQ_DATE32) {
+        const unsigned x = static_cast<unsigned>(raw);
+        ok = ((x - static_cast<unsigned>(r.lo0)) <= static_cast<unsigned>(r.span0)) != r.neg0;
+        if (r.nr > 1) ok = ok && (((x - static_cast<unsigned>(r.lo1)) <= static_cast<unsigned>(r.span1)) != r.neg1);
+    } else {
+        const unsigned long long x = static_cast<unsigned long long>(key_of(raw, kind));
+        ok = ((x - r.lo0) <= r.span0) != r.neg0;
+        if (r.nr > 1) ok = ok && (((x - r.lo1) <= r.span1) != r.neg1);
+    }
+    return ok;
+}
+
+constexpr int kStageCap = 64;     // staged qualifying rows per warp (flushed 32 at a time)
+
+template <uint32_t SHAPE, int GMODE, bool STAGED>
+__global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_scan(const __grid_constant__ ScanParams p) {
     using Sh = Shape<SHAPE>;
     extern __shared__ double smem_dyn[];
     __shared__ double red_sum[kBlock / 32][2];
     __shared__ unsigned long long red_cnt[kBlock / 32];
     __shared__ int red_err;
     __shared__ bool is_last;
+    // Qualifying rows are staged per warp and aggregated 32 at a time: at low selectivity the expensive part
+    // (table update, join payload, atomics) then runs with full warps instead of once per row position.
+    __shared__ long long st_key[STAGED ? kBlock / 32 : 1][STAGED ? kStageCap : 1];
+    __shared__ long long st_a[STAGED ? kBlock / 32 : 1][STAGED ? kStageCap : 1];
+    __shared__ long long st_b[STAGED ? kBlock / 32 : 1][STAGED ? kStageCap : 1];
+    __shared__ long long st_x[STAGED ? kBlock / 32 : 1][STAGED ? kStageCap : 1];   // probe key (hash join) or matched build row
 
     double* s_sum0 = nullptr;
     double* s_sum1 = nullptr;
@@ -307,8 +374,32 @@ __global__ void __launch_bounds__(kBlock) k_scan(const __grid_constant__ ScanPar
 
     RowSink<SHAPE, GMODE> sink(p, s_sum0, s_sum1, s_cnt);
     const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
     const size_t warps_total = static_cast<size_t>(gridDim.x) * (kBlock / 32);
-    const size_t warp_global = static_cast<size_t>(blockIdx.x) * (kBlock / 32) + (threadIdx.x >> 5);
+    const size_t warp_global = static_cast<size_t>(blockIdx.x) * (kBlock / 32) + warp;
+    // global aggregate without a multi-match probe: branch-free accumulation in registers, no staging
+    const bool direct_path = (GMODE == G_NONE) && !STAGED;
+    const bool dense_join = p.jmode == BQ_JOIN_BITMAP || p.jmode == BQ_JOIN_DIRECT;
+
+    RangeRegs rr[N_SLOTS];
+#pragma unroll
+    for (int s = 0; s < N_SLOTS; ++s)
+        if (Sh::streamed(p, s)) rr[s] = range_regs(p.s[s]);
+    int staged = 0;       // warp-uniform
+
+    auto flush32 = [&](int first, int n) {
+        // lanes [0,n) take staged entries [first, first+n)
+        if (!STAGED) return;
+        __syncwarp();
+        if (lane < n) {
+            const int e = first + lane;
+            if (p.jmode == BQ_JOIN_HASH) sink.probe_hash(st_key[warp][e], st_a[warp][e], st_b[warp][e], st_x[warp][e]);
+            else if (dense_join) sink.build_add(st_key[warp][e], st_a[warp][e], st_b[warp][e], static_cast<unsigned>(st_x[warp][e]));
+            else sink.add(st_key[warp][e], st_a[warp][e], st_b[warp][e]);
+        }
+        __syncwarp();
+    };
 
     // ---- vector region: whole 128-row chunks -----------------------------------------------------
     for (size_t c = warp_global; c < p.n_chunks; c += warps_total) {
@@ -322,37 +413,62 @@ __global__ void __launch_bounds__(kBlock) k_scan(const __grid_constant__ ScanPar
         }
         if (p.mask) load_quad(p.mask, BQ_INT64, base, lane, mk);
         // phase 2: range tests
-        unsigned pass = 0xFu;
+        bool pass[4] = {true, true, true, true};
 #pragma unroll
         for (int s = 0; s < N_SLOTS; ++s) {
-            if (Sh::streamed(p, s) && p.s[s].nr > 0) {
-                const int kind = Sh::kind(p, s);
+            if (Sh::streamed(p, s) && rr[s].nr > 0) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    long long k = key_of(raw[s][r], kind);
-                    bool ok = in_range(k, p.s[s].lo0, p.s[s].hi0, p.s[s].neg0);
-                    if (p.s[s].nr > 1) ok = ok && in_range(k, p.s[s].lo1, p.s[s].hi1, p.s[s].neg1);
-                    if (!ok) pass &= ~(1u << r);
-                }
+                for (int r = 0; r < 4; ++r) pass[r] = pass[r] && range_pass(rr[s], raw[s][r], Sh::kind(p, s));
             }
         }
         if (p.mask) {
 #pragma unroll
+            for (int r = 0; r < 4; ++r) pass[r] = pass[r] && (mk[r] != 0);
+        }
+        // phase 2b: bitmap / direct-address probes of the survivors, four independent loads in flight
+        unsigned brow[4] = {0, 0, 0, 0};
+        if (dense_join) {
+#pragma unroll
             for (int r = 0; r < 4; ++r)
-                if (mk[r] == 0) pass &= ~(1u << r);
+                if (pass[r]) pass[r] = sink.probe_dense(raw[S_JK][r], brow[r]);
         }
         // phase 3: aggregate the survivors
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            if (pass & (1u << r)) {
-                long long kr = Sh::streamed(p, S_KEY) ? raw[S_KEY][r] : 0;
-                long long a = Sh::streamed(p, S_A) ? raw[S_A][r] : 0;
-                long long b = Sh::streamed(p, S_B) ? raw[S_B][r] : 0;
-                long long jk = Sh::streamed(p, S_JK) ? raw[S_JK][r] : 0;
-                sink.row(kr, a, b, jk);
+            const long long kr = Sh::streamed(p, S_KEY) ? raw[S_KEY][r] : 0;
+            long long a = Sh::streamed(p, S_A) ? raw[S_A][r] : 0;
+            long long b = Sh::streamed(p, S_B) ? raw[S_B][r] : 0;
+            const long long jk = Sh::streamed(p, S_JK) ? raw[S_JK][r] : 0;
+            if (direct_path) {
+                if (Sh::present(p, S_A) && Sh::from_build(p, S_A)) a = pass[r] ? load_raw(p.s[S_A].ptr, Sh::kind(p, S_A), brow[r]) : 0;
+                if (Sh::present(p, S_B) && Sh::from_build(p, S_B)) b = pass[r] ? load_raw(p.s[S_B].ptr, Sh::kind(p, S_B), brow[r]) : 0;
+                sink.add_masked(pass[r], a, b);
+            } else if (!STAGED) {
+                // most rows qualify (join-only pipelines): update the table straight from registers
+                if (pass[r]) {
+                    if (dense_join) sink.build_add(kr, a, b, brow[r]);
+                    else sink.add(kr, a, b);
+                }
+            } else {
+                const unsigned ballot = __ballot_sync(0xffffffffu, pass[r]);
+                if (ballot) {
+                    if (pass[r]) {
+                        const int pos = staged + __popc(ballot & lt_mask);
+                        st_key[warp][pos] = kr;
+                        st_a[warp][pos] = a;
+                        st_b[warp][pos] = b;
+                        st_x[warp][pos] = p.jmode == BQ_JOIN_HASH ? jk : static_cast<long long>(brow[r]);
+                    }
+                    staged += __popc(ballot);
+                    if (staged >= 32) {
+                        flush32(staged - 32, 32);
+                        staged -= 32;
+                    }
+                }
             }
         }
     }
+    if (STAGED && staged > 0) flush32(0, staged);
 
     // ---- head and tail rows (fewer than 4 + 128): one row per thread, CTA 0 -----------------------
     if (blockIdx.x == 0) {
@@ -368,7 +484,7 @@ __global__ void __launch_bounds__(kBlock) k_scan(const __grid_constant__ ScanPar
                 val[s] = 0;
                 if (Sh::streamed(p, s)) {
                     val[s] = load_raw(p.s[s].ptr, Sh::kind(p, s), i);
-                    ok = ok && slot_pass(p.s[s], val[s]);
+                    if (rr[s].nr > 0) ok = ok && range_pass(rr[s], val[s], Sh::kind(p, s));
                 }
             }
             if (p.mask && __ldg(p.mask + i) == 0) ok = false;
@@ -382,9 +498,9 @@ __global__ void __launch_bounds__(kBlock) k_scan(const __grid_constant__ ScanPar
         unsigned long long c = warp_sum(sink.cnt);
         double s0 = warp_sum(sink.sum0), s1 = warp_sum(sink.sum1);
         if (lane == 0) {
-            red_cnt[threadIdx.x >> 5] = c;
-            red_sum[threadIdx.x >> 5][0] = s0;
-            red_sum[threadIdx.x >> 5][1] = s1;
+            red_cnt[warp] = c;
+            red_sum[warp][0] = s0;
+            red_sum[warp][1] = s1;
         }
     }
     __syncthreads();
@@ -499,9 +615,10 @@ using ScanKernel = void (*)(const ScanParams);
 struct ShapeEntry {
     uint32_t shape;
     int gmode;
+    bool staged;
     ScanKernel fn;
 };
-#define BQ_SHAPE(shape, gmode) {shape, gmode, k_scan<shape, gmode>}
+#define BQ_SHAPE(shape, gmode, staged) {shape, gmode, staged, k_scan<shape, gmode, staged>}
 
 // Q1: status (STRING range) AND order_date (DATE32 ranges, also the group key), SUM(total DOUBLE)
 constexpr uint32_t kShapeQ1 = shape_bits(S_KEY, BQ_DATE32, false) | shape_bits(S_A, BQ_DOUBLE, false) |
@@ -529,26 +646,26 @@ constexpr uint32_t kShapeJ5 = shape_bits(S_A, BQ_DOUBLE, false) | shape_bits(S_B
                               shape_bits(S_JK, BQ_INT64, false);
 
 static const ShapeEntry kShapes[] = {
-    BQ_SHAPE(kShapeQ1, G_SMEM),      BQ_SHAPE(kShapeQ1, G_DENSE),
-    BQ_SHAPE(kShapeF_I64, G_NONE),   BQ_SHAPE(kShapeF_F64, G_NONE),  BQ_SHAPE(kShapeF_STR, G_NONE),
-    BQ_SHAPE(kShapeF_DATE, G_NONE),  BQ_SHAPE(kShapeF2_I64, G_NONE), BQ_SHAPE(kShapeF2_F64, G_NONE),
-    BQ_SHAPE(kShapeF2_STR, G_NONE),  BQ_SHAPE(kShapeF2_DATE, G_NONE), BQ_SHAPE(kShapeA_F64, G_NONE),
-    BQ_SHAPE(kShapeQ2, G_DENSE),     BQ_SHAPE(kShapeQ2, G_HASH),     BQ_SHAPE(kShapeQ2S, G_DENSE),
-    BQ_SHAPE(kShapeQ2S, G_SMEM),     BQ_SHAPE(kShapeGB, G_HASH),     BQ_SHAPE(kShapeGB, G_DENSE),
-    BQ_SHAPE(kShapeJ5, G_NONE),
+    BQ_SHAPE(kShapeQ1, G_SMEM, true),
+    BQ_SHAPE(kShapeF_I64, G_NONE, false),   BQ_SHAPE(kShapeF_F64, G_NONE, false),  BQ_SHAPE(kShapeF_STR, G_NONE, false),
+    BQ_SHAPE(kShapeF_DATE, G_NONE, false),  BQ_SHAPE(kShapeF2_I64, G_NONE, false), BQ_SHAPE(kShapeF2_F64, G_NONE, false),
+    BQ_SHAPE(kShapeF2_STR, G_NONE, false),  BQ_SHAPE(kShapeF2_DATE, G_NONE, false), BQ_SHAPE(kShapeA_F64, G_NONE, false),
+    BQ_SHAPE(kShapeQ2, G_DENSE, false),     BQ_SHAPE(kShapeQ2, G_HASH, true),      BQ_SHAPE(kShapeQ2S, G_DENSE, false),
+    BQ_SHAPE(kShapeQ2S, G_SMEM, true),      BQ_SHAPE(kShapeGB, G_HASH, true),      BQ_SHAPE(kShapeGB, G_DENSE, false),
+    BQ_SHAPE(kShapeJ5, G_NONE, false),
     // any other slot layout: same source, run-time flags
-    BQ_SHAPE(kGenericShape, G_NONE), BQ_SHAPE(kGenericShape, G_SMEM), BQ_SHAPE(kGenericShape, G_DENSE),
-    BQ_SHAPE(kGenericShape, G_HASH),
+    BQ_SHAPE(kGenericShape, G_NONE, false), BQ_SHAPE(kGenericShape, G_NONE, true), BQ_SHAPE(kGenericShape, G_SMEM, true),
+    BQ_SHAPE(kGenericShape, G_DENSE, false), BQ_SHAPE(kGenericShape, G_DENSE, true), BQ_SHAPE(kGenericShape, G_HASH, true),
 };
 
-static ScanKernel pick_kernel(uint32_t shape, int gmode, bool* specialised) {
+static ScanKernel pick_kernel(uint32_t shape, int gmode, bool staged, bool* specialised) {
     for (const auto& e : kShapes)
-        if (e.shape == shape && e.gmode == gmode) {
+        if (e.shape == shape && e.gmode == gmode && e.staged == staged) {
             *specialised = true;
             return e.fn;
         }
     for (const auto& e : kShapes)
-        if (e.shape == kGenericShape && e.gmode == gmode) {
+        if (e.shape == kGenericShape && e.gmode == gmode && e.staged == staged) {
             *specialised = false;
             return e.fn;
         }
@@ -609,6 +726,31 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st) {
             if (p.s[s].from_build && p.s[s].nr) throw std::runtime_error("build-side predicates belong in bq_join_build");
             if (p.s[s].from_build && !spec->join) throw std::runtime_error("from_build slot without a join");
         }
+    }
+    // Ranges reach the kernel clamped to the column's domain and never empty (its unsigned range test needs lo <= hi):
+    // an always-true range is dropped, an always-false one empties the whole result without a launch.
+    bool never_passes = false;
+    for (int s = 0; s < N_SLOTS; ++s) {
+        DSlot& d = p.s[s];
+        if (!d.ptr || d.nr == 0) continue;
+        long long dmin = INT64_MIN, dmax = INT64_MAX;
+        if (d.kind == BQ_STRING) { dmin = 0; dmax = 0xFFFFFFFFLL; }
+        if (d.kind == BQ_DATE32) { dmin = INT32_MIN; dmax = INT32_MAX; }
+        long long lo[2] = {d.lo0, d.lo1}, hi[2] = {d.hi0, d.hi1};
+        int neg[2] = {d.neg0, d.neg1};
+        int kept = 0;
+        for (int i = 0; i < d.nr; ++i) {
+            long long l = lo[i] < dmin ? dmin : lo[i], h = hi[i] > dmax ? dmax : hi[i];
+            const bool empty = l > h, full = (l == dmin && h == dmax);
+            if (!neg[i] ? empty : full) never_passes = true;
+            if (!neg[i] ? full : empty) continue;          // always true
+            if (empty) continue;
+            lo[kept] = l; hi[kept] = h; neg[kept] = neg[i];
+            ++kept;
+        }
+        d.nr = kept;
+        d.lo0 = lo[0]; d.hi0 = hi[0]; d.neg0 = neg[0];
+        d.lo1 = lo[1]; d.hi1 = hi[1]; d.neg1 = neg[1];
     }
     if (spec->n_v < 0 || spec->n_v > 2) throw std::runtime_error("at most two aggregate arguments");
     p.nv = spec->n_v;
@@ -687,12 +829,23 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st) {
     p.key_min = st.key_min;
     p.key_domain = (st.gmode == G_SMEM || st.gmode == G_DENSE) ? st.slots : 0;
 
+    // Staging pays when few rows survive the predicates or the table update is expensive (shared-memory CAS, hash
+    // claim, multi-match probe); a join-only pipeline into a dense global table updates straight from registers,
+    // and the global aggregate accumulates branch-free in registers.
+    bool has_ranges = p.mask != nullptr;
+    for (int s = 0; s < N_SLOTS; ++s) has_ranges = has_ranges || p.s[s].nr > 0;
+    bool staged = false;
+    if (p.jmode == BQ_JOIN_HASH || st.gmode == G_SMEM || st.gmode == G_HASH) staged = true;
+    else if (st.gmode == G_DENSE) staged = has_ranges;
+    p.staged = staged ? 1 : 0;
     bool specialised = false;
-    ScanKernel fn = pick_kernel(shape, st.gmode, &specialised);
+    ScanKernel fn = pick_kernel(shape, st.gmode, staged, &specialised);
     size_t rows = spec->row_end - spec->row_begin;
+    if (smem > 0) BQ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int blocks_per_sm = 4;
-    if (smem > 24 * 1024) blocks_per_sm = 2;
-    int grid = grid_for(ctx, rows, blocks_per_sm);
+    BQ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, kBlock, smem));
+    if (blocks_per_sm < 1) blocks_per_sm = 1;
+    int grid = grid_for(ctx, rows, blocks_per_sm);      // a whole number of resident CTAs per SM: one wave
 
     // one allocation: cnt | sum0 | sum1 | keys | part_cnt | part_sum | ticket | err
     size_t n = st.slots;
@@ -722,9 +875,7 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st) {
     p.ticket = reinterpret_cast<unsigned*>(base + off_tk);
     p.err = reinterpret_cast<int*>(base + off_tk + 8);
     st.err = p.err;
-
-    if (rows > 0 || st.gmode == G_NONE) {
-        if (smem > 0) BQ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    if (!never_passes && (rows > 0 || st.gmode == G_NONE)) {
         cudaEvent_t ev0 = nullptr, ev1 = nullptr;
         if (ctx->profile) {
             BQ_CUDA(cudaEventCreate(&ev0));
