@@ -228,27 +228,23 @@ def run_ours(args):
         D = DATE_MAX - DATE_MIN + 1
         from tests.parity import q1_kernel_spec
         spec = q1_kernel_spec(bq, orders["status"], orders["order_date"], orders["total"], rows, 0, 20240101, 20240131, DATE_MIN, DATE_MAX)
-        pad = {k: torch.zeros(D, dtype=dt, device="cuda") for k, dt in
-               (("key", torch.int32), ("cnt", torch.int64), ("s0", torch.float64), ("s1", torch.float64))}
-        gath = {k: torch.zeros(D * world, dtype=v.dtype, device="cuda") for k, v in pad.items()}
-        wrapped = [ctx.wrap(t, gath[k].data_ptr(), D * world) for k, t in
-                   (("key", bq.DATE32), ("cnt", bq.INT64), ("s0", bq.DOUBLE), ("s1", bq.DOUBLE))]
-        merged_in = ctx.rel_create(wrapped)
+        from bosql_b200 import distributed as DIST
         outs = [bq.AggOut(func=bq.AGG_SUM, v=0, as_int=0)]
+        layout = ((0, "<i4", torch.int32, bq.DATE32), (1, "<i8", torch.int64, bq.INT64),
+                  (2, "<f8", torch.float64, bq.DOUBLE), (3, "<f8", torch.float64, bq.DOUBLE))
 
         def q1_step():
-            part = ctx.scan_aggregate(spec, partial=True)
+            part = ctx.scan_aggregate(spec, partial=True)          # [key, count, sum0, sum1] of this rank's rows
             r = part.rows
             with torch.cuda.stream(stream):
-                for k, c, ts in (("key", 0, "<i4"), ("cnt", 1, "<i8"), ("s0", 2, "<f8"), ("s1", 3, "<f8")):
-                    pad[k].zero_()
-                    if r:
-                        pad[k][:r].copy_(torch.as_tensor(CudaArray(part.col(c).ptr, r, ts), device="cuda"))
-                    dist.all_gather_into_tensor(gath[k], pad[k])
-            stream.synchronize()
-            fin = ctx.agg_finish([merged_in], True, bq.DATE32, outs)
+                mine = [torch.as_tensor(CudaArray(part.col(c).ptr, r, ts), device="cuda") if r else
+                        torch.empty(0, dtype=dt, device="cuda") for c, ts, dt, _ in layout]
+                gathered = DIST.gather_partials(mine, D)           # one NCCL all-gather per state column
+            merged_in = ctx.rel_create([ctx.wrap(bt, g.data_ptr(), g.numel()) for g, (_, _, _, bt) in zip(gathered, layout)])
+            fin = ctx.agg_finish([merged_in], True, bq.DATE32, outs)     # equal keys combined in rank order
             srt = ctx.rel_sort(fin, [0], [1])
             result["q1_cols"] = srt.to_numpy()
+            result["keep"] = gathered
 
     ms_step, launches, kern, clocks = timed(q1_step, args.steps, max(3, args.warmup), profile=True)
     total_rows = rows * world

@@ -1,0 +1,43 @@
+"""bosql_b200.distributed — the exchange step of partitioned aggregates (one process per GPU, torch.distributed).
+
+Scans, selections and broadcast (bitmap) joins partition by row range: every rank runs the fused kernel on its own rows
+and nothing crosses NVLink until the partial aggregate states (a few KB for Q1, 3 MB for Q2's 100 k groups) are
+exchanged with ONE all-gather per state column and merged in rank order (so results do not depend on arrival order).
+The same code runs over NCCL on GPUs and over gloo on CPU tensors (tests/test_distributed_cpu.py).
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+
+def gather_partials(cols, capacity: int, group=None):
+    """cols: this rank's partial-state columns (1-D tensors of equal length r <= capacity; the count column zero means
+    "no group").  Returns, per column, a tensor of world*capacity rows: rank 0's rows (zero-padded), then rank 1's, ..."""
+    world = dist.get_world_size(group)
+    out = []
+    for c in cols:
+        r = c.numel()
+        if r > capacity:
+            raise ValueError(f"partial state has {r} rows, capacity is {capacity}")
+        pad = torch.zeros(capacity, dtype=c.dtype, device=c.device)
+        if r:
+            pad[:r].copy_(c)
+        g = torch.empty(capacity * world, dtype=c.dtype, device=c.device)
+        dist.all_gather_into_tensor(g, pad, group=group) if c.is_cuda else _gather_cpu(g, pad, world, group)
+        out.append(g)
+    return out
+
+
+def _gather_cpu(g, pad, world, group):
+    parts = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(parts, pad, group=group)
+    torch.cat(parts, out=g)
+
+
+def or_reduce_bitmap(words: torch.Tensor, group=None):
+    """Union of per-rank join bitmaps built from disjoint build-side shards.  Bits set by different ranks never
+    coincide (the BITMAP table requires unique keys), so the integer sum of the words IS their bitwise OR — which lets
+    NCCL's all-reduce (no OR operator) do it in place."""
+    dist.all_reduce(words, op=dist.ReduceOp.SUM, group=group)
+    return words
