@@ -60,10 +60,12 @@ class ClockSampler:
 
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
+        self.t0 = self.t1 = None
 
     def start(self):
+        """Started BEFORE the warm-up so that nvidia-smi is already streaming when the timed region begins."""
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -71,21 +73,39 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def stop(self):
         if self.proc:
+            time.sleep(0.12)
             self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.06]
+        window = "timed region"
+        if not inside:                       # region shorter than the sampling period: the nearest samples around it
+            inside = [r for _, r in self.rows][-4:]
+            window = "around the timed region (it is shorter than the 50 ms sampling period)"
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = [num(r[1]) for r in inside if len(r) > 8 and num(r[1]) is not None]
+        mx = [num(r[2]) for r in inside if len(r) > 8 and num(r[2]) is not None]
         reasons = set()
-        for r in self.rows:
+        for r in inside:
             if len(r) > 8:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -175,12 +195,13 @@ def run_ours(args):
         return float(t.item())
 
     def timed(step, steps, warmup, profile=False):
-        for _ in range(warmup):
-            step()
-        barrier()
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
+        for _ in range(warmup):
+            step()
+        barrier()
+        sampler.mark_begin()
         l0 = ctx.launches
         if profile:
             ctx.profile_read()
@@ -191,6 +212,7 @@ def run_ours(args):
             step()
         e1.record(stream)
         barrier()
+        sampler.mark_end()
         ms = max_over_ranks(e0.elapsed_time(e1))
         kern = None
         if profile:

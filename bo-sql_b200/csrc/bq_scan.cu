@@ -325,23 +325,26 @@ BQ_D RangeRegs range_regs(const DSlot& s) {
     r.neg1 = s.neg1 != 0;
     return r;
 }
-BQ_D bool range_pass(const RangeRegs& r, long long raw, int kind) {
+BQ_D bool range_pass(const RangeRegs& r, long long raw, int kind, int nr) {
     bool ok;
     if (kind == BQ_STRING || kind == BQ_DATE32) {
         const unsigned x = static_cast<unsigned>(raw);
         ok = ((x - static_cast<unsigned>(r.lo0)) <= static_cast<unsigned>(r.span0)) != r.neg0;
-        if (r.nr > 1) ok = ok && (((x - static_cast<unsigned>(r.lo1)) <= static_cast<unsigned>(r.span1)) != r.neg1);
+        if (nr > 1) ok = ok && (((x - static_cast<unsigned>(r.lo1)) <= static_cast<unsigned>(r.span1)) != r.neg1);
     } else {
         const unsigned long long x = static_cast<unsigned long long>(key_of(raw, kind));
         ok = ((x - r.lo0) <= r.span0) != r.neg0;
-        if (r.nr > 1) ok = ok && (((x - r.lo1) <= r.span1) != r.neg1);
+        if (nr > 1) ok = ok && (((x - r.lo1) <= r.span1) != r.neg1);
     }
     return ok;
 }
 
 constexpr int kStageCap = 64;     // staged qualifying rows per warp (flushed 32 at a time)
 
-template <uint32_t SHAPE, int GMODE, bool STAGED>
+// RSHAPE: 2 bits per slot = how many ranges the slot carries (specialised kernels; the generic kernel reads it at run time)
+constexpr uint32_t rshape_bits(int slot, int n_ranges) { return static_cast<uint32_t>(n_ranges) << (2 * slot); }
+
+template <uint32_t SHAPE, uint32_t RSHAPE, int GMODE, bool STAGED>
 __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_scan(const __grid_constant__ ScanParams p) {
     using Sh = Shape<SHAPE>;
     extern __shared__ double smem_dyn[];
@@ -387,6 +390,9 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
     for (int s = 0; s < N_SLOTS; ++s)
         if (Sh::streamed(p, s)) rr[s] = range_regs(p.s[s]);
     int staged = 0;       // warp-uniform
+    // number of ranges per slot: a compile-time constant in the specialised kernels
+    auto nr_of = [&](int s) -> int { return Sh::generic ? rr[s].nr : static_cast<int>((RSHAPE >> (2 * s)) & 3u); };
+    const long long* mask = Sh::generic ? p.mask : nullptr;      // specialised kernels never carry a mask column
 
     auto flush32 = [&](int first, int n) {
         // lanes [0,n) take staged entries [first, first+n)
@@ -411,17 +417,17 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
         for (int s = 0; s < N_SLOTS; ++s) {
             if (Sh::streamed(p, s)) load_quad(p.s[s].ptr, Sh::kind(p, s), base, lane, raw[s]);
         }
-        if (p.mask) load_quad(p.mask, BQ_INT64, base, lane, mk);
+        if (mask) load_quad(mask, BQ_INT64, base, lane, mk);
         // phase 2: range tests
         bool pass[4] = {true, true, true, true};
 #pragma unroll
         for (int s = 0; s < N_SLOTS; ++s) {
-            if (Sh::streamed(p, s) && rr[s].nr > 0) {
+            if (Sh::streamed(p, s) && nr_of(s) > 0) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) pass[r] = pass[r] && range_pass(rr[s], raw[s][r], Sh::kind(p, s));
+                for (int r = 0; r < 4; ++r) pass[r] = pass[r] && range_pass(rr[s], raw[s][r], Sh::kind(p, s), nr_of(s));
             }
         }
-        if (p.mask) {
+        if (mask) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) pass[r] = pass[r] && (mk[r] != 0);
         }
@@ -484,10 +490,10 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
                 val[s] = 0;
                 if (Sh::streamed(p, s)) {
                     val[s] = load_raw(p.s[s].ptr, Sh::kind(p, s), i);
-                    if (rr[s].nr > 0) ok = ok && range_pass(rr[s], val[s], Sh::kind(p, s));
+                    if (nr_of(s) > 0) ok = ok && range_pass(rr[s], val[s], Sh::kind(p, s), nr_of(s));
                 }
             }
-            if (p.mask && __ldg(p.mask + i) == 0) ok = false;
+            if (mask && __ldg(mask + i) == 0) ok = false;
             if (ok) sink.row(val[S_KEY], val[S_A], val[S_B], val[S_JK]);
         }
     }
@@ -614,11 +620,16 @@ __global__ void __launch_bounds__(kBlock) k_fill_keys(long long* __restrict__ ke
 using ScanKernel = void (*)(const ScanParams);
 struct ShapeEntry {
     uint32_t shape;
+    uint32_t rshape;
     int gmode;
     bool staged;
     ScanKernel fn;
 };
-#define BQ_SHAPE(shape, gmode, staged) {shape, gmode, staged, k_scan<shape, gmode, staged>}
+#define BQ_SHAPE(shape, rshape, gmode, staged) {shape, rshape, gmode, staged, k_scan<shape, rshape, gmode, staged>}
+constexpr uint32_t kR_Q1 = rshape_bits(S_KEY, 1) | rshape_bits(S_P0, 1);     // one (merged) range on the date, one on status
+constexpr uint32_t kR_P0 = rshape_bits(S_P0, 1);                             // filter sweep: one range on the predicate column
+constexpr uint32_t kR_A = rshape_bits(S_A, 1);
+constexpr uint32_t kR_NONE = 0;
 
 // Q1: status (STRING range) AND order_date (DATE32 ranges, also the group key), SUM(total DOUBLE)
 constexpr uint32_t kShapeQ1 = shape_bits(S_KEY, BQ_DATE32, false) | shape_bits(S_A, BQ_DOUBLE, false) |
@@ -646,21 +657,24 @@ constexpr uint32_t kShapeJ5 = shape_bits(S_A, BQ_DOUBLE, false) | shape_bits(S_B
                               shape_bits(S_JK, BQ_INT64, false);
 
 static const ShapeEntry kShapes[] = {
-    BQ_SHAPE(kShapeQ1, G_SMEM, true),
-    BQ_SHAPE(kShapeF_I64, G_NONE, false),   BQ_SHAPE(kShapeF_F64, G_NONE, false),  BQ_SHAPE(kShapeF_STR, G_NONE, false),
-    BQ_SHAPE(kShapeF_DATE, G_NONE, false),  BQ_SHAPE(kShapeF2_I64, G_NONE, false), BQ_SHAPE(kShapeF2_F64, G_NONE, false),
-    BQ_SHAPE(kShapeF2_STR, G_NONE, false),  BQ_SHAPE(kShapeF2_DATE, G_NONE, false), BQ_SHAPE(kShapeA_F64, G_NONE, false),
-    BQ_SHAPE(kShapeQ2, G_DENSE, false),     BQ_SHAPE(kShapeQ2, G_HASH, true),      BQ_SHAPE(kShapeQ2S, G_DENSE, false),
-    BQ_SHAPE(kShapeQ2S, G_SMEM, true),      BQ_SHAPE(kShapeGB, G_HASH, true),      BQ_SHAPE(kShapeGB, G_DENSE, false),
-    BQ_SHAPE(kShapeJ5, G_NONE, false),
-    // any other slot layout: same source, run-time flags
-    BQ_SHAPE(kGenericShape, G_NONE, false), BQ_SHAPE(kGenericShape, G_NONE, true), BQ_SHAPE(kGenericShape, G_SMEM, true),
-    BQ_SHAPE(kGenericShape, G_DENSE, false), BQ_SHAPE(kGenericShape, G_DENSE, true), BQ_SHAPE(kGenericShape, G_HASH, true),
+    BQ_SHAPE(kShapeQ1, kR_Q1, G_SMEM, true),
+    BQ_SHAPE(kShapeF_I64, kR_P0, G_NONE, false),   BQ_SHAPE(kShapeF_F64, kR_P0, G_NONE, false),
+    BQ_SHAPE(kShapeF_STR, kR_P0, G_NONE, false),   BQ_SHAPE(kShapeF_DATE, kR_P0, G_NONE, false),
+    BQ_SHAPE(kShapeF2_I64, kR_P0, G_NONE, false),  BQ_SHAPE(kShapeF2_F64, kR_P0, G_NONE, false),
+    BQ_SHAPE(kShapeF2_STR, kR_P0, G_NONE, false),  BQ_SHAPE(kShapeF2_DATE, kR_P0, G_NONE, false),
+    BQ_SHAPE(kShapeA_F64, kR_A, G_NONE, false),
+    BQ_SHAPE(kShapeQ2, kR_NONE, G_DENSE, false),   BQ_SHAPE(kShapeQ2, kR_NONE, G_HASH, true),
+    BQ_SHAPE(kShapeQ2S, kR_NONE, G_DENSE, false),  BQ_SHAPE(kShapeQ2S, kR_NONE, G_SMEM, true),
+    BQ_SHAPE(kShapeGB, kR_NONE, G_HASH, true),     BQ_SHAPE(kShapeGB, kR_NONE, G_DENSE, false),
+    BQ_SHAPE(kShapeJ5, kR_NONE, G_NONE, false),
+    // any other slot layout / range layout / a mask column: same source, run-time flags
+    BQ_SHAPE(kGenericShape, 0, G_NONE, false), BQ_SHAPE(kGenericShape, 0, G_NONE, true), BQ_SHAPE(kGenericShape, 0, G_SMEM, true),
+    BQ_SHAPE(kGenericShape, 0, G_DENSE, false), BQ_SHAPE(kGenericShape, 0, G_DENSE, true), BQ_SHAPE(kGenericShape, 0, G_HASH, true),
 };
 
-static ScanKernel pick_kernel(uint32_t shape, int gmode, bool staged, bool* specialised) {
+static ScanKernel pick_kernel(uint32_t shape, uint32_t rshape, bool has_mask, int gmode, bool staged, bool* specialised) {
     for (const auto& e : kShapes)
-        if (e.shape == shape && e.gmode == gmode && e.staged == staged) {
+        if (!has_mask && e.shape == shape && e.rshape == rshape && e.gmode == gmode && e.staged == staged) {
             *specialised = true;
             return e.fn;
         }
@@ -839,7 +853,9 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st) {
     else if (st.gmode == G_DENSE) staged = has_ranges;
     p.staged = staged ? 1 : 0;
     bool specialised = false;
-    ScanKernel fn = pick_kernel(shape, st.gmode, staged, &specialised);
+    uint32_t rshape = 0;
+    for (int s = 0; s < N_SLOTS; ++s) rshape |= rshape_bits(s, p.s[s].nr);
+    ScanKernel fn = pick_kernel(shape, rshape, p.mask != nullptr, st.gmode, staged, &specialised);
     size_t rows = spec->row_end - spec->row_begin;
     if (smem > 0) BQ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int blocks_per_sm = 4;
