@@ -49,30 +49,65 @@ template <int KIND>
 __global__ void __launch_bounds__(kBlock) k_join_build(const __grid_constant__ BuildParams p) {
     unsigned long long local = 0;
     const size_t n = p.row_end - p.row_begin;
-    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < n; t += (size_t)gridDim.x * blockDim.x) {
-        const size_t i = p.row_begin + t;
-        bool ok = true;
+    const int lane = threadIdx.x & 31;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    // warp-uniform trip count (the bitmap path uses warp collectives)
+    for (size_t base = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+        const size_t t = base + lane;
+        bool ok = t < n;
+        const size_t i = p.row_begin + (ok ? t : 0);
+        if (ok) {
 #pragma unroll
-        for (int s = 0; s < 3; ++s)
-            if (p.s[s].ptr) ok = ok && slot_pass(p.s[s], load_raw(p.s[s].ptr, p.s[s].kind, i));
-        if (p.mask && __ldg(p.mask + i) == 0) ok = false;
-        if (!ok) continue;
-        long long k = load_raw(p.key, p.key_kind, i);
-        if (!canon_join_key(k, p.key_kind)) continue;
+            for (int s = 0; s < 3; ++s)
+                if (p.s[s].ptr) ok = ok && slot_pass(p.s[s], load_raw(p.s[s].ptr, p.s[s].kind, i));
+            if (p.mask && __ldg(p.mask + i) == 0) ok = false;
+        }
+        long long k = 0;
+        if (ok) {
+            k = load_raw(p.key, p.key_kind, i);
+            ok = canon_join_key(k, p.key_kind);
+        }
         if (KIND == BQ_JOIN_BITMAP) {
             unsigned long long idx = static_cast<unsigned long long>(k - p.key_min);
-            if (idx >= p.domain) { atomicOr(p.flags, 2); continue; }
-            unsigned bit = 1u << (idx & 31);
-            unsigned old = atomicOr(p.bitmap + (idx >> 5), bit);
-            if (old & bit) atomicOr(p.flags, 1);
-            local++;
+            if (ok && idx >= p.domain) {
+                atomicOr(p.flags, 2);
+                ok = false;
+            }
+            // Build keys usually arrive clustered (o.order_id = row + 1): when every inserting lane of the warp hits
+            // the same bitmap word, the warp combines its bits and issues ONE atomicOr instead of up to 32 that
+            // would serialise on one L2 address.  Otherwise each lane inserts on its own.
+            const unsigned word = static_cast<unsigned>(idx >> 5);
+            const unsigned bit = ok ? 1u << (idx & 31) : 0u;
+            const unsigned active = __ballot_sync(0xffffffffu, ok);
+            if (active) {
+                const int first = __ffs(active) - 1;
+                const unsigned w0 = __shfl_sync(0xffffffffu, word, first);
+                const bool same = __all_sync(0xffffffffu, !ok || word == w0);
+                if (same) {
+                    const unsigned bits = __reduce_or_sync(0xffffffffu, bit);
+                    if (lane == first) {
+                        if (__popc(bits) != __popc(active)) atomicOr(p.flags, 1);      // one key twice inside the warp
+                        unsigned old = atomicOr(p.bitmap + w0, bits);
+                        if (old & bits) atomicOr(p.flags, 1);
+                    }
+                } else if (ok) {
+                    unsigned old = atomicOr(p.bitmap + word, bit);
+                    if (old & bit) atomicOr(p.flags, 1);
+                }
+                if (ok) local++;
+            }
         } else if (KIND == BQ_JOIN_DIRECT) {
-            unsigned long long idx = static_cast<unsigned long long>(k - p.key_min);
-            if (idx >= p.domain) { atomicOr(p.flags, 2); continue; }
-            unsigned old = atomicCAS(p.direct + idx, 0u, static_cast<unsigned>(i) + 1u);
-            if (old) atomicOr(p.flags, 1);
-            local++;
-        } else {
+            if (ok) {
+                unsigned long long idx = static_cast<unsigned long long>(k - p.key_min);
+                if (idx >= p.domain) {
+                    atomicOr(p.flags, 2);
+                } else {
+                    unsigned old = atomicCAS(p.direct + idx, 0u, static_cast<unsigned>(i) + 1u);
+                    if (old) atomicOr(p.flags, 1);
+                    local++;
+                }
+            }
+        } else if (ok) {
             unsigned long long h = key_hash(static_cast<uint64_t>(k)) & p.h_mask;
             bool placed = false;
             for (unsigned long long probes = 0; probes <= p.h_mask; ++probes) {
@@ -89,7 +124,7 @@ __global__ void __launch_bounds__(kBlock) k_join_build(const __grid_constant__ B
         }
     }
     local = warp_sum(local);
-    if ((threadIdx.x & 31) == 0 && local) atomicAdd(p.n_inserted, local);
+    if (lane == 0 && local) atomicAdd(p.n_inserted, local);
 }
 
 // ---- materialising probe ---------------------------------------------------------------------------

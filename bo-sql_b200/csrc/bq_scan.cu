@@ -73,6 +73,7 @@ struct ScanParams {
     double* part_sum;                  // [grid][2]
     unsigned* ticket;
     int staged;                        // 1: qualifying rows are staged per warp and aggregated 32 at a time
+    int need_count;                    // 0: no COUNT/AVG output -> skip the per-row count atomic of the global tables
     int* err;                          // 1 = integer division by zero, 2 = group table full, 4 = key outside dense domain
 };
 
@@ -232,8 +233,14 @@ struct RowSink {
         } else if (GMODE == G_DENSE) {
             unsigned long long idx = static_cast<unsigned long long>(key_raw - p.key_min);
             if (idx < p.key_domain) {
-                atomicAdd(p.g_cnt + idx, 1ULL);
-                if (p.nv > 0) atomicAdd(p.g_sum0 + idx, v0);
+                if (p.need_count) {
+                    atomicAdd(p.g_cnt + idx, 1ULL);
+                    if (p.nv > 0) atomicAdd(p.g_sum0 + idx, v0);
+                } else {
+                    // presence rides on the sum: slots start as -0.0 and v + 0.0 is never -0.0, so a touched slot
+                    // can never read back as -0.0 (one atomic per row instead of two)
+                    atomicAdd(p.g_sum0 + idx, __dadd_rn(v0, 0.0));
+                }
                 if (p.nv > 1) atomicAdd(p.g_sum1 + idx, v1);
             } else {
                 err |= 4;
@@ -242,7 +249,7 @@ struct RowSink {
             long long k = key_raw;
             if (Sh::kind(p, S_KEY) == BQ_DOUBLE && k == INT64_MIN) k = 0;   // -0.0 groups with +0.0
             unsigned long long idx = group_slot(p.h_keys, p.h_mask, p.err, k);
-            atomicAdd(p.g_cnt + idx, 1ULL);
+            if (p.need_count || idx > p.h_mask) atomicAdd(p.g_cnt + idx, 1ULL);     // else presence = the claimed key
             if (p.nv > 0) atomicAdd(p.g_sum0 + idx, v0);
             if (p.nv > 1) atomicAdd(p.g_sum1 + idx, v1);
         }
@@ -567,6 +574,21 @@ __global__ void __launch_bounds__(kBlock) k_presence_bits(const unsigned long lo
     if ((threadIdx.x & 31) == 0 && (i >> 5) < (n + 31) / 32) bits[i >> 5] = b;
 }
 
+// presence without counts: dense tables whose sum slots started as -0.0, hash tables by their claimed keys
+__global__ void __launch_bounds__(kBlock) k_presence_sum(const double* __restrict__ sum0, size_t n, unsigned* __restrict__ bits) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    bool on = i < n && __double_as_longlong(sum0[i]) != INT64_MIN;
+    unsigned b = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0 && (i >> 5) < (n + 31) / 32) bits[i >> 5] = b;
+}
+__global__ void __launch_bounds__(kBlock) k_presence_key(const long long* __restrict__ keys, const unsigned long long* __restrict__ cnt,
+                                                         size_t n, unsigned* __restrict__ bits) {
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    bool on = i < n && (i + 1 < n ? keys[i] != kEmptyKey : cnt[i] != 0ULL);      // last entry = the spare slot
+    unsigned b = __ballot_sync(0xffffffffu, on);
+    if ((threadIdx.x & 31) == 0 && (i >> 5) < (n + 31) / 32) bits[i >> 5] = b;
+}
+
 struct EmitParams {
     const unsigned* rowids;
     size_t n;
@@ -719,13 +741,14 @@ struct AggState {
     long long* h_keys = nullptr;
     void* block = nullptr;         // one allocation behind the arrays
     int* err = nullptr;            // device error word (division by zero, table overflow, stale statistics)
+    int presence = 0;              // 0 by count, 1 by sum0 != -0.0 (dense, no counts), 2 by claimed key (hash, no counts)
     bq_ctx* ctx = nullptr;
 
     ~AggState() { dev_free(ctx, block); }
 };
 
 // Runs the fused kernel for `spec`, leaving the aggregate state on the device.
-static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st) {
+static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st, bool need_count) {
     if (spec->row_end < spec->row_begin) throw std::runtime_error("bad row range");
     if (spec->row_end > 0xFFFFFFFFull) throw std::runtime_error("row ids are 32-bit: at most 2^32 rows per scan");
     ScanParams p{};
@@ -882,6 +905,15 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st) {
         k_fill_keys<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(st.h_keys, n, kEmptyKey);
         ctx->launches++;
     }
+    if (spec->n_v == 0) need_count = true;
+    p.need_count = need_count ? 1 : 0;
+    if (!need_count && st.gmode == G_DENSE) {
+        k_fill_keys<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(reinterpret_cast<long long*>(st.sum0), n, INT64_MIN);   // -0.0
+        ctx->launches++;
+        st.presence = 1;
+    } else if (!need_count && st.gmode == G_HASH) {
+        st.presence = 2;
+    }
     p.g_cnt = st.cnt;
     p.g_sum0 = st.sum0;
     p.g_sum1 = st.sum1;
@@ -925,7 +957,9 @@ static bq_rel* emit_state(bq_ctx* ctx, AggState& st, const bq_agg_out* outs, int
         DevBuf bits_buf(ctx, n_words * 4 + 4);
         auto* bits = bits_buf.as<unsigned>();
         size_t blocks = (st.slots + kBlock - 1) / kBlock;
-        k_presence_bits<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(st.cnt, st.slots, bits);
+        if (st.presence == 1) k_presence_sum<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(st.sum0, st.slots, bits);
+        else if (st.presence == 2) k_presence_key<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(st.h_keys, st.cnt, st.slots, bits);
+        else k_presence_bits<<<(unsigned)blocks, kBlock, 0, ctx->stream>>>(st.cnt, st.slots, bits);
         ctx->launches++;
         BQ_CUDA(cudaGetLastError());
         int flags = 0;
@@ -1027,7 +1061,9 @@ extern "C" {
 int bq_scan_aggregate(bq_ctx* ctx, const bq_scan_spec* spec, bq_rel** out) {
     return guarded([&] {
         AggState st;
-        run_scan(ctx, spec, st);
+        bool need_count = false;
+        for (int o = 0; o < spec->n_out; ++o) need_count = need_count || spec->out[o].func != BQ_AGG_SUM;
+        run_scan(ctx, spec, st, need_count);
         *out = emit_state(ctx, st, spec->out, spec->n_out, false);
     });
 }
@@ -1035,7 +1071,7 @@ int bq_scan_aggregate(bq_ctx* ctx, const bq_scan_spec* spec, bq_rel** out) {
 int bq_scan_partial(bq_ctx* ctx, const bq_scan_spec* spec, bq_rel** out) {
     return guarded([&] {
         AggState st;
-        run_scan(ctx, spec, st);
+        run_scan(ctx, spec, st, true);
         *out = emit_state(ctx, st, nullptr, 0, true);
     });
 }

@@ -59,29 +59,31 @@ __global__ void __launch_bounds__(kBlock) k_rank_sort(const unsigned long long* 
 // Each 4096-row tile rank-sorts itself and keeps its first k rows; the survivors (k per tile, in tile order, so
 // ties still resolve by input position) are reduced again until one tile remains.  The reference sorts everything
 // and lets Limit copy a prefix (src/exec/operator.cpp:1115, :579-613).
-constexpr int kTopkTile = 4096;
+constexpr int kTopkTile = 512;       // keys of a tile live in shared memory; each thread ranks two of them
 
 __global__ void __launch_bounds__(kBlock) k_tile_topk(const unsigned long long* __restrict__ keys, int n_keys, size_t n,
                                                       unsigned k, unsigned* __restrict__ cand /* positions, k per tile */) {
-    const size_t tile = blockIdx.y;
+    __shared__ unsigned long long sk[4][kTopkTile];
+    const size_t tile = blockIdx.x;
     const size_t t0 = tile * kTopkTile;
-    const size_t tn = (n - t0) < (size_t)kTopkTile ? (n - t0) : (size_t)kTopkTile;
-    const size_t li = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-    if (li >= tn) return;
-    const size_t i = t0 + li;
-    unsigned long long mine[4];
-    for (int q = 0; q < n_keys; ++q) mine[q] = keys[q * n + i];
-    unsigned rank = 0;
-    for (size_t lj = 0; lj < tn; ++lj) {
-        const size_t j = t0 + lj;
-        int cmp = 0;
-        for (int q = 0; q < n_keys && cmp == 0; ++q) {
-            unsigned long long o = __ldg(keys + q * n + j);
-            cmp = o < mine[q] ? -1 : (o > mine[q] ? 1 : 0);
+    const unsigned tn = static_cast<unsigned>((n - t0) < (size_t)kTopkTile ? (n - t0) : (size_t)kTopkTile);
+    for (int q = 0; q < n_keys; ++q)
+        for (unsigned x = threadIdx.x; x < tn; x += blockDim.x) sk[q][x] = keys[q * n + t0 + x];
+    __syncthreads();
+    for (unsigned x = threadIdx.x; x < tn; x += blockDim.x) {
+        unsigned long long mine[4];
+        for (int q = 0; q < n_keys; ++q) mine[q] = sk[q][x];
+        unsigned rank = 0;
+        for (unsigned j = 0; j < tn; ++j) {
+            int cmp = 0;
+            for (int q = 0; q < n_keys && cmp == 0; ++q) {
+                unsigned long long o = sk[q][j];
+                cmp = o < mine[q] ? -1 : (o > mine[q] ? 1 : 0);
+            }
+            rank += (cmp < 0 || (cmp == 0 && j < x)) ? 1u : 0u;
         }
-        if (cmp < 0 || (cmp == 0 && lj < li)) ++rank;
+        if (rank < k) cand[tile * k + rank] = static_cast<unsigned>(t0 + x);
     }
-    if (rank < k) cand[tile * k + rank] = static_cast<unsigned>(i);
 }
 
 // out[i] = src[idx[i]] (src == nullptr: identity)
@@ -225,7 +227,7 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
                         static_cast<unsigned long long*>(keys.p), n_keys, n, perm);
                     ctx->launches++;
                     BQ_CUDA(cudaGetLastError());
-                } else if (m <= 256 && n <= 65535ull * kTopkTile) {
+                } else if (m <= 256) {
                     // top-k: tiles keep their first m rows until one tile is left
                     const size_t max_cand = ((n + kTopkTile - 1) / kTopkTile) * m;
                     DevBuf keys(ctx, static_cast<size_t>(n_keys) * n * 8), candB(ctx, max_cand * 4), idsA(ctx, max_cand * 4), idsB(ctx, max_cand * 4);
@@ -241,18 +243,16 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
                             k_make_keys<<<grid_for(ctx, cur, 8), kBlock, 0, ctx->stream>>>(c->ptr, c->type, asc[k], ids, cur, kbuf + k * cur);
                             ctx->launches++;
                         }
-                        if (cur <= (size_t)kTopkTile) {
-                            k_rank_sort<<<(unsigned)((cur + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(kbuf, n_keys, cur, cand);
-                            const size_t take = m < cur ? m : cur;
-                            k_compose<<<grid_for(ctx, take, 8), kBlock, 0, ctx->stream>>>(ids, cand, take, perm);
+                        const size_t tiles = (cur + kTopkTile - 1) / kTopkTile;
+                        k_tile_topk<<<(unsigned)tiles, kBlock, 0, ctx->stream>>>(kbuf, n_keys, cur, (unsigned)m, cand);
+                        const size_t last = cur - (tiles - 1) * kTopkTile;
+                        const size_t next = (tiles - 1) * m + (m < last ? m : last);
+                        if (tiles == 1) {        // the last tile's first rows are the answer, already in order
+                            k_compose<<<grid_for(ctx, next, 8), kBlock, 0, ctx->stream>>>(ids, cand, next, perm);
                             ctx->launches += 2;
                             BQ_CUDA(cudaGetLastError());
                             break;
                         }
-                        const size_t tiles = (cur + kTopkTile - 1) / kTopkTile;
-                        k_tile_topk<<<dim3(kTopkTile / kBlock, (unsigned)tiles), kBlock, 0, ctx->stream>>>(kbuf, n_keys, cur, (unsigned)m, cand);
-                        const size_t last = cur - (tiles - 1) * kTopkTile;
-                        const size_t next = (tiles - 1) * m + (m < last ? m : last);
                         k_compose<<<grid_for(ctx, next, 8), kBlock, 0, ctx->stream>>>(ids, cand, next, ids_next);
                         ctx->launches += 2;
                         BQ_CUDA(cudaGetLastError());
