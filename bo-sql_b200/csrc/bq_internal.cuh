@@ -21,6 +21,7 @@ struct DSlot {
     int pad;
 };
 DSlot make_dslot(const bq_slot& s, size_t need_rows, const char* what);
+bool normalise_slot(DSlot& d);     // clamp / drop always-true ranges; true = some range can never pass
 
 #if defined(__CUDACC__)
 // one range: (lo <= k && k <= hi) != neg

@@ -139,20 +139,20 @@ BQ_D void load_quad(const void* ptr, int kind, size_t base, int lane, long long 
 }
 
 // ---- aggregate argument: numeric_binary + datum_as_double ---------------------------------------
-BQ_D double eval_vexpr(const DVExpr& e, long long a, int ka, long long b, int kb, int* err) {
-    if (e.op == BQ_V_A) return as_double(a, ka);
-    if (e.op == BQ_V_B) return as_double(b, kb);
+BQ_D double eval_vexpr(const DVExpr& e, int op, int l_src, int r_src, long long a, int ka, long long b, int kb, int* err) {
+    if (op == BQ_V_A) return as_double(a, ka);
+    if (op == BQ_V_B) return as_double(b, kb);
     const long long imm = e.imm_is_f ? __double_as_longlong(e.imm_f) : e.imm_i;
     const int kimm = e.imm_is_f ? BQ_DOUBLE : BQ_INT64;
     long long l = a, r = b;
     int kl = ka, kr = kb;
-    if (e.l_src == BQ_L_B) { l = b; kl = kb; }
-    else if (e.l_src == BQ_L_IMM) { l = imm; kl = kimm; }
-    if (e.r_src == BQ_R_A) { r = a; kr = ka; }
-    else if (e.r_src == BQ_R_IMM) { r = imm; kr = kimm; }
+    if (l_src == BQ_L_B) { l = b; kl = kb; }
+    else if (l_src == BQ_L_IMM) { l = imm; kl = kimm; }
+    if (r_src == BQ_R_A) { r = a; kr = ka; }
+    else if (r_src == BQ_R_IMM) { r = imm; kr = kimm; }
     if (kl == BQ_DOUBLE || kr == BQ_DOUBLE) {       // src/exec/expression.cpp:34-44
         double x = as_double(l, kl), y = as_double(r, kr);
-        switch (e.op) {
+        switch (op) {
             case BQ_V_MUL: return __dmul_rn(x, y);
             case BQ_V_ADD: return __dadd_rn(x, y);
             case BQ_V_SUB: return __dsub_rn(x, y);
@@ -160,7 +160,7 @@ BQ_D double eval_vexpr(const DVExpr& e, long long a, int ka, long long b, int kb
         }
     }
     long long z = 0;                                // src/exec/expression.cpp:45-56 (wraps like int64_t)
-    switch (e.op) {
+    switch (op) {
         case BQ_V_MUL: z = static_cast<long long>(static_cast<unsigned long long>(l) * static_cast<unsigned long long>(r)); break;
         case BQ_V_ADD: z = static_cast<long long>(static_cast<unsigned long long>(l) + static_cast<unsigned long long>(r)); break;
         case BQ_V_SUB: z = static_cast<long long>(static_cast<unsigned long long>(l) - static_cast<unsigned long long>(r)); break;
@@ -191,9 +191,27 @@ BQ_D unsigned long long group_slot(long long* h_keys, unsigned long long h_mask,
     return h_mask + 1;
 }
 
-template <uint32_t SHAPE, int GMODE>
+// XSHAPE: join kind and aggregate-argument forms known at compile time (specialised kernels).
+//   bits 0-2 join kind (7 = run time) | bits 3-4 number of arguments | per argument 7 bits: op(3) l_src(2) r_src(2)
+constexpr uint32_t kGenericX = 0xFFFFFFFFu;
+constexpr uint32_t xshape(int jmode, int nv, int op0 = 0, int l0 = 0, int r0 = 0, int op1 = 0, int l1 = 0, int r1 = 0) {
+    return static_cast<uint32_t>(jmode) | (static_cast<uint32_t>(nv) << 3) |
+           (static_cast<uint32_t>(op0 | (l0 << 3) | (r0 << 5)) << 5) | (static_cast<uint32_t>(op1 | (l1 << 3) | (r1 << 5)) << 12);
+}
+template <uint32_t XSHAPE>
+struct XShape {
+    static constexpr bool generic = (XSHAPE == kGenericX);
+    BQ_D static int jmode(const ScanParams& p) { return generic ? p.jmode : static_cast<int>(XSHAPE & 7u); }
+    BQ_D static int nv(const ScanParams& p) { return generic ? p.nv : static_cast<int>((XSHAPE >> 3) & 3u); }
+    BQ_D static int op(const ScanParams& p, int i) { return generic ? p.v[i].op : static_cast<int>((XSHAPE >> (5 + 7 * i)) & 7u); }
+    BQ_D static int l_src(const ScanParams& p, int i) { return generic ? p.v[i].l_src : static_cast<int>((XSHAPE >> (8 + 7 * i)) & 3u); }
+    BQ_D static int r_src(const ScanParams& p, int i) { return generic ? p.v[i].r_src : static_cast<int>((XSHAPE >> (10 + 7 * i)) & 3u); }
+};
+
+template <uint32_t SHAPE, uint32_t XSHAPE, int GMODE>
 struct RowSink {
     using Sh = Shape<SHAPE>;
+    using Xs = XShape<XSHAPE>;
     const ScanParams& p;
     double* s_sum0;
     double* s_sum1;
@@ -209,8 +227,8 @@ struct RowSink {
         const int kb = Sh::present(p, S_B) ? Sh::kind(p, S_B) : BQ_INT64;
         v0 = 0.0;
         v1 = 0.0;
-        if (p.nv > 0) v0 = eval_vexpr(p.v[0], a, ka, b, kb, &err);
-        if (p.nv > 1) v1 = eval_vexpr(p.v[1], a, ka, b, kb, &err);
+        if (Xs::nv(p) > 0) v0 = eval_vexpr(p.v[0], Xs::op(p, 0), Xs::l_src(p, 0), Xs::r_src(p, 0), a, ka, b, kb, &err);
+        if (Xs::nv(p) > 1) v1 = eval_vexpr(p.v[1], Xs::op(p, 1), Xs::l_src(p, 1), Xs::r_src(p, 1), a, ka, b, kb, &err);
     }
 
     // one qualifying (probe row, build row) pair
@@ -225,8 +243,8 @@ struct RowSink {
             unsigned long long idx = static_cast<unsigned long long>(key_raw - p.key_min);
             if (idx < p.key_domain) {
                 atomicAdd(s_cnt + idx, 1u);
-                if (p.nv > 0) atomicAdd(s_sum0 + idx, v0);
-                if (p.nv > 1) atomicAdd(s_sum1 + idx, v1);
+                if (Xs::nv(p) > 0) atomicAdd(s_sum0 + idx, v0);
+                if (Xs::nv(p) > 1) atomicAdd(s_sum1 + idx, v1);
             } else {
                 err |= 4;       // key outside the catalog's [min,max]: stale statistics, the host re-plans
             }
@@ -235,13 +253,13 @@ struct RowSink {
             if (idx < p.key_domain) {
                 if (p.need_count) {
                     atomicAdd(p.g_cnt + idx, 1ULL);
-                    if (p.nv > 0) atomicAdd(p.g_sum0 + idx, v0);
+                    if (Xs::nv(p) > 0) atomicAdd(p.g_sum0 + idx, v0);
                 } else {
                     // presence rides on the sum: slots start as -0.0 and v + 0.0 is never -0.0, so a touched slot
                     // can never read back as -0.0 (one atomic per row instead of two)
                     atomicAdd(p.g_sum0 + idx, __dadd_rn(v0, 0.0));
                 }
-                if (p.nv > 1) atomicAdd(p.g_sum1 + idx, v1);
+                if (Xs::nv(p) > 1) atomicAdd(p.g_sum1 + idx, v1);
             } else {
                 err |= 4;
             }
@@ -250,8 +268,8 @@ struct RowSink {
             if (Sh::kind(p, S_KEY) == BQ_DOUBLE && k == INT64_MIN) k = 0;   // -0.0 groups with +0.0
             unsigned long long idx = group_slot(p.h_keys, p.h_mask, p.err, k);
             if (p.need_count || idx > p.h_mask) atomicAdd(p.g_cnt + idx, 1ULL);     // else presence = the claimed key
-            if (p.nv > 0) atomicAdd(p.g_sum0 + idx, v0);
-            if (p.nv > 1) atomicAdd(p.g_sum1 + idx, v1);
+            if (Xs::nv(p) > 0) atomicAdd(p.g_sum0 + idx, v0);
+            if (Xs::nv(p) > 1) atomicAdd(p.g_sum1 + idx, v1);
         }
     }
 
@@ -280,7 +298,7 @@ struct RowSink {
         }
         unsigned long long idx = static_cast<unsigned long long>(jk - p.jk_min);
         if (idx >= p.jk_domain) return false;
-        if (p.jmode == BQ_JOIN_BITMAP) return (__ldg(p.j_bitmap + (idx >> 5)) >> (idx & 31)) & 1u;
+        if (Xs::jmode(p) == BQ_JOIN_BITMAP) return (__ldg(p.j_bitmap + (idx >> 5)) >> (idx & 31)) & 1u;
         unsigned e = __ldg(p.j_direct + idx);
         brow = e - 1;
         return e != 0;
@@ -303,9 +321,9 @@ struct RowSink {
 
     // a row that passed every streamed range (scalar head/tail path and staged flushes)
     BQ_D void row(long long key_raw, long long a, long long b, long long jk) {
-        if (p.jmode == 0) {
+        if (Xs::jmode(p) == 0) {
             add(key_raw, a, b);
-        } else if (p.jmode == BQ_JOIN_HASH) {
+        } else if (Xs::jmode(p) == BQ_JOIN_HASH) {
             probe_hash(key_raw, a, b, jk);
         } else {
             unsigned brow;
@@ -351,9 +369,10 @@ constexpr int kStageCap = 64;     // staged qualifying rows per warp (flushed 32
 // RSHAPE: 2 bits per slot = how many ranges the slot carries (specialised kernels; the generic kernel reads it at run time)
 constexpr uint32_t rshape_bits(int slot, int n_ranges) { return static_cast<uint32_t>(n_ranges) << (2 * slot); }
 
-template <uint32_t SHAPE, uint32_t RSHAPE, int GMODE, bool STAGED>
+template <uint32_t SHAPE, uint32_t RSHAPE, uint32_t XSHAPE, int GMODE, bool STAGED>
 __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_scan(const __grid_constant__ ScanParams p) {
     using Sh = Shape<SHAPE>;
+    using Xs = XShape<XSHAPE>;
     extern __shared__ double smem_dyn[];
     __shared__ double red_sum[kBlock / 32][2];
     __shared__ unsigned long long red_cnt[kBlock / 32];
@@ -382,7 +401,7 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
     if (threadIdx.x == 0) red_err = 0;
     __syncthreads();
 
-    RowSink<SHAPE, GMODE> sink(p, s_sum0, s_sum1, s_cnt);
+    RowSink<SHAPE, XSHAPE, GMODE> sink(p, s_sum0, s_sum1, s_cnt);
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -390,7 +409,7 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
     const size_t warp_global = static_cast<size_t>(blockIdx.x) * (kBlock / 32) + warp;
     // global aggregate without a multi-match probe: branch-free accumulation in registers, no staging
     const bool direct_path = (GMODE == G_NONE) && !STAGED;
-    const bool dense_join = p.jmode == BQ_JOIN_BITMAP || p.jmode == BQ_JOIN_DIRECT;
+    const bool dense_join = Xs::jmode(p) == BQ_JOIN_BITMAP || Xs::jmode(p) == BQ_JOIN_DIRECT;
 
     RangeRegs rr[N_SLOTS];
 #pragma unroll
@@ -407,7 +426,7 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
         __syncwarp();
         if (lane < n) {
             const int e = first + lane;
-            if (p.jmode == BQ_JOIN_HASH) sink.probe_hash(st_key[warp][e], st_a[warp][e], st_b[warp][e], st_x[warp][e]);
+            if (Xs::jmode(p) == BQ_JOIN_HASH) sink.probe_hash(st_key[warp][e], st_a[warp][e], st_b[warp][e], st_x[warp][e]);
             else if (dense_join) sink.build_add(st_key[warp][e], st_a[warp][e], st_b[warp][e], static_cast<unsigned>(st_x[warp][e]));
             else sink.add(st_key[warp][e], st_a[warp][e], st_b[warp][e]);
         }
@@ -470,7 +489,7 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
                         st_key[warp][pos] = kr;
                         st_a[warp][pos] = a;
                         st_b[warp][pos] = b;
-                        st_x[warp][pos] = p.jmode == BQ_JOIN_HASH ? jk : static_cast<long long>(brow[r]);
+                        st_x[warp][pos] = Xs::jmode(p) == BQ_JOIN_HASH ? jk : static_cast<long long>(brow[r]);
                     }
                     staged += __popc(ballot);
                     if (staged >= 32) {
@@ -523,8 +542,8 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
             unsigned c = s_cnt[i];
             if (c) {
                 atomicAdd(p.g_cnt + i, static_cast<unsigned long long>(c));
-                if (p.nv > 0) atomicAdd(p.g_sum0 + i, s_sum0[i]);
-                if (p.nv > 1) atomicAdd(p.g_sum1 + i, s_sum1[i]);
+                if (Xs::nv(p) > 0) atomicAdd(p.g_sum0 + i, s_sum0[i]);
+                if (Xs::nv(p) > 1) atomicAdd(p.g_sum1 + i, s_sum1[i]);
             }
         }
     }
@@ -643,11 +662,16 @@ using ScanKernel = void (*)(const ScanParams);
 struct ShapeEntry {
     uint32_t shape;
     uint32_t rshape;
+    uint32_t xshape;
     int gmode;
     bool staged;
     ScanKernel fn;
 };
-#define BQ_SHAPE(shape, rshape, gmode, staged) {shape, rshape, gmode, staged, k_scan<shape, rshape, gmode, staged>}
+#define BQ_SHAPE(shape, rshape, xs, gmode, staged) {shape, rshape, xs, gmode, staged, k_scan<shape, rshape, xs, gmode, staged>}
+constexpr uint32_t kX_A = xshape(0, 1, BQ_V_A);                                   // SUM(a), no join
+constexpr uint32_t kX_AB = xshape(0, 2, BQ_V_A, 0, 0, BQ_V_B);                    // SUM(a), SUM(b), no join
+constexpr uint32_t kX_Q2 = xshape(BQ_JOIN_BITMAP, 1, BQ_V_MUL, BQ_L_A, BQ_R_B);   // bitmap probe, SUM(a * b)
+constexpr uint32_t kX_J5 = xshape(BQ_JOIN_DIRECT, 1, BQ_V_MUL, BQ_L_A, BQ_R_B);   // direct probe, SUM(a * b.w)
 constexpr uint32_t kR_Q1 = rshape_bits(S_KEY, 1) | rshape_bits(S_P0, 1);     // one (merged) range on the date, one on status
 constexpr uint32_t kR_P0 = rshape_bits(S_P0, 1);                             // filter sweep: one range on the predicate column
 constexpr uint32_t kR_A = rshape_bits(S_A, 1);
@@ -679,24 +703,25 @@ constexpr uint32_t kShapeJ5 = shape_bits(S_A, BQ_DOUBLE, false) | shape_bits(S_B
                               shape_bits(S_JK, BQ_INT64, false);
 
 static const ShapeEntry kShapes[] = {
-    BQ_SHAPE(kShapeQ1, kR_Q1, G_SMEM, true),
-    BQ_SHAPE(kShapeF_I64, kR_P0, G_NONE, false),   BQ_SHAPE(kShapeF_F64, kR_P0, G_NONE, false),
-    BQ_SHAPE(kShapeF_STR, kR_P0, G_NONE, false),   BQ_SHAPE(kShapeF_DATE, kR_P0, G_NONE, false),
-    BQ_SHAPE(kShapeF2_I64, kR_P0, G_NONE, false),  BQ_SHAPE(kShapeF2_F64, kR_P0, G_NONE, false),
-    BQ_SHAPE(kShapeF2_STR, kR_P0, G_NONE, false),  BQ_SHAPE(kShapeF2_DATE, kR_P0, G_NONE, false),
-    BQ_SHAPE(kShapeA_F64, kR_A, G_NONE, false),
-    BQ_SHAPE(kShapeQ2, kR_NONE, G_DENSE, false),   BQ_SHAPE(kShapeQ2, kR_NONE, G_HASH, true),
-    BQ_SHAPE(kShapeQ2S, kR_NONE, G_DENSE, false),  BQ_SHAPE(kShapeQ2S, kR_NONE, G_SMEM, true),
-    BQ_SHAPE(kShapeGB, kR_NONE, G_HASH, true),     BQ_SHAPE(kShapeGB, kR_NONE, G_DENSE, false),
-    BQ_SHAPE(kShapeJ5, kR_NONE, G_NONE, false),
-    // any other slot layout / range layout / a mask column: same source, run-time flags
-    BQ_SHAPE(kGenericShape, 0, G_NONE, false), BQ_SHAPE(kGenericShape, 0, G_NONE, true), BQ_SHAPE(kGenericShape, 0, G_SMEM, true),
-    BQ_SHAPE(kGenericShape, 0, G_DENSE, false), BQ_SHAPE(kGenericShape, 0, G_DENSE, true), BQ_SHAPE(kGenericShape, 0, G_HASH, true),
+    BQ_SHAPE(kShapeQ1, kR_Q1, kX_A, G_SMEM, true),
+    BQ_SHAPE(kShapeF_I64, kR_P0, kX_A, G_NONE, false),    BQ_SHAPE(kShapeF_F64, kR_P0, kX_A, G_NONE, false),
+    BQ_SHAPE(kShapeF_STR, kR_P0, kX_A, G_NONE, false),    BQ_SHAPE(kShapeF_DATE, kR_P0, kX_A, G_NONE, false),
+    BQ_SHAPE(kShapeF2_I64, kR_P0, kX_AB, G_NONE, false),  BQ_SHAPE(kShapeF2_F64, kR_P0, kX_AB, G_NONE, false),
+    BQ_SHAPE(kShapeF2_STR, kR_P0, kX_AB, G_NONE, false),  BQ_SHAPE(kShapeF2_DATE, kR_P0, kX_AB, G_NONE, false),
+    BQ_SHAPE(kShapeA_F64, kR_A, kX_A, G_NONE, false),
+    BQ_SHAPE(kShapeQ2, kR_NONE, kX_Q2, G_DENSE, false),   BQ_SHAPE(kShapeQ2, kR_NONE, kX_Q2, G_HASH, true),
+    BQ_SHAPE(kShapeQ2S, kR_NONE, kX_Q2, G_DENSE, false),  BQ_SHAPE(kShapeQ2S, kR_NONE, kX_Q2, G_SMEM, true),
+    BQ_SHAPE(kShapeGB, kR_NONE, kX_A, G_HASH, true),      BQ_SHAPE(kShapeGB, kR_NONE, kX_A, G_DENSE, false),
+    BQ_SHAPE(kShapeJ5, kR_NONE, kX_J5, G_NONE, false),
+    // any other slot / range / argument layout, join kind or a mask column: same source, run-time flags
+    BQ_SHAPE(kGenericShape, 0, kGenericX, G_NONE, false),  BQ_SHAPE(kGenericShape, 0, kGenericX, G_NONE, true),
+    BQ_SHAPE(kGenericShape, 0, kGenericX, G_SMEM, true),   BQ_SHAPE(kGenericShape, 0, kGenericX, G_DENSE, false),
+    BQ_SHAPE(kGenericShape, 0, kGenericX, G_DENSE, true),  BQ_SHAPE(kGenericShape, 0, kGenericX, G_HASH, true),
 };
 
-static ScanKernel pick_kernel(uint32_t shape, uint32_t rshape, bool has_mask, int gmode, bool staged, bool* specialised) {
+static ScanKernel pick_kernel(uint32_t shape, uint32_t rshape, uint32_t xs, bool has_mask, int gmode, bool staged, bool* specialised) {
     for (const auto& e : kShapes)
-        if (!has_mask && e.shape == shape && e.rshape == rshape && e.gmode == gmode && e.staged == staged) {
+        if (!has_mask && e.shape == shape && e.rshape == rshape && e.xshape == xs && e.gmode == gmode && e.staged == staged) {
             *specialised = true;
             return e.fn;
         }
@@ -706,6 +731,31 @@ static ScanKernel pick_kernel(uint32_t shape, uint32_t rshape, bool has_mask, in
             return e.fn;
         }
     throw std::runtime_error("no scan kernel for group mode");
+}
+
+// Clamp a slot's ranges to its column's domain, drop always-true ranges; returns true when some range can never pass.
+bool normalise_slot(DSlot& d) {
+    bool never = false;
+    if (!d.ptr || d.nr == 0) return false;
+    long long dmin = INT64_MIN, dmax = INT64_MAX;
+    if (d.kind == BQ_STRING) { dmin = 0; dmax = 0xFFFFFFFFLL; }
+    if (d.kind == BQ_DATE32) { dmin = INT32_MIN; dmax = INT32_MAX; }
+    long long lo[2] = {d.lo0, d.lo1}, hi[2] = {d.hi0, d.hi1};
+    int neg[2] = {d.neg0, d.neg1};
+    int kept = 0;
+    for (int i = 0; i < d.nr; ++i) {
+        long long l = lo[i] < dmin ? dmin : lo[i], h = hi[i] > dmax ? dmax : hi[i];
+        const bool empty = l > h, full = (l == dmin && h == dmax);
+        if (!neg[i] ? empty : full) never = true;
+        if (!neg[i] ? full : empty) continue;          // always true
+        if (empty) continue;
+        lo[kept] = l; hi[kept] = h; neg[kept] = neg[i];
+        ++kept;
+    }
+    d.nr = kept;
+    d.lo0 = lo[0]; d.hi0 = hi[0]; d.neg0 = neg[0];
+    d.lo1 = lo[1]; d.hi1 = hi[1]; d.neg1 = neg[1];
+    return never;
 }
 
 DSlot make_dslot(const bq_slot& s, size_t need_rows, const char* what) {
@@ -767,28 +817,7 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st, bool n
     // Ranges reach the kernel clamped to the column's domain and never empty (its unsigned range test needs lo <= hi):
     // an always-true range is dropped, an always-false one empties the whole result without a launch.
     bool never_passes = false;
-    for (int s = 0; s < N_SLOTS; ++s) {
-        DSlot& d = p.s[s];
-        if (!d.ptr || d.nr == 0) continue;
-        long long dmin = INT64_MIN, dmax = INT64_MAX;
-        if (d.kind == BQ_STRING) { dmin = 0; dmax = 0xFFFFFFFFLL; }
-        if (d.kind == BQ_DATE32) { dmin = INT32_MIN; dmax = INT32_MAX; }
-        long long lo[2] = {d.lo0, d.lo1}, hi[2] = {d.hi0, d.hi1};
-        int neg[2] = {d.neg0, d.neg1};
-        int kept = 0;
-        for (int i = 0; i < d.nr; ++i) {
-            long long l = lo[i] < dmin ? dmin : lo[i], h = hi[i] > dmax ? dmax : hi[i];
-            const bool empty = l > h, full = (l == dmin && h == dmax);
-            if (!neg[i] ? empty : full) never_passes = true;
-            if (!neg[i] ? full : empty) continue;          // always true
-            if (empty) continue;
-            lo[kept] = l; hi[kept] = h; neg[kept] = neg[i];
-            ++kept;
-        }
-        d.nr = kept;
-        d.lo0 = lo[0]; d.hi0 = hi[0]; d.neg0 = neg[0];
-        d.lo1 = lo[1]; d.hi1 = hi[1]; d.neg1 = neg[1];
-    }
+    for (int s = 0; s < N_SLOTS; ++s) never_passes = normalise_slot(p.s[s]) || never_passes;
     if (spec->n_v < 0 || spec->n_v > 2) throw std::runtime_error("at most two aggregate arguments");
     p.nv = spec->n_v;
     for (int i = 0; i < spec->n_v; ++i) {
@@ -878,7 +907,10 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st, bool n
     bool specialised = false;
     uint32_t rshape = 0;
     for (int s = 0; s < N_SLOTS; ++s) rshape |= rshape_bits(s, p.s[s].nr);
-    ScanKernel fn = pick_kernel(shape, rshape, p.mask != nullptr, st.gmode, staged, &specialised);
+    uint32_t xs = xshape(p.jmode, p.nv, p.nv > 0 ? p.v[0].op : 0, p.nv > 0 && p.v[0].op >= BQ_V_MUL ? p.v[0].l_src : 0,
+                         p.nv > 0 && p.v[0].op >= BQ_V_MUL ? p.v[0].r_src : 0, p.nv > 1 ? p.v[1].op : 0,
+                         p.nv > 1 && p.v[1].op >= BQ_V_MUL ? p.v[1].l_src : 0, p.nv > 1 && p.v[1].op >= BQ_V_MUL ? p.v[1].r_src : 0);
+    ScanKernel fn = pick_kernel(shape, rshape, xs, p.mask != nullptr, st.gmode, staged, &specialised);
     size_t rows = spec->row_end - spec->row_begin;
     if (smem > 0) BQ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     int blocks_per_sm = 4;

@@ -11,5 +11,5 @@ CMD="python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu"
 $CMD > gpurun_out/plain_${R}.log 2>&1 && \
   ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${R}.csv $CMD > gpurun_out/ncu_launch_${R}.log 2>&1
 $CMD > gpurun_out/plain2_${R}.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k "regex:k_scan<" -s 4 -c 3 -o gpurun_out/prof_${R}_scan $CMD > gpurun_out/ncu_full_${R}.log 2>&1
+  ncu --set full --clock-control none --import-source on -k "regex:^k_scan$" -s 4 -c 3 -o gpurun_out/prof_${R}_scan $CMD > gpurun_out/ncu_full_${R}.log 2>&1
 tail -3 gpurun_out/pytest_${R}.log
