@@ -45,6 +45,16 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version banner) also write to fd 1, so the real
+# stdout is set aside for the result line and everything else is sent to stderr.
+_RESULT_FD = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_RESULT_FD, (json.dumps(obj) + "\n").encode())
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -117,7 +127,7 @@ def run_reference(args):
         return
     from oracle import datagen, ref_engine
     if not ref_engine.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libbosql_ref.so was not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref/libbosql_ref.so was not built (needs /root/reference at build time)"})
         return
     sample = int(min(args.rows, args.ref_rows))
     schema = datagen.orders_schema(sample)
@@ -145,7 +155,7 @@ def run_reference(args):
                          "host_cores_available": os.cpu_count()},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -261,12 +271,13 @@ def run_ours(args):
             with torch.cuda.stream(stream):
                 mine = [torch.as_tensor(CudaArray(part.col(c).ptr, r, ts), device="cuda") if r else
                         torch.empty(0, dtype=dt, device="cuda") for c, ts, dt, _ in layout]
-                gathered = DIST.gather_partials(mine, D)           # one NCCL all-gather per state column
-            merged_in = ctx.rel_create([ctx.wrap(bt, g.data_ptr(), g.numel()) for g, (_, _, _, bt) in zip(gathered, layout)])
-            fin = ctx.agg_finish([merged_in], True, bq.DATE32, outs)     # equal keys combined in rank order
+                g, views = DIST.gather_partials_packed(mine, D)    # ONE NCCL all-gather for the whole partial state
+            parts = [ctx.rel_create([ctx.wrap(bt, v.data_ptr(), v.numel()) for v, (_, _, _, bt) in zip(rank_views, layout)])
+                     for rank_views in views]
+            fin = ctx.agg_finish(parts, True, bq.DATE32, outs)     # equal keys combined, parts folded in rank order
             srt = ctx.rel_sort(fin, [0], [1])
             result["q1_cols"] = srt.to_numpy()
-            result["keep"] = gathered
+            result["keep"] = g
 
     ms_step, launches, kern, clocks = timed(q1_step, args.steps, max(3, args.warmup), profile=True)
     total_rows = rows * world
@@ -392,7 +403,7 @@ def run_ours(args):
             out["q2"] = {"error": str(e)[:300]}
 
     if rank == 0:
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -41,3 +41,32 @@ def or_reduce_bitmap(words: torch.Tensor, group=None):
     NCCL's all-reduce (no OR operator) do it in place."""
     dist.all_reduce(words, op=dist.ReduceOp.SUM, group=group)
     return words
+
+
+def gather_partials_packed(cols, capacity: int, group=None):
+    """Same exchange in ONE collective: the columns are packed (widest element first, so every column stays naturally
+    aligned) into one byte buffer of capacity rows, all-gathered once, and handed back as per-rank views
+    [rank][column] (no copies).  Padding rows are zero (count 0 = no group)."""
+    world = dist.get_world_size(group)
+    order = sorted(range(len(cols)), key=lambda i: -cols[i].element_size())
+    offs, off = {}, 0
+    for i in order:
+        offs[i] = off
+        off += cols[i].element_size() * capacity
+    block = (off + 15) // 16 * 16
+    dev = cols[0].device
+    buf = torch.zeros(block, dtype=torch.uint8, device=dev)
+    for i, c in enumerate(cols):
+        r = c.numel()
+        if r > capacity:
+            raise ValueError(f"partial state has {r} rows, capacity is {capacity}")
+        if r:
+            buf[offs[i]:offs[i] + r * c.element_size()].copy_(c.contiguous().view(torch.uint8))
+    g = torch.empty(block * world, dtype=torch.uint8, device=dev)
+    if g.is_cuda:
+        dist.all_gather_into_tensor(g, buf, group=group)
+    else:
+        _gather_cpu(g, buf, world, group)
+    views = [[g[rk * block + offs[i]: rk * block + offs[i] + capacity * cols[i].element_size()].view(cols[i].dtype)
+              for i in range(len(cols))] for rk in range(world)]
+    return g, views

@@ -64,6 +64,11 @@ def _worker(rank, world, port, n, q):
         mine = slice(rank * cap, rank * cap + len(part[0]))
         assert np.array_equal(g[0][mine], part[0]) and np.array_equal(g[1][mine], part[1])
         keys, cnt, s0 = _merge(g[0], g[1], g[2])
+        # the packed variant (one collective) must deliver the same rows, as per-rank views
+        _buf, views = D.gather_partials_packed([torch.from_numpy(np.ascontiguousarray(c)) for c in part], cap)
+        for rk in range(world):
+            for ci in range(4):
+                assert np.array_equal(views[rk][ci].numpy(), g[ci][rk * cap:(rk + 1) * cap])
         # bitmap union: disjoint bits from each rank
         words = torch.zeros(64, dtype=torch.int32)
         words[rank::world] = 1 << rank
