@@ -75,7 +75,8 @@ class ScanSpec(C.Structure):
                 ("row_begin", C.c_size_t), ("row_end", C.c_size_t), ("mask", C.c_void_p),
                 ("n_v", C.c_int32), ("v", VExpr * 2), ("group_mode", C.c_int32),
                 ("key_min", C.c_int64), ("key_max", C.c_int64), ("ndv_hint", C.c_size_t),
-                ("join", C.c_void_p), ("n_out", C.c_int32), ("out", AggOut * 8)]
+                ("join", C.c_void_p), ("n_out", C.c_int32), ("out", AggOut * 8),
+                ("hash_part_log2", C.c_int32), ("hash_part_shift", C.c_int32)]
 
 
 class SelectSpec(C.Structure):
@@ -142,6 +143,8 @@ def kernel_lib():
         "bq_scan_aggregate": ([vp, P(ScanSpec), P(vp)], C.c_int),
         "bq_scan_partial": ([vp, P(ScanSpec), P(vp)], C.c_int),
         "bq_agg_finish": ([vp, P(vp), C.c_int, C.c_int, C.c_int, P(AggOut), C.c_int, P(vp)], C.c_int),
+        "bq_partition": ([vp, vp, P(vp), C.c_int, sz, sz, C.c_int, C.c_int, P(vp), P(vp), P(vp)], C.c_int),
+        "bq_key_hash": ([i64], C.c_uint64),
         "bq_select": ([vp, P(SelectSpec), P(vp)], C.c_int),
         "bq_gather": ([vp, vp, vp, P(vp)], C.c_int),
         "bq_slice": ([vp, vp, sz, sz, P(vp)], C.c_int),
@@ -403,6 +406,16 @@ class Context:
         h = C.c_void_p()
         _check(self.L.bq_select(self.h, C.byref(s), C.byref(h)))
         return Column(self, h)
+
+    def partition(self, key, payload=(), log2_parts=8, hash_shift=None, row_begin=0, row_end=None):
+        """Rows reordered by partition = (hash(key) >> hash_shift) & (2^log2_parts - 1).  Returns (key, [payload], offsets)."""
+        hash_shift = 64 - log2_parts if hash_shift is None else hash_shift
+        pay = (C.c_void_p * max(1, len(payload)))(*[c.h for c in payload])
+        ok, off = C.c_void_p(), C.c_void_p()
+        op = (C.c_void_p * 2)()
+        _check(self.L.bq_partition(self.h, key.h, pay, len(payload), row_begin, key.n if row_end is None else row_end,
+                                   log2_parts, hash_shift, C.byref(ok), op, C.byref(off)))
+        return Column(self, ok), [Column(self, C.c_void_p(op[i])) for i in range(len(payload))], Column(self, off)
 
     def gather(self, col, rowids) -> Column:
         h = C.c_void_p()

@@ -308,6 +308,8 @@ int bq_col_minmax(bq_ctx* ctx, bq_col* col, int64_t* min_key, int64_t* max_key) 
     });
 }
 
+uint64_t bq_key_hash(int64_t key) { return key_hash(static_cast<uint64_t>(key)); }
+
 int64_t bq_f64_key(double v) {
     uint64_t b;
     std::memcpy(&b, &v, 8);

@@ -59,6 +59,7 @@ struct ScanParams {
     unsigned long long* g_cnt;
     long long* h_keys;                 // G_HASH: capacity+1 entries
     unsigned long long h_mask;
+    int h_part_log2, h_part_shift;     // > 0: partition-major table for rows ordered by bq_partition
     // join
     int jmode;
     long long jk_min;
@@ -173,6 +174,30 @@ BQ_D double eval_vexpr(const DVExpr& e, int op, int l_src, int r_src, long long 
 }
 
 // ---- group table claim (open addressing, linear probing) ----------------------------------------
+// Partition-major variant: the table is split into 2^part_log2 regions; a key probes only inside the region of its
+// partition, so rows ordered by partition touch one region (capacity / P slots) at a time.
+BQ_D unsigned long long group_slot_part(long long* h_keys, unsigned long long h_mask, int part_log2, int part_shift, int* err,
+                                        long long key) {
+    if (key == kEmptyKey) return h_mask + 1;
+    const unsigned long long hv = key_hash(static_cast<uint64_t>(key));
+    const unsigned long long sub_mask = h_mask >> part_log2;
+    const unsigned long long base = ((hv >> part_shift) & ((1ULL << part_log2) - 1)) * (sub_mask + 1);
+    unsigned long long h = hv & sub_mask;
+    for (unsigned long long probes = 0; probes <= sub_mask; ++probes) {
+        long long cur = *reinterpret_cast<volatile long long*>(h_keys + base + h);
+        if (cur == key) return base + h;
+        if (cur == kEmptyKey) {
+            long long prev = static_cast<long long>(atomicCAS(reinterpret_cast<unsigned long long*>(h_keys + base + h),
+                                                              static_cast<unsigned long long>(kEmptyKey),
+                                                              static_cast<unsigned long long>(key)));
+            if (prev == kEmptyKey || prev == key) return base + h;
+        }
+        h = (h + 1) & sub_mask;
+    }
+    *err = 2;
+    return h_mask + 1;
+}
+
 BQ_D unsigned long long group_slot(long long* h_keys, unsigned long long h_mask, int* err, long long key) {
     if (key == kEmptyKey) return h_mask + 1;        // spare slot for the one key that equals the marker
     unsigned long long h = key_hash(static_cast<uint64_t>(key)) & h_mask;
@@ -266,7 +291,8 @@ struct RowSink {
         } else {
             long long k = key_raw;
             if (Sh::kind(p, S_KEY) == BQ_DOUBLE && k == INT64_MIN) k = 0;   // -0.0 groups with +0.0
-            unsigned long long idx = group_slot(p.h_keys, p.h_mask, p.err, k);
+            unsigned long long idx = p.h_part_log2 > 0 ? group_slot_part(p.h_keys, p.h_mask, p.h_part_log2, p.h_part_shift, p.err, k)
+                                                       : group_slot(p.h_keys, p.h_mask, p.err, k);
             if (p.need_count || idx > p.h_mask) atomicAdd(p.g_cnt + idx, 1ULL);     // else presence = the claimed key
             if (Xs::nv(p) > 0) atomicAdd(p.g_sum0 + idx, v0);
             if (Xs::nv(p) > 1) atomicAdd(p.g_sum1 + idx, v1);
@@ -888,6 +914,13 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st, bool n
             st.gmode = G_HASH;
             size_t hint = spec->ndv_hint ? spec->ndv_hint : (spec->row_end - spec->row_begin);
             size_t cap = next_pow2(hint * 2 < 1024 ? 1024 : hint * 2);
+            if (spec->hash_part_log2 > 0) {
+                if (spec->hash_part_log2 > 10) throw std::runtime_error("at most 1024 hash partitions");
+                // every region gets 2x its expected share; a skewed partition raises "group table overflow"
+                while ((cap >> spec->hash_part_log2) < 1024) cap <<= 1;
+                p.h_part_log2 = spec->hash_part_log2;
+                p.h_part_shift = spec->hash_part_shift;
+            }
             st.slots = cap + 1;
             p.h_mask = cap - 1;
         }

@@ -70,3 +70,61 @@ def gather_partials_packed(cols, capacity: int, group=None):
     views = [[g[rk * block + offs[i]: rk * block + offs[i] + capacity * cols[i].element_size()].view(cols[i].dtype)
               for i in range(len(cols))] for rk in range(world)]
     return g, views
+
+
+# ---- key-hash shuffle: partition on the device, exchange with one all-to-all per column -----------------------------
+class _CudaArray:
+    """__cuda_array_interface__ over a raw device pointer, so torch can view a bq column without copying."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+_TYPESTR = {0: ("<i8", torch.int64), 1: ("<f8", torch.float64), 2: ("<i4", torch.int32), 3: ("<i4", torch.int32)}
+SHUFFLE_SHIFT = 40      # ranks are chosen by hash bits [40, 40 + log2(world)): disjoint from the L2-partition bits (top)
+                        # and from the slot bits (bottom) used by the local tables
+
+
+def as_tensor(col):
+    """A torch view of a device-resident bq column (STRING / DATE32 as int32 bit patterns)."""
+    ts, dt = _TYPESTR[col.type]
+    n = col.n
+    if n == 0:
+        return torch.empty(0, dtype=dt, device="cuda")
+    return torch.as_tensor(_CudaArray(col.ptr, n, ts), device="cuda")
+
+
+def exchange_counts(send_counts, group=None):
+    """send_counts[r] = rows this rank sends to rank r  ->  recv_counts[r] = rows rank r sends to this rank."""
+    recv = torch.empty_like(send_counts)
+    if send_counts.is_cuda:
+        dist.all_to_all_single(recv, send_counts, group=group)
+    else:                                   # gloo has no all_to_all_single on every build: gather the matrix instead
+        world = dist.get_world_size(group)
+        rows = [torch.empty_like(send_counts) for _ in range(world)]
+        dist.all_gather(rows, send_counts, group=group)
+        recv = torch.stack(rows)[:, dist.get_rank(group)].contiguous()
+    return recv
+
+
+def shuffle_by_key(ctx, key, payload, group=None):
+    """Hash-partition (key, payload...) on the device into one run per rank (bq_partition), then exchange the runs with one
+    NCCL all-to-all per column.  Returns the received columns as torch tensors (rows whose key hashes to this rank) and the
+    per-peer receive counts.  world must be a power of two."""
+    world = dist.get_world_size(group)
+    log2w = world.bit_length() - 1
+    if (1 << log2w) != world:
+        raise ValueError("shuffle_by_key needs a power-of-two world size")
+    pk, pp, off = ctx.partition(key, payload, log2_parts=log2w, hash_shift=SHUFFLE_SHIFT)
+    offs = torch.from_numpy(off.to_numpy()).to(torch.int64)
+    send = (offs[1:] - offs[:-1]).cuda()
+    recv = exchange_counts(send, group)
+    send_l, recv_l = send.tolist(), recv.tolist()
+    out = []
+    for col in [pk] + list(pp):
+        src = as_tensor(col)
+        dst = torch.empty(sum(recv_l), dtype=src.dtype, device="cuda")
+        dist.all_to_all_single(dst, src, output_split_sizes=recv_l, input_split_sizes=send_l, group=group)
+        out.append(dst)
+    torch.cuda.current_stream().synchronize()
+    return out, recv_l

@@ -188,6 +188,11 @@ typedef struct bq_scan_spec {
     const bq_join* join;     /* optional: inner-join probe on jkey                          */
     int32_t n_out;
     bq_agg_out out[BQ_MAX_AGG_OUT];
+    /* HASH grouping over rows that bq_partition has ordered by partition = (hash(key) >> hash_part_shift) & (2^log2 - 1):
+     * the table is laid out partition-major, so the slots a partition touches stay L2-resident while its rows stream by.
+     * 0 = rows are in no particular order (one table-wide probe sequence). */
+    int32_t hash_part_log2;
+    int32_t hash_part_shift;
 } bq_scan_spec;
 /* Result relation: [key] then one column per out[] — HashAggregate's emit layout (src/exec/operator.cpp:1016-1062).
  * Rows = groups that received at least one row (none at all for a global aggregate over zero rows, :990-993).
@@ -245,6 +250,16 @@ void* bq_join_bitmap_ptr(const bq_join* j, size_t* n_words);
  * order, matches of one probe row in build insertion order. `probe_rowids` (optional) restricts/ordering the probe rows. */
 int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const bq_col* probe_rowids,
                   size_t row_begin, size_t row_end, bq_col** out_probe_rows, bq_col** out_build_rows);
+
+/* ---- hash partitioning: the exchange step (no counterpart in the single-process reference) -----------------------
+ * Reorders rows [row_begin,row_end) of key and up to two payload columns so that rows of one partition
+ * ((hash(key) >> hash_shift) & (2^log2_parts - 1)) are contiguous; out_offsets is an INT64 column of 2^log2_parts + 1 row
+ * offsets.  Used (a) before a high-cardinality GROUP BY / join so each partition's table fits in L2, and (b) to fill
+ * the per-peer send buffers of the multi-GPU all-to-all (2^log2_parts = number of ranks). */
+int bq_partition(bq_ctx* ctx, const bq_col* key, const bq_col* const* payload, int n_payload, size_t row_begin, size_t row_end,
+                 int log2_parts, int hash_shift, bq_col** out_key, bq_col** out_payload, bq_col** out_offsets);
+/* the hash all tables and partitions use (so a caller can predict a key's partition) */
+uint64_t bq_key_hash(int64_t key);
 
 /* ---- OrderBy / Limit (src/exec/operator.cpp:1097-1151, 561-620) ---------------------------------------
  * Stable LSD radix sort of the relation by up to 4 key columns (asc/desc each); limit >= 0 keeps the first

@@ -73,6 +73,10 @@ def _worker(rank, world, port, n, q):
         words = torch.zeros(64, dtype=torch.int32)
         words[rank::world] = 1 << rank
         D.or_reduce_bitmap(words)
+        # the count exchange of the key-hash shuffle: rank r tells every peer how many rows it will send
+        send = torch.tensor([10 * rank + p for p in range(world)], dtype=torch.int64)
+        recv = D.exchange_counts(send)
+        assert recv.tolist() == [10 * p + rank for p in range(world)]
         q.put((rank, keys, cnt, s0, words.numpy()))
     finally:
         dist.destroy_process_group()

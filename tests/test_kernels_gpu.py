@@ -453,3 +453,70 @@ def test_partial_merge(bq, ctx):
         parts.append(ctx.scan_aggregate(sp, partial=True))
     got = ctx.agg_finish(parts, True, DATE32, [bq.AggOut(func=bq.AGG_SUM, v=0)]).to_numpy()
     assert_same_rows(got, want, what="merged partials")
+
+
+# ---- hash partitioning (the exchange step) and the partition-major group table ----------------------------------
+def _key_hash_np(k):
+    """key_hash of bq_common.cuh (murmur3 finaliser), vectorised."""
+    x = k.astype(np.int64).view(np.uint64).copy()
+    with np.errstate(over="ignore"):
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xFF51AFD7ED558CCD)
+        x ^= x >> np.uint64(33)
+        x *= np.uint64(0xC4CEB9FE1A85EC53)
+        x ^= x >> np.uint64(33)
+    return x
+
+
+@pytest.mark.parametrize("n,log2p", [(0, 3), (1, 2), (2047, 4), (2049, 8), (300_001, 8), (1_000_003, 10), (70_000, 1)])
+def test_partition(bq, ctx, n, log2p):
+    rng = np.random.default_rng(n + log2p)
+    k = rng.integers(-10**12, 10**12, size=n).astype(np.int64)
+    v = rng.normal(size=n)
+    w = rng.integers(0, 2**32 - 1, size=n, dtype=np.uint64).astype(np.uint32)
+    kc, vc, wc = ctx.upload(INT64, k), ctx.upload(DOUBLE, v), ctx.upload(STRING, w)
+    ko, (vo, wo), off = ctx.partition(kc, [vc, wc], log2_parts=log2p)
+    P = 1 << log2p
+    offs = off.to_numpy()
+    assert len(offs) == P + 1 and offs[0] == 0 and offs[-1] == n and np.all(np.diff(offs) >= 0)
+    gk, gv, gw = ko.to_numpy(), vo.to_numpy(), wo.to_numpy()
+    # the same rows, each in the partition its key hashes to
+    a = np.lexsort((w, v, k))
+    b = np.lexsort((gw, gv, gk))
+    assert np.array_equal(k[a], gk[b]) and np.array_equal(v[a], gv[b]) and np.array_equal(w[a], gw[b])
+    if n:
+        for x in k[:5].tolist():
+            assert int(_key_hash_np(np.array([x]))[0]) == bq.kernel_lib().bq_key_hash(x)
+        part = (_key_hash_np(gk) >> np.uint64(64 - log2p)).astype(np.int64) & (P - 1)
+        want = np.repeat(np.arange(P), np.diff(offs))
+        assert np.array_equal(part, want)
+
+
+def test_group_by_over_partitioned_rows(bq, ctx):
+    """High-cardinality GROUP BY the L2-friendly way: partition by hash, then the partition-major hash table."""
+    n, ids = 1_200_007, 150_000
+    rng = np.random.default_rng(44)
+    k = (rng.integers(0, ids, size=n) * 7919 - 10**9).astype(np.int64)
+    v = rng.integers(1, 1000, size=n).astype(np.float64) / 8.0
+    kc, vc = ctx.upload(INT64, k), ctx.upload(DOUBLE, v)
+    log2p = 6
+    ko, (vo,), _off = ctx.partition(kc, [vc], log2_parts=log2p)
+    s = bq.ScanSpec()
+    s.key = bq.make_slot(ko)
+    s.a = bq.make_slot(vo)
+    s.row_begin, s.row_end = 0, n
+    s.n_v = 1
+    s.v[0] = bq.VExpr(op=bq.V_A)
+    s.group_mode = bq.GROUP_HASH
+    s.ndv_hint = ids
+    s.hash_part_log2, s.hash_part_shift = log2p, 64 - log2p
+    s.n_out = 3
+    s.out[0] = bq.AggOut(func=bq.AGG_COUNT)
+    s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
+    s.out[2] = bq.AggOut(func=bq.AGG_AVG, v=0)
+    got = ctx.scan_aggregate(s).to_numpy()
+    uk, inv = np.unique(k, return_inverse=True)
+    cnt, sm = np.bincount(inv), np.bincount(inv, weights=v)
+    o = np.argsort(got[0])
+    assert np.array_equal(got[0][o], uk) and np.array_equal(got[1][o], cnt) and np.array_equal(got[2][o], sm)
+    assert np.array_equal(got[3][o], sm / cnt)
