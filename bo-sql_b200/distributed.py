@@ -81,6 +81,7 @@ class _CudaArray:
 
 
 _TYPESTR = {0: ("<i8", torch.int64), 1: ("<f8", torch.float64), 2: ("<i4", torch.int32), 3: ("<i4", torch.int32)}
+_TIMES = {}
 SHUFFLE_SHIFT = 40      # ranks are chosen by hash bits [40, 40 + log2(world)): disjoint from the L2-partition bits (top)
                         # and from the slot bits (bottom) used by the local tables
 
@@ -115,8 +116,11 @@ def shuffle_by_key(ctx, key, payload, group=None):
     log2w = world.bit_length() - 1
     if (1 << log2w) != world:
         raise ValueError("shuffle_by_key needs a power-of-two world size")
+    import time as _t
+    _t0 = _t.perf_counter()
     pk, pp, off = ctx.partition(key, payload, log2_parts=log2w, hash_shift=SHUFFLE_SHIFT)
     offs = torch.from_numpy(off.to_numpy()).to(torch.int64)
+    _TIMES["partition"] = _TIMES.get("partition", 0.0) + (_t.perf_counter() - _t0) * 1e3
     send = (offs[1:] - offs[:-1]).cuda()
     recv = exchange_counts(send, group)
     send_l, recv_l = send.tolist(), recv.tolist()

@@ -578,6 +578,29 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             }
         };
         choose_group(false);
+        // High-cardinality GROUP BY: when the hash table would be far larger than L2, order the rows by hash partition
+        // first (bq_partition) so each partition's table region is L2-resident while its rows stream by.  The reference
+        // updates one unordered_map row by row (src/exec/operator.cpp:988-1005); here it is two streaming passes.
+        std::vector<DevColPtr> partitioned;      // keeps the reordered columns alive through the scan
+        if (s.group_mode == BQ_GROUP_HASH && !p.joined && probe_conj.empty() && !s.mask && p.rows >= (1u << 22) &&
+            static_cast<uint64_t>(s.ndv_hint) * 32 > (96ull << 20) && p.cols[key_col].type != TypeId::DOUBLE) {
+            int log2p = 4;
+            while (log2p < 10 && ((static_cast<uint64_t>(s.ndv_hint) * 64) >> log2p) > (32ull << 20)) ++log2p;
+            const bq_col* pay[2];
+            int n_pay = 0;
+            if (ps.col_a >= 0) pay[n_pay++] = p.cols[ps.col_a].dev->h;
+            if (ps.col_b >= 0) pay[n_pay++] = p.cols[ps.col_b].dev->h;
+            bq_col *ok = nullptr, *off = nullptr, *op[2] = {nullptr, nullptr};
+            check(bq_partition(ctx, p.cols[key_col].dev->h, pay, n_pay, 0, p.rows, log2p, 64 - log2p, &ok, op, &off));
+            partitioned.push_back(adopt(ok));
+            partitioned.push_back(adopt(off));
+            s.key.col = ok;
+            int k = 0;
+            if (ps.col_a >= 0) { partitioned.push_back(adopt(op[k])); s.a.col = op[k++]; }
+            if (ps.col_b >= 0) { partitioned.push_back(adopt(op[k])); s.b.col = op[k++]; }
+            s.hash_part_log2 = log2p;
+            s.hash_part_shift = 64 - log2p;
+        }
         bq_rel* rel = nullptr;
         int rc = bq_scan_aggregate(ctx, &s, &rel);
         if (rc && std::strstr(bq_last_error(), "stale statistics")) {

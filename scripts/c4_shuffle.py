@@ -48,11 +48,21 @@ def main():
         log2w = world.bit_length() - 1
         LOG2P = 8
 
+        phases = {}
+
+        def mark(name, t0):
+            torch.cuda.synchronize()
+            phases[name] = phases.get(name, 0.0) + (time.perf_counter() - t0) * 1e3
+            return time.perf_counter()
+
         def step():
+            t0 = time.perf_counter()
             (rk, rv), recv = D.shuffle_by_key(ctx, k, [v])
+            t0 = mark("shuffle (partition + all-to-all)", t0)
             m = rk.numel()
             kc, vc = ctx.wrap(bq.INT64, rk.data_ptr(), m), ctx.wrap(bq.DOUBLE, rv.data_ptr(), m)
             pk, (pv,), _off = ctx.partition(kc, [vc], log2_parts=LOG2P)
+            t0 = mark("local partition", t0)
             s = bq.ScanSpec()
             s.key = bq.make_slot(pk)
             s.a = bq.make_slot(pv)
@@ -67,6 +77,7 @@ def main():
             s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
             s.out[2] = bq.AggOut(func=bq.AGG_AVG, v=0)
             rel = ctx.scan_aggregate(s)
+            mark("aggregate + emit", t0)
             return rel, m, (rk, rv, pk, pv)
 
         rel, m, keep = step()
@@ -96,6 +107,7 @@ def main():
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        phases.clear()
         e0.record(stream)
         for _ in range(a.steps):
             r_, m_, keep_ = step()
@@ -108,7 +120,8 @@ def main():
     if rank == 0:
         out = {"workload": "GROUP BY high-cardinality key, key-hash shuffle (configuration 4)", "n_gpus": world, "rows_per_gpu": n,
                "distinct_keys": int(tot[1]), "ms_per_step": float(ms), "rows_per_sec": n * world / (float(ms) * 1e-3),
-               "nvlink_bytes_out_per_gpu": 16 * n * (world - 1) // world, "checked": bool(a.check)}
+               "nvlink_bytes_out_per_gpu": 16 * n * (world - 1) // world, "checked": bool(a.check),
+               "phase_ms_rank0": {k_: v_ / a.steps for k_, v_ in phases.items()}, "shuffle_partition_ms_total": D._TIMES}
         print(json.dumps(out))
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         with open(os.path.join(ROOT, "gpurun_out", f"c4_shuffle_n{world}.json"), "w") as f:

@@ -178,3 +178,23 @@ def test_high_cardinality_group_by(bq, ctx):
     uk, inv = np.unique(kk, return_inverse=True)
     o = np.argsort(g[0])
     assert np.array_equal(g[0][o], uk) and np.array_equal(g[1][o], np.bincount(inv)) and np.array_equal(g[2][o], np.bincount(inv, weights=vv))
+
+
+def test_sql_high_cardinality_group_by_takes_the_partitioned_path(bq, ctx):
+    """Through the operator layer: catalog NDV says the table will not fit in L2, so the planner partitions first.
+    The answer must equal the unpartitioned kernel's, bit for bit (dyadic values)."""
+    n, ids = 8_000_003, 4_000_000
+    k = ctx.alloc(INT64, n).generate(dist=bq.GEN_HASHED, seed=SEED, stream=0, lo=0, hi=ids - 1, modulus=1 << 61)
+    v = ctx.alloc(DOUBLE, n).generate(dist=bq.GEN_UNIFORM_DIV, seed=SEED, stream=1, lo=1, hi=6400, div=64.0)
+    ctx.sync()
+    eng = bq.Engine()
+    eng.add_table("t", [("k", INT64, k), ("v", DOUBLE, v)], stats={"k": (0, (1 << 61) - 1, ids)})
+    before = bq.wrap_context(bq.exec_lib().bqx_context()).launches
+    r = eng.query("SELECT k, COUNT(*), SUM(v), AVG(v) FROM t GROUP BY k")
+    assert r.names == ["k", "COUNT(*)", "SUM(v)", "AVG(v)"]
+    want = agg(bq, ctx, n, key=k, group=bq.GROUP_HASH, ndv=ids, a=v, vexprs=[bq.VExpr(op=bq.V_A)],
+               outs=[bq.AggOut(func=bq.AGG_COUNT), bq.AggOut(func=bq.AGG_SUM, v=0), bq.AggOut(func=bq.AGG_AVG, v=0)])
+    a, b = np.argsort(r.cols[0]), np.argsort(want[0])
+    for g, w in zip(r.cols, want):
+        assert np.array_equal(g[a], w[b])
+    assert int(r.cols[1].sum()) == n
