@@ -44,6 +44,12 @@ def exec_lib():
         "bqx_table_add_column": ([vp, cp, C.c_int, vp, sz], C.c_int),
         "bqx_table_add_borrowed_column": ([vp, cp, C.c_int, vp, sz], C.c_int),
         "bqx_catalog_evict_device": ([vp, cp], C.c_int),
+        "bqx_catalog_load_csv": ([vp, cp, cp], C.c_int),
+        "bqx_catalog_table_info": ([vp, cp, P(sz), P(sz)], C.c_int),
+        "bqx_catalog_column_info": ([vp, cp, sz, P(cp), P(C.c_int), P(vp), P(C.c_int64), P(C.c_int64), P(C.c_double),
+                                    P(C.c_double), P(sz)], C.c_int),
+        "bqx_catalog_dict_size": ([vp, cp], sz),
+        "bqx_catalog_dict_get": ([vp, cp, C.c_uint32], cp),
         "bqx_table_add_device_column": ([vp, cp, vp, C.c_int], C.c_int),
         "bqx_table_set_stats": ([vp, cp, C.c_int64, C.c_int64, C.c_double, C.c_double, sz], C.c_int),
         "bqx_catalog_register": ([vp, vp], C.c_int),
@@ -226,6 +232,34 @@ class Engine:
             _check(self.L.bqx_table_set_stats(t, cname.encode(), 0 if is_f else int(lo), 0 if is_f else int(hi),
                                               float(lo) if is_f else 0.0, float(hi) if is_f else 0.0, int(ndv)))
         _check(self.L.bqx_catalog_register(self.cat, t))
+
+    def load_csv(self, path: str, name: str = "table"):
+        """load_csv + register (the reference CLI registers the file as "table")."""
+        _check(self.L.bqx_catalog_load_csv(self.cat, path.encode(), name.encode()))
+
+    def table_columns(self, name):
+        """(col_name, type, data copy, min, max, ndv) per column — what the loader inferred."""
+        rows, ncols = C.c_size_t(), C.c_size_t()
+        _check(self.L.bqx_catalog_table_info(self.cat, name.encode(), C.byref(rows), C.byref(ncols)))
+        out = []
+        for i in range(ncols.value):
+            cn, ty, data = C.c_char_p(), C.c_int(), C.c_void_p()
+            mi, ma, mf, xf, ndv = C.c_int64(), C.c_int64(), C.c_double(), C.c_double(), C.c_size_t()
+            _check(self.L.bqx_catalog_column_info(self.cat, name.encode(), i, C.byref(cn), C.byref(ty), C.byref(data), C.byref(mi),
+                                                  C.byref(ma), C.byref(mf), C.byref(xf), C.byref(ndv)))
+            dt = np.dtype(NP_DTYPES[ty.value])
+            if rows.value:
+                buf = (C.c_char * (dt.itemsize * rows.value)).from_address(data.value)
+                arr = np.frombuffer(buf, dtype=dt).copy()
+            else:
+                arr = np.empty(0, dtype=dt)
+            lo, hi = (mf.value, xf.value) if ty.value == 1 else (mi.value, ma.value)
+            out.append((cn.value.decode(), ty.value, arr, lo, hi, ndv.value))
+        return out
+
+    def table_dict(self, name):
+        n = self.L.bqx_catalog_dict_size(self.cat, name.encode())
+        return [self.L.bqx_catalog_dict_get(self.cat, name.encode(), i).decode() for i in range(n)]
 
     def evict_device(self, table: str):
         """Drop the HBM mirrors of `table`'s host columns (they are uploaded again by the next query)."""

@@ -5,6 +5,7 @@
 
 #include "bosql_b200_exec.h"
 #include "bosql_operator.hpp"
+#include "csv_loader.hpp"
 #include "gpu_device.hpp"
 
 using namespace bosql;
@@ -172,6 +173,53 @@ int bqx_catalog_register(bqx_catalog* c, bqx_table* tp) {
         TableMeta meta(t->table.name, std::move(t->metas), t->rows);
         c->catalog.register_table(std::move(t->table), std::move(meta));
     });
+}
+
+int bqx_catalog_load_csv(bqx_catalog* c, const char* path, const char* name) {
+    return guarded([&] {
+        auto [table, meta] = load_csv(std::string(path));
+        table.name = name;
+        meta.name = name;
+        c->catalog.register_table(std::move(table), std::move(meta));
+    });
+}
+
+int bqx_catalog_table_info(bqx_catalog* c, const char* name, size_t* rows, size_t* ncols) {
+    return guarded([&] {
+        OptionalRef<const TableMeta> m = c->catalog.get_table_meta(name);
+        if (!m.has_value()) throw std::runtime_error(std::string("Table not found: ") + name);
+        *rows = m->row_count;
+        *ncols = m->columns.size();
+    });
+}
+
+int bqx_catalog_column_info(bqx_catalog* c, const char* name, size_t i, const char** col_name, int* type, const void** data,
+                            int64_t* min_i, int64_t* max_i, double* min_f, double* max_f, size_t* ndv) {
+    return guarded([&] {
+        OptionalRef<const TableMeta> m = c->catalog.get_table_meta(name);
+        OptionalRef<const Table> t = c->catalog.get_table_data(name);
+        if (!m.has_value() || !t.has_value() || i >= m->columns.size()) throw std::runtime_error("bad column");
+        const ColumnMeta& cm = m->columns[i];
+        *col_name = cm.name.c_str();
+        *type = static_cast<int>(cm.type);
+        *ndv = cm.stats.ndv;
+        *min_f = cm.stats.min_f64;
+        *max_f = cm.stats.max_f64;
+        *min_i = cm.type == TypeId::DATE32 ? cm.stats.min_date : cm.stats.min_i64;
+        *max_i = cm.type == TypeId::DATE32 ? cm.stats.max_date : cm.stats.max_i64;
+        *data = t->columns[i].data->host_data();
+    });
+}
+
+size_t bqx_catalog_dict_size(bqx_catalog* c, const char* name) {
+    OptionalRef<const Table> t = c->catalog.get_table_data(name);
+    return (t.has_value() && t->dict) ? t->dict->strings.size() : 0;
+}
+
+const char* bqx_catalog_dict_get(bqx_catalog* c, const char* name, uint32_t id) {
+    OptionalRef<const Table> t = c->catalog.get_table_data(name);
+    if (!t.has_value() || !t->dict || id >= t->dict->strings.size()) return nullptr;
+    return t->dict->strings[id].c_str();
 }
 
 int bqx_catalog_evict_device(bqx_catalog* c, const char* table) {

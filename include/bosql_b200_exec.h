@@ -58,6 +58,15 @@ int bqx_table_set_stats(bqx_table* t, const char* column, int64_t min_i, int64_t
 /* Catalog::register_table (src/catalog/catalog.cpp:5); consumes the table handle */
 int bqx_catalog_register(bqx_catalog* c, bqx_table* t);
 
+/* load_csv (src/storage/csv_loader.cpp:168) + register under `name` (the reference CLI registers "table", src/cli/main.cpp:105) */
+int bqx_catalog_load_csv(bqx_catalog* c, const char* path, const char* name);
+/* what the loader inferred: rows / columns, then per column name, type, host data, statistics (ColumnStats) */
+int bqx_catalog_table_info(bqx_catalog* c, const char* name, size_t* rows, size_t* ncols);
+int bqx_catalog_column_info(bqx_catalog* c, const char* name, size_t i, const char** col_name, int* type, const void** data,
+                            int64_t* min_i, int64_t* max_i, double* min_f, double* max_f, size_t* ndv);
+size_t bqx_catalog_dict_size(bqx_catalog* c, const char* name);
+const char* bqx_catalog_dict_get(bqx_catalog* c, const char* name, uint32_t id);
+
 /* Drop the HBM mirrors of a registered table's host columns: the next query uploads them again (bench.py's
  * end-to-end leg pays the host->device copy inside every timed step this way). */
 int bqx_catalog_evict_device(bqx_catalog* c, const char* table);
