@@ -173,6 +173,20 @@ int bq_ctx_sync(bq_ctx* ctx) {
     return guarded([&] { BQ_CUDA(cudaStreamSynchronize(ctx->stream)); });
 }
 
+void* bq_ctx_stream(bq_ctx* ctx) { return ctx->stream; }
+
+int bq_copy_bytes(bq_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    return guarded([&] {
+        if (bytes) BQ_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    });
+}
+
+int bq_zero_bytes(bq_ctx* ctx, void* dst, size_t bytes) {
+    return guarded([&] {
+        if (bytes) BQ_CUDA(cudaMemsetAsync(dst, 0, bytes, ctx->stream));
+    });
+}
+
 int bq_ctx_info(bq_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes) {
     return guarded([&] {
         BQ_CUDA(cudaSetDevice(ctx->device));

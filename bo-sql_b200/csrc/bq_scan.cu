@@ -1106,6 +1106,11 @@ struct MergeParams {
 __global__ void __launch_bounds__(kBlock) k_merge_partial(const __grid_constant__ MergeParams m) {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= m.n) return;
+    if (m.cnt[i] == 0) return;                 // zero padding of a fixed-capacity exchange buffer: no group
+    if (m.cnt[i] < 0) {                        // a rank whose local scan failed sends -(error flags): fail here alike
+        atomicOr(m.err, static_cast<int>(-m.cnt[i]));
+        return;
+    }
     unsigned long long idx = 0;
     if (m.has_key) {
         long long k = load_raw(m.key, m.key_type, i);

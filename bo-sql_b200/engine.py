@@ -71,6 +71,7 @@ def exec_lib():
         "bqx_result_data": ([vp, sz], vp),
         "bqx_result_free": ([vp], None),
         "bqx_explain": ([cp, C.c_uint, C.c_char_p, sz], C.c_int),
+        "bqx_set_exchange": ([vp], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

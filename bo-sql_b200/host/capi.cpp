@@ -6,6 +6,7 @@
 #include "bosql_b200_exec.h"
 #include "bosql_operator.hpp"
 #include "csv_loader.hpp"
+#include "exchange.hpp"
 #include "gpu_device.hpp"
 
 using namespace bosql;
@@ -80,6 +81,22 @@ const char* bqx_last_error(void) { return g_err.c_str(); }
 
 int bqx_init(int device) {
     return guarded([&] { gpu::init_context(device); });
+}
+
+int bqx_set_exchange(const bqx_exchange* x) {
+    return guarded([&] {
+        gpu::Exchange& e = gpu::exchange();
+        if (!x || x->world <= 1) {
+            e.active = false;
+            e.fn = bqx_exchange{};
+            return;
+        }
+        if (x->rank < 0 || x->rank >= x->world) throw std::runtime_error("exchange: rank out of range");
+        if (!x->all_gather || !x->all_gather_v || !x->all_to_all_v || !x->all_reduce_sum_u32 || !x->host_all_gather_i64)
+            throw std::runtime_error("exchange: every collective must be supplied");
+        e.fn = *x;
+        e.active = true;
+    });
 }
 
 bq_ctx* bqx_context(void) {

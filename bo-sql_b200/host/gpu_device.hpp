@@ -47,6 +47,7 @@ DeviceRelationPtr relation_from(bq_rel* rel);     // consumes the bq_rel shell, 
 // Catalog statistics attached to a pipeline column (include/catalog/catalog.h:16-21).
 struct KeyStats {
     bool known = false;
+    bool measured = false;                // computed on this process's rows (a shard, when running across GPUs)
     int64_t min_key = 0, max_key = -1;    // on the integer key (f64 key for DOUBLE)
     size_t ndv = 0;
     size_t table_rows = 0;

@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "bosql_operator.hpp"
+#include "exchange.hpp"
 #include "gpu_plan.hpp"
 
 namespace bosql {
@@ -425,6 +426,8 @@ bool HashJoin::describe(Pipeline& p) {
 DeviceRelationPtr HashJoin::device_result() {
     DeviceRelationPtr l = left_child->device_result();
     DeviceRelationPtr r = right_child->device_result();
+    // across GPUs both inputs are row shards: broadcast the build side, so this rank emits the join rows of its probe rows
+    if (gpu::exchange().active) r = gpu::all_gather_relation(r, right_child->output_types());
     bq_ctx* ctx = context();
     DevColPtr probe_rows, build_rows;
     if (l->rows == 0 || r->rows == 0) return gpu::empty_relation(types_);

@@ -4,6 +4,7 @@
 // What the reference does per row at run time (HashAggregate::next, src/exec/operator.cpp:984-1014;
 // Selection::next :403-429; HashJoin::open/next :739-837) is decided here once per query.
 #include "gpu_plan.hpp"
+#include "exchange.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -54,6 +55,7 @@ void resolve_stats(PipeCol& col, bool force_device) {
     if (force_device) bq_col_invalidate_stats(col.dev->h);
     check(bq_col_minmax(context(), col.dev->h, &lo, &hi));
     col.stats.known = true;
+    col.stats.measured = true;
     col.stats.min_key = lo;
     col.stats.max_key = hi;
 }
@@ -288,9 +290,39 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
     std::vector<TypeId> out_types = req.group_types;
     for (const auto& a : req.aggs) out_types.push_back(a.result_type);
 
+    // Multi-GPU: every rank holds a row shard and must reach the same exchange points, so nothing below may leave early
+    // on a condition only this rank sees (an empty shard still takes part in the collectives).
+    Exchange& xch = exchange();
+    const bool dist = xch.active;
+    auto not_fusable = [&](const char* why) -> DeviceRelationPtr {
+        if (dist) throw std::runtime_error(std::string("not supported across GPUs: ") + why);
+        return nullptr;
+    };
+
+    // A step that can fail on this rank's rows alone (an expression program hitting an integer division by zero): across
+    // GPUs every rank learns the outcome before anyone moves on, so all of them throw - none is left inside a collective.
+    auto agreed = [&](bool evaluates_program, auto&& step) {
+        if (!dist) {
+            step();
+            return;
+        }
+        std::string err;
+        try {
+            step();
+        } catch (const std::exception& e) {
+            err = e.what();
+        }
+        if (!evaluates_program && err.empty()) return;
+        int64_t worst = 0;
+        for (int64_t f : xch.host_gather({err.empty() ? 0 : (err.find("Division by zero") != std::string::npos ? 1 : 2)})) worst = std::max(worst, f);
+        if (!err.empty()) throw std::runtime_error(err);
+        if (worst == 1) throw std::runtime_error("Division by zero");
+        if (worst) throw std::runtime_error("expression evaluation failed on another rank");
+    };
+
     // zero input rows -> zero output rows, even for a global aggregate (src/exec/operator.cpp:990-993, H5)
-    if (p.rows == 0 || (p.joined && p.build_rows == 0)) return empty_relation(out_types);
-    if (p.cross_join) return nullptr;
+    if (!dist && (p.rows == 0 || (p.joined && p.build_rows == 0))) return empty_relation(out_types);
+    if (p.cross_join) return not_fusable("a join whose ON clause is not column = column");
 
     ColumnLookup look = lookup_for(p.cols);
 
@@ -301,7 +333,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         referenced(c.expr.get(), look, refs);
         bool any_probe = false, any_build = false;
         for (int r : refs) (p.cols[r].side ? any_build : any_probe) = true;
-        if (any_probe && any_build) return nullptr;        // compares columns of both sides: materialise the join
+        if (any_probe && any_build) return not_fusable("a predicate comparing columns of both join sides");   // materialise the join
         (any_build ? build_conj : probe_conj).push_back(&c);
     }
 
@@ -323,11 +355,11 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         key_col = look.index_of(gexprs[0]->str_val);
         if (key_col < 0) throw std::runtime_error("Unknown column: " + gexprs[0]->str_val);
     } else if (gexprs.size() == 1) {
-        if (!all_on_probe(gexprs[0].get())) return nullptr;
+        if (!all_on_probe(gexprs[0].get())) return not_fusable("a GROUP BY expression over build-side columns");
         PipeCol derived;
         derived.name = "\x01group1";
         derived.type = req.group_types[0];
-        derived.dev = eval_to_column(gexprs[0].get(), p.cols, p.rows, req.dict, derived.type, false);
+        agreed(true, [&] { derived.dev = eval_to_column(gexprs[0].get(), p.cols, p.rows, req.dict, derived.type, false); });
         p.cols.push_back(std::move(derived));
         key_col = static_cast<int>(p.cols.size()) - 1;
         look = lookup_for(p.cols);
@@ -340,9 +372,13 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             int idx = look.index_of(g->str_val);
             if (idx < 0) throw std::runtime_error("Unknown column: " + g->str_val);
             if (p.cols[idx].type == TypeId::DOUBLE) throw std::runtime_error("GROUP BY over several keys needs integer-typed keys on the GPU path");
-            if (p.cols[idx].side) return nullptr;
+            if (p.cols[idx].side) return not_fusable("several GROUP BY keys from the build side");
             key_cols.push_back(idx);
+            // the packing is only injective over the TRUE value range: measure it (cached in the column handle) rather
+            // than trust catalog bounds, which nothing downstream could catch if they were stale
+            p.cols[idx].stats.known = false;
             resolve_stats(p.cols[idx]);
+            if (dist) xch.minmax(p.cols[idx].stats.min_key, p.cols[idx].stats.max_key);
             Domain d{p.cols[idx].stats.min_key, p.cols[idx].stats.max_key};
             if (d.size() == 0) d = Domain{0, 0};
             if (total > (1ULL << 62) / d.size()) throw std::runtime_error("GROUP BY key domain too large to pack");
@@ -367,7 +403,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         PipeCol derived;
         derived.name = "\x01packed";
         derived.type = TypeId::INT64;
-        derived.dev = eval_program(code, kcols, p.rows, TypeId::INT64);
+        agreed(true, [&] { derived.dev = eval_program(code, kcols, p.rows, TypeId::INT64); });
         derived.stats.known = true;
         derived.stats.min_key = 0;
         derived.stats.max_key = static_cast<int64_t>(total - 1);
@@ -395,11 +431,11 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             Value val;
             val.text = text;
             if (!simple_value_form(a.arg, p.cols, look, val.form)) {
-                if (!all_on_probe(a.arg)) return nullptr;
+                if (!all_on_probe(a.arg)) return not_fusable("an aggregate argument mixing both join sides");
                 PipeCol derived;
                 derived.name = "\x01value" + std::to_string(values.size());
                 derived.type = value_type(a.arg, look);
-                derived.dev = eval_to_column(a.arg, p.cols, p.rows, req.dict, derived.type, false);
+                agreed(true, [&] { derived.dev = eval_to_column(a.arg, p.cols, p.rows, req.dict, derived.type, false); });
                 p.cols.push_back(std::move(derived));
                 look = lookup_for(p.cols);
                 val.form = ValueForm{};
@@ -463,6 +499,28 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         for (const auto& v : values)
             for (int c : {v.form.col_l, v.form.col_r})
                 if (c >= 0 && p.cols[c].side) need_rows = true;
+        // Across GPUs the build side is sharded too.  A semi-join over unique, dense keys needs only its bitmap: each
+        // rank sets the bits of its own build rows over the GLOBAL key domain and the words are summed (= OR, keys
+        // being unique) - the probe side never moves.  Anything else is a broadcast join: the build columns are
+        // all-gathered and every rank builds the full table.
+        bool dist_bitmap = false;
+        if (dist) {
+            auto rows_by_rank = xch.host_gather({static_cast<int64_t>(p.build_rows)});
+            uint64_t global_build = 0;
+            for (int64_t r : rows_by_rank) global_build += static_cast<uint64_t>(r);
+            if (bk.type != TypeId::DOUBLE && !need_rows) {
+                resolve_stats(bk);
+                if (bk.stats.measured) xch.minmax(bk.stats.min_key, bk.stats.max_key);
+                const uint64_t dom = bk.stats.max_key >= bk.stats.min_key ? static_cast<uint64_t>(bk.stats.max_key - bk.stats.min_key) + 1 : 0;
+                dist_bitmap = dom > 0 && dom <= (1ULL << 32) && dom <= 8 * global_build + 1024 && bk.stats.ndv && bk.stats.ndv == global_build;
+            }
+            if (!dist_bitmap) {
+                for (auto& c : p.cols)
+                    if (c.side) c.dev = xch.all_gather_column(c.dev, p.build_rows, rows_by_rank);
+                p.build_rows = static_cast<size_t>(global_build);
+                if (bk.stats.measured) bk.stats.known = false;        // shard-local bounds no longer describe the column
+            }
+        }
         // build-side columns as a column set of their own (length build_rows)
         std::vector<PipeCol> bcols;
         std::vector<int> bmap(p.cols.size(), -1);
@@ -471,14 +529,16 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                 bmap[i] = static_cast<int>(bcols.size());
                 bcols.push_back(p.cols[i]);
             }
-        SlotPlan bplan = plan_slots(build_conj, bcols, p.build_rows, {}, 3);
+        SlotPlan bplan;
+        agreed(false, [&] { bplan = plan_slots(build_conj, bcols, p.build_rows, {}, 3); });
+        if (dist && bplan.mask) agreed(true, [] {});
         bq_join_spec js{};
         js.key = bk.dev->h;
         for (size_t i = 0; i < bplan.pred.size(); ++i) js.pred[i] = make_slot(bcols[bplan.pred[i].first].dev, bplan.pred[i].second);
         js.mask = bplan.mask ? bplan.mask->h : nullptr;
         js.row_begin = 0;
         js.row_end = p.build_rows;
-        js.kind = BQ_JOIN_AUTO;
+        js.kind = dist_bitmap ? BQ_JOIN_BITMAP : BQ_JOIN_AUTO;
         js.need_rows = need_rows ? 1 : 0;
         if (bk.type != TypeId::DOUBLE) {
             resolve_stats(bk);
@@ -489,6 +549,14 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             js.kind = BQ_JOIN_HASH;
         }
         check(bq_join_build(ctx, &js, &join));
+        if (dist_bitmap) {
+            // a duplicate key inside one shard makes that rank fall back to a hash table: agree before summing
+            if (!xch.host_all(bq_join_kind(join) == BQ_JOIN_BITMAP))
+                throw std::runtime_error("join key statistics claim unique keys (ndv == row count) but a shard holds duplicates");
+            size_t words = 0;
+            void* bits = bq_join_bitmap_ptr(join, &words);
+            xch.sum_words(bits, words);
+        }
     }
 
     // ---- run the passes ---------------------------------------------------------------------------------------------------
@@ -500,7 +568,9 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         std::vector<int> range_roles = roles;
         for (int& r : range_roles)
             if (r >= 0 && p.cols[r].side) r = -1;
-        SlotPlan plan = plan_slots(probe_conj, p.cols, p.rows, range_roles, 3);
+        SlotPlan plan;
+        agreed(false, [&] { plan = plan_slots(probe_conj, p.cols, p.rows, range_roles, 3); });
+        if (dist && plan.mask) agreed(true, [] {});
 
         bq_scan_spec s{};
         auto slot_for = [&](int role_index) {
@@ -565,6 +635,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                 return;
             }
             resolve_stats(kc, force_device_stats);
+            if (dist && kc.stats.measured) xch.minmax(kc.stats.min_key, kc.stats.max_key);
             Domain d{kc.stats.min_key, kc.stats.max_key};
             const uint64_t est_rows = p.rows;
             if (d.size() > 0 && d.size() <= (1ULL << 26) && d.size() <= 4 * est_rows + 4096) {
@@ -578,37 +649,147 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             }
         };
         choose_group(false);
+        const bool has_key = key_col >= 0;
+        const bool int_key = has_key && p.cols[key_col].type != TypeId::DOUBLE;
+        const bool plain_stream = !p.joined && probe_conj.empty() && !s.mask;      // key / a / b are read as they lie
+        size_t cur_rows = p.rows;
+        std::vector<DevColPtr> reordered;        // keeps shuffled / partitioned columns alive through the scan
+
+        // Across GPUs, a GROUP BY with more groups than fit a partial-state exchange moves the ROWS instead: hash-partition
+        // by key, all-to-all, and every rank aggregates the keys it owns (SURVEY.md 8e, high-cardinality GROUP BY).
+        bool shuffled = false;
+        if (dist && int_key && plain_stream) {
+            const PipeCol& kc = p.cols[key_col];
+            const Domain d{kc.stats.min_key, kc.stats.max_key};
+            uint64_t groups = kc.stats.ndv;                      // catalog statistics describe the whole table
+            if (!groups) {
+                groups = d.size();
+                if (groups == 0 || groups * 32 > (96ull << 20)) {
+                    const uint64_t global_rows = static_cast<uint64_t>(xch.host_sum(static_cast<int64_t>(p.rows)));
+                    groups = groups ? std::min(groups, global_rows) : global_rows;
+                }
+            }
+            if (groups * 32 > (96ull << 20)) {
+                std::vector<DevColPtr> pay;
+                if (ps.col_a >= 0) pay.push_back(p.cols[ps.col_a].dev);
+                if (ps.col_b >= 0) pay.push_back(p.cols[ps.col_b].dev);
+                Shuffled sh = shuffle_by_key(kc.dev, pay, p.rows);
+                reordered.push_back(sh.key);
+                s.key.col = sh.key->h;
+                size_t k = 0;
+                if (ps.col_a >= 0) { reordered.push_back(sh.payload[k]); s.a.col = sh.payload[k++]->h; }
+                if (ps.col_b >= 0) { reordered.push_back(sh.payload[k]); s.b.col = sh.payload[k++]->h; }
+                cur_rows = sh.rows;
+                s.row_end = cur_rows;
+                shuffled = true;
+                if (s.group_mode == BQ_GROUP_HASH) {
+                    // the keys a rank owns: about groups / world of them, never more than its rows
+                    const uint64_t share = groups / static_cast<uint64_t>(xch.world()) + groups / (4 * static_cast<uint64_t>(xch.world())) + 4096;
+                    s.ndv_hint = static_cast<size_t>(std::min<uint64_t>(share, std::max<uint64_t>(cur_rows, 1)));
+                }
+            }
+        }
+
         // High-cardinality GROUP BY: when the hash table would be far larger than L2, order the rows by hash partition
         // first (bq_partition) so each partition's table region is L2-resident while its rows stream by.  The reference
         // updates one unordered_map row by row (src/exec/operator.cpp:988-1005); here it is two streaming passes.
-        std::vector<DevColPtr> partitioned;      // keeps the reordered columns alive through the scan
-        if (s.group_mode == BQ_GROUP_HASH && !p.joined && probe_conj.empty() && !s.mask && p.rows >= (1u << 22) &&
-            static_cast<uint64_t>(s.ndv_hint) * 32 > (96ull << 20) && p.cols[key_col].type != TypeId::DOUBLE) {
+        if (s.group_mode == BQ_GROUP_HASH && plain_stream && int_key && cur_rows >= (1u << 22) &&
+            static_cast<uint64_t>(s.ndv_hint) * 32 > (96ull << 20)) {
             int log2p = 4;
             while (log2p < 10 && ((static_cast<uint64_t>(s.ndv_hint) * 64) >> log2p) > (32ull << 20)) ++log2p;
             const bq_col* pay[2];
             int n_pay = 0;
-            if (ps.col_a >= 0) pay[n_pay++] = p.cols[ps.col_a].dev->h;
-            if (ps.col_b >= 0) pay[n_pay++] = p.cols[ps.col_b].dev->h;
+            if (ps.col_a >= 0) pay[n_pay++] = s.a.col;
+            if (ps.col_b >= 0) pay[n_pay++] = s.b.col;
             bq_col *ok = nullptr, *off = nullptr, *op[2] = {nullptr, nullptr};
-            check(bq_partition(ctx, p.cols[key_col].dev->h, pay, n_pay, 0, p.rows, log2p, 64 - log2p, &ok, op, &off));
-            partitioned.push_back(adopt(ok));
-            partitioned.push_back(adopt(off));
+            check(bq_partition(ctx, s.key.col, pay, n_pay, 0, cur_rows, log2p, 64 - log2p, &ok, op, &off));
+            reordered.push_back(adopt(ok));
+            reordered.push_back(adopt(off));
             s.key.col = ok;
             int k = 0;
-            if (ps.col_a >= 0) { partitioned.push_back(adopt(op[k])); s.a.col = op[k++]; }
-            if (ps.col_b >= 0) { partitioned.push_back(adopt(op[k])); s.b.col = op[k++]; }
+            if (ps.col_a >= 0) { reordered.push_back(adopt(op[k])); s.a.col = op[k++]; }
+            if (ps.col_b >= 0) { reordered.push_back(adopt(op[k])); s.b.col = op[k++]; }
             s.hash_part_log2 = log2p;
             s.hash_part_shift = 64 - log2p;
         }
-        bq_rel* rel = nullptr;
-        int rc = bq_scan_aggregate(ctx, &s, &rel);
-        if (rc && std::strstr(bq_last_error(), "stale statistics")) {
-            choose_group(true);                 // the catalog's min/max were wrong: measure and retry
-            rc = bq_scan_aggregate(ctx, &s, &rel);
+
+        DeviceRelationPtr r;
+        if (!dist) {
+            bq_rel* rel = nullptr;
+            int rc = bq_scan_aggregate(ctx, &s, &rel);
+            if (rc && std::strstr(bq_last_error(), "stale statistics")) {
+                choose_group(true);                 // the catalog's min/max were wrong: measure and retry
+                rc = bq_scan_aggregate(ctx, &s, &rel);
+            }
+            check(rc);
+            r = relation_from(rel);
+        } else if (shuffled) {
+            // every rank owns a disjoint set of keys: aggregate locally, agree on the outcome, then replicate the groups
+            auto attempt = [&](std::string& message) {
+                bq_rel* rel = nullptr;
+                int rc = bq_scan_aggregate(ctx, &s, &rel);
+                if (rc) message = bq_last_error();
+                else r = relation_from(rel);
+                int64_t mine = rc ? (message.find("stale statistics") != std::string::npos ? 2 : 1) : 0, worst = 0;
+                for (int64_t f : xch.host_gather({mine})) worst = std::max(worst, f);
+                return worst;
+            };
+            std::string message;
+            int64_t outcome = attempt(message);
+            if (outcome == 2) {
+                choose_group(true);
+                if (s.group_mode == BQ_GROUP_HASH) s.ndv_hint = std::max<size_t>(cur_rows, 1);
+                message.clear();
+                outcome = attempt(message);
+            }
+            if (outcome) throw std::runtime_error(message.empty() ? "aggregation failed on another rank" : message);
+            if (!xch.fn.keep_sharded) {
+                std::vector<TypeId> rel_types;
+                if (has_key) rel_types.push_back(p.cols[key_col].type);
+                for (int o = 0; o < s.n_out; ++o)
+                    rel_types.push_back(s.out[o].func == BQ_AGG_COUNT ? TypeId::INT64 : (s.out[o].func == BQ_AGG_SUM && s.out[o].as_int ? TypeId::INT64 : TypeId::DOUBLE));
+                r = all_gather_relation(r, rel_types);
+            }
+        } else {
+            // local fused scan -> partial states [key] count sum0 sum1 -> one all-gather -> merge in rank order.  A failed
+            // local scan (division by zero, stale bounds) travels as a poisoned partial, so every rank's merge fails alike.
+            const TypeId key_type = has_key ? p.cols[key_col].type : TypeId::INT64;
+            auto attempt = [&]() {
+                bq_rel* rel = nullptr;
+                int rc = bq_scan_partial(ctx, &s, &rel);
+                int flags = 0;
+                DeviceRelationPtr local;
+                if (rc) {
+                    const char* m = bq_last_error();
+                    flags = std::strstr(m, "Division by zero") ? 1 : std::strstr(m, "table overflow") ? 2 : std::strstr(m, "stale statistics") ? 4 : 0;
+                    if (!flags) check(rc);
+                } else {
+                    local = relation_from(rel);
+                }
+                int64_t cap = -1;
+                if (!has_key) cap = 1;
+                else if (int_key) {
+                    const Domain d{p.cols[key_col].stats.min_key, p.cols[key_col].stats.max_key};
+                    if (p.cols[key_col].stats.known && d.size() > 0 && d.size() <= 65536) cap = static_cast<int64_t>(d.size());
+                }
+                if (cap >= 0 && local && static_cast<int64_t>(local->rows) > cap) {
+                    local.reset();
+                    flags = 4;                      // more groups than the bounds allow: they are stale
+                }
+                GatheredPartials g;
+                gather_partials(local.get(), flags, has_key, key_type, cap, g);
+                bq_rel* fin = nullptr;
+                int rc2 = bq_agg_finish(ctx, g.parts.data(), static_cast<int>(g.parts.size()), has_key ? 1 : 0, static_cast<int>(key_type), s.out, s.n_out, &fin);
+                if (!rc2) r = relation_from(fin);
+                return rc2;
+            };
+            int rc = attempt();
+            if (rc && std::strstr(bq_last_error(), "stale statistics")) {
+                choose_group(true);
+                rc = attempt();
+            }
+            check(rc);
         }
-        check(rc);
-        DeviceRelationPtr r = relation_from(rel);
         // with several passes over a keyed aggregate, bring every pass into key order so rows line up
         if (passes.size() > 1 && key_col >= 0 && r->rows > 1) {
             std::vector<bq_col*> hs;

@@ -38,6 +38,10 @@ int bq_ctx_create(int device, bq_ctx** out);
 void bq_ctx_destroy(bq_ctx* ctx);
 int bq_ctx_set_stream(bq_ctx* ctx, void* cuda_stream);    /* cudaStream_t; NULL = the context's own stream */
 int bq_ctx_sync(bq_ctx* ctx);
+void* bq_ctx_stream(bq_ctx* ctx);                         /* the cudaStream_t every launch is ordered on */
+/* stream-ordered device-to-device copy / zero fill of raw bytes (packing exchange buffers for the multi-GPU path) */
+int bq_copy_bytes(bq_ctx* ctx, void* dst, const void* src, size_t bytes);
+int bq_zero_bytes(bq_ctx* ctx, void* dst, size_t bytes);
 int bq_ctx_info(bq_ctx* ctx, int* sm_count, size_t* free_bytes, size_t* total_bytes);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 uint64_t bq_ctx_launches(bq_ctx* ctx);

@@ -95,6 +95,36 @@ double bqx_result_seconds(const bqx_result* r);
 const void* bqx_result_data(const bqx_result* r, size_t i);
 void bqx_result_free(bqx_result* r);
 
+/* ---- multi-GPU exchange ------------------------------------------------------------------------------
+ * One process per GPU, each holding a ROW SHARD of every table under the same name and schema.  The host supplies the
+ * collectives (torch.distributed over NCCL in bosql_b200.distributed; any NCCL/MPI host can fill the same table); the
+ * operators call them at the exchange points of a plan:
+ *   scan -> selection -> aggregate      local fused kernel, partial states all-gathered, merged in rank order
+ *   bitmap (semi) join                  per-rank bitmaps over the global key domain summed (= OR: keys are unique)
+ *   other joins                         build side all-gathered (broadcast join), probe side never moves
+ *   high-cardinality GROUP BY           rows hash-partitioned by key and exchanged all-to-all, then aggregated locally
+ * Every rank must run the same statements in the same order.  Catalog statistics (min / max / ndv) passed with
+ * bqx_table_set_stats describe the WHOLE table, not the shard.  The reference is one process (no counterpart).
+ * All device pointers are ordered on `stream` (the context's cudaStream_t); byte counts are exact. */
+typedef struct bqx_exchange {
+    void* user;
+    int32_t world, rank;
+    int32_t keep_sharded;    /* nonzero: a shuffled GROUP BY leaves each rank with the groups it owns (no final gather) */
+    int32_t pad;
+    /* recv[r*bytes .. (r+1)*bytes) = rank r's send[0 .. bytes) */
+    int (*all_gather)(void* user, const void* send, void* recv, size_t bytes, void* stream);
+    /* rank r contributes bytes_by_rank[r] bytes; recv holds them back to back in rank order */
+    int (*all_gather_v)(void* user, const void* send, void* recv, const int64_t* bytes_by_rank, void* stream);
+    /* send holds send_bytes[r] bytes for each rank r back to back; recv receives recv_bytes[r] from each rank r */
+    int (*all_to_all_v)(void* user, const void* send, const int64_t* send_bytes, void* recv, const int64_t* recv_bytes, void* stream);
+    /* in-place element-wise sum of 32-bit words over all ranks */
+    int (*all_reduce_sum_u32)(void* user, void* buf, size_t words, void* stream);
+    /* HOST exchange of n int64 per rank: all[r*n + i] = rank r's mine[i] (row counts, min/max, status words) */
+    int (*host_all_gather_i64)(void* user, const int64_t* mine, int32_t n, int64_t* all);
+} bqx_exchange;
+/* Installs (copies) the table for this process; NULL or world <= 1 returns to single-GPU execution. */
+int bqx_set_exchange(const bqx_exchange* x);
+
 /* LogicalOp::to_string of the planned statement (plan-shape tests, tests/test_logical.cpp of the reference) */
 int bqx_explain(const char* sql, unsigned parse_flags, char* out, size_t cap);
 

@@ -105,3 +105,95 @@ def test_partitioned_aggregate_world2():
         for r in range(world):
             want[r::world] = 1 << r
         assert np.array_equal(words, want)
+
+
+# ---- the operator layer's exchange table (bqx_exchange) over gloo with host pointers ---------------------------------
+def _exchange_worker(rank, world, port, q):
+    import ctypes as C
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from __graft_entry__ import load_package
+        load_package()
+        from bosql_b200 import distributed as D
+        ex = D.Exchange(device="cpu")
+        t = ex.table
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        i64 = lambda xs: (C.c_int64 * len(xs))(*xs)
+
+        # all_gather: fixed-size blocks in rank order
+        mine = np.arange(16, dtype=np.uint8) + 16 * rank
+        got = np.zeros(16 * world, dtype=np.uint8)
+        assert t.all_gather(None, ptr(mine), ptr(got), 16, None) == 0, ex.error
+        assert np.array_equal(got, np.arange(16 * world, dtype=np.uint8))
+
+        # all_gather_v: rank r contributes 8*(r+1) bytes, one rank may contribute nothing
+        sizes = [0 if r == 1 else 8 * (r + 1) for r in range(world)]
+        mine = np.full(max(sizes[rank], 1), rank + 1, dtype=np.uint8)
+        got = np.zeros(sum(sizes), dtype=np.uint8)
+        assert t.all_gather_v(None, ptr(mine), ptr(got), i64(sizes), None) == 0, ex.error
+        assert np.array_equal(got, np.concatenate([np.full(s, r + 1, dtype=np.uint8) for r, s in enumerate(sizes)]))
+
+        # all_to_all_v: rank s sends (s + d + 1) int64 of value 100*s + d to rank d
+        send_rows = [rank + d + 1 for d in range(world)]
+        recv_rows = [s + rank + 1 for s in range(world)]
+        send = np.concatenate([np.full(n, 100 * rank + d, dtype=np.int64) for d, n in enumerate(send_rows)])
+        recv = np.zeros(sum(recv_rows), dtype=np.int64)
+        assert t.all_to_all_v(None, ptr(send), i64([8 * n for n in send_rows]), ptr(recv), i64([8 * n for n in recv_rows]), None) == 0, ex.error
+        assert np.array_equal(recv, np.concatenate([np.full(n, 100 * s + rank, dtype=np.int64) for s, n in enumerate(recv_rows)]))
+
+        # all_reduce_sum_u32 on disjoint bits == bitwise OR, including the top bit
+        words = np.zeros(64, dtype=np.uint32)
+        words[rank::world] = 0x80000001
+        words[63] = np.uint32(1) << np.uint32(31 - rank)
+        assert t.all_reduce_sum_u32(None, ptr(words), 64, None) == 0, ex.error
+        ref = np.zeros(64, dtype=np.uint64)
+        for r in range(world):
+            w = np.zeros(64, dtype=np.uint64)
+            w[r::world] = 0x80000001
+            w[63] = 1 << (31 - r)
+            ref += w
+        assert np.array_equal(words, (ref & 0xFFFFFFFF).astype(np.uint32))
+
+        # host_all_gather_i64
+        out = (C.c_int64 * (2 * world))()
+        assert t.host_all_gather_i64(None, i64([rank, -rank]), 2, out) == 0, ex.error
+        assert list(out) == [v for r in range(world) for v in (r, -r)]
+        assert ex.calls["all_gather"] == 1 and ex.calls["all_to_all_v"] == 1
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        q.put((rank, "FAIL " + traceback.format_exc()[-1500:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_exchange_table_over_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_exchange_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_set_exchange_validates():
+    import ctypes as C
+    from __graft_entry__ import load_package
+    bq = load_package()
+    from bosql_b200 import distributed as D
+    L = bq.exec_lib()
+    assert L.bqx_set_exchange(None) == 0                       # back to single-GPU execution
+    t = D.ExchangeTable()                                      # world 0: treated as "no exchange"
+    assert L.bqx_set_exchange(C.byref(t)) == 0
+    t.world, t.rank = 2, 5
+    assert L.bqx_set_exchange(C.byref(t)) != 0 and b"rank" in L.bqx_last_error()
+    t.rank = 1                                                 # missing callbacks
+    assert L.bqx_set_exchange(C.byref(t)) != 0 and b"collective" in L.bqx_last_error()
+    assert L.bqx_set_exchange(None) == 0
