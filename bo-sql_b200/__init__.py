@@ -117,6 +117,9 @@ def kernel_lib():
         "bq_ctx_destroy": ([vp], None),
         "bq_ctx_set_stream": ([vp, vp], C.c_int),
         "bq_ctx_sync": ([vp], C.c_int),
+        "bq_ctx_stream": ([vp], vp),
+        "bq_copy_bytes": ([vp, vp, vp, sz], C.c_int),
+        "bq_zero_bytes": ([vp, vp, sz], C.c_int),
         "bq_ctx_info": ([vp, P(C.c_int), P(sz), P(sz)], C.c_int),
         "bq_ctx_launches": ([vp], C.c_uint64),
         "bq_ctx_profile": ([vp, C.c_int], C.c_int),
