@@ -121,6 +121,19 @@ class Dict:
             pass
 
 
+class _ResultOwner:
+    """Frees a bqx_result when the last numpy view of it is gone."""
+
+    def __init__(self, lib, handle):
+        self.L, self.h = lib, handle
+
+    def __del__(self):
+        try:
+            self.L.bqx_result_free(self.h)
+        except Exception:
+            pass
+
+
 class Plan:
     """A planned statement: the root Operator behind open / next / close."""
 
@@ -171,23 +184,29 @@ class Plan:
     def close(self):
         _check(self.L.bqx_plan_close(self.h))
 
-    def run(self) -> Result:
+    def run(self, copy=None) -> Result:
+        """open .. next* .. close.  Small results are copied into numpy arrays; large ones (>= 1 MB per column, or copy=False)
+        are numpy VIEWS of the C result, which is released when the last array goes away."""
         r = C.c_void_p()
         _check(self.L.bqx_plan_run(self.h, C.byref(r)))
-        try:
-            rows = self.L.bqx_result_rows(r)
-            cols = []
-            for i, t in enumerate(self.types):
-                dt = np.dtype(NP_DTYPES[t])
-                if rows:
-                    buf = (C.c_char * (dt.itemsize * rows)).from_address(self.L.bqx_result_data(r, i))
-                    cols.append(np.frombuffer(buf, dtype=dt).copy())
-                else:
-                    cols.append(np.empty(0, dtype=dt))
-            return Result(list(self.names), list(self.types), cols, rows, self.L.bqx_result_seconds(r), self.has_dict,
-                          self.dict_strings() if self.has_dict else [])
-        finally:
-            self.L.bqx_result_free(r)
+        owner = _ResultOwner(self.L, r)
+        rows = self.L.bqx_result_rows(r)
+        cols = []
+        for i, t in enumerate(self.types):
+            dt = np.dtype(NP_DTYPES[t])
+            if not rows:
+                cols.append(np.empty(0, dtype=dt))
+                continue
+            nbytes = dt.itemsize * rows
+            buf = (C.c_char * nbytes).from_address(self.L.bqx_result_data(r, i))
+            view = np.frombuffer(buf, dtype=dt)
+            if copy is True or (copy is None and nbytes < (1 << 20)):
+                cols.append(view.copy())
+            else:
+                buf._owner = owner                # the ctypes array is the view's base: it keeps the C result alive
+                cols.append(view)
+        return Result(list(self.names), list(self.types), cols, rows, self.L.bqx_result_seconds(r), self.has_dict,
+                      self.dict_strings() if self.has_dict else [])
 
 
 class Engine:

@@ -48,6 +48,9 @@ struct Operator {
     virtual std::shared_ptr<gpu::DeviceRelation> device_result() = 0;
     // Describe this subtree as a fusable pipeline; false = not a scan/selection/join chain.
     virtual bool describe(gpu::Pipeline&) { return false; }
+    // After the first next(): the whole result as host columns, when this operator pages out of one materialised copy
+    // (lets a caller that wants everything skip the 4096-row batches; the batches alias the same memory).
+    bool host_result(std::vector<std::shared_ptr<void>>& cols, size_t& rows) const;
 
 protected:
     std::vector<std::string> names_;

@@ -30,6 +30,7 @@ struct bqx_plan {
 };
 struct bqx_result {
     std::vector<std::vector<unsigned char>> cols;
+    std::vector<std::shared_ptr<void>> whole;       // set instead of cols when the root handed over its host copy
     size_t rows = 0;
     double seconds = 0.0;
 };
@@ -300,7 +301,10 @@ int bqx_plan_run(bqx_plan* p, bqx_result** out) {
         auto t0 = std::chrono::steady_clock::now();
         p->root->open();
         ExecBatch batch;
+        bool first = true;
         while (p->root->next(batch)) {
+            if (first && p->root->host_result(res->whole, res->rows)) break;     // zero-copy: the batches alias these columns
+            first = false;
             for (size_t j = 0; j < batch.columns.size() && j < res->cols.size(); ++j) {
                 const auto& s = batch.columns[j];
                 const auto* b = static_cast<const unsigned char*>(s.data);
@@ -317,7 +321,7 @@ int bqx_plan_run(bqx_plan* p, bqx_result** out) {
 size_t bqx_result_rows(const bqx_result* r) { return r->rows; }
 size_t bqx_result_cols(const bqx_result* r) { return r->cols.size(); }
 double bqx_result_seconds(const bqx_result* r) { return r->seconds; }
-const void* bqx_result_data(const bqx_result* r, size_t i) { return r->cols.at(i).data(); }
+const void* bqx_result_data(const bqx_result* r, size_t i) { return r->whole.empty() ? r->cols.at(i).data() : r->whole.at(i).get(); }
 void bqx_result_free(bqx_result* r) { delete r; }
 
 int bqx_explain(const char* sql, unsigned parse_flags, char* out, size_t cap) {

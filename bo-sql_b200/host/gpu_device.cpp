@@ -97,6 +97,57 @@ DevCol::~DevCol() {
 
 DevColPtr adopt(bq_col* h) { return std::make_shared<DevCol>(h, true); }
 
+namespace {
+struct PinnedPool {
+    struct Buf { void* p; size_t bytes; };
+    std::vector<Buf> free_list;
+    size_t cached = 0;
+    static constexpr size_t kMaxCached = 8ull << 30;
+    ~PinnedPool() {
+        for (auto& b : free_list) bq_host_free(b.p);
+    }
+    void* take(size_t& bytes) {
+        bytes = (bytes + (2u << 20) - 1) & ~static_cast<size_t>((2u << 20) - 1);
+        size_t best = free_list.size();
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].bytes >= bytes && free_list[i].bytes <= 2 * bytes &&
+                (best == free_list.size() || free_list[i].bytes < free_list[best].bytes)) best = i;
+        if (best != free_list.size()) {
+            Buf b = free_list[best];
+            free_list.erase(free_list.begin() + static_cast<long>(best));
+            cached -= b.bytes;
+            bytes = b.bytes;
+            return b.p;
+        }
+        void* p = nullptr;
+        check(bq_host_alloc(bytes, &p));
+        return p;
+    }
+    void give(void* p, size_t bytes) {
+        if (cached + bytes > kMaxCached) {
+            bq_host_free(p);
+            return;
+        }
+        free_list.push_back({p, bytes});
+        cached += bytes;
+    }
+};
+PinnedPool& pinned_pool() {
+    static PinnedPool* pool = new PinnedPool();      // leaked on purpose: results may outlive static destruction order
+    return *pool;
+}
+}  // namespace
+
+std::shared_ptr<void> host_buffer(size_t bytes) {
+    if (bytes < (256u << 10)) {
+        auto v = std::make_shared<std::vector<unsigned char>>(bytes);
+        return std::shared_ptr<void>(v, v->data());
+    }
+    size_t got = bytes;
+    void* p = pinned_pool().take(got);
+    return std::shared_ptr<void>(p, [got](void* q) { pinned_pool().give(q, got); });
+}
+
 DevColPtr mirror_of(const Column& col) {
     if (const auto* dc = dynamic_cast<const DeviceColumn*>(&col)) {
         bq_col* h = dc->handle();

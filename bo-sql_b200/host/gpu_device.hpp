@@ -44,6 +44,10 @@ struct DeviceRelation {
 using DeviceRelationPtr = std::shared_ptr<DeviceRelation>;
 DeviceRelationPtr relation_from(bq_rel* rel);     // consumes the bq_rel shell, keeps its columns
 
+// Host memory for result columns.  Small results are plain heap memory; large ones (>= 256 KB) are pinned buffers from a
+// recycling pool, so the device-to-host copy of a large result runs at PCIe speed and repeated queries pay no allocation.
+std::shared_ptr<void> host_buffer(size_t bytes);
+
 // Catalog statistics attached to a pipeline column (include/catalog/catalog.h:16-21).
 struct KeyStats {
     bool known = false;

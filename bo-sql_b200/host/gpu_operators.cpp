@@ -102,9 +102,9 @@ gpu::KeyStats stats_from_meta(const ColumnMeta& m, size_t table_rows) {
 
 template <typename T>
 std::shared_ptr<void> download(const DevColPtr& col, size_t rows) {
-    auto v = std::make_shared<std::vector<T>>(rows);
-    if (rows) check(bq_col_read(context(), col->h, 0, rows, v->data()));
-    return std::shared_ptr<void>(v, v->data());
+    std::shared_ptr<void> buf = gpu::host_buffer(rows * sizeof(T));
+    if (rows) check(bq_col_read(context(), col->h, 0, rows, buf.get()));
+    return buf;
 }
 
 }  // namespace
@@ -141,6 +141,13 @@ bool Operator::page_out(ExecBatch& out) {
     }
     out.length = take;
     emit_offset_ += take;
+    return true;
+}
+
+bool Operator::host_result(std::vector<std::shared_ptr<void>>& cols, size_t& rows) const {
+    if (!paged_ || !result_) return false;
+    cols = host_cols_;
+    rows = result_->rows;
     return true;
 }
 
