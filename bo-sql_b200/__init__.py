@@ -118,6 +118,7 @@ def kernel_lib():
         "bq_ctx_set_stream": ([vp, vp], C.c_int),
         "bq_ctx_sync": ([vp], C.c_int),
         "bq_ctx_stream": ([vp], vp),
+        "bq_ctx_pool_stats": ([vp, P(sz), P(sz)], C.c_int),
         "bq_copy_bytes": ([vp, vp, vp, sz], C.c_int),
         "bq_zero_bytes": ([vp, vp, sz], C.c_int),
         "bq_ctx_info": ([vp, P(C.c_int), P(sz), P(sz)], C.c_int),
@@ -147,6 +148,12 @@ def kernel_lib():
         "bq_scan_partial": ([vp, P(ScanSpec), P(vp)], C.c_int),
         "bq_agg_finish": ([vp, P(vp), C.c_int, C.c_int, C.c_int, P(AggOut), C.c_int, P(vp)], C.c_int),
         "bq_partition": ([vp, vp, P(vp), C.c_int, sz, sz, C.c_int, C.c_int, P(vp), P(vp), P(vp)], C.c_int),
+        "bq_partition_count": ([vp, vp, sz, sz, C.c_int, C.c_int, P(i64), P(vp)], C.c_int),
+        "bq_partition_scatter": ([vp, vp, P(vp), C.c_int, P(vp), P(vp), P(vp)], C.c_int),
+        "bq_part_plan_free": ([vp], None),
+        "bq_col_alloc_shared": ([vp, C.c_int, sz, P(vp)], C.c_int),
+        "bq_col_ipc_export": ([vp, vp, vp], C.c_int),
+        "bq_ipc_open": ([vp, vp, P(vp)], C.c_int),
         "bq_key_hash": ([i64], C.c_uint64),
         "bq_select": ([vp, P(SelectSpec), P(vp)], C.c_int),
         "bq_gather": ([vp, vp, vp, P(vp)], C.c_int),

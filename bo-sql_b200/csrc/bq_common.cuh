@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <array>
 #include <vector>
 
 #include "bosql_b200.h"
@@ -122,6 +123,15 @@ struct bq_ctx {
     size_t scratch_bytes = 0;
     void* pinned = nullptr;      // small pinned staging for scalar results
     size_t pinned_bytes = 0;
+    // Large blocks (>= 32 MB) bypass the driver's stream-ordered pool: when a query's multi-GB temporaries change size from
+    // one step to the next (exchange buffers), that pool re-maps physical memory under new addresses at ~40 ms per GB.
+    // Blocks here are recycled whole on the context's stream (same-stream ordering makes reuse safe).
+    struct BigBlock { void* p; size_t bytes; bool free; uint64_t stamp; bool exported = false; };
+    // peer allocations mapped through CUDA IPC, keyed by the 64-byte handle (recycled blocks keep their handle)
+    std::vector<std::pair<std::array<unsigned char, 64>, void*>> ipc_mappings;
+    std::vector<BigBlock> big_blocks;
+    size_t big_free_bytes = 0;
+    uint64_t big_clock = 0;
     bool profile = false;        // bracket the fused scan kernel with events (bench.py roofline)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profile_events;
 };

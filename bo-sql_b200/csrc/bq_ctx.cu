@@ -21,16 +21,65 @@ static bool is_live(bq_ctx* ctx) {
     return ctx && g_live.count(ctx);
 }
 
+static constexpr size_t kBigBlock = 32ull << 20;          // allocations from this size up are recycled whole
+static constexpr size_t kBigFreeCap = 64ull << 30;        // idle bytes kept before the oldest idle block goes back
+
+static void big_release_idle(bq_ctx* ctx, size_t keep_bytes) {
+    while (ctx->big_free_bytes > keep_bytes) {
+        size_t oldest = ctx->big_blocks.size();
+        for (size_t i = 0; i < ctx->big_blocks.size(); ++i)
+            if (ctx->big_blocks[i].free && !ctx->big_blocks[i].exported &&          // a peer may still hold a mapping of an exported block
+                (oldest == ctx->big_blocks.size() || ctx->big_blocks[i].stamp < ctx->big_blocks[oldest].stamp)) oldest = i;
+        if (oldest == ctx->big_blocks.size()) break;
+        cudaFree(ctx->big_blocks[oldest].p);              // synchronises the device: nothing can still be using it
+        ctx->big_free_bytes -= ctx->big_blocks[oldest].bytes;
+        ctx->big_blocks.erase(ctx->big_blocks.begin() + static_cast<long>(oldest));
+    }
+}
+
 void* dev_alloc(bq_ctx* ctx, size_t bytes) {
     void* p = nullptr;
-    BQ_CUDA(cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream));
+    if (bytes < kBigBlock) {
+        BQ_CUDA(cudaMallocAsync(&p, bytes ? bytes : 16, ctx->stream));
+        return p;
+    }
+    const size_t want = (bytes + kBigBlock - 1) / kBigBlock * kBigBlock;
+    size_t best = ctx->big_blocks.size();
+    for (size_t i = 0; i < ctx->big_blocks.size(); ++i) {
+        const auto& b = ctx->big_blocks[i];
+        if (b.free && b.bytes >= want && b.bytes <= want + want / 4 && (best == ctx->big_blocks.size() || b.bytes < ctx->big_blocks[best].bytes)) best = i;
+    }
+    if (best != ctx->big_blocks.size()) {
+        auto& b = ctx->big_blocks[best];
+        b.free = false;
+        ctx->big_free_bytes -= b.bytes;
+        return b.p;
+    }
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        big_release_idle(ctx, 0);                          // out of memory: give every idle block back and try once more
+        BQ_CUDA(cudaMalloc(&p, want));
+    }
+    ctx->big_blocks.push_back({p, want, false, 0});
     return p;
 }
 
 void dev_free(bq_ctx* ctx, void* p) {
     if (!p) return;
-    if (is_live(ctx)) cudaFreeAsync(p, ctx->stream);
-    else cudaFree(p);
+    if (!is_live(ctx)) {
+        cudaFree(p);
+        return;
+    }
+    for (auto& b : ctx->big_blocks)
+        if (b.p == p) {
+            b.free = true;
+            b.stamp = ++ctx->big_clock;
+            ctx->big_free_bytes += b.bytes;
+            if (ctx->big_free_bytes > kBigFreeCap) big_release_idle(ctx, kBigFreeCap);
+            return;
+        }
+    cudaFreeAsync(p, ctx->stream);
 }
 
 bq_col* new_col(bq_ctx* ctx, int type, size_t n) {
@@ -156,6 +205,11 @@ void bq_ctx_destroy(bq_ctx* ctx) {
         std::lock_guard<std::mutex> lk(g_live_mu);
         g_live.erase(ctx);
     }
+    for (auto& m : ctx->ipc_mappings) cudaIpcCloseMemHandle(m.second);
+    ctx->ipc_mappings.clear();
+    for (auto& b : ctx->big_blocks)
+        if (b.free) cudaFree(b.p);           // blocks still held by a column are freed by that column (dev_free, dead context)
+    ctx->big_blocks.clear();
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -174,6 +228,74 @@ int bq_ctx_sync(bq_ctx* ctx) {
 }
 
 void* bq_ctx_stream(bq_ctx* ctx) { return ctx->stream; }
+
+// ---- peer memory: one process per GPU, buffers shared through CUDA IPC ---------------------------------------------
+int bq_col_alloc_shared(bq_ctx* ctx, int type, size_t n, bq_col** out) {
+    return guarded([&] {
+        if (type < 0 || type > 3) throw std::runtime_error("Unknown column type");
+        auto* c = new bq_col();
+        c->ctx = ctx;
+        c->type = type;
+        c->n = n;
+        try {
+            size_t bytes = n * width_of(type);
+            c->ptr = dev_alloc(ctx, bytes < kBigBlock ? kBigBlock : bytes);      // IPC needs a cudaMalloc'ed block of its own
+        } catch (...) {
+            delete c;
+            throw;
+        }
+        *out = c;
+    });
+}
+
+int bq_col_ipc_export(bq_ctx* ctx, const bq_col* col, void* handle64) {
+    return guarded([&] {
+        static_assert(sizeof(cudaIpcMemHandle_t) == BQ_IPC_HANDLE_BYTES, "handle size");
+        for (auto& b : ctx->big_blocks)
+            if (b.p == col->ptr) {
+                cudaIpcMemHandle_t h;
+                BQ_CUDA(cudaIpcGetMemHandle(&h, col->ptr));
+                std::memcpy(handle64, &h, sizeof h);
+                b.exported = true;
+                return;
+            }
+        throw std::runtime_error("only columns from bq_col_alloc_shared (or >= 32 MB) can be shared with a peer");
+    });
+}
+
+int bq_ipc_open(bq_ctx* ctx, const void* handle64, void** device_ptr) {
+    return guarded([&] {
+        std::array<unsigned char, 64> key;
+        std::memcpy(key.data(), handle64, 64);
+        for (auto& m : ctx->ipc_mappings)
+            if (m.first == key) {
+                *device_ptr = m.second;
+                return;
+            }
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, handle64, sizeof h);
+        void* p = nullptr;
+        BQ_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->ipc_mappings.emplace_back(key, p);
+        *device_ptr = p;
+    });
+}
+
+int bq_ctx_pool_stats(bq_ctx* ctx, size_t* reserved_bytes, size_t* used_bytes) {
+    return guarded([&] {
+        cudaMemPool_t pool;
+        BQ_CUDA(cudaDeviceGetMemPool(&pool, ctx->device));
+        uint64_t r = 0, u = 0;
+        BQ_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &r));
+        BQ_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &u));
+        for (const auto& b : ctx->big_blocks) {          // recycled large blocks count as held; the ones handed out as used
+            r += b.bytes;
+            if (!b.free) u += b.bytes;
+        }
+        if (reserved_bytes) *reserved_bytes = r;
+        if (used_bytes) *used_bytes = u;
+    });
+}
 
 int bq_copy_bytes(bq_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return guarded([&] {

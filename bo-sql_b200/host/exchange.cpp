@@ -2,6 +2,9 @@
 #include "exchange.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 
@@ -31,6 +34,30 @@ DevColPtr alloc_col(TypeId t, size_t n) {
 char* ptr_of(const DevColPtr& c) { return static_cast<char*>(bq_col_ptr(c->h)); }
 
 }  // namespace
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+PhaseTrace::PhaseTrace() {
+    const char* e = std::getenv("BOSQL_TRACE");
+    on = e && *e && *e != '0';
+    if (on) {
+        bq_ctx_sync(context());
+        last = now_ms();
+    }
+}
+
+void PhaseTrace::mark(const char* what) {
+    if (!on) return;
+    bq_ctx_sync(context());
+    const double t = now_ms();
+    size_t reserved = 0, used = 0;
+    bq_ctx_pool_stats(context(), &reserved, &used);
+    std::fprintf(stderr, "[bosql trace rank %d] %-28s %8.3f ms   pool %.2f / %.2f GiB\n", exchange().active ? exchange().rank() : 0, what,
+                 t - last, used / 1073741824.0, reserved / 1073741824.0);
+    last = now_ms();
+}
 
 Exchange& exchange() {
     static Exchange x;
@@ -166,21 +193,31 @@ void gather_partials(const DeviceRelation* local, int error_flags, bool has_key,
     // `send` may be released here: the allocator is stream ordered, and the collective was enqueued on the same stream
 }
 
-Shuffled shuffle_by_key(const DevColPtr& key, const std::vector<DevColPtr>& payload, size_t rows) {
+// Partition count shared by both shuffle implementations: a power of two >= world (x8 when world is not a power of two, so
+// the contiguous runs handed to the ranks stay balanced); hash bits [40, 40 + log2 P) are disjoint from the bits the local
+// tables use (top bits: L2 partition, bottom bits: slot).
+static int shuffle_log2_parts(int W) {
+    int log2p = 0;
+    while ((1 << log2p) < W) ++log2p;
+    if ((1 << log2p) != W) log2p += 3;
+    if (log2p > 10) throw std::runtime_error("too many ranks for one partition pass");
+    return log2p;
+}
+
+static Shuffled shuffle_collective(const DevColPtr& key, const std::vector<DevColPtr>& payload, size_t rows) {
     Exchange& x = exchange();
     bq_ctx* ctx = context();
     const int W = x.world();
     // partitions: a power of two >= 8 * world, handed to ranks in contiguous runs so any world size works and the
     // runs stay balanced; hash bits [40, 40 + log2 P) are disjoint from the bits the local tables use (top and bottom)
-    int log2p = 0;
-    while ((1 << log2p) < W * 8 && log2p < 10) ++log2p;
-    while ((1 << log2p) < W) ++log2p;
-    if (log2p > 10) throw std::runtime_error("too many ranks for one partition pass");
+    const int log2p = shuffle_log2_parts(W);
     const int P = 1 << log2p;
     std::vector<const bq_col*> pay;
     for (const auto& c : payload) pay.push_back(c->h);
     bq_col *pk = nullptr, *off = nullptr, *pp[2] = {nullptr, nullptr};
+    PhaseTrace trace;
     check(bq_partition(ctx, key->h, pay.data(), static_cast<int>(pay.size()), 0, rows, log2p, 40, &pk, pp, &off));
+    trace.mark("shuffle: partition by rank");
     DevColPtr part_key = adopt(pk), offsets = adopt(off);
     std::vector<DevColPtr> part_pay;
     for (size_t i = 0; i < payload.size(); ++i) part_pay.push_back(adopt(pp[i]));
@@ -212,12 +249,104 @@ Shuffled shuffle_by_key(const DevColPtr& key, const std::vector<DevColPtr>& payl
             rb[static_cast<size_t>(r)] = recv_rows[static_cast<size_t>(r)] * static_cast<int64_t>(w);
         }
         DevColPtr dst = alloc_col(src->type(), total);
+        trace.mark("shuffle:   alloc recv");
         xcheck(x.fn.all_to_all_v(x.fn.user, ptr_of(src), sb.data(), ptr_of(dst), rb.data(), stream), "all_to_all_v");
         return dst;
     };
+    trace.mark("shuffle: size exchange");
     out.key = move(part_key);
+    trace.mark("shuffle:   all-to-all key");
     for (const auto& c : part_pay) out.payload.push_back(move(c));
+    trace.mark("shuffle:   all-to-all payload");
     return out;
+}
+
+// The shuffle as ONE pass: count, agree on sizes, then the partitioning kernel writes every row straight into the owning
+// rank's receive buffer over NVLink (peer memory mapped through CUDA IPC) - no send buffer, no collective on the data path.
+static Shuffled shuffle_peer_write(const DevColPtr& key, const std::vector<DevColPtr>& payload, size_t rows) {
+    Exchange& x = exchange();
+    bq_ctx* ctx = context();
+    const int W = x.world(), me = x.rank();
+    const int log2p = shuffle_log2_parts(W);
+    const int P = 1 << log2p;
+    PhaseTrace trace;
+    std::vector<int64_t> counts(static_cast<size_t>(P));
+    bq_part_plan* plan = nullptr;
+    check(bq_partition_count(ctx, key->h, 0, rows, log2p, 40, counts.data(), &plan));
+    struct PlanGuard {
+        bq_part_plan* p;
+        ~PlanGuard() { bq_part_plan_free(p); }
+    } guard{plan};
+    trace.mark("shuffle: count");
+
+    auto first_part = [&](int r) { return static_cast<size_t>(r) * P / W; };
+    std::vector<int64_t> send_rows(static_cast<size_t>(W), 0);
+    for (int r = 0; r < W; ++r)
+        for (size_t q = first_part(r); q < first_part(r + 1); ++q) send_rows[static_cast<size_t>(r)] += counts[q];
+    auto matrix = x.host_gather(send_rows);                 // matrix[s*W + d] = rows rank s sends to rank d
+    size_t total = 0;
+    for (int s = 0; s < W; ++s) total += static_cast<size_t>(matrix[static_cast<size_t>(s) * W + me]);
+    if (total > 0xFFFFFFFFull) throw std::runtime_error("a rank would own more than 2^32 rows after the shuffle");
+
+    // receive buffers (blocks of their own, exportable) and their handles
+    const size_t n_cols = 1 + payload.size();
+    std::vector<DevColPtr> recv;
+    std::vector<int64_t> my_handles(n_cols * 8);
+    for (size_t c = 0; c < n_cols; ++c) {
+        const TypeId t = c == 0 ? key->type() : payload[c - 1]->type();
+        bq_col* h = nullptr;
+        check(bq_col_alloc_shared(ctx, static_cast<int>(t), total, &h));
+        recv.push_back(adopt(h));
+        check(bq_col_ipc_export(ctx, h, &my_handles[c * 8]));
+    }
+    // (this exchange is also the barrier that says: every receive buffer exists and its previous contents are dead)
+    auto handles = x.host_gather(my_handles);
+    std::vector<std::vector<char*>> peer(static_cast<size_t>(W), std::vector<char*>(n_cols, nullptr));
+    for (int r = 0; r < W; ++r)
+        for (size_t c = 0; c < n_cols; ++c) {
+            if (r == me) {
+                peer[static_cast<size_t>(r)][c] = ptr_of(recv[c]);
+            } else {
+                void* p = nullptr;
+                check(bq_ipc_open(ctx, &handles[(static_cast<size_t>(r) * n_cols + c) * 8], &p));
+                peer[static_cast<size_t>(r)][c] = static_cast<char*>(p);
+            }
+        }
+    trace.mark("shuffle: sizes + handles");
+
+    // where my rows of partition q start inside the owning rank's buffers
+    std::vector<void*> dest(static_cast<size_t>(P) * 3, nullptr);
+    for (int d = 0; d < W; ++d) {
+        size_t row = 0;
+        for (int s = 0; s < me; ++s) row += static_cast<size_t>(matrix[static_cast<size_t>(s) * W + d]);
+        for (size_t q = first_part(d); q < first_part(d + 1); ++q) {
+            for (size_t c = 0; c < n_cols; ++c) {
+                const TypeId t = c == 0 ? key->type() : payload[c - 1]->type();
+                dest[c * P + q] = peer[static_cast<size_t>(d)][c] + row * width_of(t);
+            }
+            row += static_cast<size_t>(counts[q]);
+        }
+    }
+    std::vector<const bq_col*> pay;
+    for (const auto& c : payload) pay.push_back(c->h);
+    check(bq_partition_scatter(ctx, plan, pay.data(), static_cast<int>(pay.size()), dest.data(), dest.data() + P, dest.data() + 2 * P));
+    // every rank's writes have landed once every rank's kernel has finished
+    x.host_gather({0});
+    trace.mark("shuffle: scatter over NVLink");
+
+    Shuffled out;
+    out.rows = total;
+    out.key = recv[0];
+    for (size_t c = 1; c < n_cols; ++c) out.payload.push_back(recv[c]);
+    return out;
+}
+
+Shuffled shuffle_by_key(const DevColPtr& key, const std::vector<DevColPtr>& payload, size_t rows) {
+    // $BOSQL_SHUFFLE=collective keeps the two-step form (partition into a send buffer, then the host's all-to-all): the
+    // comparison point for the fused peer-write kernel, and the way out on a box without CUDA IPC between the ranks
+    const char* mode = std::getenv("BOSQL_SHUFFLE");
+    if (mode && std::string(mode) == "collective") return shuffle_collective(key, payload, rows);
+    return shuffle_peer_write(key, payload, rows);
 }
 
 DeviceRelationPtr all_gather_relation(const DeviceRelationPtr& local, const std::vector<TypeId>& types) {

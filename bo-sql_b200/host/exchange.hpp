@@ -52,6 +52,14 @@ struct Shuffled {
 };
 Shuffled shuffle_by_key(const DevColPtr& key, const std::vector<DevColPtr>& payload, size_t rows);
 
+// $BOSQL_TRACE=1: synchronise and print the time since the previous mark (stderr) - phase breakdowns for tuning.
+struct PhaseTrace {
+    PhaseTrace();
+    void mark(const char* what);
+    bool on = false;
+    double last = 0.0;
+};
+
 // Concatenates every rank's relation (same schema) in rank order.
 DeviceRelationPtr all_gather_relation(const DeviceRelationPtr& local, const std::vector<TypeId>& types);
 

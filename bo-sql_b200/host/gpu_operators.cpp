@@ -119,7 +119,9 @@ void Operator::reset_paging() {
 
 bool Operator::page_out(ExecBatch& out) {
     if (!paged_) {
+        gpu::PhaseTrace trace;
         result_ = device_result();
+        trace.mark("device_result total");
         host_cols_.clear();
         for (size_t c = 0; c < result_->cols.size(); ++c) {
             switch (types_[c]) {
@@ -129,6 +131,7 @@ bool Operator::page_out(ExecBatch& out) {
                 case TypeId::DATE32: host_cols_.push_back(download<int32_t>(result_->cols[c], result_->rows)); break;
             }
         }
+        trace.mark("result to host");
         emit_offset_ = 0;
         paged_ = true;
     }

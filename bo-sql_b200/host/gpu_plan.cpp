@@ -702,7 +702,9 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             if (ps.col_a >= 0) pay[n_pay++] = s.a.col;
             if (ps.col_b >= 0) pay[n_pay++] = s.b.col;
             bq_col *ok = nullptr, *off = nullptr, *op[2] = {nullptr, nullptr};
+            PhaseTrace ptrace;
             check(bq_partition(ctx, s.key.col, pay, n_pay, 0, cur_rows, log2p, 64 - log2p, &ok, op, &off));
+            ptrace.mark("local L2 partition");
             reordered.push_back(adopt(ok));
             reordered.push_back(adopt(off));
             s.key.col = ok;
@@ -713,6 +715,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             s.hash_part_shift = 64 - log2p;
         }
 
+        PhaseTrace trace;
         DeviceRelationPtr r;
         if (!dist) {
             bq_rel* rel = nullptr;
@@ -805,6 +808,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             check(rc2);
             r = relation_from(sorted);
         }
+        trace.mark("aggregate (+ exchange)");
         pass_results.push_back(r);
         pass_aggs.push_back(agg_index);
     }

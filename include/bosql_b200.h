@@ -39,6 +39,8 @@ void bq_ctx_destroy(bq_ctx* ctx);
 int bq_ctx_set_stream(bq_ctx* ctx, void* cuda_stream);    /* cudaStream_t; NULL = the context's own stream */
 int bq_ctx_sync(bq_ctx* ctx);
 void* bq_ctx_stream(bq_ctx* ctx);                         /* the cudaStream_t every launch is ordered on */
+/* bytes the stream-ordered allocator holds from the driver / has handed out (diagnostics) */
+int bq_ctx_pool_stats(bq_ctx* ctx, size_t* reserved_bytes, size_t* used_bytes);
 /* stream-ordered device-to-device copy / zero fill of raw bytes (packing exchange buffers for the multi-GPU path) */
 int bq_copy_bytes(bq_ctx* ctx, void* dst, const void* src, size_t bytes);
 int bq_zero_bytes(bq_ctx* ctx, void* dst, size_t bytes);
@@ -262,6 +264,24 @@ int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const 
  * the per-peer send buffers of the multi-GPU all-to-all (2^log2_parts = number of ranks). */
 int bq_partition(bq_ctx* ctx, const bq_col* key, const bq_col* const* payload, int n_payload, size_t row_begin, size_t row_end,
                  int log2_parts, int hash_shift, bq_col** out_key, bq_col** out_payload, bq_col** out_offsets);
+/* The same pass in two halves, for the multi-GPU shuffle: count first (host_counts[2^log2_parts] = rows per partition, one
+ * host round trip), then scatter every partition to an address of the caller's choice - dest_key[q] / dest_pay*[q] is
+ * where THIS launch's first row of partition q goes.  The addresses may lie in a peer GPU's memory (bq_ipc_open): the
+ * kernel then writes the exchange straight over NVLink, fused with the partitioning - no send buffer, no collective. */
+typedef struct bq_part_plan bq_part_plan;
+int bq_partition_count(bq_ctx* ctx, const bq_col* key, size_t row_begin, size_t row_end, int log2_parts, int hash_shift,
+                       int64_t* host_counts, bq_part_plan** out);
+int bq_partition_scatter(bq_ctx* ctx, bq_part_plan* plan, const bq_col* const* payload, int n_payload,
+                         void* const* dest_key, void* const* dest_pay0, void* const* dest_pay1);
+void bq_part_plan_free(bq_part_plan* plan);
+/* ---- peer memory (one process per GPU on one NVSwitch domain) ----------------------------------------------------
+ * bq_col_alloc_shared: a column in a block of its own that can be exported; bq_col_ipc_export: its 64-byte CUDA IPC handle
+ * (send it to the peers by any host channel); bq_ipc_open: the peer's view of that block (mapped once per handle, cached
+ * for the life of the context).  Ordering between processes is the caller's job (a host barrier before and after). */
+#define BQ_IPC_HANDLE_BYTES 64
+int bq_col_alloc_shared(bq_ctx* ctx, int type, size_t n, bq_col** out);
+int bq_col_ipc_export(bq_ctx* ctx, const bq_col* col, void* handle64);
+int bq_ipc_open(bq_ctx* ctx, const void* handle64, void** device_ptr);
 /* the hash all tables and partitions use (so a caller can predict a key's partition) */
 uint64_t bq_key_hash(int64_t key);
 

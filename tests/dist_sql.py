@@ -155,26 +155,32 @@ def run_rank(rank, world, backend, results):
         k = (datagen.row_hash(5, 0, rows) % np.uint64(BIG_KEYS)).astype(np.int64) * 7 - 3_000_000
         v = ((datagen.row_hash(5, 1, rows) % np.uint64(1 << 20)).astype(np.float64)) / 64.0       # dyadic: sums are exact
         lo, hi = shard(BIG_ROWS, rank, world, False)
-        for keep in (False, True):
-            D.install(xl, device="cuda", keep_sharded=keep)
-            eng = bq.Engine()
-            eng.add_table("t", [("k", bq.INT64, np.ascontiguousarray(k[lo:hi])), ("v", bq.DOUBLE, np.ascontiguousarray(v[lo:hi]))])
-            before = dict(D._INSTALLED.calls)
-            got = eng.query("SELECT k, SUM(v), COUNT(*) FROM t GROUP BY k")
-            assert D._INSTALLED.calls["all_to_all_v"] == before["all_to_all_v"] + 2, "the shuffle path was not taken"
-            cols = gather_rows(got.cols) if keep else got.cols
-            uk, inv = np.unique(k, return_inverse=True)
-            cnt = np.bincount(inv, minlength=len(uk)).astype(np.int64)
-            sm = np.bincount(inv, weights=v, minlength=len(uk))
-            order = np.argsort(cols[0], kind="stable")
-            assert np.array_equal(cols[0][order], uk), "group keys differ"
-            assert np.array_equal(cols[2][order], cnt), "counts differ"
-            assert np.array_equal(cols[1][order], sm), "sums differ (dyadic values: must be exact)"
-            if keep:
-                owned = len(got.cols[0])
-                assert 0 < owned < len(uk), "keep_sharded: a rank should own a strict subset of the groups"
-            results.append((f"shuffle_groupby[keep_sharded={keep}]", "ok"))
-            del eng
+        uk, inv = np.unique(k, return_inverse=True)
+        cnt = np.bincount(inv, minlength=len(uk)).astype(np.int64)
+        sm = np.bincount(inv, weights=v, minlength=len(uk))
+        # "peer": the partition kernel writes straight into the owning rank's buffer (CUDA IPC); "collective": partition into
+        # a send buffer, then the host's all-to-all.  Same rows, same owners.
+        for mode in ("peer", "collective"):
+            os.environ["BOSQL_SHUFFLE"] = mode
+            for keep in (True, False):
+                D.install(xl, device="cuda", keep_sharded=keep)
+                eng = bq.Engine()
+                eng.add_table("t", [("k", bq.INT64, np.ascontiguousarray(k[lo:hi])), ("v", bq.DOUBLE, np.ascontiguousarray(v[lo:hi]))])
+                before = dict(D._INSTALLED.calls)
+                got = eng.query("SELECT k, SUM(v), COUNT(*) FROM t GROUP BY k")
+                moved = D._INSTALLED.calls["all_to_all_v"] - before["all_to_all_v"]
+                assert moved == (2 if mode == "collective" else 0), f"{mode}: {moved} all-to-all calls"
+                cols = gather_rows(got.cols) if keep else got.cols
+                order = np.argsort(cols[0], kind="stable")
+                assert np.array_equal(cols[0][order], uk), "group keys differ"
+                assert np.array_equal(cols[2][order], cnt), "counts differ"
+                assert np.array_equal(cols[1][order], sm), "sums differ (dyadic values: must be exact)"
+                if keep:
+                    owned = len(got.cols[0])
+                    assert 0 < owned < len(uk), "keep_sharded: a rank should own a strict subset of the groups (was the shuffle taken?)"
+                results.append((f"shuffle_groupby[{mode},keep_sharded={keep}]", "ok"))
+                del eng
+        os.environ.pop("BOSQL_SHUFFLE", None)
     except Exception:  # noqa: BLE001
         results.append(("shuffle_groupby", traceback.format_exc()[-1500:]))
     D.uninstall(xl)
