@@ -221,6 +221,9 @@ class Exchange:
                 device_dst = None
                 if self.staged:
                     device_dst, dst, src = dst, torch.empty(dst.numel(), dtype=torch.uint8), src.cpu()
+                if not self.staged and self.device == "cuda" and len(set(sizes)) == 1 and sizes[0]:
+                    dist.all_gather_into_tensor(dst, src, group=self.group)        # equal shards: one collective
+                    return
                 off = 0
                 # one broadcast per contributing rank, straight into its slot of the output (no padding, no staging copy)
                 for r, n in enumerate(sizes):

@@ -65,6 +65,7 @@ def exec_lib():
         "bqx_plan_next": ([vp, P(vp), sz, P(sz), P(C.c_int)], C.c_int),
         "bqx_plan_close": ([vp], C.c_int),
         "bqx_plan_run": ([vp, P(vp)], C.c_int),
+        "bqx_plan_run_device": ([vp, P(vp)], C.c_int),
         "bqx_result_rows": ([vp], sz),
         "bqx_result_cols": ([vp], sz),
         "bqx_result_seconds": ([vp], C.c_double),
@@ -183,6 +184,13 @@ class Plan:
 
     def close(self):
         _check(self.L.bqx_plan_close(self.h))
+
+    def run_device(self):
+        """Runs the plan and leaves its output in HBM: a bosql_b200.Relation (kernel-layer handle) the caller owns."""
+        from . import Relation, wrap_context
+        rel = C.c_void_p()
+        _check(self.L.bqx_plan_run_device(self.h, C.byref(rel)))
+        return Relation(wrap_context(self.L.bqx_context()), rel)
 
     def run(self, copy=None) -> Result:
         """open .. next* .. close.  Small results are copied into numpy arrays; large ones (>= 1 MB per column, or copy=False)

@@ -164,6 +164,7 @@ struct OrderBy : public Operator {
     std::shared_ptr<gpu::DeviceRelation> device_result() override;
     // Limit above an OrderBy asks for the first k rows only (top-k instead of a full sort)
     std::shared_ptr<gpu::DeviceRelation> sorted_prefix(int64_t limit);
+    std::shared_ptr<gpu::DeviceRelation> sort_relation(const std::shared_ptr<gpu::DeviceRelation>& in, int64_t limit);
 private:
     std::unique_ptr<Operator> child;
     std::vector<SortKey> sort_keys;

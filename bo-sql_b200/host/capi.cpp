@@ -318,6 +318,28 @@ int bqx_plan_run(bqx_plan* p, bqx_result** out) {
     });
 }
 
+int bqx_plan_run_device(bqx_plan* p, bq_rel** out) {
+    return guarded([&] {
+        p->root->open();
+        gpu::DeviceRelationPtr rel;
+        try {
+            rel = p->root->device_result();
+        } catch (...) {
+            p->root->close();
+            throw;
+        }
+        p->root->close();
+        // an owning relation for the caller: device-to-device copies, so a scan's table columns stay with the table
+        std::vector<bq_col*> cols;
+        for (auto& c : rel->cols) {
+            bq_col* v = nullptr;
+            gpu::check(bq_slice(gpu::context(), c->h, 0, rel->rows, &v));
+            cols.push_back(v);
+        }
+        gpu::check(bq_rel_create(gpu::context(), cols.data(), static_cast<int>(cols.size()), out));
+    });
+}
+
 size_t bqx_result_rows(const bqx_result* r) { return r->rows; }
 size_t bqx_result_cols(const bqx_result* r) { return r->cols.size(); }
 double bqx_result_seconds(const bqx_result* r) { return r->seconds; }

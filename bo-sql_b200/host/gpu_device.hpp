@@ -40,6 +40,9 @@ DevColPtr mirror_of(const Column& col);
 struct DeviceRelation {
     std::vector<DevColPtr> cols;
     size_t rows = 0;
+    // Across GPUs: false = these are the rows THIS rank produced from its shard (scan, selection, join, a GROUP BY whose
+    // groups stay with their owner); true = every rank holds the same complete relation (merged aggregates).
+    bool replicated = false;
 };
 using DeviceRelationPtr = std::shared_ptr<DeviceRelation>;
 DeviceRelationPtr relation_from(bq_rel* rel);     // consumes the bq_rel shell, keeps its columns

@@ -248,7 +248,9 @@ DeviceRelationPtr Selection::device_result() {
     gpu::split_conjuncts(predicate.get(), dict_, conj);
     std::vector<const gpu::Conjunct*> ptrs;
     for (const auto& c : conj) ptrs.push_back(&c);
-    return gpu::run_selection(pipe_cols(names_, types_, *in), in->rows, ptrs);
+    DeviceRelationPtr out = gpu::run_selection(pipe_cols(names_, types_, *in), in->rows, ptrs);
+    out->replicated = in->replicated;
+    return out;
 }
 
 // ---- Project (src/exec/operator.cpp:435-559) ------------------------------------------------------------------------
@@ -296,6 +298,7 @@ void Project::close() { child->close(); }
 DeviceRelationPtr Project::device_result() {
     DeviceRelationPtr in = child->device_result();
     auto out = std::make_shared<DeviceRelation>();
+    out->replicated = in->replicated;
     out->rows = in->rows;
     std::vector<PipeCol> cols = pipe_cols(input_names, input_types, *in);
     for (size_t i = 0; i < expressions.size(); ++i) {
@@ -335,15 +338,23 @@ DeviceRelationPtr Limit::device_result() {
     const int64_t want = limit < 0 ? 0 : limit;
     if (auto* ob = dynamic_cast<OrderBy*>(child.get())) return ob->sorted_prefix(want);      // top-k
     DeviceRelationPtr in = child->device_result();
-    if (static_cast<uint64_t>(want) >= in->rows) return in;
-    auto out = std::make_shared<DeviceRelation>();
-    out->rows = static_cast<size_t>(want);
-    for (auto& c : in->cols) {
-        bq_col* h = nullptr;
-        check(bq_slice(context(), c->h, 0, out->rows, &h));      // copy_range, :51-82
-        out->cols.push_back(gpu::adopt(h));
-    }
-    return out;
+    auto prefix = [&](const DeviceRelationPtr& rel) {
+        if (static_cast<uint64_t>(want) >= rel->rows) return rel;
+        auto out = std::make_shared<DeviceRelation>();
+        out->rows = static_cast<size_t>(want);
+        out->replicated = rel->replicated;
+        for (auto& c : rel->cols) {
+            bq_col* h = nullptr;
+            check(bq_slice(context(), c->h, 0, out->rows, &h));      // copy_range, :51-82
+            out->cols.push_back(gpu::adopt(h));
+        }
+        return DeviceRelationPtr(out);
+    };
+    if (!gpu::exchange().active || in->replicated) return prefix(in);
+    // across GPUs: the first `limit` rows in table order = rank order; each rank contributes at most `limit` of its own
+    DeviceRelationPtr all = gpu::all_gather_relation(prefix(in), types_);
+    all->replicated = true;
+    return prefix(all);
 }
 
 // ---- HashJoin (src/exec/operator.cpp:671-858) ------------------------------------------------------------------------------
@@ -615,6 +626,22 @@ DeviceRelationPtr OrderBy::device_result() { return sorted_prefix(-1); }
 
 DeviceRelationPtr OrderBy::sorted_prefix(int64_t limit) {
     DeviceRelationPtr in = child->device_result();
+    if (!gpu::exchange().active || in->replicated) {
+        DeviceRelationPtr out = sort_relation(in, limit);
+        out->replicated = in->replicated;
+        return out;
+    }
+    // Across GPUs the input is this rank's share of the rows: a local top-k first when there is a LIMIT (each rank's k
+    // best rows are the only candidates), one all-gather, then the same sort on the gathered candidates - every rank ends
+    // up with the complete ordered result (ORDER BY ... LIMIT k).  Without a LIMIT everything is gathered.
+    DeviceRelationPtr local = limit >= 0 ? sort_relation(in, limit) : in;
+    DeviceRelationPtr all = gpu::all_gather_relation(local, types_);
+    DeviceRelationPtr out = sort_relation(all, limit);
+    out->replicated = true;
+    return out;
+}
+
+DeviceRelationPtr OrderBy::sort_relation(const DeviceRelationPtr& in, int64_t limit) {
     if (in->rows == 0 || limit == 0) return gpu::empty_relation(types_);
     if (sort_keys.size() > 4) throw std::runtime_error("more than 4 ORDER BY keys are not supported on the GPU path");
     bq_ctx* ctx = context();

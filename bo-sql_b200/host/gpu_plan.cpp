@@ -560,6 +560,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
     }
 
     // ---- run the passes ---------------------------------------------------------------------------------------------------
+    bool groups_stay_sharded = false;
     std::vector<DeviceRelationPtr> pass_results;
     std::vector<std::vector<size_t>> pass_aggs;      // which aggregates each pass produced, in column order
     for (const Pass& ps : passes) {
@@ -746,6 +747,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                 outcome = attempt(message);
             }
             if (outcome) throw std::runtime_error(message.empty() ? "aggregation failed on another rank" : message);
+            if (xch.fn.keep_sharded) groups_stay_sharded = true;
             if (!xch.fn.keep_sharded) {
                 std::vector<TypeId> rel_types;
                 if (has_key) rel_types.push_back(p.cols[key_col].type);
@@ -815,6 +817,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
 
     // ---- stitch: [keys] then aggregates in declaration order ----------------------------------------------------
     auto out = std::make_shared<DeviceRelation>();
+    out->replicated = dist && !groups_stay_sharded;
     out->rows = pass_results.front()->rows;
     for (auto& pr : pass_results)
         if (pr->rows != out->rows) throw std::runtime_error("internal: aggregate passes disagree on the group count");

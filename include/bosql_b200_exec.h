@@ -89,6 +89,9 @@ int bqx_plan_close(bqx_plan* p);
 
 /* open .. next* .. close into typed columns; seconds = host wall time of that interval */
 int bqx_plan_run(bqx_plan* p, bqx_result** out);
+/* open .. (the root's whole output) .. close, left in HBM: *out is a kernel-layer relation (bq_rel_*; the caller frees it with
+ * bq_rel_free).  For results that feed further device work or are too large to page out (a sharded 10^8-group table). */
+int bqx_plan_run_device(bqx_plan* p, bq_rel** out);
 size_t bqx_result_rows(const bqx_result* r);
 size_t bqx_result_cols(const bqx_result* r);
 double bqx_result_seconds(const bqx_result* r);

@@ -76,6 +76,26 @@ def main():
             ms = float(t)
         return r, ms, wall, (ctx.launches - l0) // steps
 
+    def timed_device(plan, steps):
+        """The same statement with its output left in HBM (bqx_plan_run_device): what a consumer on the GPU would see."""
+        for _ in range(2):
+            plan.run_device().free()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            plan.run_device().free()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t)
+        return ms
+
     def total(x):
         if world == 1:
             return int(x)
@@ -95,12 +115,14 @@ def main():
         calls0 = dict(ex.calls) if ex else {}
         sent0 = ex.bytes_sent if ex else 0
         r, ms, wall, launches = timed(plan, a.steps)
+        ms_dev = timed_device(plan, a.steps)
         groups = total(len(r.cols[0]))
         rows_seen = total(int(r.cols[2].sum()))
         assert rows_seen == n * world, (rows_seen, n * world)
         assert groups <= ids and groups > ids * 0.99, (groups, ids)
         o = {"config": "C4 GROUP BY high-cardinality key", "n_gpus": world, "rows_per_gpu": n, "distinct_keys": groups, "ms_per_step": ms,
-             "host_ms_per_step": wall, "rows_per_sec": n * world / (ms * 1e-3), "algorithmic_gbs": (16 * n * world + 24 * groups) / (ms * 1e-3) / 1e9,
+             "ms_per_step_result_left_in_hbm": ms_dev, "rows_per_sec_result_left_in_hbm": n * world / (ms_dev * 1e-3),
+             "result_bytes_to_host_per_gpu": int(sum(c.nbytes for c in r.cols)), "host_ms_per_step": wall, "rows_per_sec": n * world / (ms * 1e-3), "algorithmic_gbs": (16 * n * world + 24 * groups) / (ms * 1e-3) / 1e9,
              "launches_per_step": int(launches), "sql": "SELECT k, SUM(v), COUNT(*) FROM t GROUP BY k",
              "checked": "counts add up to the input rows; distinct keys within 1 % of the generator's domain"}
         if ex:

@@ -55,6 +55,12 @@ QUERIES = [
                      "GROUP BY o.status ORDER BY o.status", [(0, True)]),
     ("join_rows", "SELECT l.order_id, l.sku, o.status FROM lineitem l JOIN orders o ON l.order_id = o.order_id WHERE l.qty > 49", "sharded"),
     ("filter_rows", "SELECT o.order_id, o.total FROM orders o WHERE o.total > 990", "sharded"),
+    # ORDER BY / LIMIT over sharded rows: local top-k, one all-gather, final top-k - the same complete answer on every rank
+    ("topk_rows", "SELECT o.order_id, o.total FROM orders o WHERE o.status = 'PENDING' ORDER BY o.order_id DESC LIMIT 37", [(0, False)]),
+    ("sort_rows", "SELECT l.order_id, l.qty FROM lineitem l WHERE l.qty > 49 AND l.sku < 40 ORDER BY l.order_id", [(0, True)]),
+    ("limit_rows", "SELECT o.order_id FROM orders o WHERE o.total > 500 LIMIT 25", [(0, True)]),
+    ("topk_join", "SELECT l.order_id, l.sku, o.status FROM lineitem l JOIN orders o ON l.order_id = o.order_id WHERE l.qty > 49 "
+                  "ORDER BY l.order_id DESC, l.sku DESC LIMIT 11", [(0, False), (1, False)]),
 ]
 
 
