@@ -17,7 +17,10 @@
 namespace bq {
 
 constexpr int kPartTile = 2048;                 // rows staged per CTA iteration
-constexpr int kPartRows = kPartTile / kBlock;   // rows per thread per tile
+constexpr int kPartThreads = 512;               // scatter CTA: 4 rows per thread keeps it at 64 registers, two CTAs per SM
+constexpr int kPartRows = kPartTile / kPartThreads;
+constexpr int kHistThreads = 1024;              // histogram CTA (two per SM: one wave, same grid as the scatter)
+constexpr int kHistCells = 2048;                // shared counters per CTA: P partitions x (kHistCells / P) lane-private copies
 constexpr int kMaxPartLog2 = 10;
 
 struct PartParams {
@@ -42,19 +45,35 @@ BQ_D unsigned part_of(long long k, int shift, unsigned mask) {
     return static_cast<unsigned>(key_hash(static_cast<uint64_t>(k)) >> shift) & mask;
 }
 
-__global__ void __launch_bounds__(kBlock) k_part_hist(const __grid_constant__ PartParams p) {
-    extern __shared__ unsigned h[];
+__global__ void __launch_bounds__(kHistThreads) k_part_hist(const __grid_constant__ PartParams p) {
+    __shared__ unsigned h[kHistCells];
     const unsigned P = 1u << p.log2p;
-    for (unsigned i = threadIdx.x; i < P; i += blockDim.x) h[i] = 0;
+    // lanes of a warp use different copies of the counters, so a skewed or tiny partition set does not serialise the atomics
+    const unsigned copies = P >= kHistCells ? 1u : kHistCells / P;
+    const unsigned mine = (threadIdx.x % (copies < 32 ? copies : 32)) * P;
+    for (unsigned i = threadIdx.x; i < kHistCells; i += blockDim.x) h[i] = 0;
     __syncthreads();
     const size_t lo = blockIdx.x * p.rows_per_block;
     const size_t hi = lo + p.rows_per_block < p.n ? lo + p.rows_per_block : p.n;
-    for (size_t t = lo + threadIdx.x; t < hi; t += blockDim.x) {
-        long long k = load_raw(p.key, p.key_kind, p.row_begin + t);
-        atomicAdd(&h[part_of(k, p.shift, P - 1)], 1u);
+    size_t t = lo + threadIdx.x;
+    for (; t + 3 * (size_t)kHistThreads < hi; t += 4 * (size_t)kHistThreads) {          // four independent loads in flight
+        long long k0 = load_raw(p.key, p.key_kind, p.row_begin + t);
+        long long k1 = load_raw(p.key, p.key_kind, p.row_begin + t + kHistThreads);
+        long long k2 = load_raw(p.key, p.key_kind, p.row_begin + t + 2 * kHistThreads);
+        long long k3 = load_raw(p.key, p.key_kind, p.row_begin + t + 3 * kHistThreads);
+        atomicAdd(&h[mine + part_of(k0, p.shift, P - 1)], 1u);
+        atomicAdd(&h[mine + part_of(k1, p.shift, P - 1)], 1u);
+        atomicAdd(&h[mine + part_of(k2, p.shift, P - 1)], 1u);
+        atomicAdd(&h[mine + part_of(k3, p.shift, P - 1)], 1u);
     }
+    for (; t < hi; t += kHistThreads) atomicAdd(&h[mine + part_of(load_raw(p.key, p.key_kind, p.row_begin + t), p.shift, P - 1)], 1u);
     __syncthreads();
-    for (unsigned i = threadIdx.x; i < P; i += blockDim.x) p.hist[static_cast<size_t>(i) * gridDim.x + blockIdx.x] = h[i];
+    const unsigned used = copies < 32 ? copies : 32;
+    for (unsigned i = threadIdx.x; i < P; i += blockDim.x) {
+        unsigned c = 0;
+        for (unsigned r = 0; r < used; ++r) c += h[r * P + i];
+        p.hist[static_cast<size_t>(i) * gridDim.x + blockIdx.x] = c;
+    }
 }
 
 BQ_D void store_narrow(void* base, int width, size_t i, long long v) {
@@ -65,7 +84,7 @@ BQ_D long long load_width(const void* base, int width, size_t i) {
     return width == 8 ? __ldg(static_cast<const long long*>(base) + i) : static_cast<long long>(__ldg(static_cast<const int*>(base) + i));
 }
 
-__global__ void __launch_bounds__(kBlock) k_part_scatter(const __grid_constant__ PartParams p) {
+__global__ void __launch_bounds__(kPartThreads, 2) k_part_scatter(const __grid_constant__ PartParams p) {
     extern __shared__ unsigned char smem_raw[];
     const unsigned P = 1u << p.log2p;
     // layout: skey[T] spay0[T] spay1[T] (8 B each) | cursor[P] dkey[P] dpay0[P] dpay1[P] (8 B) | cnt[P] start[P] (4 B) | spart[T] (2 B)
@@ -79,7 +98,7 @@ __global__ void __launch_bounds__(kBlock) k_part_scatter(const __grid_constant__
     unsigned* cnt = reinterpret_cast<unsigned*>(dpay1 + P);
     unsigned* start = cnt + P;
     unsigned short* spart = reinterpret_cast<unsigned short*>(start + P);
-    __shared__ unsigned warp_tot[kBlock / 32];
+    __shared__ unsigned warp_tot[kPartThreads / 32];
 
     for (unsigned i = threadIdx.x; i < P; i += blockDim.x) {
         // rows of partition i written by the CTAs before this one
@@ -100,7 +119,7 @@ __global__ void __launch_bounds__(kBlock) k_part_scatter(const __grid_constant__
         unsigned part[kPartRows], rank[kPartRows];
 #pragma unroll
         for (int j = 0; j < kPartRows; ++j) {
-            const unsigned x = j * kBlock + threadIdx.x;
+            const unsigned x = j * kPartThreads + threadIdx.x;
             if (x < tn) {
                 const size_t row = p.row_begin + tile + x;
                 k[j] = load_raw(p.key, p.key_kind, row);
@@ -110,16 +129,16 @@ __global__ void __launch_bounds__(kBlock) k_part_scatter(const __grid_constant__
         }
 #pragma unroll
         for (int j = 0; j < kPartRows; ++j) {
-            const unsigned x = j * kBlock + threadIdx.x;
+            const unsigned x = j * kPartThreads + threadIdx.x;
             if (x < tn) {
                 part[j] = part_of(k[j], p.shift, P - 1);
                 rank[j] = atomicAdd(&cnt[part[j]], 1u);
             }
         }
         __syncthreads();
-        // exclusive scan of cnt[0..P) into start[]: each thread owns P/kBlock consecutive entries (P >= kBlock) or one
+        // exclusive scan of cnt[0..P) into start[]: each thread owns P/kPartThreads consecutive entries (P >= kPartThreads) or one
         {
-            const unsigned per = P > (unsigned)kBlock ? P / kBlock : 1;
+            const unsigned per = P > (unsigned)kPartThreads ? P / kPartThreads : 1;
             const unsigned first = threadIdx.x * per;
             unsigned local = 0;
             if (first < P)
@@ -145,7 +164,7 @@ __global__ void __launch_bounds__(kBlock) k_part_scatter(const __grid_constant__
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < kPartRows; ++j) {
-            const unsigned x = j * kBlock + threadIdx.x;
+            const unsigned x = j * kPartThreads + threadIdx.x;
             if (x < tn) {
                 const unsigned at = start[part[j]] + rank[j];
                 skey[at] = k[j];
@@ -212,7 +231,7 @@ static bq_part_plan* part_count(bq_ctx* ctx, const bq_col* key, size_t row_begin
     p.n = n;
     p.log2p = log2_parts;
     p.shift = hash_shift;
-    unsigned G = static_cast<unsigned>(ctx->sm_count) * 3;
+    unsigned G = static_cast<unsigned>(ctx->sm_count) * 2;        // what is resident at once: one wave for both kernels
     const size_t tiles = (n + kPartTile - 1) / kPartTile;
     if (tiles < G) G = static_cast<unsigned>(tiles ? tiles : 1);
     pl->G = G;
@@ -225,7 +244,7 @@ static bq_part_plan* part_count(bq_ctx* ctx, const bq_col* key, size_t row_begin
         p.base = static_cast<unsigned long long*>(pl->base);
         pl->counts.assign(pl->P, 0);
         if (n) {
-            k_part_hist<<<G, kBlock, pl->P * 4, ctx->stream>>>(p);
+            k_part_hist<<<G, kHistThreads, 0, ctx->stream>>>(p);
             ctx->launches++;
             BQ_CUDA(cudaGetLastError());
             exclusive_scan_u32(ctx, p.hist, cells, static_cast<unsigned long long*>(pl->base));
@@ -262,7 +281,7 @@ static void part_scatter(bq_part_plan* pl, const bq_col* const* payload, int n_p
     if (!p.n) return;
     const size_t smem = static_cast<size_t>(kPartTile) * 24 + pl->P * 40 + kPartTile * 2;
     BQ_CUDA(cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    k_part_scatter<<<pl->G, kBlock, smem, ctx->stream>>>(p);
+    k_part_scatter<<<pl->G, kPartThreads, smem, ctx->stream>>>(p);
     ctx->launches++;
     BQ_CUDA(cudaGetLastError());
 }
