@@ -520,3 +520,52 @@ def test_group_by_over_partitioned_rows(bq, ctx):
     o = np.argsort(got[0])
     assert np.array_equal(got[0][o], uk) and np.array_equal(got[1][o], cnt) and np.array_equal(got[2][o], sm)
     assert np.array_equal(got[3][o], sm / cnt)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("log2p", [1, 4, 9])
+def test_partition_count_then_scatter_to_chosen_destinations(bq, ctx, log2p):
+    """The two halves of the partition pass as the multi-GPU shuffle uses them: counts on the host first, then every
+    partition is written where the caller says - here in REVERSE partition order inside one buffer (a peer's buffer in the
+    shuffle).  Rows must arrive complete and each partition must be contiguous at its destination."""
+    import ctypes as C
+    K = bq.kernel_lib()
+    n, P = 300_017, 1 << log2p
+    rng = np.random.default_rng(log2p)
+    k = rng.integers(-10**15, 10**15, size=n).astype(np.int64)
+    v = rng.normal(size=n)
+    d = rng.integers(0, 2**31 - 1, size=n).astype(np.int32)
+    kc, vc, dc = ctx.upload(INT64, k), ctx.upload(DOUBLE, v), ctx.upload(DATE32, d)
+    counts = (C.c_int64 * P)()
+    plan = C.c_void_p()
+    assert K.bq_partition_count(ctx.h, kc.h, 0, n, log2p, 40, counts, C.byref(plan)) == 0, K.bq_last_error()
+    counts = np.array(list(counts), dtype=np.int64)
+    part = ((_key_hash_np(k) >> np.uint64(40)).astype(np.int64)) & (P - 1)
+    assert np.array_equal(counts, np.bincount(part, minlength=P))
+    ko, vo, do = ctx.alloc(INT64, n), ctx.alloc(DOUBLE, n), ctx.alloc(DATE32, n)
+    start = np.concatenate([[0], np.cumsum(counts[::-1])])[:-1][::-1]          # partition P-1 first, partition 0 last
+    mk = lambda base, w: (C.c_void_p * P)(*[base + int(start[q]) * w for q in range(P)])
+    pay = (C.c_void_p * 2)(vc.h, dc.h)
+    assert K.bq_partition_scatter(ctx.h, plan, pay, 2, mk(ko.ptr, 8), mk(vo.ptr, 8), mk(do.ptr, 4)) == 0, K.bq_last_error()
+    K.bq_part_plan_free(plan)
+    gk, gv, gd = ko.to_numpy(), vo.to_numpy(), do.to_numpy()
+    a, b = np.lexsort((d, v, k)), np.lexsort((gd, gv, gk))
+    assert np.array_equal(k[a], gk[b]) and np.array_equal(v[a], gv[b]) and np.array_equal(d[a], gd[b])
+    gpart = ((_key_hash_np(gk) >> np.uint64(40)).astype(np.int64)) & (P - 1)
+    assert np.array_equal(gpart, np.repeat(np.arange(P)[::-1], counts[::-1]))
+
+
+@pytest.mark.gpu
+def test_ipc_export_needs_a_block_of_its_own(bq, ctx):
+    import ctypes as C
+    K = bq.kernel_lib()
+    small = ctx.alloc(INT64, 1000)                       # from the stream-ordered pool: not exportable
+    handle = (C.c_char * 64)()
+    assert K.bq_col_ipc_export(ctx.h, small.h, handle) != 0 and b"shared" in K.bq_last_error()
+    h = C.c_void_p()
+    assert K.bq_col_alloc_shared(ctx.h, INT64, 1000, C.byref(h)) == 0
+    assert K.bq_col_ipc_export(ctx.h, h, handle) == 0, K.bq_last_error()
+    assert any(bytes(handle))                            # a real handle came back
+    K.bq_col_free(ctx.h, h)
+    r, u = C.c_size_t(), C.c_size_t()
+    assert K.bq_ctx_pool_stats(ctx.h, C.byref(r), C.byref(u)) == 0 and r.value >= u.value
