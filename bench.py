@@ -64,22 +64,52 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons while the timed region runs: NVML polled every 5 ms from a thread (the timed region of
+    the default run is ~50 ms), or `nvidia-smi -lms 50` when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NVML_REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("sw_power_cap", 0x4))
 
     def __init__(self, device):
         self.device, self.rows, self.proc = device, [], None
         self.t0 = self.t1 = None
+        self.nvml = None
+        self.samples = []            # (time, sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self._stop = False
 
     def start(self):
-        """Started BEFORE the warm-up so that nvidia-smi is already streaming when the timed region begins."""
+        """Started BEFORE the warm-up so that sampling is already running when the timed region begins."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            index = self.device
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            if vis:
+                index = int(vis.split(",")[self.device])
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml = (pynvml, h)
+            threading.Thread(target=self._poll, daemon=True).start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self._stop:
+            try:
+                self.samples.append((time.time(), float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)),
+                                     int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -92,6 +122,16 @@ class ClockSampler:
         self.t1 = time.time()
 
     def stop(self):
+        if self.nvml:
+            self._stop = True
+            inside = [s for s in self.samples if self.t0 is not None and self.t0 <= s[0] <= (self.t1 or s[0])]
+            window = "timed region"
+            if not inside:
+                inside, window = self.samples[-4:], "around the timed region"
+            reasons = sorted({name for _, _, bits in inside for name, mask in self.NVML_REASONS if bits & mask})
+            sm = [s[1] for s in inside]
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "window": window, "source": "NVML, 5 ms period"}
         if self.proc:
             time.sleep(0.12)
             self.proc.terminate()
@@ -115,7 +155,7 @@ class ClockSampler:
                     if v.lower().startswith("active"):
                         reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm), "window": window}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window, "source": "nvidia-smi -lms 50"}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
