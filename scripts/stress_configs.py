@@ -127,7 +127,9 @@ def main():
              "checked": "counts add up to the input rows; distinct keys within 1 % of the generator's domain"}
         if ex:
             steps_all = a.steps + 2
-            o["nvlink_bytes_sent_per_gpu_per_step"] = (ex.bytes_sent - sent0) // steps_all
+            # the peer-write shuffle moves its rows inside the partition kernel, not through a callback: count them here
+            o["nvlink_bytes_stored_per_gpu_per_step"] = 16 * n * (world - 1) // world
+            o["collective_bytes_sent_per_gpu_per_step"] = (ex.bytes_sent - sent0) // steps_all
             o["collectives_per_step"] = {c: (ex.calls[c] - calls0[c]) // steps_all for c in ex.calls}
         out.append(o)
         del plan, eng, r
