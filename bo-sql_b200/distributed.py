@@ -165,6 +165,8 @@ class Exchange:
         self.staged = device == "cuda" and dist.get_backend(group) == "gloo"
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
+        self._views = {}             # (ptr, nbytes) -> uint8 tensor view (non-owning; building one costs ~20 us)
+        self._streams = {}           # cudaStream_t -> torch.cuda.ExternalStream
         self.calls = {"all_gather": 0, "all_gather_v": 0, "all_to_all_v": 0, "all_reduce_sum_u32": 0, "host_all_gather_i64": 0}
         self.bytes_sent = 0
         self.error = None
@@ -178,13 +180,22 @@ class Exchange:
             return torch.empty(0, dtype=torch.uint8, device=self.device)
         if self.device == "cpu":
             return torch.frombuffer((_C.c_char * n).from_address(ptr), dtype=torch.uint8)
-        return torch.as_tensor(_CudaArray(ptr, n, "|u1"), device="cuda")
+        key = (ptr, n)
+        t = self._views.get(key)
+        if t is None:
+            if len(self._views) > 256:
+                self._views.clear()
+            t = self._views[key] = torch.as_tensor(_CudaArray(ptr, n, "|u1"), device="cuda")
+        return t
 
     def _on(self, stream):
         if self.device == "cpu":
             import contextlib
             return contextlib.nullcontext()
-        return torch.cuda.stream(torch.cuda.ExternalStream(stream or 0))
+        st = self._streams.get(stream)
+        if st is None:
+            st = self._streams[stream] = torch.cuda.ExternalStream(stream or 0)
+        return torch.cuda.stream(st)
 
     def _guard(self, name, fn):
         try:
