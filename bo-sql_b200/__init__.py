@@ -149,6 +149,7 @@ def kernel_lib():
         "bq_agg_finish": ([vp, P(vp), C.c_int, C.c_int, C.c_int, P(AggOut), C.c_int, P(vp)], C.c_int),
         "bq_partition": ([vp, vp, P(vp), C.c_int, sz, sz, C.c_int, C.c_int, P(vp), P(vp), P(vp)], C.c_int),
         "bq_partition_count": ([vp, vp, sz, sz, C.c_int, C.c_int, P(i64), P(vp)], C.c_int),
+        "bq_partition_count_hot": ([vp, vp, sz, sz, C.c_int, C.c_int, P(i64), C.c_int, P(i64), P(vp)], C.c_int),
         "bq_partition_scatter": ([vp, vp, P(vp), C.c_int, P(vp), P(vp), P(vp)], C.c_int),
         "bq_part_plan_free": ([vp], None),
         "bq_col_alloc_shared": ([vp, C.c_int, sz, P(vp)], C.c_int),

@@ -22,6 +22,7 @@ constexpr int kPartRows = kPartTile / kPartThreads;
 constexpr int kHistThreads = 1024;              // histogram CTA (two per SM: one wave, same grid as the scatter)
 constexpr int kHistCells = 2048;                // shared counters per CTA: P partitions x (kHistCells / P) lane-private copies
 constexpr int kMaxPartLog2 = 10;
+constexpr int kMaxHotKeys = 16;
 
 struct PartParams {
     const void* key;
@@ -30,8 +31,11 @@ struct PartParams {
     int pay_w[2];
     int n_pay;
     size_t row_begin, n;
-    int log2p;
+    int log2p;                         // size of the partition tables (hash partitions, plus the hot partition's half)
     int shift;
+    unsigned hash_mask;                // hash partitions - 1
+    int n_hot;                         // rows whose key is one of hot[] go to partition hash_mask + 1 instead (skew handling)
+    long long hot[kMaxHotKeys];
     size_t rows_per_block;
     unsigned* hist;                    // [P][G]
     const unsigned long long* base;    // [P][G]
@@ -41,8 +45,15 @@ struct PartParams {
     void* const* dest_pay[2];          // [P] each
 };
 
-BQ_D unsigned part_of(long long k, int shift, unsigned mask) {
-    return static_cast<unsigned>(key_hash(static_cast<uint64_t>(k)) >> shift) & mask;
+BQ_D unsigned part_of(const PartParams& p, long long k) {
+    unsigned q = static_cast<unsigned>(key_hash(static_cast<uint64_t>(k)) >> p.shift) & p.hash_mask;
+    if (p.n_hot) {
+        bool hot = false;
+#pragma unroll
+        for (int i = 0; i < kMaxHotKeys; ++i) hot = hot || (i < p.n_hot && k == p.hot[i]);
+        if (hot) q = p.hash_mask + 1;
+    }
+    return q;
 }
 
 __global__ void __launch_bounds__(kHistThreads) k_part_hist(const __grid_constant__ PartParams p) {
@@ -61,12 +72,12 @@ __global__ void __launch_bounds__(kHistThreads) k_part_hist(const __grid_constan
         long long k1 = load_raw(p.key, p.key_kind, p.row_begin + t + kHistThreads);
         long long k2 = load_raw(p.key, p.key_kind, p.row_begin + t + 2 * kHistThreads);
         long long k3 = load_raw(p.key, p.key_kind, p.row_begin + t + 3 * kHistThreads);
-        atomicAdd(&h[mine + part_of(k0, p.shift, P - 1)], 1u);
-        atomicAdd(&h[mine + part_of(k1, p.shift, P - 1)], 1u);
-        atomicAdd(&h[mine + part_of(k2, p.shift, P - 1)], 1u);
-        atomicAdd(&h[mine + part_of(k3, p.shift, P - 1)], 1u);
+        atomicAdd(&h[mine + part_of(p, k0)], 1u);
+        atomicAdd(&h[mine + part_of(p, k1)], 1u);
+        atomicAdd(&h[mine + part_of(p, k2)], 1u);
+        atomicAdd(&h[mine + part_of(p, k3)], 1u);
     }
-    for (; t < hi; t += kHistThreads) atomicAdd(&h[mine + part_of(load_raw(p.key, p.key_kind, p.row_begin + t), p.shift, P - 1)], 1u);
+    for (; t < hi; t += kHistThreads) atomicAdd(&h[mine + part_of(p, load_raw(p.key, p.key_kind, p.row_begin + t))], 1u);
     __syncthreads();
     const unsigned used = copies < 32 ? copies : 32;
     for (unsigned i = threadIdx.x; i < P; i += blockDim.x) {
@@ -131,7 +142,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_part_scatter(const __grid_c
         for (int j = 0; j < kPartRows; ++j) {
             const unsigned x = j * kPartThreads + threadIdx.x;
             if (x < tn) {
-                part[j] = part_of(k[j], p.shift, P - 1);
+                part[j] = part_of(p, k[j]);
                 rank[j] = atomicAdd(&cnt[part[j]], 1u);
             }
         }
@@ -216,7 +227,10 @@ static void part_plan_release(bq_part_plan* pl) {
 
 // histogram + scan; `want_host_counts` costs one device-to-host copy (the shuffle needs the sizes on the host anyway)
 static bq_part_plan* part_count(bq_ctx* ctx, const bq_col* key, size_t row_begin, size_t row_end, int log2_parts, int hash_shift,
-                                bool want_host_counts) {
+                                bool want_host_counts, const int64_t* hot_keys = nullptr, int n_hot = 0) {
+    if (n_hot < 0 || n_hot > kMaxHotKeys) throw std::runtime_error("at most 16 hot keys per partition pass");
+    const int log2_hash = log2_parts;
+    if (n_hot) ++log2_parts;           // the hot partition is index 2^log2_hash; the rest of the upper half stays empty
     if (log2_parts < 0 || log2_parts > kMaxPartLog2) throw std::runtime_error("partition count must be 1 .. 1024 (a power of two)");
     if (row_end < row_begin || row_end > key->n) throw std::runtime_error("bad row range");
     const size_t n = row_end - row_begin;
@@ -231,6 +245,9 @@ static bq_part_plan* part_count(bq_ctx* ctx, const bq_col* key, size_t row_begin
     p.n = n;
     p.log2p = log2_parts;
     p.shift = hash_shift;
+    p.hash_mask = (1u << log2_hash) - 1;
+    p.n_hot = n_hot;
+    for (int i = 0; i < n_hot; ++i) p.hot[i] = hot_keys[i];
     unsigned G = static_cast<unsigned>(ctx->sm_count) * 2;        // what is resident at once: one wave for both kernels
     const size_t tiles = (n + kPartTile - 1) / kPartTile;
     if (tiles < G) G = static_cast<unsigned>(tiles ? tiles : 1);
@@ -341,6 +358,15 @@ extern "C" int bq_partition_count(bq_ctx* ctx, const bq_col* key, size_t row_beg
                                   int64_t* host_counts, bq_part_plan** out) {
     return guarded([&] {
         bq_part_plan* pl = part_count(ctx, key, row_begin, row_end, log2_parts, hash_shift, true);
+        for (unsigned q = 0; q < pl->P; ++q) host_counts[q] = pl->counts[q];
+        *out = pl;
+    });
+}
+
+extern "C" int bq_partition_count_hot(bq_ctx* ctx, const bq_col* key, size_t row_begin, size_t row_end, int log2_parts, int hash_shift,
+                                      const int64_t* hot_keys, int n_hot, int64_t* host_counts, bq_part_plan** out) {
+    return guarded([&] {
+        bq_part_plan* pl = part_count(ctx, key, row_begin, row_end, log2_parts, hash_shift, true, hot_keys, n_hot);
         for (unsigned q = 0; q < pl->P; ++q) host_counts[q] = pl->counts[q];
         *out = pl;
     });

@@ -263,16 +263,20 @@ static Shuffled shuffle_collective(const DevColPtr& key, const std::vector<DevCo
 
 // The shuffle as ONE pass: count, agree on sizes, then the partitioning kernel writes every row straight into the owning
 // rank's receive buffer over NVLink (peer memory mapped through CUDA IPC) - no send buffer, no collective on the data path.
-static Shuffled shuffle_peer_write(const DevColPtr& key, const std::vector<DevColPtr>& payload, size_t rows) {
+static Shuffled shuffle_peer_write(const DevColPtr& key, const std::vector<DevColPtr>& payload, size_t rows,
+                                   const std::vector<int64_t>& hot_keys, bool keep_hot_local) {
     Exchange& x = exchange();
     bq_ctx* ctx = context();
     const int W = x.world(), me = x.rank();
     const int log2p = shuffle_log2_parts(W);
     const int P = 1 << log2p;
     PhaseTrace trace;
-    std::vector<int64_t> counts(static_cast<size_t>(P));
+    const bool hot = !hot_keys.empty();
+    const size_t tables = hot ? 2 * static_cast<size_t>(P) : static_cast<size_t>(P);      // entry P = the hot partition
+    std::vector<int64_t> counts(tables);
     bq_part_plan* plan = nullptr;
-    check(bq_partition_count(ctx, key->h, 0, rows, log2p, 40, counts.data(), &plan));
+    if (hot) check(bq_partition_count_hot(ctx, key->h, 0, rows, log2p, 40, hot_keys.data(), static_cast<int>(hot_keys.size()), counts.data(), &plan));
+    else check(bq_partition_count(ctx, key->h, 0, rows, log2p, 40, counts.data(), &plan));
     struct PlanGuard {
         bq_part_plan* p;
         ~PlanGuard() { bq_part_plan_free(p); }
@@ -283,9 +287,19 @@ static Shuffled shuffle_peer_write(const DevColPtr& key, const std::vector<DevCo
     std::vector<int64_t> send_rows(static_cast<size_t>(W), 0);
     for (int r = 0; r < W; ++r)
         for (size_t q = first_part(r); q < first_part(r + 1); ++q) send_rows[static_cast<size_t>(r)] += counts[q];
-    auto matrix = x.host_gather(send_rows);                 // matrix[s*W + d] = rows rank s sends to rank d
-    size_t total = 0;
-    for (int s = 0; s < W; ++s) total += static_cast<size_t>(matrix[static_cast<size_t>(s) * W + me]);
+    const int64_t my_hot = hot ? counts[static_cast<size_t>(P)] : 0;
+    send_rows.push_back(my_hot);
+    const size_t M = static_cast<size_t>(W) + 1;
+    auto matrix = x.host_gather(send_rows);                 // matrix[s*M + d] = rows rank s sends to rank d; [s*M + W] = its hot rows
+    size_t cold = 0, hot_before_me = 0, hot_all = 0;
+    for (int s = 0; s < W; ++s) {
+        cold += static_cast<size_t>(matrix[static_cast<size_t>(s) * M + static_cast<size_t>(me)]);
+        if (s < me) hot_before_me += static_cast<size_t>(matrix[static_cast<size_t>(s) * M + W]);
+        hot_all += static_cast<size_t>(matrix[static_cast<size_t>(s) * M + W]);
+    }
+    // the hot rows follow the hashed ones: mine only, or every rank's in rank order
+    const size_t total = cold + (keep_hot_local ? static_cast<size_t>(my_hot) : hot_all);
+    const size_t my_hot_at = cold + (keep_hot_local ? 0 : hot_before_me);
     if (total > 0xFFFFFFFFull) throw std::runtime_error("a rank would own more than 2^32 rows after the shuffle");
 
     // receive buffers (blocks of their own, exportable) and their handles
@@ -315,24 +329,38 @@ static Shuffled shuffle_peer_write(const DevColPtr& key, const std::vector<DevCo
     trace.mark("shuffle: sizes + handles");
 
     // where my rows of partition q start inside the owning rank's buffers
-    std::vector<void*> dest(static_cast<size_t>(P) * 3, nullptr);
+    std::vector<void*> dest(tables * 3, nullptr);
+    auto type_of = [&](size_t c) { return c == 0 ? key->type() : payload[c - 1]->type(); };
     for (int d = 0; d < W; ++d) {
         size_t row = 0;
-        for (int s = 0; s < me; ++s) row += static_cast<size_t>(matrix[static_cast<size_t>(s) * W + d]);
+        for (int s = 0; s < me; ++s) row += static_cast<size_t>(matrix[static_cast<size_t>(s) * M + static_cast<size_t>(d)]);
         for (size_t q = first_part(d); q < first_part(d + 1); ++q) {
-            for (size_t c = 0; c < n_cols; ++c) {
-                const TypeId t = c == 0 ? key->type() : payload[c - 1]->type();
-                dest[c * P + q] = peer[static_cast<size_t>(d)][c] + row * width_of(t);
-            }
+            for (size_t c = 0; c < n_cols; ++c) dest[c * tables + q] = peer[static_cast<size_t>(d)][c] + row * width_of(type_of(c));
             row += static_cast<size_t>(counts[q]);
         }
     }
+    if (hot)
+        for (size_t c = 0; c < n_cols; ++c) {
+            dest[c * tables + static_cast<size_t>(P)] = ptr_of(recv[c]) + my_hot_at * width_of(type_of(c));
+            for (size_t q = static_cast<size_t>(P) + 1; q < tables; ++q) dest[c * tables + q] = ptr_of(recv[c]);      // never written (0 rows)
+        }
     std::vector<const bq_col*> pay;
     for (const auto& c : payload) pay.push_back(c->h);
-    check(bq_partition_scatter(ctx, plan, pay.data(), static_cast<int>(pay.size()), dest.data(), dest.data() + P, dest.data() + 2 * P));
+    check(bq_partition_scatter(ctx, plan, pay.data(), static_cast<int>(pay.size()), dest.data(), dest.data() + tables, dest.data() + 2 * tables));
     // every rank's writes have landed once every rank's kernel has finished
     x.host_gather({0});
     trace.mark("shuffle: scatter over NVLink");
+    if (hot && !keep_hot_local && hot_all) {
+        // replicate the hot rows: every rank's slice of the tail, gathered in place (rank order)
+        std::vector<int64_t> bytes(static_cast<size_t>(W));
+        for (size_t c = 0; c < n_cols; ++c) {
+            const size_t w = width_of(type_of(c));
+            for (int s = 0; s < W; ++s) bytes[static_cast<size_t>(s)] = matrix[static_cast<size_t>(s) * M + W] * static_cast<int64_t>(w);
+            xcheck(x.fn.all_gather_v(x.fn.user, ptr_of(recv[c]) + my_hot_at * w, ptr_of(recv[c]) + cold * w, bytes.data(), bq_ctx_stream(ctx)),
+                   "all_gather_v");
+        }
+        trace.mark("shuffle: replicate hot rows");
+    }
 
     Shuffled out;
     out.rows = total;
@@ -341,12 +369,16 @@ static Shuffled shuffle_peer_write(const DevColPtr& key, const std::vector<DevCo
     return out;
 }
 
-Shuffled shuffle_by_key(const DevColPtr& key, const std::vector<DevColPtr>& payload, size_t rows) {
+Shuffled shuffle_by_key(const DevColPtr& key, const std::vector<DevColPtr>& payload, size_t rows, const std::vector<int64_t>& hot_keys,
+                        bool keep_hot_local) {
     // $BOSQL_SHUFFLE=collective keeps the two-step form (partition into a send buffer, then the host's all-to-all): the
     // comparison point for the fused peer-write kernel, and the way out on a box without CUDA IPC between the ranks
     const char* mode = std::getenv("BOSQL_SHUFFLE");
-    if (mode && std::string(mode) == "collective") return shuffle_collective(key, payload, rows);
-    return shuffle_peer_write(key, payload, rows);
+    if (mode && std::string(mode) == "collective") {
+        if (!hot_keys.empty()) throw std::runtime_error("BOSQL_SHUFFLE=collective has no hot-key handling");
+        return shuffle_collective(key, payload, rows);
+    }
+    return shuffle_peer_write(key, payload, rows, hot_keys, keep_hot_local);
 }
 
 DeviceRelationPtr all_gather_relation(const DeviceRelationPtr& local, const std::vector<TypeId>& types) {

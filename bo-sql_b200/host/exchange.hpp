@@ -50,7 +50,11 @@ struct Shuffled {
     std::vector<DevColPtr> payload;
     size_t rows = 0;
 };
-Shuffled shuffle_by_key(const DevColPtr& key, const std::vector<DevColPtr>& payload, size_t rows);
+// hot_keys (<= 16, the same list on every rank): rows with one of these keys are NOT moved by hash.  keep_hot_local: they
+// stay on the rank that holds them (the probe side of a skewed join); otherwise every rank receives all of them (the
+// matching build rows, replicated), so the join still sees every pair exactly once.
+Shuffled shuffle_by_key(const DevColPtr& key, const std::vector<DevColPtr>& payload, size_t rows,
+                        const std::vector<int64_t>& hot_keys = {}, bool keep_hot_local = true);
 
 // $BOSQL_TRACE=1: synchronise and print the time since the previous mark (stderr) - phase breakdowns for tuning.
 struct PhaseTrace {

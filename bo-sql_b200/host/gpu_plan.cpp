@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstring>
 #include <limits>
+#include <map>
 
 namespace bosql::gpu {
 
@@ -285,6 +286,74 @@ struct Domain {
 
 }  // namespace
 
+// Heavy hitters of a (probe-side) join key, agreed by all ranks: every rank counts the keys of a sample of its rows
+// (the fused GROUP BY kernel over the first 2^20 rows, top 16 by count), the candidates are pooled on the host, and a key
+// is hot when its estimated share of all rows exceeds 1 / (8 * world) - enough to overload the rank that would own it.
+static std::vector<int64_t> find_hot_keys(PipeCol& key, size_t rows) {
+    Exchange& xch = exchange();
+    bq_ctx* ctx = context();
+    constexpr size_t kSample = 1u << 20;
+    constexpr int kTop = 16;
+    const size_t sample = std::min(rows, kSample);
+    std::vector<int64_t> mine(2 * kTop + 1, 0);          // keys, counts, sample size
+    mine[2 * kTop] = static_cast<int64_t>(sample);
+    if (sample) {
+        bq_scan_spec s{};
+        s.key = make_slot(key.dev, {});
+        s.row_begin = 0;
+        s.row_end = sample;
+        s.group_mode = BQ_GROUP_HASH;
+        s.ndv_hint = sample;
+        s.n_out = 1;
+        s.out[0].func = BQ_AGG_COUNT;
+        bq_rel* rel = nullptr;
+        check(bq_scan_aggregate(ctx, &s, &rel));
+        DeviceRelationPtr counted = relation_from(rel);
+        if (counted->rows) {
+            std::vector<bq_col*> hs = {counted->cols[0]->h, counted->cols[1]->h};
+            bq_rel* shell = nullptr;
+            check(bq_rel_create(ctx, hs.data(), 2, &shell));
+            int by = 1, asc = 0;
+            bq_rel* top = nullptr;
+            int rc = bq_rel_sort(ctx, shell, 1, &by, &asc, kTop, &top);
+            std::vector<bq_col*> back(2);
+            bq_rel_release(shell, back.data());
+            check(rc);
+            DeviceRelationPtr t = relation_from(top);
+            std::vector<int64_t> counts(t->rows);
+            check(bq_col_read(ctx, t->cols[1]->h, 0, t->rows, counts.data()));
+            if (key.type == TypeId::INT64) {
+                std::vector<int64_t> keys(t->rows);
+                check(bq_col_read(ctx, t->cols[0]->h, 0, t->rows, keys.data()));
+                for (size_t i = 0; i < t->rows; ++i) mine[i] = keys[i];
+            } else {
+                std::vector<int32_t> keys(t->rows);                 // DATE32 / STRING ids: 4-byte keys, widened as the kernels do
+                check(bq_col_read(ctx, t->cols[0]->h, 0, t->rows, keys.data()));
+                for (size_t i = 0; i < t->rows; ++i)
+                    mine[i] = key.type == TypeId::STRING ? static_cast<int64_t>(static_cast<uint32_t>(keys[i])) : static_cast<int64_t>(keys[i]);
+            }
+            for (size_t i = 0; i < t->rows; ++i) mine[kTop + i] = counts[i];
+        }
+    }
+    auto all = xch.host_gather(mine);
+    const size_t stride = mine.size();
+    std::map<int64_t, int64_t> pooled;
+    int64_t sampled = 0;
+    for (int r = 0; r < xch.world(); ++r) {
+        sampled += all[r * stride + 2 * kTop];
+        for (int i = 0; i < kTop; ++i)
+            if (all[r * stride + kTop + i] > 0) pooled[all[r * stride + i]] += all[r * stride + kTop + i];
+    }
+    std::vector<std::pair<int64_t, int64_t>> ranked;       // (count, key)
+    for (const auto& kv : pooled)
+        if (sampled > 0 && kv.second * 8 * xch.world() > sampled) ranked.emplace_back(kv.second, kv.first);
+    std::sort(ranked.rbegin(), ranked.rend());
+    std::vector<int64_t> hot;
+    for (size_t i = 0; i < ranked.size() && i < static_cast<size_t>(kTop); ++i) hot.push_back(ranked[i].second);
+    std::sort(hot.begin(), hot.end());                      // the same list, in the same order, on every rank
+    return hot;
+}
+
 DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
     bq_ctx* ctx = context();
     std::vector<TypeId> out_types = req.group_types;
@@ -514,7 +583,59 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                 const uint64_t dom = bk.stats.max_key >= bk.stats.min_key ? static_cast<uint64_t>(bk.stats.max_key - bk.stats.min_key) + 1 : 0;
                 dist_bitmap = dom > 0 && dom <= (1ULL << 32) && dom <= 8 * global_build + 1024 && bk.stats.ndv && bk.stats.ndv == global_build;
             }
+            // Neither: either broadcast the build side, or CO-PARTITION both sides by hash(join key) so that every rank joins
+            // the keys it owns.  The choice is bytes over NVLink; skewed probe keys are handled by keeping the
+            // heavy hitters' probe rows where they are and replicating their (few) build rows to every rank.
+            bool shuffled_join = false;
             if (!dist_bitmap) {
+                PipeCol& pkc = p.cols[p.probe_key];
+                std::vector<int> probe_refs, build_refs;          // columns read downstream, besides the two keys
+                auto note = [&](int c) {
+                    if (c < 0 || c == p.probe_key || c == p.build_key) return;
+                    auto& list = p.cols[c].side ? build_refs : probe_refs;
+                    if (std::find(list.begin(), list.end(), c) == list.end()) list.push_back(c);
+                };
+                note(key_col);
+                for (const auto& v : values) {
+                    note(v.form.col_l);
+                    note(v.form.col_r);
+                }
+                auto row_bytes = [&](const std::vector<int>& refs) {
+                    uint64_t b = 8;
+                    for (int c : refs) b += (p.cols[c].type == TypeId::INT64 || p.cols[c].type == TypeId::DOUBLE) ? 8 : 4;
+                    return b;
+                };
+                const uint64_t W = static_cast<uint64_t>(xch.world());
+                const uint64_t global_probe = static_cast<uint64_t>(xch.host_sum(static_cast<int64_t>(p.rows)));
+                const uint64_t broadcast_in = global_build * row_bytes(build_refs) * (W - 1) / W;                  // per rank
+                const uint64_t shuffle_out = (global_probe * row_bytes(probe_refs) + global_build * row_bytes(build_refs)) / W * (W - 1) / W;
+                const char* force = std::getenv("BOSQL_JOIN");
+                const bool possible = bk.type != TypeId::DOUBLE && pkc.type != TypeId::DOUBLE && probe_conj.empty() && build_conj.empty() &&
+                                      probe_refs.size() <= 2 && build_refs.size() <= 2 && !(std::getenv("BOSQL_SHUFFLE") && std::string(std::getenv("BOSQL_SHUFFLE")) == "collective");
+                bool want = shuffle_out * 4 < broadcast_in * 3;
+                if (force && std::string(force) == "shuffle") want = true;
+                if (force && std::string(force) == "broadcast") want = false;
+                if (possible && want) {
+                    std::vector<int64_t> hot = find_hot_keys(pkc, p.rows);
+                    auto devs = [&](const std::vector<int>& refs) {
+                        std::vector<DevColPtr> d;
+                        for (int c : refs) d.push_back(p.cols[c].dev);
+                        return d;
+                    };
+                    Shuffled sp = shuffle_by_key(pkc.dev, devs(probe_refs), p.rows, hot, true);
+                    pkc.dev = sp.key;
+                    for (size_t i = 0; i < probe_refs.size(); ++i) p.cols[probe_refs[i]].dev = sp.payload[i];
+                    p.rows = sp.rows;
+                    Shuffled sb = shuffle_by_key(bk.dev, devs(build_refs), p.build_rows, hot, false);
+                    bk.dev = sb.key;
+                    for (size_t i = 0; i < build_refs.size(); ++i) p.cols[build_refs[i]].dev = sb.payload[i];
+                    p.build_rows = sb.rows;
+                    // bounds from the catalog still hold for the keys a rank owns; measured (shard) bounds do not
+                    if (bk.stats.measured) bk.stats.known = false;
+                    shuffled_join = true;
+                }
+            }
+            if (!dist_bitmap && !shuffled_join) {
                 for (auto& c : p.cols)
                     if (c.side) c.dev = xch.all_gather_column(c.dev, p.build_rows, rows_by_rank);
                 p.build_rows = static_cast<size_t>(global_build);

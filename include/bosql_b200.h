@@ -271,6 +271,11 @@ int bq_partition(bq_ctx* ctx, const bq_col* key, const bq_col* const* payload, i
 typedef struct bq_part_plan bq_part_plan;
 int bq_partition_count(bq_ctx* ctx, const bq_col* key, size_t row_begin, size_t row_end, int log2_parts, int hash_shift,
                        int64_t* host_counts, bq_part_plan** out);
+/* Skew handling: rows whose key is one of hot_keys[0..n_hot) (<= 16) are counted in, and later scattered to, partition
+ * 2^log2_parts instead of their hash partition; host_counts and the destination tables then have 2^(log2_parts+1) entries
+ * (the entries above the hot one stay empty).  A shuffle keeps that partition local. */
+int bq_partition_count_hot(bq_ctx* ctx, const bq_col* key, size_t row_begin, size_t row_end, int log2_parts, int hash_shift,
+                           const int64_t* hot_keys, int n_hot, int64_t* host_counts, bq_part_plan** out);
 int bq_partition_scatter(bq_ctx* ctx, bq_part_plan* plan, const bq_col* const* payload, int n_payload,
                          void* const* dest_key, void* const* dest_pay0, void* const* dest_pay1);
 void bq_part_plan_free(bq_part_plan* plan);
