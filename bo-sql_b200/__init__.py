@@ -155,6 +155,7 @@ def kernel_lib():
         "bq_col_alloc_shared": ([vp, C.c_int, sz, P(vp)], C.c_int),
         "bq_col_ipc_export": ([vp, vp, vp], C.c_int),
         "bq_ipc_open": ([vp, vp, P(vp)], C.c_int),
+        "bq_ctx_ipc_mappings": ([vp], sz),
         "bq_key_hash": ([i64], C.c_uint64),
         "bq_select": ([vp, P(SelectSpec), P(vp)], C.c_int),
         "bq_gather": ([vp, vp, vp, P(vp)], C.c_int),

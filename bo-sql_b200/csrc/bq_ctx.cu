@@ -281,6 +281,8 @@ int bq_ipc_open(bq_ctx* ctx, const void* handle64, void** device_ptr) {
     });
 }
 
+size_t bq_ctx_ipc_mappings(bq_ctx* ctx) { return ctx->ipc_mappings.size(); }
+
 int bq_ctx_pool_stats(bq_ctx* ctx, size_t* reserved_bytes, size_t* used_bytes) {
     return guarded([&] {
         cudaMemPool_t pool;

@@ -54,8 +54,9 @@ void PhaseTrace::mark(const char* what) {
     const double t = now_ms();
     size_t reserved = 0, used = 0;
     bq_ctx_pool_stats(context(), &reserved, &used);
-    std::fprintf(stderr, "[bosql trace rank %d] %-28s %8.3f ms   pool %.2f / %.2f GiB\n", exchange().active ? exchange().rank() : 0, what,
-                 t - last, used / 1073741824.0, reserved / 1073741824.0);
+    std::fprintf(stderr, "[bosql trace rank %d] %-28s %8.3f ms   pool %.2f / %.2f GiB   peer blocks mapped %zu\n",
+                 exchange().active ? exchange().rank() : 0, what, t - last, used / 1073741824.0, reserved / 1073741824.0,
+                 bq_ctx_ipc_mappings(context()));
     last = now_ms();
 }
 

@@ -573,6 +573,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         // being unique) - the probe side never moves.  Anything else is a broadcast join: the build columns are
         // all-gathered and every rank builds the full table.
         bool dist_bitmap = false;
+        uint64_t shuffled_global_build = 0;      // > 0: both sides were co-partitioned; the key domain is still the global one
         if (dist) {
             auto rows_by_rank = xch.host_gather({static_cast<int64_t>(p.build_rows)});
             uint64_t global_build = 0;
@@ -587,6 +588,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             // the keys it owns.  The choice is bytes over NVLink; skewed probe keys are handled by keeping the
             // heavy hitters' probe rows where they are and replicating their (few) build rows to every rank.
             bool shuffled_join = false;
+            shuffled_global_build = 0;
             if (!dist_bitmap) {
                 PipeCol& pkc = p.cols[p.probe_key];
                 std::vector<int> probe_refs, build_refs;          // columns read downstream, besides the two keys
@@ -612,7 +614,10 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                 const char* force = std::getenv("BOSQL_JOIN");
                 const bool possible = bk.type != TypeId::DOUBLE && pkc.type != TypeId::DOUBLE && probe_conj.empty() && build_conj.empty() &&
                                       probe_refs.size() <= 2 && build_refs.size() <= 2 && !(std::getenv("BOSQL_SHUFFLE") && std::string(std::getenv("BOSQL_SHUFFLE")) == "collective");
-                bool want = shuffle_out * 4 < broadcast_in * 3;
+                // measured on configuration 5, 8 GPUs (profiles/README.md): at 0.63 of the broadcast's bytes the shuffle wins by
+                // 7 % (13.7 vs 14.7 ms) - its two partition passes, heavy-hitter detection and size/handle exchanges eat most
+                // of the saving - so it is chosen from 0.7 down
+                bool want = shuffle_out * 10 < broadcast_in * 7;
                 if (force && std::string(force) == "shuffle") want = true;
                 if (force && std::string(force) == "broadcast") want = false;
                 if (possible && want) {
@@ -633,6 +638,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                     // bounds from the catalog still hold for the keys a rank owns; measured (shard) bounds do not
                     if (bk.stats.measured) bk.stats.known = false;
                     shuffled_join = true;
+                    shuffled_global_build = global_build;
                 }
             }
             if (!dist_bitmap && !shuffled_join) {
@@ -668,6 +674,12 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             js.unique = (bk.stats.ndv && bk.stats.ndv == p.build_rows) ? 1 : 0;
         } else {
             js.kind = BQ_JOIN_HASH;
+        }
+        if (shuffled_global_build && js.kind == BQ_JOIN_AUTO && js.key_max >= js.key_min) {
+            // a rank owns 1/world of a domain that is dense GLOBALLY: judge the density on the whole build side, or ranks
+            // just under the threshold would fall back to a hash table (measured: 27 ms instead of 2 on configuration 5)
+            const uint64_t dom = static_cast<uint64_t>(js.key_max - js.key_min) + 1;
+            if (dom <= (1ULL << 32) && dom <= 8 * shuffled_global_build + 1024) js.kind = need_rows ? BQ_JOIN_DIRECT : BQ_JOIN_BITMAP;
         }
         check(bq_join_build(ctx, &js, &join));
         if (dist_bitmap) {

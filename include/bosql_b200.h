@@ -287,6 +287,7 @@ void bq_part_plan_free(bq_part_plan* plan);
 int bq_col_alloc_shared(bq_ctx* ctx, int type, size_t n, bq_col** out);
 int bq_col_ipc_export(bq_ctx* ctx, const bq_col* col, void* handle64);
 int bq_ipc_open(bq_ctx* ctx, const void* handle64, void** device_ptr);
+size_t bq_ctx_ipc_mappings(bq_ctx* ctx);                 /* peer blocks mapped so far (diagnostics) */
 /* the hash all tables and partitions use (so a caller can predict a key's partition) */
 uint64_t bq_key_hash(int64_t key);
 
