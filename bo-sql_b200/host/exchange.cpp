@@ -209,8 +209,7 @@ static Shuffled shuffle_collective(const DevColPtr& key, const std::vector<DevCo
     Exchange& x = exchange();
     bq_ctx* ctx = context();
     const int W = x.world();
-    // partitions: a power of two >= 8 * world, handed to ranks in contiguous runs so any world size works and the
-    // runs stay balanced; hash bits [40, 40 + log2 P) are disjoint from the bits the local tables use (top and bottom)
+    // the two-step form: partition into a send buffer (one contiguous run per rank), then the host's all-to-all
     const int log2p = shuffle_log2_parts(W);
     const int P = 1 << log2p;
     std::vector<const bq_col*> pay;
