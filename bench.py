@@ -212,9 +212,9 @@ def run_ours(args):
     import torch.distributed as dist
 
     from __graft_entry__ import load_package
-    from oracle import datagen
 
     bq = load_package()
+    from bosql_b200 import synthetic as datagen        # workload definitions only; the oracle is imported in the cpu_baseline leg
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -1,0 +1,58 @@
+"""bosql_b200.synthetic — the synthetic workload definitions of SURVEY.md section 8d (which columns, which distributions).
+
+Pure descriptions: a schema is a list of (column name, type, generator spec) that `Column.generate` (bo-sql_b200/csrc/
+bq_gen.cu) turns into HBM-resident columns; value(row) = f(seed, stream, global row), so any rank can generate any shard.
+`oracle/datagen.py` restates the generator's arithmetic in numpy for the tests and re-exports these definitions; nothing here
+imports the oracle.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+GEN_SEQ, GEN_UNIFORM, GEN_UNIFORM_DIV, GEN_DATE, GEN_TABLE, GEN_HASHED = range(6)
+INT64, DOUBLE, STRING, DATE32 = 0, 1, 2, 3
+
+STATUS_DICT = ["COMPLETE", "PENDING", "CANCELLED", "RETURNED"]     # ids 0..3 (first-seen order)
+
+
+def orders_schema(n_orders, prefix="", div=100.0):
+    """o.order_id unique dense 1..N; o.status uniform over 4 ids; o.order_date 2024 days; o.total k/div."""
+    p = prefix
+    return [
+        (p + "order_id", INT64, dict(dist=GEN_SEQ, lo=1)),
+        (p + "status", STRING, dict(dist=GEN_UNIFORM, lo=0, hi=3)),
+        (p + "order_date", DATE32, dict(dist=GEN_DATE, base_year=2024, n_years=1)),
+        (p + "total", DOUBLE, dict(dist=GEN_UNIFORM_DIV, lo=100, hi=100000, div=div)),
+    ]
+
+
+def lineitem_schema(n_orders, n_sku=100000, prefix="l.", div=100.0, sku_type=INT64):
+    p = prefix
+    return [
+        (p + "order_id", INT64, dict(dist=GEN_UNIFORM, lo=1, hi=n_orders)),
+        (p + "sku", sku_type, dict(dist=GEN_UNIFORM, lo=0, hi=n_sku - 1)),
+        (p + "qty", INT64, dict(dist=GEN_UNIFORM, lo=1, hi=50)),
+        (p + "price", DOUBLE, dict(dist=GEN_UNIFORM_DIV, lo=100, hi=10000, div=div)),
+    ]
+
+
+def sweep_schema(div=100.0):
+    """Filter-sweep table: one predicate column per type + v DOUBLE + w INT64 (sum of w stays below 2^53)."""
+    return [
+        ("c_i64", INT64, dict(dist=GEN_UNIFORM, lo=0, hi=999999)),
+        ("c_f64", DOUBLE, dict(dist=GEN_UNIFORM_DIV, lo=0, hi=999999, div=div)),
+        ("c_str", STRING, dict(dist=GEN_UNIFORM, lo=0, hi=99)),
+        ("c_date", DATE32, dict(dist=GEN_DATE, base_year=2015, n_years=10)),
+        ("v", DOUBLE, dict(dist=GEN_UNIFORM_DIV, lo=100, hi=100000, div=div)),
+        ("w", INT64, dict(dist=GEN_UNIFORM, lo=1, hi=1000)),
+    ]
+
+
+def zipf_cdf(n_keys: int, s: float = 1.1) -> np.ndarray:
+    """53-bit integer thresholds of a Zipf(s) distribution over n_keys ranks (for GEN_TABLE)."""
+    w = 1.0 / np.power(np.arange(1, n_keys + 1, dtype=np.float64), s)
+    c = np.cumsum(w)
+    c /= c[-1]
+    t = np.floor(c * float(1 << 53)).astype(np.uint64)
+    t[-1] = np.uint64(1 << 53)
+    return t

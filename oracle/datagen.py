@@ -76,53 +76,27 @@ def generate(typ, n, dist, seed, stream, lo=0, hi=0, div=1.0, base_year=2024, n_
     return v.astype(NP_DTYPES[typ])
 
 
-# ---- table schemas -------------------------------------------------------------------
-STATUS_DICT = ["COMPLETE", "PENDING", "CANCELLED", "RETURNED"]     # ids 0..3 (first-seen order)
+# ---- table schemas: defined once, next to the product's generator binding --------------------------------
+def _load_workload_definitions():
+    """bo-sql_b200/synthetic.py loaded by path (the directory name has a hyphen, and the oracle must not pull the package's
+    native libraries in just to read a few dictionaries)."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bo-sql_b200", "synthetic.py")
+    spec = importlib.util.spec_from_file_location("_bosql_synthetic_definitions", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
 
 
-def orders_schema(n_orders, prefix="", div=100.0):
-    """o.order_id unique dense 1..N; o.status uniform over 4 ids; o.order_date 2024 days; o.total k/div."""
-    p = prefix
-    return [
-        (p + "order_id", INT64, dict(dist=GEN_SEQ, lo=1)),
-        (p + "status", STRING, dict(dist=GEN_UNIFORM, lo=0, hi=3)),
-        (p + "order_date", DATE32, dict(dist=GEN_DATE, base_year=2024, n_years=1)),
-        (p + "total", DOUBLE, dict(dist=GEN_UNIFORM_DIV, lo=100, hi=100000, div=div)),
-    ]
-
-
-def lineitem_schema(n_orders, n_sku=100000, prefix="l.", div=100.0, sku_type=INT64):
-    p = prefix
-    return [
-        (p + "order_id", INT64, dict(dist=GEN_UNIFORM, lo=1, hi=n_orders)),
-        (p + "sku", sku_type, dict(dist=GEN_UNIFORM, lo=0, hi=n_sku - 1)),
-        (p + "qty", INT64, dict(dist=GEN_UNIFORM, lo=1, hi=50)),
-        (p + "price", DOUBLE, dict(dist=GEN_UNIFORM_DIV, lo=100, hi=10000, div=div)),
-    ]
-
-
-def sweep_schema(div=100.0):
-    """Filter-sweep table: one predicate column per type + v DOUBLE + w INT64 (sum of w stays below 2^53)."""
-    return [
-        ("c_i64", INT64, dict(dist=GEN_UNIFORM, lo=0, hi=999999)),
-        ("c_f64", DOUBLE, dict(dist=GEN_UNIFORM_DIV, lo=0, hi=999999, div=div)),
-        ("c_str", STRING, dict(dist=GEN_UNIFORM, lo=0, hi=99)),
-        ("c_date", DATE32, dict(dist=GEN_DATE, base_year=2015, n_years=10)),
-        ("v", DOUBLE, dict(dist=GEN_UNIFORM_DIV, lo=100, hi=100000, div=div)),
-        ("w", INT64, dict(dist=GEN_UNIFORM, lo=1, hi=1000)),
-    ]
+_defs = _load_workload_definitions()
+STATUS_DICT = _defs.STATUS_DICT
+orders_schema = _defs.orders_schema
+lineitem_schema = _defs.lineitem_schema
+sweep_schema = _defs.sweep_schema
+zipf_cdf = _defs.zipf_cdf
 
 
 def host_table(schema, n, seed, row0=0):
     """[(name, type, numpy array)] for rows [row0, row0+n) — stream id = column position."""
     return [(name, typ, generate(typ, n, seed=seed, stream=i, row0=row0, **spec)) for i, (name, typ, spec) in enumerate(schema)]
-
-
-def zipf_cdf(n_keys: int, s: float = 1.1) -> np.ndarray:
-    """53-bit integer thresholds of a Zipf(s) distribution over n_keys ranks (for GEN_TABLE)."""
-    w = 1.0 / np.power(np.arange(1, n_keys + 1, dtype=np.float64), s)
-    c = np.cumsum(w)
-    c /= c[-1]
-    t = np.floor(c * float(1 << 53)).astype(np.uint64)
-    t[-1] = np.uint64(1 << 53)
-    return t

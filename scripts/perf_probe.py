@@ -7,10 +7,10 @@ import time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
-from oracle import datagen  # noqa: E402
 from tests.parity import q1_kernel_spec  # noqa: E402
 
 bq = load_package()
+from bosql_b200 import synthetic as datagen  # noqa: E402
 n = int(float(sys.argv[1])) if len(sys.argv) > 1 else 1_000_000_000
 ctx = bq.Context(0)
 print("sm, free, total:", ctx.info())

@@ -24,7 +24,6 @@ import torch.distributed as dist
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from __graft_entry__ import load_package  # noqa: E402
-from oracle import datagen  # noqa: E402
 
 
 def main():
@@ -41,6 +40,7 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     bq = load_package()
+    from bosql_b200 import synthetic as datagen
     xl = bq.exec_lib()
     if xl.bqx_init(local):
         raise RuntimeError(xl.bqx_last_error().decode())

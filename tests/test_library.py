@@ -73,3 +73,26 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert not pat.search(text), f"{f} references the oracle"
+
+
+def test_bench_uses_the_oracle_only_in_its_checker_legs():
+    """bench.py may touch oracle/ in the reference arm (run_reference) and in the cpu_baseline block of run_ours, nowhere
+    else: the measured path imports the workload definitions from the package (bosql_b200.synthetic)."""
+    import ast
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    tree = ast.parse(src)
+    lines = src.splitlines()
+    funcs = {n.name: n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef)}
+    for node in ast.walk(tree):
+        if isinstance(node, ast.ImportFrom) and node.module and node.module.split(".")[0] == "oracle" or \
+           isinstance(node, ast.Import) and any(a.name.split(".")[0] == "oracle" for a in node.names):
+            inside = [name for name, f in funcs.items() if f.lineno <= node.lineno <= f.end_lineno]
+            if "run_reference" in inside:
+                continue
+            assert "run_ours" in inside, f"bench.py:{node.lineno} imports the oracle at module level"
+            # inside run_ours: only under the cpu_baseline block
+            back = "\n".join(lines[max(0, node.lineno - 12):node.lineno])
+            assert "cpu_baseline" in back, f"bench.py:{node.lineno}: oracle import outside the cpu_baseline leg"
+    for script in ("stress_configs.py", "perf_probe.py"):
+        text = open(os.path.join(ROOT, "scripts", script)).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"scripts/{script} imports the oracle"
