@@ -1,8 +1,11 @@
-"""CPU, world_size 2, gloo: the exchange step of a row-range-partitioned aggregate (bosql_b200.distributed).
+"""CPU, world_size 2 and 3, gloo: the exchange table the C++ operator layer calls (bosql_b200.distributed.Exchange).
 
-Each rank aggregates its own row range (numpy restatement of the fused kernel's partial state), the partial states are
-all-gathered and merged in rank order; the result must equal the single-process aggregate of the whole table.  On GPUs the
-same functions run over NCCL with the kernels producing / consuming the states (bench.py --gpus N)."""
+First test: the exchange step of a row-range-partitioned aggregate exactly as `gather_partials` (bo-sql_b200/host/
+exchange.cpp) drives it - each rank's partial state [key, count, sum0, sum1] packed into one zero-padded block of fixed
+capacity, ONE all_gather callback, per-rank views, merge in rank order (numpy restatements of the kernels on both ends) - must
+equal the single-process aggregate of the whole table.  On GPUs the same callbacks run over NCCL with the kernels producing and
+consuming the blocks (tests/test_distributed_gpu.py, bench.py --gpus N).  Second test: every callback of the table against
+known answers, over host pointers."""
 import os
 import socket
 
@@ -44,40 +47,45 @@ def _merge(g_key, g_cnt, g_s0):
     return keys, cnt, s0
 
 
+def _align16(b):
+    return (b + 15) // 16 * 16
+
+
 def _worker(rank, world, port, n, q):
+    import ctypes as C
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from __graft_entry__ import load_package
-        bq = load_package()
+        load_package()
         from bosql_b200 import distributed as D
+        ex = D.Exchange(device="cpu")
         tab = datagen.host_table(datagen.orders_schema(n), n, seed=11)
         cols = {name: a for name, _t, a in tab}
         lo, hi = rank * n // world, (rank + 1) * n // world
         part = _partial(cols, lo, hi)
         cap = 20241228 - 20240101 + 1
-        gathered = D.gather_partials([torch.from_numpy(np.ascontiguousarray(c)) for c in part], cap)
-        g = [x.numpy() for x in gathered]
-        assert all(len(x) == cap * world for x in g)
-        # rank r's rows sit in [r*cap, r*cap + len(part_r)) in rank order
+        # the block layout of gather_partials: columns back to back, each padded to 16 bytes, `cap` rows each, zero filled
+        widths = [c.dtype.itemsize for c in part]
+        offs = np.concatenate([[0], np.cumsum([_align16(w * cap) for w in widths])]).astype(int)
+        block = int(offs[-1])
+        send = np.zeros(block, dtype=np.uint8)
+        for c, o in zip(part, offs):
+            send[o:o + c.nbytes] = np.frombuffer(c.tobytes(), dtype=np.uint8)
+        recv = np.zeros(block * world, dtype=np.uint8)
+        assert ex.table.all_gather(None, send.ctypes.data_as(C.c_void_p), recv.ctypes.data_as(C.c_void_p), block, None) == 0, ex.error
+        g = [np.concatenate([recv[r * block + o: r * block + o + w * cap].view(c.dtype) for r in range(world)])
+             for c, o, w in zip(part, offs, widths)]
+        # rank r's rows sit in [r*cap, r*cap + len(part_r)) in rank order, padding rows have count 0
         mine = slice(rank * cap, rank * cap + len(part[0]))
         assert np.array_equal(g[0][mine], part[0]) and np.array_equal(g[1][mine], part[1])
         keys, cnt, s0 = _merge(g[0], g[1], g[2])
-        # the packed variant (one collective) must deliver the same rows, as per-rank views
-        _buf, views = D.gather_partials_packed([torch.from_numpy(np.ascontiguousarray(c)) for c in part], cap)
-        for rk in range(world):
-            for ci in range(4):
-                assert np.array_equal(views[rk][ci].numpy(), g[ci][rk * cap:(rk + 1) * cap])
-        # bitmap union: disjoint bits from each rank
-        words = torch.zeros(64, dtype=torch.int32)
+        # bitmap union: disjoint bits from each rank, summed
+        words = np.zeros(64, dtype=np.int32)
         words[rank::world] = 1 << rank
-        D.or_reduce_bitmap(words)
-        # the count exchange of the key-hash shuffle: rank r tells every peer how many rows it will send
-        send = torch.tensor([10 * rank + p for p in range(world)], dtype=torch.int64)
-        recv = D.exchange_counts(send)
-        assert recv.tolist() == [10 * p + rank for p in range(world)]
-        q.put((rank, keys, cnt, s0, words.numpy()))
+        assert ex.table.all_reduce_sum_u32(None, words.ctypes.data_as(C.c_void_p), 64, None) == 0, ex.error
+        q.put((rank, keys, cnt, s0, words))
     finally:
         dist.destroy_process_group()
 
