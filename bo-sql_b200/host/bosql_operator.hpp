@@ -66,12 +66,16 @@ protected:
     bool paged_ = false;
 };
 
+// Every operator overrides the reference's open / next / close and the device-side device_result().
+#define BQ_OPERATOR_LIFECYCLE                   \
+    void open() override;                       \
+    bool next(ExecBatch& out) override;         \
+    void close() override;                      \
+    std::shared_ptr<gpu::DeviceRelation> device_result() override;
+
 struct ColumnarScan : public Operator {
     ColumnarScan(Table* t, std::vector<size_t> idx, size_t batch = 4096);
-    void open() override;
-    bool next(ExecBatch& out) override;
-    void close() override;
-    std::shared_ptr<gpu::DeviceRelation> device_result() override;
+    BQ_OPERATOR_LIFECYCLE
     bool describe(gpu::Pipeline&) override;
     // Catalog statistics for this table (the planner attaches them; the reference's scan sees only Table*).
     void set_table_meta(const TableMeta* meta) { meta_ = meta; }
@@ -85,25 +89,19 @@ private:
 
 struct Selection : public Operator {
     Selection(std::unique_ptr<Operator> c, std::unique_ptr<Expr> pred);
-    void open() override;
-    bool next(ExecBatch& out) override;
-    void close() override;
-    std::shared_ptr<gpu::DeviceRelation> device_result() override;
+    BQ_OPERATOR_LIFECYCLE
     bool describe(gpu::Pipeline&) override;
 private:
-    std::unique_ptr<Operator> child;
+    std::unique_ptr<Operator> input_;
     std::unique_ptr<Expr> predicate;
     ExprBindings bindings;
 };
 
 struct Project : public Operator {
     Project(std::unique_ptr<Operator> c, std::vector<std::unique_ptr<Expr>> exprs, std::vector<std::string> aliases);
-    void open() override;
-    bool next(ExecBatch& out) override;
-    void close() override;
-    std::shared_ptr<gpu::DeviceRelation> device_result() override;
+    BQ_OPERATOR_LIFECYCLE
 private:
-    std::unique_ptr<Operator> child;
+    std::unique_ptr<Operator> input_;
     std::vector<std::unique_ptr<Expr>> expressions;
     std::vector<std::string> aliases;
     ExprBindings bindings;
@@ -115,10 +113,7 @@ private:
 struct HashJoin : public Operator {
     HashJoin(std::unique_ptr<Operator> left, std::unique_ptr<Operator> right, std::vector<std::string> left_keys,
              std::vector<std::string> right_keys, std::unique_ptr<Expr> residual);
-    void open() override;
-    bool next(ExecBatch& out) override;
-    void close() override;
-    std::shared_ptr<gpu::DeviceRelation> device_result() override;
+    BQ_OPERATOR_LIFECYCLE
     bool describe(gpu::Pipeline&) override;
 private:
     std::unique_ptr<Operator> left_child, right_child;
@@ -137,14 +132,11 @@ struct AggregateSpec {
 };
 
 struct HashAggregate : public Operator {
-    HashAggregate(std::unique_ptr<Operator> child, std::vector<std::unique_ptr<Expr>> group_exprs,
+    HashAggregate(std::unique_ptr<Operator> input, std::vector<std::unique_ptr<Expr>> group_exprs,
                   std::vector<AggregateSpec> aggregates);
-    void open() override;
-    bool next(ExecBatch& out) override;
-    void close() override;
-    std::shared_ptr<gpu::DeviceRelation> device_result() override;
+    BQ_OPERATOR_LIFECYCLE
 private:
-    std::unique_ptr<Operator> child;
+    std::unique_ptr<Operator> input_;
     std::vector<std::unique_ptr<Expr>> group_exprs;
     std::vector<AggregateSpec> aggregates;
     ExprBindings child_bindings;
@@ -157,16 +149,13 @@ struct OrderBy : public Operator {
         std::unique_ptr<Expr> expr;
         bool asc;
     };
-    OrderBy(std::unique_ptr<Operator> child, std::vector<SortKey> sort_keys);
-    void open() override;
-    bool next(ExecBatch& out) override;
-    void close() override;
-    std::shared_ptr<gpu::DeviceRelation> device_result() override;
+    OrderBy(std::unique_ptr<Operator> input, std::vector<SortKey> sort_keys);
+    BQ_OPERATOR_LIFECYCLE
     // Limit above an OrderBy asks for the first k rows only (top-k instead of a full sort)
     std::shared_ptr<gpu::DeviceRelation> sorted_prefix(int64_t limit);
     std::shared_ptr<gpu::DeviceRelation> sort_relation(const std::shared_ptr<gpu::DeviceRelation>& in, int64_t limit);
 private:
-    std::unique_ptr<Operator> child;
+    std::unique_ptr<Operator> input_;
     std::vector<SortKey> sort_keys;
     ExprBindings bindings;
     bool child_consumed = false;
@@ -174,12 +163,9 @@ private:
 
 struct Limit : public Operator {
     Limit(std::unique_ptr<Operator> c, int64_t n);
-    void open() override;
-    bool next(ExecBatch& out) override;
-    void close() override;
-    std::shared_ptr<gpu::DeviceRelation> device_result() override;
+    BQ_OPERATOR_LIFECYCLE
 private:
-    std::unique_ptr<Operator> child;
+    std::unique_ptr<Operator> input_;
     int64_t limit;
 };
 

@@ -100,18 +100,21 @@ protected:
     std::string with_children(std::string head, int indent) const;
 };
 
+// every node prints itself the way the reference's LogicalOp::to_string does (plan-shape tests compare the text)
+#define BQ_PLAN_TEXT std::string to_string(int indent = 0) const override;
+
 struct LogicalScan : LogicalOp {
     std::string table_name;
     std::vector<std::string> columns;
     LogicalScan(const std::string& table, const std::vector<std::string>& cols)
         : LogicalOp(LogicalOpType::SCAN), table_name(table), columns(cols) {}
-    std::string to_string(int indent = 0) const override;
+    BQ_PLAN_TEXT
 };
 
 struct LogicalFilter : LogicalOp {
     std::unique_ptr<Expr> predicate;
     explicit LogicalFilter(std::unique_ptr<Expr> pred) : LogicalOp(LogicalOpType::FILTER), predicate(std::move(pred)) {}
-    std::string to_string(int indent = 0) const override;
+    BQ_PLAN_TEXT
 };
 
 struct LogicalProject : LogicalOp {
@@ -119,7 +122,7 @@ struct LogicalProject : LogicalOp {
     std::vector<std::string> aliases;
     LogicalProject(std::vector<std::unique_ptr<Expr>>&& selects, std::vector<std::string>&& alias_list)
         : LogicalOp(LogicalOpType::PROJECT), select_list(std::move(selects)), aliases(std::move(alias_list)) {}
-    std::string to_string(int indent = 0) const override;
+    BQ_PLAN_TEXT
 };
 
 struct LogicalHashJoin : LogicalOp {
@@ -127,7 +130,7 @@ struct LogicalHashJoin : LogicalOp {
     std::unique_ptr<Expr> join_filter;
     LogicalHashJoin(std::vector<std::string> l, std::vector<std::string> r, std::unique_ptr<Expr> filter = nullptr)
         : LogicalOp(LogicalOpType::HASH_JOIN), left_keys(std::move(l)), right_keys(std::move(r)), join_filter(std::move(filter)) {}
-    std::string to_string(int indent = 0) const override;
+    BQ_PLAN_TEXT
 };
 
 struct LogicalAggregate : LogicalOp {
@@ -140,7 +143,7 @@ struct LogicalAggregate : LogicalOp {
     std::vector<AggExpr> aggregates;
     LogicalAggregate(std::vector<std::unique_ptr<Expr>>&& keys, std::vector<AggExpr>&& aggs)
         : LogicalOp(LogicalOpType::AGGREGATE), group_keys(std::move(keys)), aggregates(std::move(aggs)) {}
-    std::string to_string(int indent = 0) const override;
+    BQ_PLAN_TEXT
 };
 
 struct LogicalOrder : LogicalOp {
@@ -150,13 +153,13 @@ struct LogicalOrder : LogicalOp {
     };
     std::vector<OrderItem> order_by;
     explicit LogicalOrder(std::vector<OrderItem>&& order) : LogicalOp(LogicalOpType::ORDER), order_by(std::move(order)) {}
-    std::string to_string(int indent = 0) const override;
+    BQ_PLAN_TEXT
 };
 
 struct LogicalLimit : LogicalOp {
     int64_t limit;
     explicit LogicalLimit(int64_t lim) : LogicalOp(LogicalOpType::LIMIT), limit(lim) {}
-    std::string to_string(int indent = 0) const override;
+    BQ_PLAN_TEXT
 };
 
 class LogicalPlanner {

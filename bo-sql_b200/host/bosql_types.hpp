@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <istream>
 #include <memory>
 #include <optional>
 #include <span>
@@ -228,5 +229,13 @@ public:
     OptionalRef<const TableMeta> get_table_meta(const std::string& name) const;
     std::vector<std::string> list_tables() const;
 };
+
+// ---- CSV ingest (host/csv_ingest.cpp) -----------------------------------------------------------------
+// The reference's load_csv contract (include/storage/csv_loader.h:18-19, src/storage/csv_loader.cpp:7-166): header line,
+// comma separated, no quoting; per column DATE32 (all values 8 characters, stoi in [19000000, 21000000]) else INT64 (all
+// values stod-integral) else DOUBLE (all values stod-parsable) else STRING (dictionary ids in first-seen order); min / max /
+// ndv recorded in the TableMeta.
+std::pair<Table, TableMeta> load_csv(std::istream& stream);
+std::pair<Table, TableMeta> load_csv(const std::string& filename);
 
 }  // namespace bosql

@@ -11,7 +11,7 @@
 #include <sstream>
 
 #include "bosql_operator.hpp"
-#include "csv_loader.hpp"
+#include "bosql_types.hpp"
 
 using namespace bosql;
 

@@ -5,7 +5,7 @@
 
 #include "bosql_b200_exec.h"
 #include "bosql_operator.hpp"
-#include "csv_loader.hpp"
+#include "bosql_types.hpp"
 #include "exchange.hpp"
 #include "gpu_device.hpp"
 

@@ -1,11 +1,11 @@
-// csv_loader.cpp — see csv_loader.hpp.
+// csv_ingest.cpp — CSV ingest with the reference's type inference (declared in bosql_types.hpp; src/storage/csv_loader.cpp:7-166).
 //
 // The reference keeps every cell as a std::string in a vector<vector<string>> and parses each column up to four times
 // (src/storage/csv_loader.cpp:26-38, 48-162; 1.85 s for a 1 M-row file).  Here the file is read once into one buffer whose
 // separators are overwritten with NULs, so every cell is a C string in place; a column is classified in one pass that
 // runs the same libc conversions the reference's std::stoi / std::stod wrap (strtol / strtod: prefix parsing, errno range
 // errors), which keeps the inferred types and values identical.  Columns then go to the device at first use.
-#include "csv_loader.hpp"
+#include "bosql_types.hpp"
 
 #include <cerrno>
 #include <cmath>

@@ -220,29 +220,29 @@ bool ColumnarScan::describe(Pipeline& p) {
 }
 
 // ---- Selection (src/exec/operator.cpp:388-433) -------------------------------------------------------------------
-Selection::Selection(std::unique_ptr<Operator> c, std::unique_ptr<Expr> pred) : child(std::move(c)), predicate(std::move(pred)) {
-    if (!child) throw std::runtime_error("Selection child is null");
-    names_ = child->output_names();
-    types_ = child->output_types();
-    dict_ = child->dictionary();
+Selection::Selection(std::unique_ptr<Operator> c, std::unique_ptr<Expr> pred) : input_(std::move(c)), predicate(std::move(pred)) {
+    if (!input_) throw std::runtime_error("Selection input_ is null");
+    names_ = input_->output_names();
+    types_ = input_->output_types();
+    dict_ = input_->dictionary();
     bindings = make_bindings(names_, types_, dict_);
 }
 
 void Selection::open() {
-    child->open();
+    input_->open();
     reset_paging();
 }
 bool Selection::next(ExecBatch& out) { return page_out(out); }
-void Selection::close() { child->close(); }
+void Selection::close() { input_->close(); }
 
 bool Selection::describe(Pipeline& p) {
-    if (!child->describe(p)) return false;
+    if (!input_->describe(p)) return false;
     if (predicate) gpu::split_conjuncts(predicate.get(), dict_, p.conjuncts);
     return true;
 }
 
 DeviceRelationPtr Selection::device_result() {
-    DeviceRelationPtr in = child->device_result();
+    DeviceRelationPtr in = input_->device_result();
     if (!predicate) return in;                       // null predicate = pass-through (:406-409)
     std::vector<gpu::Conjunct> conj;
     gpu::split_conjuncts(predicate.get(), dict_, conj);
@@ -255,11 +255,11 @@ DeviceRelationPtr Selection::device_result() {
 
 // ---- Project (src/exec/operator.cpp:435-559) ------------------------------------------------------------------------
 Project::Project(std::unique_ptr<Operator> c, std::vector<std::unique_ptr<Expr>> exprs, std::vector<std::string> alias_list)
-    : child(std::move(c)), expressions(std::move(exprs)), aliases(std::move(alias_list)) {
-    if (!child) throw std::runtime_error("Project child is null");
-    input_names = child->output_names();
-    input_types = child->output_types();
-    dict_ = child->dictionary();
+    : input_(std::move(c)), expressions(std::move(exprs)), aliases(std::move(alias_list)) {
+    if (!input_) throw std::runtime_error("Project input_ is null");
+    input_names = input_->output_names();
+    input_types = input_->output_types();
+    dict_ = input_->dictionary();
     bindings = make_bindings(input_names, input_types, dict_);
     direct_indices.assign(expressions.size(), -1);
     for (size_t i = 0; i < expressions.size(); ++i) {
@@ -289,14 +289,14 @@ Project::Project(std::unique_ptr<Operator> c, std::vector<std::unique_ptr<Expr>>
 }
 
 void Project::open() {
-    child->open();
+    input_->open();
     reset_paging();
 }
 bool Project::next(ExecBatch& out) { return page_out(out); }
-void Project::close() { child->close(); }
+void Project::close() { input_->close(); }
 
 DeviceRelationPtr Project::device_result() {
-    DeviceRelationPtr in = child->device_result();
+    DeviceRelationPtr in = input_->device_result();
     auto out = std::make_shared<DeviceRelation>();
     out->replicated = in->replicated;
     out->rows = in->rows;
@@ -320,24 +320,24 @@ DeviceRelationPtr Project::device_result() {
 }
 
 // ---- Limit (src/exec/operator.cpp:561-620) -----------------------------------------------------------------------------
-Limit::Limit(std::unique_ptr<Operator> c, int64_t n) : child(std::move(c)), limit(n) {
-    if (!child) throw std::runtime_error("Limit child is null");
-    names_ = child->output_names();
-    types_ = child->output_types();
-    dict_ = child->dictionary();
+Limit::Limit(std::unique_ptr<Operator> c, int64_t n) : input_(std::move(c)), limit(n) {
+    if (!input_) throw std::runtime_error("Limit input_ is null");
+    names_ = input_->output_names();
+    types_ = input_->output_types();
+    dict_ = input_->dictionary();
 }
 
 void Limit::open() {
-    child->open();
+    input_->open();
     reset_paging();
 }
 bool Limit::next(ExecBatch& out) { return page_out(out); }
-void Limit::close() { child->close(); }
+void Limit::close() { input_->close(); }
 
 DeviceRelationPtr Limit::device_result() {
     const int64_t want = limit < 0 ? 0 : limit;
-    if (auto* ob = dynamic_cast<OrderBy*>(child.get())) return ob->sorted_prefix(want);      // top-k
-    DeviceRelationPtr in = child->device_result();
+    if (auto* ob = dynamic_cast<OrderBy*>(input_.get())) return ob->sorted_prefix(want);      // top-k
+    DeviceRelationPtr in = input_->device_result();
     auto prefix = [&](const DeviceRelationPtr& rel) {
         if (static_cast<uint64_t>(want) >= rel->rows) return rel;
         auto out = std::make_shared<DeviceRelation>();
@@ -517,10 +517,10 @@ DeviceRelationPtr HashJoin::device_result() {
 // ---- HashAggregate (src/exec/operator.cpp:907-1074) ------------------------------------------------------------------------
 HashAggregate::HashAggregate(std::unique_ptr<Operator> child_op, std::vector<std::unique_ptr<Expr>> group_exprs_in,
                              std::vector<AggregateSpec> aggregates_in)
-    : child(std::move(child_op)), group_exprs(std::move(group_exprs_in)), aggregates(std::move(aggregates_in)) {
-    if (!child) throw std::runtime_error("HashAggregate child is null");
-    dict_ = child->dictionary();
-    child_bindings = make_bindings(child->output_names(), child->output_types(), dict_);
+    : input_(std::move(child_op)), group_exprs(std::move(group_exprs_in)), aggregates(std::move(aggregates_in)) {
+    if (!input_) throw std::runtime_error("HashAggregate input_ is null");
+    dict_ = input_->dictionary();
+    child_bindings = make_bindings(input_->output_names(), input_->output_types(), dict_);
     for (size_t i = 0; i < group_exprs.size(); ++i) {
         TypeId t = infer_type(group_exprs[i].get(), child_bindings);
         group_types.push_back(t);
@@ -542,14 +542,14 @@ HashAggregate::HashAggregate(std::unique_ptr<Operator> child_op, std::vector<std
 
 void HashAggregate::open() {
     child_consumed = false;
-    child->open();
+    input_->open();
     reset_paging();
 }
 
 bool HashAggregate::next(ExecBatch& out) {
     bool more = page_out(out);
     if (!child_consumed) {
-        child->close();
+        input_->close();
         child_consumed = true;
     }
     return more;
@@ -557,7 +557,7 @@ bool HashAggregate::next(ExecBatch& out) {
 
 void HashAggregate::close() {
     if (!child_consumed) {
-        child->close();
+        input_->close();
         child_consumed = true;
     }
     reset_paging();
@@ -575,15 +575,15 @@ DeviceRelationPtr HashAggregate::device_result() {
         req.aggs.push_back({a.func_name, a.arg.get(), agg_types[i]});
     }
     Pipeline p;
-    if (child->describe(p)) {
+    if (input_->describe(p)) {
         if (DeviceRelationPtr r = gpu::run_aggregate(p, req)) return r;
     }
     // not a fusable chain (or it mixes both join sides in one predicate): materialise the child, then the same kernels
-    DeviceRelationPtr in = child->device_result();
+    DeviceRelationPtr in = input_->device_result();
     Pipeline plain;
     plain.rows = in->rows;
     plain.dict = dict_;
-    plain.cols = pipe_cols(child->output_names(), child->output_types(), *in);
+    plain.cols = pipe_cols(input_->output_names(), input_->output_types(), *in);
     DeviceRelationPtr r = gpu::run_aggregate(plain, req);
     if (!r) throw std::runtime_error("internal: aggregate over a materialised relation was not planned");
     return r;
@@ -591,24 +591,24 @@ DeviceRelationPtr HashAggregate::device_result() {
 
 // ---- OrderBy (src/exec/operator.cpp:1076-1161) -----------------------------------------------------------------------------
 OrderBy::OrderBy(std::unique_ptr<Operator> child_op, std::vector<SortKey> sort_keys_in)
-    : child(std::move(child_op)), sort_keys(std::move(sort_keys_in)) {
-    if (!child) throw std::runtime_error("OrderBy child is null");
-    names_ = child->output_names();
-    types_ = child->output_types();
-    dict_ = child->dictionary();
+    : input_(std::move(child_op)), sort_keys(std::move(sort_keys_in)) {
+    if (!input_) throw std::runtime_error("OrderBy input_ is null");
+    names_ = input_->output_names();
+    types_ = input_->output_types();
+    dict_ = input_->dictionary();
     bindings = make_bindings(names_, types_, dict_);
 }
 
 void OrderBy::open() {
     child_consumed = false;
-    child->open();
+    input_->open();
     reset_paging();
 }
 
 bool OrderBy::next(ExecBatch& out) {
     bool more = page_out(out);
     if (!child_consumed) {
-        child->close();
+        input_->close();
         child_consumed = true;
     }
     return more;
@@ -616,7 +616,7 @@ bool OrderBy::next(ExecBatch& out) {
 
 void OrderBy::close() {
     if (!child_consumed) {
-        child->close();
+        input_->close();
         child_consumed = true;
     }
     reset_paging();
@@ -625,7 +625,7 @@ void OrderBy::close() {
 DeviceRelationPtr OrderBy::device_result() { return sorted_prefix(-1); }
 
 DeviceRelationPtr OrderBy::sorted_prefix(int64_t limit) {
-    DeviceRelationPtr in = child->device_result();
+    DeviceRelationPtr in = input_->device_result();
     if (!gpu::exchange().active || in->replicated) {
         DeviceRelationPtr out = sort_relation(in, limit);
         out->replicated = in->replicated;

@@ -1,4 +1,4 @@
-"""CPU: CSV ingest (bo-sql_b200/host/csv_loader.cpp) against the reference's load_csv, cell for cell.
+"""CPU: CSV ingest (bo-sql_b200/host/csv_ingest.cpp) against the reference's load_csv, cell for cell.
 
 Golden facts from the reference's own tests/test_csv.cpp:7-54 first (types INT64/STRING/DOUBLE, min/max, NDV, dictionary ids
 in first-seen order), then a differential run against the compiled reference on files that exercise every inference rule
