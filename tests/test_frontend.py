@@ -72,3 +72,37 @@ def test_plan_construction_errors_need_no_gpu(bq):
     assert plan.root_kind == "HashAggregate" and plan.names == ["COUNT(*)"] and plan.types == [0]
     plan = eng.plan("SELECT orders.id, SUM(orders.qty) AS total, AVG(orders.qty) FROM orders GROUP BY orders.id ORDER BY total LIMIT 1")
     assert plan.root_kind == "Limit" and plan.names == ["orders.id", "total", "AVG(orders.qty)"] and plan.types == [0, 0, 1]
+
+
+def test_reference_parser_facts(bq):
+    """tests/test_parser.cpp of the reference, restated on the plan text: precedence (:27-37), aggregate calls (:39-53),
+    the three statements that must throw (:87-96), a trailing ';' and JOIN aliases (:98-123, :144-157).  Where the compiled
+    reference is present the text is also compared with its own."""
+    from oracle import ref_engine
+    L = bq.exec_lib()
+    buf = C.create_string_buffer(8192)
+
+    def explain(sql):
+        rc = L.bqx_explain(sql.encode(), 0, buf, 8192)
+        return (rc, buf.value.decode() if rc == 0 else L.bqx_last_error().decode())
+
+    rc, text = explain("SELECT 1 + 2 * 3 FROM t")
+    assert rc == 0 and "(1 + (2 * 3))" in text                       # MUL binds tighter than ADD
+    rc, text = explain("SELECT SUM(price), COUNT(*) FROM products")
+    assert rc == 0 and "SUM(price)" in text and "COUNT(*)" in text
+    for bad in ("SELECT name", "SELECT @name FROM table", "SELECT name FROM table WHERE"):
+        assert explain(bad)[0] != 0, bad
+    rc, text = explain("SELECT a, b FROM t;")
+    assert rc == 0 and text == "LogicalProject(a, b)\n  LogicalScan(table=t, cols=a, b)"
+    rc, text = explain("SELECT x FROM orders o JOIN lineitem l ON o.id = l.id WHERE qty > 10;")
+    assert rc == 0 and "LogicalHashJoin" in text and "(qty > 10)" in text
+    if ref_engine.available():
+        ref = ref_engine.RefEngine()
+        for sql in ("SELECT 1 + 2 * 3 FROM t", "SELECT SUM(price), COUNT(*) FROM products", "SELECT a, b FROM t;",
+                    "SELECT x FROM orders o JOIN lineitem l ON o.id = l.id WHERE qty > 10;",
+                    "SELECT a - b - c, a / b * c, a + b > c AND d = 1 OR e != 2 FROM t"):
+            assert explain(sql) == (0, ref.explain(sql)), sql
+        for bad in ("SELECT name", "SELECT @name FROM table", "SELECT name FROM table WHERE"):
+            with pytest.raises(Exception) as e:
+                ref.explain(bad)
+            assert explain(bad) == (1, str(e.value)) or explain(bad)[1] == str(e.value), bad
