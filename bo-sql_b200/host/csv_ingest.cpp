@@ -21,6 +21,76 @@ namespace bosql {
 
 namespace {
 
+// Fast paths for the cells that make up almost every numeric file: plain decimals.  They are taken only when the WHOLE
+// cell is [+-]digits[.digits] with at most 15 significant digits and at most 22 fractional digits; then the value is
+// mantissa / 10^k with both operands exact in binary64, so the one IEEE division is correctly rounded (Clinger's fast
+// path) - the same bits glibc's correctly rounded strtod returns.  Anything else (exponents, hex, inf/nan, blanks, a
+// trailing '\r' or other suffix, long digit strings) goes to strtol / strtod below, whose prefix semantics the reference's
+// std::stoi / std::stod have.
+const double kPow10[23] = {1e0,  1e1,  1e2,  1e3,  1e4,  1e5,  1e6,  1e7,  1e8,  1e9,  1e10, 1e11,
+                           1e12, 1e13, 1e14, 1e15, 1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22};
+
+bool fast_decimal(const char* s, size_t len, double& out) {
+    size_t i = 0;
+    bool neg = false;
+    if (i < len && (s[i] == '+' || s[i] == '-')) neg = s[i++] == '-';
+    uint64_t mant = 0;
+    int digits = 0, sig = 0, frac = 0;
+    for (; i < len && s[i] >= '0' && s[i] <= '9'; ++i, ++digits) {
+        mant = mant * 10 + static_cast<uint64_t>(s[i] - '0');
+        if (mant) ++sig;
+        if (sig > 15) return false;
+    }
+    if (i < len && s[i] == '.') {
+        ++i;
+        for (; i < len && s[i] >= '0' && s[i] <= '9'; ++i, ++digits, ++frac) {
+            mant = mant * 10 + static_cast<uint64_t>(s[i] - '0');
+            if (mant) ++sig;
+            if (sig > 15 || frac >= 22) return false;
+        }
+    }
+    if (i != len || digits == 0) return false;
+    const double v = static_cast<double>(mant) / kPow10[frac];
+    out = neg ? -v : v;
+    return true;
+}
+
+bool fast_int8(const char* s, size_t len, int& out) {       // the DATE32 test only ever accepts 8-character cells
+    if (len != 8) return false;
+    int v = 0;
+    for (size_t i = 0; i < 8; ++i) {
+        if (s[i] < '0' || s[i] > '9') return false;
+        v = v * 10 + (s[i] - '0');
+    }
+    out = v;
+    return true;
+}
+
+// number of distinct values (std::set / unordered_set size in the reference): open addressing over the 64-bit patterns
+template <typename T>
+size_t count_distinct(const std::vector<T>& v) {
+    if (v.empty()) return 0;
+    size_t cap = 16;
+    while (cap < v.size() * 2) cap <<= 1;
+    std::vector<uint64_t> slots(cap, 0);
+    std::vector<uint8_t> used(cap, 0);
+    size_t n = 0;
+    for (const T& x : v) {
+        uint64_t k = 0;
+        std::memcpy(&k, &x, sizeof(T));
+        uint64_t h = k * 0x9E3779B97F4A7C15ull;
+        h ^= h >> 32;
+        size_t i = static_cast<size_t>(h) & (cap - 1);
+        while (used[i] && slots[i] != k) i = (i + 1) & (cap - 1);
+        if (!used[i]) {
+            used[i] = 1;
+            slots[i] = k;
+            ++n;
+        }
+    }
+    return n;
+}
+
 // std::stoi: strtol, throws when nothing converts or the value leaves int's range
 bool stoi_like(const char* s, int& out) {
     errno = 0;
@@ -46,7 +116,12 @@ bool stod_like(const char* s, double& out) {
 }  // namespace
 
 std::pair<Table, TableMeta> load_csv(std::istream& stream) {
-    std::string buf((std::istreambuf_iterator<char>(stream)), std::istreambuf_iterator<char>());
+    std::string buf;
+    {
+        std::ostringstream all;                       // one bulk copy through the stream buffer (not a per-character iterator)
+        all << stream.rdbuf();
+        buf = std::move(all).str();
+    }
     Table table;
     table.dict = std::make_shared<Dictionary>();
     std::vector<ColumnMeta> metas;
@@ -103,25 +178,25 @@ std::pair<Table, TableMeta> load_csv(std::istream& stream) {
 
         // DATE32 (:48-82)
         bool all_date = n_rows > 0;
+        std::vector<Date32> dates;
+        if (all_date && lens[c][0] == 8) dates.resize(n_rows);
         for (size_t r = 0; r < n_rows && all_date; ++r) {
             int d;
-            if (lens[c][r] != 8 || !stoi_like(cells[r], d)) all_date = false;
+            if (lens[c][r] != 8 || !(fast_int8(cells[r], 8, d) || stoi_like(cells[r], d))) all_date = false;
             else if (d < 19000000 || d > 21000000) all_date = false;
+            else dates[r] = d;
         }
         if (all_date) {
-            std::vector<Date32> data(n_rows);
+            std::vector<Date32> data = std::move(dates);
             Date32 lo = std::numeric_limits<Date32>::max(), hi = std::numeric_limits<Date32>::min();
-            for (size_t r = 0; r < n_rows; ++r) {
-                int d = 0;
-                stoi_like(cells[r], d);
-                data[r] = d;
+            for (Date32 d : data) {
                 lo = std::min(lo, d);
                 hi = std::max(hi, d);
             }
             meta.type = TypeId::DATE32;
             meta.stats.min_date = lo;
             meta.stats.max_date = hi;
-            meta.stats.ndv = std::unordered_set<Date32>(data.begin(), data.end()).size();
+            meta.stats.ndv = count_distinct(data);
             column.data = std::make_unique<ColumnVector<Date32>>(std::move(data));
             table.columns.push_back(std::move(column));
             metas.push_back(std::move(meta));
@@ -132,7 +207,7 @@ std::pair<Table, TableMeta> load_csv(std::istream& stream) {
         std::vector<double> as_f(n_rows);
         bool all_f64 = n_rows > 0, all_i64 = n_rows > 0;
         for (size_t r = 0; r < n_rows && all_f64; ++r) {
-            if (!stod_like(cells[r], as_f[r])) {
+            if (!fast_decimal(cells[r], lens[c][r], as_f[r]) && !stod_like(cells[r], as_f[r])) {
                 all_f64 = all_i64 = false;
                 break;
             }
@@ -153,7 +228,7 @@ std::pair<Table, TableMeta> load_csv(std::istream& stream) {
             meta.type = TypeId::INT64;
             meta.stats.min_i64 = lo;
             meta.stats.max_i64 = hi;
-            meta.stats.ndv = std::unordered_set<i64>(data.begin(), data.end()).size();
+            meta.stats.ndv = count_distinct(data);
             column.data = std::make_unique<ColumnVector<i64>>(std::move(data));
             table.columns.push_back(std::move(column));
             metas.push_back(std::move(meta));
@@ -169,13 +244,15 @@ std::pair<Table, TableMeta> load_csv(std::istream& stream) {
             meta.stats.min_f64 = lo;
             meta.stats.max_f64 = hi;
             // std::set<double> semantics: -0.0 and 0.0 are one value, every NaN is "equivalent" to everything else
-            std::unordered_set<double> uniq;
+            std::vector<double> keys;
+            keys.reserve(as_f.size());
             bool has_nan = false;
             for (double v : as_f) {
                 if (std::isnan(v)) has_nan = true;
-                else uniq.insert(v == 0.0 ? 0.0 : v);
+                else keys.push_back(v == 0.0 ? 0.0 : v);
             }
-            meta.stats.ndv = uniq.size() + ((has_nan && uniq.empty()) ? 1 : 0);
+            const size_t uniq = count_distinct(keys);
+            meta.stats.ndv = uniq + ((has_nan && uniq == 0) ? 1 : 0);
             column.data = std::make_unique<ColumnVector<double>>(std::move(as_f));
             table.columns.push_back(std::move(column));
             metas.push_back(std::move(meta));
@@ -184,7 +261,7 @@ std::pair<Table, TableMeta> load_csv(std::istream& stream) {
         // STRING: dictionary ids in first-seen order (:152-161)
         std::vector<StrId> data(n_rows);
         for (size_t r = 0; r < n_rows; ++r) data[r] = table.dict->get_or_add(std::string(cells[r], lens[c][r]));
-        meta.stats.ndv = std::unordered_set<StrId>(data.begin(), data.end()).size();
+        meta.stats.ndv = count_distinct(data);
         column.data = std::make_unique<ColumnVector<StrId>>(std::move(data));
         table.columns.push_back(std::move(column));
         metas.push_back(std::move(meta));

@@ -50,6 +50,40 @@ FILES = {
 }
 
 
+def _numeric_stress():
+    """One column per numeric spelling, 4000 rows each: every spelling the fast decimal path accepts, sits next to, or must
+    hand to strtod (long digit strings, exponents, hex, signs, bare points, 16-17 significant digits, 2^53 neighbours)."""
+    rng = np.random.default_rng(2024)
+    n = 4000
+    x = rng.uniform(-1e6, 1e6, n)
+    big = rng.integers(2**52, 2**54, n)
+    cols = {
+        "f2": [f"{v:.2f}" for v in x],
+        "f15": [f"{v:.15g}" for v in x],
+        "f17": [f"{v:.17g}" for v in x],                                   # 17 significant digits: not the fast path
+        "tiny": [f"{v * 1e-12:.22f}" for v in x],                          # many fractional digits
+        "frac23": [f"0.{int(abs(v)) % 10}{'0' * 21}{int(abs(v)) % 7}" for v in x],   # 23 fractional digits
+        "exp": [f"{v:.6e}" for v in x],
+        "ints": [str(int(v)) for v in x],
+        "big": [str(int(v)) for v in big],                                 # around 2^53: INT64 parsed through double
+        "plus": [f"+{abs(v):.3f}" for v in x],
+        "lead0": [f"000{abs(v):.4f}" for v in x],
+        "point": [(f".{int(abs(v)) % 1000:03d}" if i % 2 else f"{int(abs(v))}.") for i, v in enumerate(x)],
+        "negzero": ["-0" if i % 3 == 0 else ("-0.000" if i % 3 == 1 else "0") for i in range(n)],
+        "sig16": [f"{int(abs(v) * 1e10) + 10**15}" for v in x],            # 16 digits
+        "suffix": [f"{v:.2f}abc" if i % 5 == 0 else f"{v:.2f}" for i, v in enumerate(x)],
+        "spaces": [f" {v:.2f}" if i % 4 == 0 else f"{v:.2f}" for i, v in enumerate(x)],
+        "hex": ["0x1A" if i % 9 == 0 else str(i) for i in range(n)],
+        "dates": [str(20240000 + 100 * (1 + i % 12) + 1 + i % 28) for i in range(n)],
+        "dates_pad": [f"{i % 99999999:08d}" for i in range(n)],           # 8 characters but mostly outside the date range
+    }
+    names = list(cols)
+    return ",".join(names) + "\n" + "".join(",".join(cols[k][i] for k in names) + "\n" for i in range(n))
+
+
+FILES["numeric_stress"] = _numeric_stress()
+
+
 @pytest.mark.parametrize("name", sorted(FILES))
 def test_loader_matches_reference(bq, ref, tmp_path, name):
     path = write(tmp_path, name + ".csv", FILES[name])
