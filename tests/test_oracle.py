@@ -90,3 +90,21 @@ def test_datagen_frozen_values():
                 head = np.asarray(arr)[:5]
                 got = [float(x).hex() for x in head.tolist()] if head.dtype.kind == "f" else [int(x) for x in head.tolist()]
                 assert got == frozen, f"{tset}.{name}.{cname}"
+
+
+def test_oracle_is_pinned_on_the_sharded_suite_statements(ref):
+    """tests/dist_sql.py checks the multi-GPU operator layer against the numpy oracle; here the oracle itself is checked
+    against the compiled reference on exactly those statements and tables (joins with payload, top-k over joins, LIMIT
+    without ORDER BY, multi-key GROUP BY, the skewed join)."""
+    from oracle import datagen
+    from tests import dist_sql
+    orders, lines = dist_sql.tables()
+    o, r = orc.Oracle(), ref.RefEngine()
+    od, rd = o.new_dict(datagen.STATUS_DICT), r.new_dict(datagen.STATUS_DICT)
+    for eng, d in ((o, od), (r, rd)):
+        eng.add_table("orders", orders, d)
+        eng.add_table("lineitem", lines, d)
+    for name, sql, order in dist_sql.QUERIES:
+        got, want = o.query(sql), r.query(sql)
+        assert got.names == want.names and got.types == want.types, name
+        assert_same_rows(got.cols, want.cols, ordered_by=None if order in (None, "sharded") else order, what=name)
