@@ -19,6 +19,13 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (runs on the B200 box only)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A hung kernel or collective must fail the test, not stall the run: every test gets a generous default timeout."""
+    for item in items:
+        if item.get_closest_marker("timeout") is None:
+            item.add_marker(pytest.mark.timeout(1200))
+
+
 @pytest.fixture(scope="session")
 def bq():
     return load_package()

@@ -34,6 +34,8 @@ def orders_csv(tmp_path_factory):
 
 def _run(binary, csv, sql, fmt=None, stdin=None):
     if not os.path.exists(binary):
+        if binary == REF:
+            pytest.skip("oracle/_ref/bq_ref was not built (needs /root/reference at build time)")
         pytest.fail(f"{binary} is missing: run __graft_entry__.build()")
     cmd = [binary] + ([csv] if csv else []) + ["--sql", sql] + (["--output-format", fmt] if fmt else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=120, stdin=stdin)
