@@ -189,6 +189,14 @@ TypeId value_type(const Expr* e, const ColumnLookup& cols) {
     return TypeId::INT64;
 }
 
+bool may_throw_per_row(const Expr* e, const ColumnLookup& cols) {
+    if (!e || e->type != ExprType::BINARY_OP) return false;
+    if (may_throw_per_row(e->left.get(), cols) || may_throw_per_row(e->right.get(), cols)) return true;
+    if (e->op != BinaryOp::DIV) return false;
+    if (value_type(e->left.get(), cols) == TypeId::DOUBLE || value_type(e->right.get(), cols) == TypeId::DOUBLE) return false;   // +inf
+    return !(e->right->type == ExprType::LITERAL_INT && e->right->i64_val != 0);
+}
+
 void referenced(const Expr* e, const ColumnLookup& cols, std::vector<int>& out) {
     if (!e) return;
     if (e->type == ExprType::COLUMN_REF) {

@@ -48,6 +48,10 @@ struct ColumnRange {
 // produce the equivalent key range.  Returns false when the conjunct needs the general program.
 bool to_range(const Expr* e, const ColumnLookup& cols, Dictionary* dict, ColumnRange& out);
 
+// True when evaluating `e` can throw for SOME row values (an integer division whose divisor is not a non-zero literal,
+// src/exec/expression.cpp:52).  Such an expression must only be evaluated for the rows the reference would evaluate it for.
+bool may_throw_per_row(const Expr* e, const ColumnLookup& cols);
+
 // Collects the lookup indices of every column `e` references (throws "Unknown column: x").
 void referenced(const Expr* e, const ColumnLookup& cols, std::vector<int>& out);
 

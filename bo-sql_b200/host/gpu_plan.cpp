@@ -395,6 +395,28 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
 
     ColumnLookup look = lookup_for(p.cols);
 
+    // The reference evaluates aggregate arguments and GROUP BY expressions only for rows that survived the Selection and the
+    // join, and a WHERE above a join only for joined rows (src/logical/planner.cpp builds Filter above HashJoin).  The fused
+    // pipeline evaluates derived columns and predicate programs over ALL probe rows - harmless unless the expression can
+    // throw for a row the reference never looks at (integer division by zero, H10).  Those plans are materialised step by
+    // step instead (selection / join first, then the same kernels over the surviving rows).
+    {
+        const bool filtered = !p.conjuncts.empty() || p.joined;
+        bool risky = false;
+        if (filtered) {
+            for (const auto& g : *req.group_exprs)
+                if (g->type != ExprType::COLUMN_REF && may_throw_per_row(g.get(), look)) risky = true;
+            for (const auto& a : req.aggs) {
+                ValueForm form;
+                if (a.arg && a.func != "COUNT" && may_throw_per_row(a.arg, look) && !simple_value_form(a.arg, p.cols, look, form)) risky = true;
+            }
+        }
+        if (p.joined)
+            for (const Conjunct& c : p.conjuncts)
+                if (may_throw_per_row(c.expr.get(), look)) risky = true;
+        if (risky) return nullptr;
+    }
+
     // ---- split predicates by the side they read ---------------------------------------------------------
     std::vector<const Conjunct*> probe_conj, build_conj;
     for (const Conjunct& c : p.conjuncts) {
