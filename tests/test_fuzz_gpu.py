@@ -41,3 +41,35 @@ def test_random_statements_gpu_vs_reference(bq):
         assert_same_rows(got.cols, want.cols, ordered_by=order, what=f"#{i} {sql}")
         ran += 1
     assert ran >= 200, (ran, errors)
+
+
+def test_random_sweep_statements_gpu_vs_reference(bq):
+    """The filter-sweep family: predicates over every type (dictionary ids, dates, DOUBLE against integer literals, truthiness,
+    INT64-left against DOUBLE-right), GROUP BY dictionary / date / negative-integer keys, ORDER BY an aggregate alias."""
+    from oracle import ref_engine
+    from tests import golden_util as G
+    from tests.test_oracle_fuzz import _sweep_statement
+    (name, cols, dname), = cases.sweep_tables()
+    checker = ref_engine.RefEngine() if ref_engine.available() else orc.Oracle()
+    g = bq.Engine()
+    for eng in (checker, g):
+        eng.add_table(name, cols, eng.new_dict(cases.DICTS[dname]))
+    rng = np.random.default_rng(7)
+    ran = 0
+    for i in range(300):
+        sql = _sweep_statement(rng)
+        try:
+            want = checker.query(sql)
+        except Exception as e:  # noqa: BLE001
+            with pytest.raises(bq.BqError) as mine:
+                g.query(sql)
+            assert str(mine.value) == str(e), f"#{i} {sql}: GPU says {mine.value!r}, reference says {e!r}"
+            continue
+        try:
+            got = g.query(sql)
+        except bq.BqError as e:
+            raise AssertionError(f"#{i} {sql}: the reference answers, the GPU path raises {e}") from e
+        assert got.names == want.names and got.types == want.types, f"#{i} {sql}"
+        assert_same_rows(got.cols, want.cols, ordered_by=G.order_spec(sql, want.names), what=f"#{i} {sql}")
+        ran += 1
+    assert ran >= 250, ran

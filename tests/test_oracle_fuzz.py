@@ -73,6 +73,67 @@ def _statement(rng):
     return sql, None
 
 
+def _sweep_pred(rng, depth=0):
+    if depth < 2 and rng.random() < 0.35:
+        return f"({_sweep_pred(rng, depth + 1)} {rng.choice(['AND', 'OR'])} {_sweep_pred(rng, depth + 1)})"
+    cmp_op = str(rng.choice(["<", "<=", ">", ">=", "=", "!="]))
+    kind = rng.integers(0, 9)
+    if kind == 0:
+        return f"c_i64 {cmp_op} {int(rng.integers(0, 1000000))}"
+    if kind == 1:
+        return f"c_f64 {cmp_op} {int(rng.integers(0, 10000))}"          # DOUBLE column against an integer literal
+    if kind == 2:
+        return f"c_date {cmp_op} {20150000 + 10000 * int(rng.integers(0, 10)) + 100 * int(rng.integers(1, 13)) + int(rng.integers(1, 29))}"
+    if kind == 3:
+        return f"c_str {rng.choice(['=', '!='])} {int(rng.integers(0, 100))}"
+    if kind == 4:
+        return f"s {rng.choice(['=', '!='])} '{rng.choice(['zero', 'one', 'two', 'five', 'unseen'])}'"
+    if kind == 5:
+        return str(rng.choice(["z", "s", "w"]))                             # truthiness of a bare column (H7: StrId 0 is false)
+    if kind == 6:
+        return f"{int(rng.integers(-60, 60))} {cmp_op} z"                   # literal on the left: compare dispatches on INT64
+    if kind == 7:
+        return f"c_i64 {cmp_op} c_f64"                                      # INT64-left vs DOUBLE-right truncation (H6)
+    return f"(z * {int(rng.integers(1, 5))} + w) {cmp_op} (v / {int(rng.integers(1, 9))})"
+
+
+def _sweep_statement(rng):
+    """The filter-sweep table: predicates over every type, GROUP BY dictionary / date / negative-integer keys, ORDER BY an alias."""
+    where = f" WHERE {_sweep_pred(rng)}" if rng.random() < 0.8 else ""
+    shape = rng.integers(0, 3)
+    if shape == 0:
+        return f"SELECT COUNT(*) AS n, SUM(v) AS sv, SUM(w) AS sw, AVG(v * w) AS a FROM t{where}"
+    if shape == 1:
+        key = str(rng.choice(["c_str", "s", "z", "c_date"]))
+        order = " ORDER BY " + str(rng.choice(["n", "sv", key])) + str(rng.choice(["", " DESC"])) if rng.random() < 0.6 else ""
+        return f"SELECT {key}, COUNT(*) AS n, SUM(v) AS sv, AVG(w) AS aw FROM t{where} GROUP BY {key}{order}"
+    return f"SELECT c_i64, z, s, v * 2 AS v2 FROM t{where} ORDER BY c_i64{rng.choice(['', ' DESC'])}, z"
+
+
+def test_random_sweep_statements_oracle_vs_reference(ref):
+    from tests import golden_util as G
+    (name, cols, dname), = cases.sweep_tables()
+    o, r = orc.Oracle(), ref.RefEngine()
+    o.add_table(name, cols, o.new_dict(cases.DICTS[dname]))
+    r.add_table(name, cols, r.new_dict(cases.DICTS[dname]))
+    rng = np.random.default_rng(7)
+    ran = 0
+    for i in range(300):
+        sql = _sweep_statement(rng)
+        try:
+            want = r.query(sql)
+        except RuntimeError as e:
+            with pytest.raises(Exception) as mine:
+                o.query(sql)
+            assert str(mine.value) == str(e), f"#{i} {sql}: oracle says {mine.value!r}, reference says {e!r}"
+            continue
+        got = o.query(sql)
+        assert got.names == want.names and got.types == want.types, f"#{i} {sql}"
+        assert_same_rows(got.cols, want.cols, ordered_by=G.order_spec(sql, want.names), what=f"#{i} {sql}")
+        ran += 1
+    assert ran >= 250, ran
+
+
 def test_random_statements_oracle_vs_reference(ref):
     tables = {name: (cols, dname) for name, cols, dname in cases.star_tables()}
     o, r = orc.Oracle(), ref.RefEngine()
