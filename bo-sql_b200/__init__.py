@@ -165,6 +165,8 @@ def kernel_lib():
         "bq_join_kind": ([vp], C.c_int),
         "bq_join_bytes": ([vp], sz),
         "bq_join_bitmap_ptr": ([vp, P(sz)], vp),
+        "bq_join_build_rows": ([vp], sz),
+        "bq_join_bitmap_popcount": ([vp, vp, P(C.c_uint64)], C.c_int),
         "bq_join_probe": ([vp, vp, vp, vp, sz, sz, P(vp), P(vp)], C.c_int),
         "bq_rel_sort": ([vp, vp, C.c_int, P(C.c_int), P(C.c_int), i64, P(vp)], C.c_int),
         "bq_rel_create": ([vp, P(vp), C.c_int, P(vp)], C.c_int),

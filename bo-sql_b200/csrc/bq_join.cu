@@ -214,6 +214,13 @@ __global__ void __launch_bounds__(kBlock) k_probe_fill(const __grid_constant__ P
     for (unsigned a = 0; a < m; ++a) pr[a] = static_cast<unsigned>(i);
 }
 
+__global__ void __launch_bounds__(kBlock) k_popcount_words(const unsigned* __restrict__ w, size_t n, unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c += __popc(w[i]);
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 static size_t next_pow2(size_t v) {
     size_t p = 1;
     while (p < v) p <<= 1;
@@ -354,6 +361,25 @@ void bq_join_free(bq_ctx* ctx, bq_join* j) {
 
 int bq_join_kind(const bq_join* j) { return j->kind; }
 size_t bq_join_bytes(const bq_join* j) { return j->bytes; }
+size_t bq_join_build_rows(const bq_join* j) { return j->build_rows; }
+
+int bq_join_bitmap_popcount(bq_ctx* ctx, const bq_join* j, uint64_t* out) {
+    return guarded([&] {
+        if (j->kind != BQ_JOIN_BITMAP) throw std::runtime_error("not a bitmap join");
+        auto* d = static_cast<unsigned long long*>(scratch(ctx, 16));
+        BQ_CUDA(cudaMemsetAsync(d, 0, 8, ctx->stream));
+        if (j->bitmap_words) {
+            k_popcount_words<<<grid_for(ctx, j->bitmap_words, 8), kBlock, 0, ctx->stream>>>(j->bitmap, j->bitmap_words, d);
+            ctx->launches++;
+            BQ_CUDA(cudaGetLastError());
+        }
+        auto* h = static_cast<unsigned long long*>(pinned(ctx, 8));
+        BQ_CUDA(cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        *out = *h;
+    });
+}
+
 void* bq_join_bitmap_ptr(const bq_join* j, size_t* n_words) {
     if (n_words) *n_words = j->bitmap_words;
     return j->bitmap;

@@ -198,7 +198,10 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
     return guarded([&] {
         const size_t n = rel->rows;
         const int nc = static_cast<int>(rel->cols.size());
-        if (n_keys < 0 || n_keys > 4) throw std::runtime_error("at most 4 sort keys");
+        if (n_keys < 0 || n_keys > 64) throw std::runtime_error("at most 64 sort keys");
+        // the rank kernel and the top-k tiles hold up to 4 keys per row in registers / shared memory; longer key lists
+        // (src/exec/operator.cpp:1115-1122 loops over any number) take the LSD radix passes, one sort column at a time
+        const bool few_keys = n_keys <= 4;
         for (int k = 0; k < n_keys; ++k)
             if (key_cols[k] < 0 || key_cols[k] >= nc) throw std::runtime_error("sort key column out of range");
         if (n > 0xFFFFFFFFull) throw std::runtime_error("row ids are 32-bit: at most 2^32 rows per sort");
@@ -215,7 +218,7 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
                 if (n_keys == 0) {
                     k_iota<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(perm, n);
                     ctx->launches++;
-                } else if (n <= 4096) {
+                } else if (n <= 4096 && few_keys) {
                     DevBuf keys(ctx, static_cast<size_t>(n_keys) * n * 8);
                     for (int k = 0; k < n_keys; ++k) {
                         const bq_col* c = rel->cols[key_cols[k]];
@@ -227,7 +230,7 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
                         static_cast<unsigned long long*>(keys.p), n_keys, n, perm);
                     ctx->launches++;
                     BQ_CUDA(cudaGetLastError());
-                } else if (m <= 256) {
+                } else if (m <= 256 && few_keys) {
                     // top-k: tiles keep their first m rows until one tile is left
                     const size_t max_cand = ((n + kTopkTile - 1) / kTopkTile) * m;
                     DevBuf keys(ctx, static_cast<size_t>(n_keys) * n * 8), candB(ctx, max_cand * 4), idsA(ctx, max_cand * 4), idsB(ctx, max_cand * 4);

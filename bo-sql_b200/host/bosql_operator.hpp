@@ -46,6 +46,11 @@ struct Operator {
     // ---- device-side protocol (not part of the reference interface) --------------------------------
     // The operator's whole output as a device relation (computed on first call after open()).
     virtual std::shared_ptr<gpu::DeviceRelation> device_result() = 0;
+    // What a consumer that stops pulling after `want` (> 0) rows makes this operator compute (Limit::next stops calling
+    // next() once it has its rows, src/exec/operator.cpp:577-613): a relation whose first min(want, total) rows are the
+    // first rows of device_result(), for which no expression was evaluated on a row the reference would not have reached.
+    // Blocking operators compute everything either way (the default).
+    virtual std::shared_ptr<gpu::DeviceRelation> device_prefix(size_t want) { (void)want; return device_result(); }
     // Describe this subtree as a fusable pipeline; false = not a scan/selection/join chain.
     virtual bool describe(gpu::Pipeline&) { return false; }
     // After the first next(): the whole result as host columns, when this operator pages out of one materialised copy
@@ -77,6 +82,11 @@ struct ColumnarScan : public Operator {
     ColumnarScan(Table* t, std::vector<size_t> idx, size_t batch = 4096);
     BQ_OPERATOR_LIFECYCLE
     bool describe(gpu::Pipeline&) override;
+    std::shared_ptr<gpu::DeviceRelation> device_prefix(size_t want) override;
+    // rows [begin, end) of the scan's output, zero-copy (the batches [begin, end) covers, src/exec/operator.cpp:345-384)
+    std::shared_ptr<gpu::DeviceRelation> device_window(size_t begin, size_t end);
+    size_t table_rows() const;
+    size_t batch_rows() const { return batch_size; }
     // Catalog statistics for this table (the planner attaches them; the reference's scan sees only Table*).
     void set_table_meta(const TableMeta* meta) { meta_ = meta; }
 private:
@@ -91,7 +101,9 @@ struct Selection : public Operator {
     Selection(std::unique_ptr<Operator> c, std::unique_ptr<Expr> pred);
     BQ_OPERATOR_LIFECYCLE
     bool describe(gpu::Pipeline&) override;
+    std::shared_ptr<gpu::DeviceRelation> device_prefix(size_t want) override;
 private:
+    std::shared_ptr<gpu::DeviceRelation> select_from(const std::shared_ptr<gpu::DeviceRelation>& in);
     std::unique_ptr<Operator> input_;
     std::unique_ptr<Expr> predicate;
     ExprBindings bindings;
@@ -100,7 +112,9 @@ private:
 struct Project : public Operator {
     Project(std::unique_ptr<Operator> c, std::vector<std::unique_ptr<Expr>> exprs, std::vector<std::string> aliases);
     BQ_OPERATOR_LIFECYCLE
+    std::shared_ptr<gpu::DeviceRelation> device_prefix(size_t want) override;
 private:
+    std::shared_ptr<gpu::DeviceRelation> project_from(const std::shared_ptr<gpu::DeviceRelation>& in);
     std::unique_ptr<Operator> input_;
     std::vector<std::unique_ptr<Expr>> expressions;
     std::vector<std::string> aliases;

@@ -146,8 +146,9 @@ std::pair<Table, TableMeta> load_csv(std::istream& stream) {
         row_lens.clear();
         size_t c0 = line_begin;
         while (c0 < line_end) {
-            size_t comma = buf.find(',', c0);
-            if (comma == std::string::npos || comma > line_end) comma = line_end;
+            // bounded by the line: the last cell of a line must not scan on to the next comma anywhere in the file
+            const void* hit = std::memchr(buf.data() + c0, ',', line_end - c0);
+            const size_t comma = hit ? static_cast<size_t>(static_cast<const char*>(hit) - buf.data()) : line_end;
             row_cells.push_back(buf.data() + c0);
             row_lens.push_back(comma - c0);
             if (comma < buf.size()) buf[comma] = '\0';

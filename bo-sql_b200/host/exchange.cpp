@@ -65,6 +65,25 @@ Exchange& exchange() {
     return x;
 }
 
+void agree_on(const std::function<void()>& step) {
+    Exchange& x = exchange();
+    if (!x.active) {
+        step();
+        return;
+    }
+    std::string err;
+    try {
+        step();
+    } catch (const std::exception& e) {
+        err = e.what();
+    }
+    int64_t worst = 0;
+    for (int64_t f : x.host_gather({err.empty() ? 0 : (err.find("Division by zero") != std::string::npos ? 1 : 2)})) worst = std::max(worst, f);
+    if (!err.empty()) throw std::runtime_error(err);
+    if (worst == 1) throw std::runtime_error("Division by zero");      // src/exec/expression.cpp:52, raised by another rank's rows
+    if (worst) throw std::runtime_error("expression evaluation failed on another rank");
+}
+
 std::vector<int64_t> Exchange::host_gather(const std::vector<int64_t>& mine) {
     std::vector<int64_t> all(mine.size() * static_cast<size_t>(world()));
     check(bq_ctx_sync(context()));

@@ -4,6 +4,7 @@
 #pragma once
 
 #include <cstdint>
+#include <functional>
 #include <vector>
 
 #include "bosql_b200_exec.h"
@@ -28,6 +29,11 @@ struct Exchange {
     DevColPtr all_gather_column(const DevColPtr& col, size_t rows, const std::vector<int64_t>& rows_by_rank);
 };
 Exchange& exchange();
+
+// A step that can fail on this rank's rows alone (an expression program hitting an integer division by zero in its shard):
+// across GPUs every rank learns the outcome before anyone moves on, so that all of them throw and none is left waiting
+// inside the next collective.  Single-GPU: just runs the step.  Every rank must call this at the same point of the plan.
+void agree_on(const std::function<void()>& step);
 
 // Partial aggregate states of every rank, ready for bq_agg_finish.  `local` is this rank's [key] count sum0 sum1 relation
 // (nullptr with error_flags != 0 when the local scan failed: the flags travel as a negative count so that every rank's

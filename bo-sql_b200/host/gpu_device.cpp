@@ -97,6 +97,16 @@ DevCol::~DevCol() {
 
 DevColPtr adopt(bq_col* h) { return std::make_shared<DevCol>(h, true); }
 
+DevColPtr view_of(const DevColPtr& col, size_t begin, size_t end) {
+    if (begin == 0 && end == col->rows()) return col;
+    const size_t w = type_width(col->type());
+    bq_col* h = nullptr;
+    check(bq_col_wrap(context(), static_cast<int>(col->type()), static_cast<char*>(bq_col_ptr(col->h)) + begin * w, end - begin, &h));
+    DevColPtr v = std::make_shared<DevCol>(h, true);      // owns the (non-owning) handle, not the memory
+    v->parent = col;
+    return v;
+}
+
 namespace {
 struct PinnedPool {
     struct Buf { void* p; size_t bytes; };

@@ -30,9 +30,12 @@ struct DevCol {
     DevCol& operator=(const DevCol&) = delete;
     size_t rows() const { return bq_col_size(h); }
     TypeId type() const { return static_cast<TypeId>(bq_col_type(h)); }
+    std::shared_ptr<DevCol> parent;                // a view keeps the column it points into alive
 };
 using DevColPtr = std::shared_ptr<DevCol>;
 DevColPtr adopt(bq_col* h);                       // takes ownership
+// rows [begin, end) of `col` as a column of its own, without copying (ColumnarScan's zero-copy slices, on the device)
+DevColPtr view_of(const DevColPtr& col, size_t begin, size_t end);
 
 // The HBM mirror of a table column: uploaded on first use, cached in Column::device.
 DevColPtr mirror_of(const Column& col);

@@ -197,8 +197,29 @@ void ColumnarScan::close() {}
 DeviceRelationPtr ColumnarScan::device_result() {
     auto rel = std::make_shared<DeviceRelation>();
     for (size_t i : indices) rel->cols.push_back(gpu::mirror_of(*table->columns[i].data));
-    rel->rows = indices.empty() ? 0 : table->columns[indices[0]].data->size();
+    rel->rows = table_rows();
     return rel;
+}
+
+size_t ColumnarScan::table_rows() const { return indices.empty() ? 0 : table->columns[indices[0]].data->size(); }
+
+DeviceRelationPtr ColumnarScan::device_window(size_t begin, size_t end) {
+    DeviceRelationPtr all = device_result();
+    end = std::min(end, all->rows);
+    begin = std::min(begin, end);
+    if (begin == 0 && end == all->rows) return all;
+    auto rel = std::make_shared<DeviceRelation>();
+    for (auto& c : all->cols) rel->cols.push_back(gpu::view_of(c, begin, end));
+    rel->rows = end - begin;
+    return rel;
+}
+
+// the batches a consumer of `want` rows pulls: ceil(want / batch) of them
+DeviceRelationPtr ColumnarScan::device_prefix(size_t want) {
+    const size_t b = batch_size ? batch_size : kBatchRows;
+    const size_t n = table_rows();
+    const size_t batches = want / b + (want % b ? 1 : 0);
+    return device_window(0, batches > n / b ? n : batches * b);
 }
 
 bool ColumnarScan::describe(Pipeline& p) {
@@ -241,8 +262,7 @@ bool Selection::describe(Pipeline& p) {
     return true;
 }
 
-DeviceRelationPtr Selection::device_result() {
-    DeviceRelationPtr in = input_->device_result();
+DeviceRelationPtr Selection::select_from(const DeviceRelationPtr& in) {
     if (!predicate) return in;                       // null predicate = pass-through (:406-409)
     std::vector<gpu::Conjunct> conj;
     gpu::split_conjuncts(predicate.get(), dict_, conj);
@@ -251,6 +271,43 @@ DeviceRelationPtr Selection::device_result() {
     DeviceRelationPtr out = gpu::run_selection(pipe_cols(names_, types_, *in), in->rows, ptrs);
     out->replicated = in->replicated;
     return out;
+}
+
+DeviceRelationPtr Selection::device_result() { return select_from(input_->device_result()); }
+
+// The reference's Selection evaluates its predicate batch by batch and is asked for no further batch once the consumer
+// has its rows (:403-429 under Limit::next :577-613), so a row beyond that point is never evaluated - which matters when the
+// predicate can throw there (integer division by zero, H10).  Over a scan the same is done in windows of whole batches that
+// grow geometrically; a window that throws is redone batch by batch, so the first failing batch is reached exactly when
+// the reference reaches it.  Across GPUs the number of windows would differ per rank while predicate programs exchange
+// their outcome collectively, so the sharded path evaluates its whole shard.
+DeviceRelationPtr Selection::device_prefix(size_t want) {
+    auto* scan = dynamic_cast<ColumnarScan*>(input_.get());
+    if (!scan || !predicate || gpu::exchange().active) return select_from(input_->device_prefix(predicate ? static_cast<size_t>(-1) : want));
+    const size_t n = scan->table_rows();
+    const size_t b = scan->batch_rows() ? scan->batch_rows() : kBatchRows;
+    std::vector<DeviceRelationPtr> parts;
+    size_t have = 0, at = 0;
+    size_t window = std::max(b, (want + b - 1) / b * b);
+    auto take = [&](size_t begin, size_t end) {
+        DeviceRelationPtr part = select_from(scan->device_window(begin, end));
+        have += part->rows;
+        if (part->rows) parts.push_back(part);
+    };
+    while (at < n && have < want) {
+        const size_t end = std::min(n, at + window);
+        try {
+            take(at, end);
+        } catch (const std::runtime_error& e) {
+            if (std::string(e.what()) != "Division by zero" || end - at <= b) throw;
+            for (size_t s = at; s < end && have < want; s += b) take(s, std::min(end, s + b));      // throws at the batch the reference throws at
+        }
+        at = end;
+        window *= 4;
+    }
+    if (parts.empty()) return gpu::empty_relation(types_);
+    if (parts.size() == 1) return parts[0];
+    return gpu::concat_relations(parts, types_);
 }
 
 // ---- Project (src/exec/operator.cpp:435-559) ------------------------------------------------------------------------
@@ -295,8 +352,11 @@ void Project::open() {
 bool Project::next(ExecBatch& out) { return page_out(out); }
 void Project::close() { input_->close(); }
 
-DeviceRelationPtr Project::device_result() {
-    DeviceRelationPtr in = input_->device_result();
+DeviceRelationPtr Project::device_result() { return project_from(input_->device_result()); }
+// Project::next evaluates every row of every batch it is asked for (:498-555): the child's prefix, whole
+DeviceRelationPtr Project::device_prefix(size_t want) { return project_from(input_->device_prefix(want)); }
+
+DeviceRelationPtr Project::project_from(const DeviceRelationPtr& in) {
     auto out = std::make_shared<DeviceRelation>();
     out->replicated = in->replicated;
     out->rows = in->rows;
@@ -306,7 +366,9 @@ DeviceRelationPtr Project::device_result() {
             out->cols.push_back(in->cols[direct_indices[i]]);
             continue;
         }
-        if (in->rows == 0) {                 // no row is ever evaluated, so nothing can throw (:505-551)
+        // no row is ever evaluated, so nothing can throw (:505-551); across GPUs an empty shard still takes part in the
+        // outcome exchange of a program that can fail on another rank's rows
+        if (in->rows == 0 && !gpu::exchange().active) {
             bq_col* h = nullptr;
             check(bq_col_alloc(context(), static_cast<int>(types_[i]), 0, &h));
             out->cols.push_back(gpu::adopt(h));
@@ -336,8 +398,10 @@ void Limit::close() { input_->close(); }
 
 DeviceRelationPtr Limit::device_result() {
     const int64_t want = limit < 0 ? 0 : limit;
+    if (want == 0) return gpu::empty_relation(types_);        // next() never pulls the child (:578-580): nothing is evaluated
     if (auto* ob = dynamic_cast<OrderBy*>(input_.get())) return ob->sorted_prefix(want);      // top-k
-    DeviceRelationPtr in = input_->device_result();
+    // the child computes what a consumer of `want` rows would have made it compute, not its whole output
+    DeviceRelationPtr in = input_->device_prefix(static_cast<size_t>(want));
     auto prefix = [&](const DeviceRelationPtr& rel) {
         if (static_cast<uint64_t>(want) >= rel->rows) return rel;
         auto out = std::make_shared<DeviceRelation>();
@@ -473,8 +537,9 @@ DeviceRelationPtr HashJoin::device_result() {
         check(bq_eval(ctx, m, 7, cols, 1, 0, total, BQ_STRING, &br));
         build_rows = gpu::adopt(br);
     } else {
-        if (left_key_indices.size() > 1) throw std::runtime_error("multi-column join keys are not supported on the GPU path");
-        if (left_key_types[0] != right_key_types[0]) return gpu::empty_relation(types_);   // KeyEqual (:652)
+        // KeyEqual: a component whose two sides differ in TypeId never matches (:652)
+        for (size_t i = 0; i < left_key_types.size(); ++i)
+            if (left_key_types[i] != right_key_types[i]) return gpu::empty_relation(types_);
         DevColPtr bk = r->cols[right_key_indices[0]];
         DevColPtr pk = l->cols[left_key_indices[0]];
         bq_join_spec js{};
@@ -498,6 +563,45 @@ DeviceRelationPtr HashJoin::device_result() {
         check(rc);
         probe_rows = gpu::adopt(pr);
         build_rows = gpu::adopt(br);
+        // Several key columns (Key holds one Datum per column, include/exec/operator.hpp:107-117; build_key :847-858): the
+        // table is keyed on the first column, the candidate pairs are then filtered on the remaining components with
+        // KeyEqual's per-type `==` (:646-667).  The compaction is stable, so pairs stay in probe order and, per probe row,
+        // in build insertion order (:802-816).
+        for (size_t first = 1; first < left_key_indices.size() && probe_rows->rows() > 0; first += BQ_MAX_PROGRAM_COLS / 2) {
+            const size_t last = std::min(left_key_indices.size(), first + BQ_MAX_PROGRAM_COLS / 2);
+            std::vector<DevColPtr> sides;
+            std::vector<const bq_col*> prog_cols;
+            std::vector<bq_insn> code;
+            for (size_t k = first; k < last; ++k) {
+                bq_col *lg = nullptr, *rg = nullptr;
+                check(bq_gather(ctx, l->cols[left_key_indices[k]]->h, probe_rows->h, &lg));
+                sides.push_back(gpu::adopt(lg));
+                check(bq_gather(ctx, r->cols[right_key_indices[k]]->h, build_rows->h, &rg));
+                sides.push_back(gpu::adopt(rg));
+                const int c = static_cast<int>(2 * (k - first));
+                code.push_back({BQ_OP_COL, c, {0}});
+                code.push_back({BQ_OP_COL, c + 1, {0}});
+                code.push_back({left_key_types[k] == TypeId::DOUBLE ? BQ_OP_EQ_F : BQ_OP_EQ_I, 0, {0}});
+                if (k > first) code.push_back({BQ_OP_AND, 0, {0}});
+            }
+            for (auto& c : sides) prog_cols.push_back(c->h);
+            bq_col* m = nullptr;
+            check(bq_eval(ctx, code.data(), static_cast<int>(code.size()), prog_cols.data(), static_cast<int>(prog_cols.size()), 0,
+                          probe_rows->rows(), BQ_INT64, &m));
+            DevColPtr mask = gpu::adopt(m);
+            bq_select_spec ss{};
+            ss.mask = mask->h;
+            ss.row_begin = 0;
+            ss.row_end = probe_rows->rows();
+            bq_col* keep = nullptr;
+            check(bq_select(ctx, &ss, &keep));
+            DevColPtr kept = gpu::adopt(keep);
+            bq_col *p2 = nullptr, *b2 = nullptr;
+            check(bq_gather(ctx, probe_rows->h, kept->h, &p2));
+            probe_rows = gpu::adopt(p2);
+            check(bq_gather(ctx, build_rows->h, kept->h, &b2));
+            build_rows = gpu::adopt(b2);
+        }
     }
     auto out = std::make_shared<DeviceRelation>();
     out->rows = probe_rows->rows();
@@ -642,8 +746,9 @@ DeviceRelationPtr OrderBy::sorted_prefix(int64_t limit) {
 }
 
 DeviceRelationPtr OrderBy::sort_relation(const DeviceRelationPtr& in, int64_t limit) {
-    if (in->rows == 0 || limit == 0) return gpu::empty_relation(types_);
-    if (sort_keys.size() > 4) throw std::runtime_error("more than 4 ORDER BY keys are not supported on the GPU path");
+    // (across GPUs a rank with an empty shard still evaluates its sort-key programs: they exchange their outcome)
+    const bool must_evaluate = gpu::exchange().active && !in->replicated;
+    if ((in->rows == 0 || limit == 0) && !must_evaluate) return gpu::empty_relation(types_);
     bq_ctx* ctx = context();
     std::vector<PipeCol> cols = pipe_cols(names_, types_, *in);
     // sort columns: plain column references sort the column itself; anything else is evaluated first (:1105-1107)
@@ -663,6 +768,7 @@ DeviceRelationPtr OrderBy::sort_relation(const DeviceRelationPtr& in, int64_t li
         key_cols.push_back(idx);
         asc.push_back(k.asc ? 1 : 0);
     }
+    if (in->rows == 0 || limit == 0) return gpu::empty_relation(types_);
     std::vector<bq_col*> hs;
     for (auto& c : rel_cols) hs.push_back(c->h);
     bq_rel* shell = nullptr;

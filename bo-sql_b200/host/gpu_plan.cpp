@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <functional>
 #include <limits>
 #include <map>
 
@@ -50,6 +51,25 @@ DeviceRelationPtr empty_relation(const std::vector<TypeId>& types) {
     return rel;
 }
 
+DeviceRelationPtr concat_relations(const std::vector<DeviceRelationPtr>& parts, const std::vector<TypeId>& types) {
+    auto out = std::make_shared<DeviceRelation>();
+    for (const auto& p : parts) out->rows += p->rows;
+    for (size_t c = 0; c < types.size(); ++c) {
+        bq_col* h = nullptr;
+        check(bq_col_alloc(context(), static_cast<int>(types[c]), out->rows, &h));
+        DevColPtr col = adopt(h);
+        const size_t w = type_width(types[c]);
+        size_t at = 0;
+        for (const auto& p : parts) {
+            if (!p->rows) continue;
+            check(bq_copy_bytes(context(), static_cast<char*>(bq_col_ptr(h)) + at * w, bq_col_ptr(p->cols[c]->h), p->rows * w));
+            at += p->rows;
+        }
+        out->cols.push_back(col);
+    }
+    return out;
+}
+
 void resolve_stats(PipeCol& col, bool force_device) {
     if (col.stats.known && !force_device) return;
     int64_t lo = 0, hi = -1;
@@ -61,6 +81,17 @@ void resolve_stats(PipeCol& col, bool force_device) {
     col.stats.max_key = hi;
 }
 
+// An expression program fails only through an integer division by zero in the rows it is given (src/exec/expression.cpp:52).
+// Across GPUs that is a fact about ONE rank's shard, so programs containing such a division exchange their outcome: either
+// every rank continues or every rank throws (none is left alone inside the next collective).  Whether a program divides is
+// a property of the plan, so all ranks agree on whether the exchange happens - also a rank whose shard is empty.
+static void run_program(const std::function<void()>& launch, const std::vector<bq_insn>& code) {
+    bool divides = false;
+    for (const bq_insn& in : code) divides = divides || in.op == BQ_OP_DIV_I;
+    if (divides && exchange().active) agree_on(launch);
+    else launch();
+}
+
 DevColPtr eval_to_column(const Expr* e, const std::vector<PipeCol>& cols, size_t rows, Dictionary* dict, TypeId out_type,
                          bool as_predicate) {
     Program prog = compile(e, lookup_for(cols), dict, as_predicate);
@@ -68,8 +99,10 @@ DevColPtr eval_to_column(const Expr* e, const std::vector<PipeCol>& cols, size_t
     for (int idx : prog.columns) cs.push_back(cols[idx].dev->h);
     bq_col* out = nullptr;
     const bq_col* none = nullptr;
-    check(bq_eval(context(), prog.code.data(), static_cast<int>(prog.code.size()), cs.empty() ? &none : cs.data(),
-                  static_cast<int>(cs.size()), 0, rows, static_cast<int>(out_type), &out));
+    run_program([&] {
+        check(bq_eval(context(), prog.code.data(), static_cast<int>(prog.code.size()), cs.empty() ? &none : cs.data(),
+                      static_cast<int>(cs.size()), 0, rows, static_cast<int>(out_type), &out));
+    }, prog.code);
     return adopt(out);
 }
 
@@ -78,8 +111,10 @@ static DevColPtr eval_program(const std::vector<bq_insn>& code, const std::vecto
     std::vector<const bq_col*> cs;
     for (const auto& c : cols) cs.push_back(c->h);
     bq_col* out = nullptr;
-    check(bq_eval(context(), code.data(), static_cast<int>(code.size()), cs.data(), static_cast<int>(cs.size()), 0, rows,
-                  static_cast<int>(out_type), &out));
+    run_program([&] {
+        check(bq_eval(context(), code.data(), static_cast<int>(code.size()), cs.data(), static_cast<int>(cs.size()), 0, rows,
+                      static_cast<int>(out_type), &out));
+    }, code);
     return adopt(out);
 }
 static bq_insn insn(int op, int arg = 0, int64_t imm = 0) {
@@ -196,6 +231,8 @@ SlotPlan plan_slots(const std::vector<const Conjunct*>& conjuncts, const std::ve
 DeviceRelationPtr run_selection(const std::vector<PipeCol>& cols, size_t rows, const std::vector<const Conjunct*>& conjuncts) {
     auto out = std::make_shared<DeviceRelation>();
     if (rows == 0) {
+        // across GPUs an empty shard still takes part in the outcome exchange of a predicate program
+        if (exchange().active) plan_slots(conjuncts, cols, 0, {}, 4);
         std::vector<TypeId> types;
         for (const auto& c : cols) types.push_back(c.type);
         return empty_relation(types);
@@ -368,27 +405,6 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         return nullptr;
     };
 
-    // A step that can fail on this rank's rows alone (an expression program hitting an integer division by zero): across
-    // GPUs every rank learns the outcome before anyone moves on, so all of them throw - none is left inside a collective.
-    auto agreed = [&](bool evaluates_program, auto&& step) {
-        if (!dist) {
-            step();
-            return;
-        }
-        std::string err;
-        try {
-            step();
-        } catch (const std::exception& e) {
-            err = e.what();
-        }
-        if (!evaluates_program && err.empty()) return;
-        int64_t worst = 0;
-        for (int64_t f : xch.host_gather({err.empty() ? 0 : (err.find("Division by zero") != std::string::npos ? 1 : 2)})) worst = std::max(worst, f);
-        if (!err.empty()) throw std::runtime_error(err);
-        if (worst == 1) throw std::runtime_error("Division by zero");
-        if (worst) throw std::runtime_error("expression evaluation failed on another rank");
-    };
-
     // zero input rows -> zero output rows, even for a global aggregate (src/exec/operator.cpp:990-993, H5)
     if (!dist && (p.rows == 0 || (p.joined && p.build_rows == 0))) return empty_relation(out_types);
     if (p.cross_join) return not_fusable("a join whose ON clause is not column = column");
@@ -450,7 +466,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         PipeCol derived;
         derived.name = "\x01group1";
         derived.type = req.group_types[0];
-        agreed(true, [&] { derived.dev = eval_to_column(gexprs[0].get(), p.cols, p.rows, req.dict, derived.type, false); });
+        derived.dev = eval_to_column(gexprs[0].get(), p.cols, p.rows, req.dict, derived.type, false);
         p.cols.push_back(std::move(derived));
         key_col = static_cast<int>(p.cols.size()) - 1;
         look = lookup_for(p.cols);
@@ -458,10 +474,22 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         // GROUP BY a, b, ...: pack (a-min_a, b-min_b, ...) into one integer, most significant first
         uint64_t total = 1;
         std::vector<int> key_cols;
-        for (const auto& g : gexprs) {
-            if (g->type != ExprType::COLUMN_REF) throw std::runtime_error("GROUP BY over several expressions is not supported on the GPU path");
-            int idx = look.index_of(g->str_val);
-            if (idx < 0) throw std::runtime_error("Unknown column: " + g->str_val);
+        for (size_t gi = 0; gi < gexprs.size(); ++gi) {
+            const auto& g = gexprs[gi];
+            int idx = -1;
+            if (g->type == ExprType::COLUMN_REF) {
+                idx = look.index_of(g->str_val);
+                if (idx < 0) throw std::runtime_error("Unknown column: " + g->str_val);
+            } else {
+                // evaluate_key_row evaluates every group expression per row (src/exec/operator.cpp:972-982): a derived column
+                if (!all_on_probe(g.get())) return not_fusable("a GROUP BY expression over build-side columns");
+                PipeCol derived;
+                derived.name = "\x01group" + std::to_string(gi + 1);
+                derived.type = req.group_types[gi];
+                derived.dev = eval_to_column(g.get(), p.cols, p.rows, req.dict, derived.type, false);
+                p.cols.push_back(std::move(derived));
+                idx = static_cast<int>(p.cols.size()) - 1;
+            }
             if (p.cols[idx].type == TypeId::DOUBLE) throw std::runtime_error("GROUP BY over several keys needs integer-typed keys on the GPU path");
             if (p.cols[idx].side) return not_fusable("several GROUP BY keys from the build side");
             key_cols.push_back(idx);
@@ -494,7 +522,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         PipeCol derived;
         derived.name = "\x01packed";
         derived.type = TypeId::INT64;
-        agreed(true, [&] { derived.dev = eval_program(code, kcols, p.rows, TypeId::INT64); });
+        derived.dev = eval_program(code, kcols, p.rows, TypeId::INT64);
         derived.stats.known = true;
         derived.stats.min_key = 0;
         derived.stats.max_key = static_cast<int64_t>(total - 1);
@@ -526,7 +554,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                 PipeCol derived;
                 derived.name = "\x01value" + std::to_string(values.size());
                 derived.type = value_type(a.arg, look);
-                agreed(true, [&] { derived.dev = eval_to_column(a.arg, p.cols, p.rows, req.dict, derived.type, false); });
+                derived.dev = eval_to_column(a.arg, p.cols, p.rows, req.dict, derived.type, false);
                 p.cols.push_back(std::move(derived));
                 look = lookup_for(p.cols);
                 val.form = ValueForm{};
@@ -582,7 +610,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         bq_join*& j;
         ~JoinGuard() { if (j) bq_join_free(nullptr, j); }
     } join_guard{join};
-    if (p.joined) {
+    if (p.joined) for (int attempt = 0;; ++attempt) {
         PipeCol& bk = p.cols[p.build_key];
         const PipeCol& pk = p.cols[p.probe_key];
         if (bk.type != pk.type) return empty_relation(out_types);     // KeyEqual: different TypeId never match (:652)
@@ -604,7 +632,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                 resolve_stats(bk);
                 if (bk.stats.measured) xch.minmax(bk.stats.min_key, bk.stats.max_key);
                 const uint64_t dom = bk.stats.max_key >= bk.stats.min_key ? static_cast<uint64_t>(bk.stats.max_key - bk.stats.min_key) + 1 : 0;
-                dist_bitmap = dom > 0 && dom <= (1ULL << 32) && dom <= 8 * global_build + 1024 && bk.stats.ndv && bk.stats.ndv == global_build;
+                dist_bitmap = attempt == 0 && dom > 0 && dom <= (1ULL << 32) && dom <= 8 * global_build + 1024 && bk.stats.ndv && bk.stats.ndv == global_build;
             }
             // Neither: either broadcast the build side, or CO-PARTITION both sides by hash(join key) so that every rank joins
             // the keys it owns.  The choice is bytes over NVLink; skewed probe keys are handled by keeping the
@@ -679,8 +707,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                 bcols.push_back(p.cols[i]);
             }
         SlotPlan bplan;
-        agreed(false, [&] { bplan = plan_slots(build_conj, bcols, p.build_rows, {}, 3); });
-        if (dist && bplan.mask) agreed(true, [] {});
+        bplan = plan_slots(build_conj, bcols, p.build_rows, {}, 3);
         bq_join_spec js{};
         js.key = bk.dev->h;
         for (size_t i = 0; i < bplan.pred.size(); ++i) js.pred[i] = make_slot(bcols[bplan.pred[i].first].dev, bplan.pred[i].second);
@@ -710,8 +737,21 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                 throw std::runtime_error("join key statistics claim unique keys (ndv == row count) but a shard holds duplicates");
             size_t words = 0;
             void* bits = bq_join_bitmap_ptr(join, &words);
+            const uint64_t inserted = static_cast<uint64_t>(xch.host_sum(static_cast<int64_t>(bq_join_build_rows(join))));
             xch.sum_words(bits, words);
+            // The sum of the ranks' words equals their OR only while no key was inserted by two ranks (statistics that call
+            // the key unique may be stale, or a dimension table may be partly replicated): a doubly set bit would carry into
+            // its neighbour.  The merged bitmap must hold exactly one bit per inserted row; if it does not, every rank sees
+            // the same count and the join is redone as a broadcast join.
+            uint64_t set_bits = 0;
+            check(bq_join_bitmap_popcount(ctx, join, &set_bits));
+            if (set_bits != inserted) {
+                bq_join_free(ctx, join);
+                join = nullptr;
+                continue;
+            }
         }
+        break;
     }
 
     // ---- run the passes ---------------------------------------------------------------------------------------------------
@@ -725,8 +765,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         for (int& r : range_roles)
             if (r >= 0 && p.cols[r].side) r = -1;
         SlotPlan plan;
-        agreed(false, [&] { plan = plan_slots(probe_conj, p.cols, p.rows, range_roles, 3); });
-        if (dist && plan.mask) agreed(true, [] {});
+        plan = plan_slots(probe_conj, p.cols, p.rows, range_roles, 3);
 
         bq_scan_spec s{};
         auto slot_for = [&](int role_index) {
@@ -871,6 +910,13 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             s.hash_part_shift = 64 - log2p;
         }
 
+        // a hash table sized from a stale (too low) ndv overflows: the retry sizes it from the rows themselves and gives up
+        // the partition-major layout, whose regions assume an even spread of the keys
+        auto widen_table = [&] {
+            s.ndv_hint = std::max<size_t>(cur_rows, 1);
+            s.hash_part_log2 = 0;
+            s.hash_part_shift = 0;
+        };
         PhaseTrace trace;
         DeviceRelationPtr r;
         if (!dist) {
@@ -878,6 +924,10 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             int rc = bq_scan_aggregate(ctx, &s, &rel);
             if (rc && std::strstr(bq_last_error(), "stale statistics")) {
                 choose_group(true);                 // the catalog's min/max were wrong: measure and retry
+                rc = bq_scan_aggregate(ctx, &s, &rel);
+            }
+            if (rc && std::strstr(bq_last_error(), "table overflow")) {
+                widen_table();                      // the catalog's ndv was too low (or a partition is skewed): size by rows
                 rc = bq_scan_aggregate(ctx, &s, &rel);
             }
             check(rc);
@@ -889,15 +939,15 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                 int rc = bq_scan_aggregate(ctx, &s, &rel);
                 if (rc) message = bq_last_error();
                 else r = relation_from(rel);
-                int64_t mine = rc ? (message.find("stale statistics") != std::string::npos ? 2 : 1) : 0, worst = 0;
+                int64_t mine = rc ? (message.find("stale statistics") != std::string::npos ? 2 : message.find("table overflow") != std::string::npos ? 3 : 1) : 0, worst = 0;
                 for (int64_t f : xch.host_gather({mine})) worst = std::max(worst, f);
                 return worst;
             };
             std::string message;
             int64_t outcome = attempt(message);
-            if (outcome == 2) {
-                choose_group(true);
-                if (s.group_mode == BQ_GROUP_HASH) s.ndv_hint = std::max<size_t>(cur_rows, 1);
+            if (outcome == 2 || outcome == 3) {       // the worst outcome over the ranks: every rank retries the same way
+                if (outcome == 2) choose_group(true);
+                if (s.group_mode == BQ_GROUP_HASH) widen_table();
                 message.clear();
                 outcome = attempt(message);
             }
@@ -946,6 +996,10 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             int rc = attempt();
             if (rc && std::strstr(bq_last_error(), "stale statistics")) {
                 choose_group(true);
+                rc = attempt();
+            }
+            if (rc && std::strstr(bq_last_error(), "table overflow")) {
+                widen_table();
                 rc = attempt();
             }
             check(rc);

@@ -14,6 +14,8 @@ ColumnLookup lookup_for(const std::vector<PipeCol>& cols);
 ColumnLookup lookup_for(const std::vector<std::string>& names, const std::vector<TypeId>& types);
 
 DeviceRelationPtr empty_relation(const std::vector<TypeId>& types);
+// the rows of `parts`, in order, as one relation (device-to-device copies)
+DeviceRelationPtr concat_relations(const std::vector<DeviceRelationPtr>& parts, const std::vector<TypeId>& types);
 
 // min/max of the column's key from the catalog, else computed on the device (cached in the handle)
 void resolve_stats(PipeCol& col, bool force_device = false);

@@ -250,8 +250,12 @@ int bq_join_build(bq_ctx* ctx, const bq_join_spec* spec, bq_join** out);
 void bq_join_free(bq_ctx* ctx, bq_join* j);
 int bq_join_kind(const bq_join* j);
 size_t bq_join_bytes(const bq_join* j);
+size_t bq_join_build_rows(const bq_join* j);               /* rows inserted (after the build-side predicates) */
 /* BITMAP joins: raw words, so ranks can exchange/OR partial bitmaps (multi-GPU broadcast join) */
 void* bq_join_bitmap_ptr(const bq_join* j, size_t* n_words);
+/* number of set bits (after ranks merged their bitmaps by summing words: must equal the rows they inserted, or two ranks
+ * held the same key and the sum was not an OR) */
+int bq_join_bitmap_popcount(bq_ctx* ctx, const bq_join* j, uint64_t* out);
 /* Materialising probe (HashJoin::next, src/exec/operator.cpp:764-837): all (probe row, build row) pairs in probe
  * order, matches of one probe row in build insertion order. `probe_rowids` (optional) restricts/ordering the probe rows. */
 int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const bq_col* probe_rowids,
@@ -292,7 +296,8 @@ size_t bq_ctx_ipc_mappings(bq_ctx* ctx);                 /* peer blocks mapped s
 uint64_t bq_key_hash(int64_t key);
 
 /* ---- OrderBy / Limit (src/exec/operator.cpp:1097-1151, 561-620) ---------------------------------------
- * Stable LSD radix sort of the relation by up to 4 key columns (asc/desc each); limit >= 0 keeps the first
+ * Stable sort of the relation by its key columns (asc/desc each; rank sort / tile top-k for up to 4 keys, LSD radix passes
+ * for any number); limit >= 0 keeps the first
  * `limit` rows (top-k when the relation is large).  Ties keep input order (the reference's std::sort leaves
  * them unspecified). */
 int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int* key_cols, const int* asc,
