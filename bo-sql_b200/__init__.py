@@ -157,6 +157,17 @@ def kernel_lib():
         "bq_ipc_open": ([vp, vp, P(vp)], C.c_int),
         "bq_ctx_ipc_mappings": ([vp], sz),
         "bq_key_hash": ([i64], C.c_uint64),
+        "bq_comm_unique_id": ([vp], C.c_int),
+        "bq_comm_init": ([vp, C.c_int, C.c_int, vp], C.c_int),
+        "bq_comm_destroy": ([vp], None),
+        "bq_comm_world": ([vp], C.c_int),
+        "bq_comm_rank": ([vp], C.c_int),
+        "bq_comm_all_gather": ([vp, vp, vp, sz], C.c_int),
+        "bq_comm_all_gather_v": ([vp, vp, vp, P(i64)], C.c_int),
+        "bq_comm_all_to_all_v": ([vp, vp, P(i64), vp, P(i64)], C.c_int),
+        "bq_comm_all_reduce_sum_u32": ([vp, vp, sz], C.c_int),
+        "bq_comm_host_all_gather_i64": ([vp, P(i64), C.c_int32, P(i64)], C.c_int),
+        "bq_comm_stats": ([vp, P(C.c_uint64), P(C.c_uint64)], C.c_int),
         "bq_select": ([vp, P(SelectSpec), P(vp)], C.c_int),
         "bq_gather": ([vp, vp, vp, P(vp)], C.c_int),
         "bq_slice": ([vp, vp, sz, sz, P(vp)], C.c_int),

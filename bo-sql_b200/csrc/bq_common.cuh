@@ -132,6 +132,7 @@ struct bq_ctx {
     std::vector<BigBlock> big_blocks;
     size_t big_free_bytes = 0;
     uint64_t big_clock = 0;
+    void* comm = nullptr;        // bq::Comm (bq_comm.cu): this rank's NCCL communicator, when the process is one of several
     bool profile = false;        // bracket the fused scan kernel with events (bench.py roofline)
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profile_events;
 };

@@ -201,6 +201,7 @@ void bq_ctx_destroy(bq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    bq_comm_destroy(ctx);
     {
         std::lock_guard<std::mutex> lk(g_live_mu);
         g_live.erase(ctx);

@@ -215,6 +215,54 @@ def _all_to_all_cpu(outs, ins, rank, world, group):
 _INSTALLED = None
 
 
+class NativeExchange:
+    """The library's own NCCL exchange (bqx_comm_init): after this call no Python runs between plan.run() and a collective.
+    torch.distributed is used ONCE, to hand rank 0's NCCL unique id to the other ranks."""
+
+    def __init__(self, exec_library, group=None, keep_sharded=False):
+        self.lib = exec_library
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        ident = (_C.c_ubyte * 128)()
+        if self.rank == 0 and exec_library.bqx_comm_unique_id(ident):
+            raise RuntimeError(exec_library.bqx_last_error().decode())
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        ident = (_C.c_ubyte * 128).from_buffer_copy(box[0])
+        if exec_library.bqx_comm_init(self.world, self.rank, ident, 1 if keep_sharded else 0):
+            raise RuntimeError(exec_library.bqx_last_error().decode())
+        self.error = None
+
+    KINDS = ("all_gather", "all_gather_v", "all_to_all_v", "all_reduce_sum_u32", "host_all_gather_i64")
+
+    def _stats(self):
+        calls, sent = (_C.c_uint64 * 5)(), _C.c_uint64(0)
+        if self.lib.bqx_comm_stats(calls, _C.byref(sent)):
+            raise RuntimeError(self.lib.bqx_last_error().decode())
+        return [int(c) for c in calls], int(sent.value)
+
+    @property
+    def calls(self):
+        return dict(zip(self.KINDS, self._stats()[0]))
+
+    def keep_sharded(self, on):
+        self.lib.bqx_exchange_keep_sharded(1 if on else 0)
+
+    @property
+    def bytes_sent(self):
+        return self._stats()[1]
+
+
+def install_native(exec_library=None, group=None, keep_sharded=False):
+    """Make this process one rank of `group` with the collectives inside libbosql_b200.so (NCCL over NVLink)."""
+    global _INSTALLED
+    if exec_library is None:
+        from .engine import exec_lib
+        exec_library = exec_lib()
+    _INSTALLED = NativeExchange(exec_library, group, keep_sharded)
+    return _INSTALLED
+
+
 def install(exec_library=None, group=None, device="cuda", keep_sharded=False):
     """Make this process one rank of `group` for every plan it runs from now on (tables hold row shards; statistics passed
     to Engine.add_table describe the whole table).  Returns the Exchange (its .calls / .bytes_sent count the traffic)."""

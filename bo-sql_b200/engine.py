@@ -73,6 +73,11 @@ def exec_lib():
         "bqx_result_free": ([vp], None),
         "bqx_explain": ([cp, C.c_uint, C.c_char_p, sz], C.c_int),
         "bqx_set_exchange": ([vp], C.c_int),
+        "bqx_comm_unique_id": ([vp], C.c_int),
+        "bqx_comm_init": ([C.c_int, C.c_int, vp, C.c_int], C.c_int),
+        "bqx_comm_init_file": ([cp, C.c_int, C.c_int, C.c_int], C.c_int),
+        "bqx_comm_stats": ([P(C.c_uint64), P(C.c_uint64)], C.c_int),
+        "bqx_exchange_keep_sharded": ([C.c_int], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

@@ -1,6 +1,9 @@
 // capi.cpp — include/bosql_b200_exec.h over the C++ operator layer.
 #include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <thread>
 #include <typeinfo>
 
 #include "bosql_b200_exec.h"
@@ -87,6 +90,7 @@ int bqx_init(int device) {
 int bqx_set_exchange(const bqx_exchange* x) {
     return guarded([&] {
         gpu::Exchange& e = gpu::exchange();
+        e.native = false;
         if (!x || x->world <= 1) {
             e.active = false;
             e.fn = bqx_exchange{};
@@ -98,6 +102,84 @@ int bqx_set_exchange(const bqx_exchange* x) {
         e.fn = *x;
         e.active = true;
     });
+}
+
+namespace {
+// the native exchange table: plain functions over bq_comm_* on this process's context (`user` is unused)
+int native_all_gather(void*, const void* send, void* recv, size_t bytes, void*) { return bq_comm_all_gather(gpu::context(), send, recv, bytes); }
+int native_all_gather_v(void*, const void* send, void* recv, const int64_t* bytes_by_rank, void*) {
+    return bq_comm_all_gather_v(gpu::context(), send, recv, bytes_by_rank);
+}
+int native_all_to_all_v(void*, const void* send, const int64_t* sb, void* recv, const int64_t* rb, void*) {
+    return bq_comm_all_to_all_v(gpu::context(), send, sb, recv, rb);
+}
+int native_sum_u32(void*, void* buf, size_t words, void*) { return bq_comm_all_reduce_sum_u32(gpu::context(), buf, words); }
+int native_host_gather(void*, const int64_t* mine, int32_t n, int64_t* all) { return bq_comm_host_all_gather_i64(gpu::context(), mine, n, all); }
+
+void install_native(int world, int rank, const void* id128, int keep_sharded) {
+    if (bq_comm_init(gpu::context(), world, rank, id128)) gpu::throw_last_error();
+    gpu::Exchange& e = gpu::exchange();
+    e.fn = bqx_exchange{};
+    e.fn.world = world;
+    e.fn.rank = rank;
+    e.fn.keep_sharded = keep_sharded;
+    e.fn.all_gather = native_all_gather;
+    e.fn.all_gather_v = native_all_gather_v;
+    e.fn.all_to_all_v = native_all_to_all_v;
+    e.fn.all_reduce_sum_u32 = native_sum_u32;
+    e.fn.host_all_gather_i64 = native_host_gather;
+    e.native = true;
+    e.active = world > 1;
+}
+}  // namespace
+
+int bqx_comm_unique_id(void* id128) {
+    return guarded([&] {
+        if (bq_comm_unique_id(id128)) gpu::throw_last_error();
+    });
+}
+
+int bqx_comm_init(int world, int rank, const void* id128, int keep_sharded) {
+    return guarded([&] { install_native(world, rank, id128, keep_sharded); });
+}
+
+int bqx_comm_init_file(const char* path, int world, int rank, int keep_sharded) {
+    return guarded([&] {
+        if (world < 0) world = std::getenv("WORLD_SIZE") ? std::atoi(std::getenv("WORLD_SIZE")) : 1;
+        if (rank < 0) rank = std::getenv("RANK") ? std::atoi(std::getenv("RANK")) : 0;
+        unsigned char id[BQ_COMM_ID_BYTES];
+        const std::string file(path);
+        if (rank == 0) {
+            if (bq_comm_unique_id(id)) gpu::throw_last_error();
+            const std::string tmp = file + ".tmp";
+            FILE* f = std::fopen(tmp.c_str(), "wb");
+            if (!f || std::fwrite(id, 1, sizeof id, f) != sizeof id) throw std::runtime_error("cannot write the rendezvous file " + tmp);
+            std::fclose(f);
+            if (std::rename(tmp.c_str(), file.c_str())) throw std::runtime_error("cannot publish the rendezvous file " + file);
+        } else {
+            bool got = false;
+            for (int tries = 0; tries < 6000 && !got; ++tries) {           // up to a minute
+                if (FILE* f = std::fopen(file.c_str(), "rb")) {
+                    got = std::fread(id, 1, sizeof id, f) == sizeof id;
+                    std::fclose(f);
+                }
+                if (!got) std::this_thread::sleep_for(std::chrono::milliseconds(10));
+            }
+            if (!got) throw std::runtime_error("rendezvous file " + file + " did not appear");
+        }
+        install_native(world, rank, id, keep_sharded);
+    });
+}
+
+int bqx_comm_stats(uint64_t* calls5, uint64_t* bytes_sent) {
+    return guarded([&] {
+        if (bq_comm_stats(gpu::context(), calls5, bytes_sent)) gpu::throw_last_error();
+    });
+}
+
+int bqx_exchange_keep_sharded(int on) {
+    gpu::exchange().fn.keep_sharded = on ? 1 : 0;
+    return 0;
 }
 
 bq_ctx* bqx_context(void) {

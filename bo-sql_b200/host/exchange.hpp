@@ -15,6 +15,7 @@ namespace bosql::gpu {
 struct Exchange {
     bqx_exchange fn{};
     bool active = false;
+    bool native = false;      // fn points at the library's own NCCL collectives (bqx_comm_init), not at host callbacks
     int world() const { return fn.world; }
     int rank() const { return fn.rank; }
 

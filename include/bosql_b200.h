@@ -292,6 +292,25 @@ int bq_col_alloc_shared(bq_ctx* ctx, int type, size_t n, bq_col** out);
 int bq_col_ipc_export(bq_ctx* ctx, const bq_col* col, void* handle64);
 int bq_ipc_open(bq_ctx* ctx, const void* handle64, void** device_ptr);
 size_t bq_ctx_ipc_mappings(bq_ctx* ctx);                 /* peer blocks mapped so far (diagnostics) */
+/* ---- collectives (one process per GPU; NCCL over NVLink / NVSwitch) -----------------------------------------------
+ * The multi-GPU exchange points of a plan (bo-sql_b200/host/exchange.cpp) run on these.  Rank 0 makes a
+ * unique id (bq_comm_unique_id) and hands its 128 bytes to every rank over any host channel; every rank then calls
+ * bq_comm_init on its own context.  All collectives are enqueued on the context's stream and return at once; only
+ * bq_comm_host_all_gather_i64 synchronises, because it returns values to the CPU (row counts, statistics, outcome words:
+ * all[r*n + i] = rank r's mine[i], n <= 512).  Byte counts are exact; *_v forms take one count per rank. */
+#define BQ_COMM_ID_BYTES 128
+int bq_comm_unique_id(void* id128);
+int bq_comm_init(bq_ctx* ctx, int world, int rank, const void* id128);
+void bq_comm_destroy(bq_ctx* ctx);
+int bq_comm_world(bq_ctx* ctx);
+int bq_comm_rank(bq_ctx* ctx);
+int bq_comm_all_gather(bq_ctx* ctx, const void* send, void* recv, size_t bytes);
+int bq_comm_all_gather_v(bq_ctx* ctx, const void* send, void* recv, const int64_t* bytes_by_rank);
+int bq_comm_all_to_all_v(bq_ctx* ctx, const void* send, const int64_t* send_bytes, void* recv, const int64_t* recv_bytes);
+int bq_comm_all_reduce_sum_u32(bq_ctx* ctx, void* buf, size_t words);
+int bq_comm_host_all_gather_i64(bq_ctx* ctx, const int64_t* mine, int32_t n, int64_t* all);
+/* calls5: all_gather, all_gather_v, all_to_all_v, all_reduce_sum_u32, host_all_gather_i64 issued so far; payload bytes sent */
+int bq_comm_stats(bq_ctx* ctx, uint64_t* calls5, uint64_t* bytes_sent);
 /* the hash all tables and partitions use (so a caller can predict a key's partition) */
 uint64_t bq_key_hash(int64_t key);
 

@@ -128,6 +128,21 @@ typedef struct bqx_exchange {
 /* Installs (copies) the table for this process; NULL or world <= 1 returns to single-GPU execution. */
 int bqx_set_exchange(const bqx_exchange* x);
 
+/* The native exchange: NCCL inside the library (bq_comm_*, include/bosql_b200.h), so that nothing but C++ runs between
+ * a plan's open() and its collectives.  Rank 0 calls bqx_comm_unique_id and passes the 128 bytes to the other ranks (MPI,
+ * torch.distributed, a file: any host channel); every rank then calls bqx_comm_init once, after bqx_init.  The callback
+ * table above remains for hosts that bring their own collectives (the gloo-backed CPU tests). */
+int bqx_comm_unique_id(void* id128);
+int bqx_comm_init(int world, int rank, const void* id128, int keep_sharded);
+/* The same over a rendezvous file for hosts without any channel of their own (the C++ command line): rank 0 writes the
+ * id to `path` (created atomically), the others wait for it.  world / rank default to $WORLD_SIZE / $RANK when < 0. */
+int bqx_comm_init_file(const char* path, int world, int rank, int keep_sharded);
+/* collectives issued (calls5: all_gather, all_gather_v, all_to_all_v, all_reduce_sum_u32, host_all_gather_i64) and payload
+ * bytes sent by this rank since bqx_comm_init (bench.py's exchange record) */
+int bqx_comm_stats(uint64_t* calls5, uint64_t* bytes_sent);
+/* switch the installed exchange between "a shuffled GROUP BY leaves the groups with their owners" and "gathers them" */
+int bqx_exchange_keep_sharded(int on);
+
 /* LogicalOp::to_string of the planned statement (plan-shape tests, tests/test_logical.cpp of the reference) */
 int bqx_explain(const char* sql, unsigned parse_flags, char* out, size_t cap);
 

@@ -85,9 +85,25 @@ __global__ void __launch_bounds__(256) k_agg(const long long* __restrict__ keys,
                 atomicAdd(&t16[k[r]].cnt, 1ULL);
                 atomicAdd(&t16[k[r]].sum, v[r]);
             }
-        } else {
+        } else if (MODE == 3) {
 #pragma unroll
             for (int r = 0; r < 4; ++r) atomicAdd(tsum + k[r], v[r]);
+        } else if (MODE == 4) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) atomicAdd(tcnt + k[r], (unsigned long long)k[r] | 1ULL);
+        } else if (MODE == 5) {
+            // plain (non-atomic) read-modify-write: what the L2 does without the atomic unit
+#pragma unroll
+            for (int r = 0; r < 4; ++r) tsum[k[r]] = v[r];
+        } else {
+            // claim path like the product kernel: load key; CAS when empty; then two REDs
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                long long cur = *reinterpret_cast<volatile long long*>(tkeys + k[r]);
+                if (cur != k[r]) atomicCAS(reinterpret_cast<unsigned long long*>(tkeys + k[r]), 0ULL, (unsigned long long)k[r]);
+                atomicAdd(tcnt + k[r], 1ULL);
+                atomicAdd(tsum + k[r], v[r]);
+            }
         }
     }
     if (bad == 0xFFFFFFFFFFFFULL) *sink = bad;
@@ -129,13 +145,13 @@ int main(int argc, char** argv) {
     printf("SMs %d rows %zu\n", sm, n);
     const size_t total_slots = 1ull << 27;             // 128 Mi slots: 4 GB at 32 B
     void* table; CK(cudaMalloc(&table, total_slots * 32));
-    const char* names[4] = {"soa ", "aos32", "aos16", "red1"};
+    const char* names[7] = {"soa ", "aos32", "aos16", "red1", "red1u64", "store", "soa+claim"};
     // region = slots touched by one window of rows; rows per slot = 10 inside a window
-    for (size_t region : {(size_t)1 << 18, (size_t)1 << 20, (size_t)1 << 21, (size_t)1 << 22, total_slots}) {
+    for (size_t region : {(size_t)1 << 19, (size_t)1 << 21, total_slots}) {
         const size_t window = region == total_slots ? n : region * 5;       // load factor 0.5 at 10 rows per key
         k_gen<<<sm * 8, 256>>>(keys, vals, n, window, region, total_slots);
         CK(cudaDeviceSynchronize());
-        for (int mode = 0; mode < 4; ++mode) {
+        for (int mode = 0; mode < 7; ++mode) {
             CK(cudaMemset(table, 0, total_slots * 32));
             // keys[s] = s so the key check passes
             long long* tkeys = (long long*)table;
@@ -148,7 +164,10 @@ int main(int argc, char** argv) {
                     case 0: k_agg<0><<<sm * 8, 256>>>(keys, vals, n, tkeys, tcnt, tsum, nullptr, nullptr, sink); break;
                     case 1: k_agg<1><<<sm * 8, 256>>>(keys, vals, n, nullptr, nullptr, nullptr, (Slot32*)table, nullptr, sink); break;
                     case 2: k_agg<2><<<sm * 8, 256>>>(keys, vals, n, nullptr, nullptr, nullptr, nullptr, (Slot16*)table, sink); break;
-                    default: k_agg<3><<<sm * 8, 256>>>(keys, vals, n, nullptr, nullptr, tsum, nullptr, nullptr, sink); break;
+                    case 3: k_agg<3><<<sm * 8, 256>>>(keys, vals, n, nullptr, nullptr, tsum, nullptr, nullptr, sink); break;
+                    case 4: k_agg<4><<<sm * 8, 256>>>(keys, vals, n, nullptr, tcnt, nullptr, nullptr, nullptr, sink); break;
+                    case 5: k_agg<5><<<sm * 8, 256>>>(keys, vals, n, nullptr, nullptr, tsum, nullptr, nullptr, sink); break;
+                    default: k_agg<6><<<sm * 8, 256>>>(keys, vals, n, tkeys, tcnt, tsum, nullptr, nullptr, sink); break;
                 }
                 CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1));
                 float ms; CK(cudaEventElapsedTime(&ms, e0, e1));

@@ -94,7 +94,16 @@ def run_rank(rank, world, backend, results):
     xl = bq.exec_lib()
     if xl.bqx_init(local):
         raise RuntimeError(xl.bqx_last_error().decode())
-    ex = D.install(xl, device="cuda")
+    # BOSQL_TEST_EXCHANGE=native: the library's own NCCL collectives (bqx_comm_init; one GPU per rank) instead of the
+    # torch.distributed callback table
+    native = os.environ.get("BOSQL_TEST_EXCHANGE") == "native"
+    ex = D.install_native(xl) if native else D.install(xl, device="cuda")
+
+    def reinstall(keep_sharded=False):
+        if native:
+            ex.keep_sharded(keep_sharded)
+            return ex
+        return D.install(xl, device="cuda", keep_sharded=keep_sharded)
     orders, lines = tables()
     ora = ORA.Oracle()
     sdict = ora.new_dict(datagen.STATUS_DICT)              # one dictionary shared by both tables, as in the engine
@@ -180,7 +189,7 @@ def run_rank(rank, world, backend, results):
             for mode in ("shuffle", "broadcast"):
                 os.environ["BOSQL_JOIN"] = mode
                 for stats in (True, False):
-                    D.install(xl, device="cuda")
+                    reinstall()
                     eng = bq.Engine()
                     eng.add_table("probe", [("p.k", bq.INT64, np.ascontiguousarray(pk[plo:phi])), ("p.v", bq.DOUBLE, np.ascontiguousarray(pv[plo:phi]))],
                                   stats={"p.k": (1, nb, nb)} if stats else None)
@@ -213,12 +222,12 @@ def run_rank(rank, world, backend, results):
         for mode in ("peer", "collective"):
             os.environ["BOSQL_SHUFFLE"] = mode
             for keep in (True, False):
-                D.install(xl, device="cuda", keep_sharded=keep)
+                cur = reinstall(keep)
                 eng = bq.Engine()
                 eng.add_table("t", [("k", bq.INT64, np.ascontiguousarray(k[lo:hi])), ("v", bq.DOUBLE, np.ascontiguousarray(v[lo:hi]))])
-                before = dict(D._INSTALLED.calls)
+                before = dict(cur.calls)
                 got = eng.query("SELECT k, SUM(v), COUNT(*) FROM t GROUP BY k")
-                moved = D._INSTALLED.calls["all_to_all_v"] - before["all_to_all_v"]
+                moved = cur.calls["all_to_all_v"] - before["all_to_all_v"]
                 assert moved == (2 if mode == "collective" else 0), f"{mode}: {moved} all-to-all calls"
                 cols = gather_rows(got.cols) if keep else got.cols
                 order = np.argsort(cols[0], kind="stable")
@@ -233,7 +242,8 @@ def run_rank(rank, world, backend, results):
         os.environ.pop("BOSQL_SHUFFLE", None)
     except Exception:  # noqa: BLE001
         results.append(("shuffle_groupby", traceback.format_exc()[-1500:]))
-    D.uninstall(xl)
+    if not native:
+        D.uninstall(xl)
     if ex.error:
         results.append(("exchange_callbacks", ex.error))
 

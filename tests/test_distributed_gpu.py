@@ -62,10 +62,12 @@ def test_sharded_sql_matches_oracle_shared_gpu(world):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs for NCCL")
-def test_sharded_sql_matches_oracle_nccl():
+@pytest.mark.parametrize("exchange", ["native", "callbacks"])
+def test_sharded_sql_matches_oracle_nccl(exchange):
+    """native: the library's own NCCL collectives (bq_comm_*); callbacks: torch.distributed behind the exchange table."""
     n = min(4, torch.cuda.device_count())
     n = 1 << (n.bit_length() - 1)
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
                         "--master-port", str(_free_port()), os.path.join(ROOT, "tests", "dist_sql.py")],
-                       capture_output=True, text=True, timeout=1500, cwd=ROOT)
+                       capture_output=True, text=True, timeout=1500, cwd=ROOT, env=dict(os.environ, BOSQL_TEST_EXCHANGE=exchange))
     assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-2000:])

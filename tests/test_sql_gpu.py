@@ -326,3 +326,86 @@ def test_stale_catalog_statistics_are_survived(bq, ref):
     g.add_table("t", [("k", INT64, k), ("v", DOUBLE, np.ones(n))], stats={"k": (10, 20, 11)})
     r.add_table("t", [("k", INT64, k), ("v", DOUBLE, np.ones(n))])
     check(g, r, "SELECT k, COUNT(*), SUM(v) FROM t GROUP BY k")
+
+
+# ---- LIMIT stops pulling: rows past the batches a consumer of k rows reaches are never evaluated (Limit::next, :577-613) ----
+def _div_table(n, zero_at):
+    a = np.arange(1, n + 1, dtype=np.int64)
+    b = np.ones(n, dtype=np.int64)
+    b[zero_at] = 0
+    return [("a", INT64, a), ("b", INT64, b), ("c", INT64, a % 10)]
+
+
+@pytest.mark.parametrize("sql,raises", [
+    ("SELECT a / b FROM t LIMIT 5", False),                       # the zero divisor sits in a later batch
+    ("SELECT a / b FROM t LIMIT 4096", False),                    # exactly one batch
+    ("SELECT a / b FROM t LIMIT 4097", True),                     # second batch is evaluated whole
+    ("SELECT a / b FROM t LIMIT 0", False),
+    ("SELECT a FROM t WHERE a / b > 0 LIMIT 10", False),          # predicate evaluated on the first batch only
+    ("SELECT a FROM t WHERE a / b > 0 AND c = 3 LIMIT 500", True),  # needs 5000 rows of matches: reaches the bad batch
+    ("SELECT a / b FROM t WHERE c = 3 LIMIT 400", False),         # 400 matches come from the first 4000 rows
+    ("SELECT a / b FROM t WHERE c = 3 LIMIT 420", True),          # the 411th match lies in the second batch, evaluated whole
+    ("SELECT a / b FROM t", True),
+])
+def test_limit_evaluates_only_what_the_reference_reaches(bq, ref, sql, raises):
+    cols = _div_table(20_000, 6000)
+    g, r = bq.Engine(), ref.RefEngine()
+    for e in (g, r):
+        e.add_table("t", cols)
+    if raises:
+        with pytest.raises(RuntimeError) as want:
+            r.query(sql)
+        with pytest.raises(bq.BqError) as got:
+            g.query(sql)
+        assert str(got.value) == str(want.value) == "Division by zero"
+    else:
+        check(g, r, sql, exact_order=True)
+
+
+def test_limit_window_growth_keeps_scan_order(bq, ref):
+    """A selective predicate under LIMIT: windows of batches grow until k rows are found; rows stay in scan order."""
+    n = 300_000
+    rng = np.random.default_rng(5)
+    cols = [("a", INT64, np.arange(n)), ("x", INT64, rng.integers(0, 1000, size=n))]
+    g, r = bq.Engine(), ref.RefEngine()
+    for e in (g, r):
+        e.add_table("t", cols)
+    for k in (1, 7, 250, 299, 100000):
+        check(g, r, f"SELECT a, x FROM t WHERE x = 3 LIMIT {k}", exact_order=True)
+    check(g, r, "SELECT a FROM t WHERE x = 5000 LIMIT 3", exact_order=True)      # no row qualifies
+
+
+# ---- ORDER BY with more than four keys (the comparator loops over any number, :1115-1122) ---------------------------------
+def test_order_by_six_keys(bq, ref):
+    n = 9000
+    rng = np.random.default_rng(8)
+    cols = [(f"k{i}", INT64, rng.integers(0, 3, size=n)) for i in range(5)] + [("u", INT64, rng.permutation(n))]
+    g, r = bq.Engine(), ref.RefEngine()
+    for e in (g, r):
+        e.add_table("t", cols)
+    check(g, r, "SELECT k0, k1, k2, k3, k4, u FROM t ORDER BY k0, k1 DESC, k2, k3 DESC, k4, u DESC", exact_order=True)
+    check(g, r, "SELECT k0, k1, k2, k3, k4, u FROM t WHERE u < 900 ORDER BY k4 DESC, k3, k2 DESC, k1, k0 DESC, u LIMIT 50", exact_order=True)
+
+
+# ---- GROUP BY over several expressions (evaluate_key_row evaluates each per row, :972-982) ----------------------------------
+def test_group_by_several_expressions(bq, ref):
+    n = 50_000
+    rng = np.random.default_rng(9)
+    cols = [("a", INT64, rng.integers(0, 40, size=n)), ("b", INT64, rng.integers(-5, 5, size=n)), ("v", DOUBLE, rng.integers(0, 999, size=n) / 8.0)]
+    g, r = bq.Engine(), ref.RefEngine()
+    for e in (g, r):
+        e.add_table("t", cols)
+    got, want = check(g, r, "SELECT a + b, a * 2, COUNT(*), SUM(v) FROM t GROUP BY a + b, a * 2")
+    assert got.names == want.names
+    check(g, r, "SELECT b, a - b, AVG(v) FROM t WHERE v > 10 GROUP BY b, a - b")
+
+
+def test_stale_ndv_statistic_is_survived(bq, ref):
+    """A catalog ndv far below the truth under-sizes the hash table: the overflow is retried with a table sized by rows."""
+    n = 200_000
+    rng = np.random.default_rng(10)
+    k = rng.integers(0, 1 << 40, size=n)
+    g, r = bq.Engine(), ref.RefEngine()
+    g.add_table("t", [("k", INT64, k), ("v", DOUBLE, np.ones(n))], stats={"k": (0, (1 << 40) - 1, 100)})
+    r.add_table("t", [("k", INT64, k), ("v", DOUBLE, np.ones(n))])
+    check(g, r, "SELECT k, COUNT(*), SUM(v) FROM t GROUP BY k")
