@@ -285,14 +285,33 @@ DeviceRelationPtr Selection::device_prefix(size_t want) {
     auto* scan = dynamic_cast<ColumnarScan*>(input_.get());
     if (!scan || !predicate || gpu::exchange().active) return select_from(input_->device_prefix(predicate ? static_cast<size_t>(-1) : want));
     const size_t n = scan->table_rows();
+    if (want >= n) return select_from(input_->device_result());      // every batch would be pulled anyway
     const size_t b = scan->batch_rows() ? scan->batch_rows() : kBatchRows;
+    std::vector<gpu::Conjunct> conj;
+    gpu::split_conjuncts(predicate.get(), dict_, conj);
+    std::vector<const gpu::Conjunct*> ptrs;
+    for (const auto& c : conj) ptrs.push_back(&c);
     std::vector<DeviceRelationPtr> parts;
     size_t have = 0, at = 0;
     size_t window = std::max(b, (want + b - 1) / b * b);
+    // rows [begin, end) of the scan: the selected rows, cut after the batch in which the consumer has its `want` rows -
+    // an operator above (a Project that can throw) must not see rows of batches the reference never pulls
     auto take = [&](size_t begin, size_t end) {
-        DeviceRelationPtr part = select_from(scan->device_window(begin, end));
-        have += part->rows;
-        if (part->rows) parts.push_back(part);
+        DeviceRelationPtr in = scan->device_window(begin, end);
+        std::vector<PipeCol> cols = pipe_cols(names_, types_, *in);
+        DevColPtr ids = gpu::select_rowids(cols, in->rows, ptrs);
+        if (have + ids->rows() >= want && end - begin > b) {
+            uint32_t local = 0;                               // position, inside the window, of the row that completes `want`
+            check(bq_col_read(context(), ids->h, want - have - 1, 1, &local));
+            const size_t cut = std::min(end, begin + (local / b + 1) * b);
+            if (cut < end) {
+                in = scan->device_window(begin, cut);
+                cols = pipe_cols(names_, types_, *in);
+                ids = gpu::select_rowids(cols, in->rows, ptrs);
+            }
+        }
+        have += ids->rows();
+        if (ids->rows()) parts.push_back(gpu::gather_rows(cols, ids));
     };
     while (at < n && have < want) {
         const size_t end = std::min(n, at + window);

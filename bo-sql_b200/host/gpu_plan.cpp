@@ -228,15 +228,7 @@ SlotPlan plan_slots(const std::vector<const Conjunct*>& conjuncts, const std::ve
     return plan;
 }
 
-DeviceRelationPtr run_selection(const std::vector<PipeCol>& cols, size_t rows, const std::vector<const Conjunct*>& conjuncts) {
-    auto out = std::make_shared<DeviceRelation>();
-    if (rows == 0) {
-        // across GPUs an empty shard still takes part in the outcome exchange of a predicate program
-        if (exchange().active) plan_slots(conjuncts, cols, 0, {}, 4);
-        std::vector<TypeId> types;
-        for (const auto& c : cols) types.push_back(c.type);
-        return empty_relation(types);
-    }
+DevColPtr select_rowids(const std::vector<PipeCol>& cols, size_t rows, const std::vector<const Conjunct*>& conjuncts) {
     SlotPlan plan = plan_slots(conjuncts, cols, rows, {}, 4);
     bq_select_spec spec{};
     for (size_t i = 0; i < plan.pred.size(); ++i) spec.pred[i] = make_slot(cols[plan.pred[i].first].dev, plan.pred[i].second);
@@ -245,7 +237,11 @@ DeviceRelationPtr run_selection(const std::vector<PipeCol>& cols, size_t rows, c
     spec.row_end = rows;
     bq_col* ids = nullptr;
     check(bq_select(context(), &spec, &ids));
-    DevColPtr rowids = adopt(ids);
+    return adopt(ids);
+}
+
+DeviceRelationPtr gather_rows(const std::vector<PipeCol>& cols, const DevColPtr& rowids) {
+    auto out = std::make_shared<DeviceRelation>();
     out->rows = rowids->rows();
     for (const auto& c : cols) {
         bq_col* g = nullptr;
@@ -253,6 +249,17 @@ DeviceRelationPtr run_selection(const std::vector<PipeCol>& cols, size_t rows, c
         out->cols.push_back(adopt(g));
     }
     return out;
+}
+
+DeviceRelationPtr run_selection(const std::vector<PipeCol>& cols, size_t rows, const std::vector<const Conjunct*>& conjuncts) {
+    if (rows == 0) {
+        // across GPUs an empty shard still takes part in the outcome exchange of a predicate program
+        if (exchange().active) plan_slots(conjuncts, cols, 0, {}, 4);
+        std::vector<TypeId> types;
+        for (const auto& c : cols) types.push_back(c.type);
+        return empty_relation(types);
+    }
+    return gather_rows(cols, select_rowids(cols, rows, conjuncts));
 }
 
 // ---- aggregate ------------------------------------------------------------------------------------------

@@ -51,6 +51,9 @@ struct AggRequest {
 // cannot be fused as described (the caller materialises the child and calls again on the plain relation).
 DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req);
 
+// Selection in two halves: the ascending row ids (uint32) of the rows passing `conjuncts`, and the gather of those rows.
+DevColPtr select_rowids(const std::vector<PipeCol>& cols, size_t rows, const std::vector<const Conjunct*>& conjuncts);
+DeviceRelationPtr gather_rows(const std::vector<PipeCol>& cols, const DevColPtr& rowids);
 // Rows of `rel` passing `conjuncts`, in order (Selection).
 DeviceRelationPtr run_selection(const std::vector<PipeCol>& cols, size_t rows, const std::vector<const Conjunct*>& conjuncts);
 

@@ -348,7 +348,7 @@ def _div_table(n, zero_at):
     ("SELECT a / b FROM t", True),
 ])
 def test_limit_evaluates_only_what_the_reference_reaches(bq, ref, sql, raises):
-    cols = _div_table(20_000, 6000)
+    cols = _div_table(20_000, 6002)          # a = 6003, c = 3: second batch
     g, r = bq.Engine(), ref.RefEngine()
     for e in (g, r):
         e.add_table("t", cols)
@@ -360,6 +360,21 @@ def test_limit_evaluates_only_what_the_reference_reaches(bq, ref, sql, raises):
         assert str(got.value) == str(want.value) == "Division by zero"
     else:
         check(g, r, sql, exact_order=True)
+
+
+def test_limit_cuts_at_the_batch_the_reference_stops_at(bq, ref):
+    """The zero divisor sits in the THIRD batch; LIMIT 420 is satisfied inside the second, so the Project above the Selection
+    must never see the third batch's rows - although the Selection's own windows may already have covered them."""
+    cols = _div_table(40_000, 10_002)        # a = 10003, c = 3: batch 2 (rows 8192..12287)
+    g, r = bq.Engine(), ref.RefEngine()
+    for e in (g, r):
+        e.add_table("t", cols)
+    check(g, r, "SELECT a / b FROM t WHERE c = 3 LIMIT 420", exact_order=True)
+    check(g, r, "SELECT a / b FROM t WHERE c = 3 LIMIT 819", exact_order=True)       # 410 + 409 matches in batches 0 and 1
+    with pytest.raises(bq.BqError, match="Division by zero"):
+        g.query("SELECT a / b FROM t WHERE c = 3 LIMIT 821")
+    with pytest.raises(RuntimeError, match="Division by zero"):
+        r.query("SELECT a / b FROM t WHERE c = 3 LIMIT 821")
 
 
 def test_limit_window_growth_keeps_scan_order(bq, ref):
