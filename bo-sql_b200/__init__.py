@@ -27,7 +27,7 @@ INT64, DOUBLE, STRING, DATE32 = 0, 1, 2, 3
 NP_DTYPES = {INT64: np.int64, DOUBLE: np.float64, STRING: np.uint32, DATE32: np.int32}
 TYPE_NAMES = {INT64: "INT64", DOUBLE: "DOUBLE", STRING: "STRING", DATE32: "DATE32"}
 
-GEN_SEQ, GEN_UNIFORM, GEN_UNIFORM_DIV, GEN_DATE, GEN_TABLE, GEN_HASHED = range(6)
+GEN_SEQ, GEN_UNIFORM, GEN_UNIFORM_DIV, GEN_DATE, GEN_TABLE, GEN_HASHED, GEN_BUCKETS = range(7)
 V_NONE, V_A, V_B, V_MUL, V_ADD, V_SUB, V_DIV = range(7)
 L_A, L_B, L_IMM = range(3)      # left operand of a binary aggregate argument
 R_B, R_A, R_IMM = range(3)      # right operand (zero values = A op B)
@@ -50,7 +50,7 @@ class BqError(RuntimeError):
 class GenSpec(C.Structure):
     _fields_ = [("dist", C.c_int), ("seed", C.c_uint64), ("stream", C.c_uint64), ("lo", C.c_int64), ("hi", C.c_int64),
                 ("div", C.c_double), ("base_year", C.c_int32), ("n_years", C.c_int32), ("cdf", C.c_void_p),
-                ("n_cdf", C.c_size_t), ("modulus", C.c_uint64)]
+                ("n_cdf", C.c_size_t), ("modulus", C.c_uint64), ("starts", C.c_void_p)]
 
 
 class Range(C.Structure):
@@ -75,7 +75,7 @@ class ScanSpec(C.Structure):
                 ("row_begin", C.c_size_t), ("row_end", C.c_size_t), ("mask", C.c_void_p),
                 ("n_v", C.c_int32), ("v", VExpr * 2), ("group_mode", C.c_int32),
                 ("key_min", C.c_int64), ("key_max", C.c_int64), ("ndv_hint", C.c_size_t),
-                ("join", C.c_void_p), ("n_out", C.c_int32), ("out", AggOut * 8),
+                ("join", C.c_void_p), ("row_bits", C.c_void_p), ("n_out", C.c_int32), ("out", AggOut * 8),
                 ("hash_part_log2", C.c_int32), ("hash_part_shift", C.c_int32)]
 
 
@@ -147,6 +147,11 @@ def kernel_lib():
         "bq_scan_aggregate": ([vp, P(ScanSpec), P(vp)], C.c_int),
         "bq_scan_partial": ([vp, P(ScanSpec), P(vp)], C.c_int),
         "bq_agg_finish": ([vp, P(vp), C.c_int, C.c_int, C.c_int, P(AggOut), C.c_int, P(vp)], C.c_int),
+        "bq_scan_state": ([vp, P(ScanSpec), P(vp)], C.c_int),
+        "bq_agg_state_dense": ([vp, P(vp), P(sz)], C.c_int),
+        "bq_agg_state_fold": ([vp, vp, vp, C.c_int], C.c_int),
+        "bq_agg_state_emit": ([vp, vp, P(AggOut), C.c_int, P(vp)], C.c_int),
+        "bq_agg_state_free": ([vp], None),
         "bq_partition": ([vp, vp, P(vp), C.c_int, sz, sz, C.c_int, C.c_int, P(vp), P(vp), P(vp)], C.c_int),
         "bq_partition_count": ([vp, vp, sz, sz, C.c_int, C.c_int, P(i64), P(vp)], C.c_int),
         "bq_partition_count_hot": ([vp, vp, sz, sz, C.c_int, C.c_int, P(i64), C.c_int, P(i64), P(vp)], C.c_int),
@@ -179,6 +184,7 @@ def kernel_lib():
         "bq_join_build_rows": ([vp], sz),
         "bq_join_bitmap_popcount": ([vp, vp, P(C.c_uint64)], C.c_int),
         "bq_join_probe": ([vp, vp, vp, vp, sz, sz, P(vp), P(vp)], C.c_int),
+        "bq_join_probe_bits": ([vp, vp, vp, sz, sz, sz, P(vp)], C.c_int),
         "bq_rel_sort": ([vp, vp, C.c_int, P(C.c_int), P(C.c_int), i64, P(vp)], C.c_int),
         "bq_rel_create": ([vp, P(vp), C.c_int, P(vp)], C.c_int),
         "bq_rel_rows": ([vp], sz),
@@ -230,14 +236,18 @@ class Column:
             _check(kernel_lib().bq_col_read(self.ctx.h, self.h, offset, n, out.ctypes.data_as(C.c_void_p)))
         return out
 
-    def generate(self, dist, seed, stream, lo=0, hi=0, div=1.0, base_year=2024, n_years=1, cdf=None, modulus=0, row0=0):
+    def generate(self, dist, seed, stream, lo=0, hi=0, div=1.0, base_year=2024, n_years=1, cdf=None, modulus=0, row0=0, starts=None):
         s = GenSpec(dist=dist, seed=seed, stream=stream, lo=lo, hi=hi, div=div, base_year=base_year, n_years=n_years,
-                    cdf=None, n_cdf=0, modulus=modulus)
-        keep = None
+                    cdf=None, n_cdf=0, modulus=modulus, starts=None)
+        keep = keep2 = None
         if cdf is not None:
             keep = np.ascontiguousarray(cdf, dtype=np.uint64)
             s.cdf = keep.ctypes.data_as(C.c_void_p)
             s.n_cdf = keep.size
+        if starts is not None:
+            keep2 = np.ascontiguousarray(starts, dtype=np.uint64)
+            assert keep2.size == s.n_cdf + 1, "GEN_BUCKETS: one start per bucket plus the end"
+            s.starts = keep2.ctypes.data_as(C.c_void_p)
         _check(kernel_lib().bq_col_generate(self.ctx.h, self.h, C.byref(s), row0))
         return self
 
@@ -310,6 +320,22 @@ class Join:
         n = C.c_size_t()
         p = kernel_lib().bq_join_bitmap_ptr(self.h, C.byref(n))
         return p, n.value
+
+    @property
+    def build_rows(self):
+        return kernel_lib().bq_join_build_rows(self.h)
+
+    def popcount(self):
+        out = C.c_uint64(0)
+        _check(kernel_lib().bq_join_bitmap_popcount(self.ctx.h, self.h, C.byref(out)))
+        return int(out.value)
+
+    def probe_bits(self, probe_key, row_begin=0, row_end=None, slice_bytes=48 << 20):
+        """Per-row match bits (uint32 column, bit i = row i) computed in key-range passes over an L2-sized bitmap slice."""
+        out = C.c_void_p()
+        end = probe_key.n if row_end is None else row_end
+        _check(kernel_lib().bq_join_probe_bits(self.ctx.h, self.h, probe_key.h, row_begin, end, slice_bytes, C.byref(out)))
+        return Column(self.ctx, out.value)
 
     def free(self):
         if self.h:

@@ -18,6 +18,7 @@ struct GenParams {
     int base_year, n_years;
     const uint64_t* cdf;
     size_t n_cdf;
+    const uint64_t* starts;
     uint64_t modulus;
     uint64_t row0;
     size_t n;
@@ -41,6 +42,7 @@ BQ_D int64_t gen_value(const GenParams& p, uint64_t row, double* as_f) {
             v = y * 10000 + m * 100 + d;
             break;
         }
+        case BQ_GEN_BUCKETS:
         case BQ_GEN_TABLE: {
             uint64_t u = h >> 11;   // 53 uniform bits
             size_t lo = 0, hi = p.n_cdf;   // first i with cdf[i] > u
@@ -49,7 +51,12 @@ BQ_D int64_t gen_value(const GenParams& p, uint64_t row, double* as_f) {
                 if (__ldg(p.cdf + mid) > u) hi = mid; else lo = mid + 1;
             }
             if (lo >= p.n_cdf) lo = p.n_cdf - 1;
-            v = p.lo + static_cast<int64_t>(lo);
+            if (p.dist == BQ_GEN_BUCKETS) {
+                const uint64_t s0 = __ldg(p.starts + lo), s1 = __ldg(p.starts + lo + 1);
+                v = p.lo + static_cast<int64_t>(s0 + mix64(h) % (s1 - s0));
+            } else {
+                v = p.lo + static_cast<int64_t>(lo);
+            }
             break;
         }
         case BQ_GEN_HASHED: {
@@ -93,16 +100,24 @@ extern "C" int bq_col_generate(bq_ctx* ctx, bq_col* col, const bq_gen_spec* s, u
         p.modulus = s->modulus ? s->modulus : 1;
         p.row0 = global_row0;
         p.n = col->n;
-        if (s->dist < BQ_GEN_SEQ || s->dist > BQ_GEN_HASHED) throw std::runtime_error("bad generator dist");
-        if (s->dist != BQ_GEN_SEQ && s->dist != BQ_GEN_DATE && s->dist != BQ_GEN_TABLE && s->hi < s->lo)
+        if (s->dist < BQ_GEN_SEQ || s->dist > BQ_GEN_BUCKETS) throw std::runtime_error("bad generator dist");
+        const bool table = s->dist == BQ_GEN_TABLE || s->dist == BQ_GEN_BUCKETS;
+        if (s->dist != BQ_GEN_SEQ && s->dist != BQ_GEN_DATE && !table && s->hi < s->lo)
             throw std::runtime_error("generator needs lo <= hi");
         uint64_t* d_cdf = nullptr;
-        if (s->dist == BQ_GEN_TABLE) {
+        if (table) {
             if (!s->cdf || !s->n_cdf) throw std::runtime_error("BQ_GEN_TABLE needs a cdf");
-            d_cdf = static_cast<uint64_t*>(dev_alloc(ctx, s->n_cdf * 8));
+            const bool buckets = s->dist == BQ_GEN_BUCKETS;
+            if (buckets && !s->starts) throw std::runtime_error("BQ_GEN_BUCKETS needs bucket starts");
+            if (buckets)
+                for (size_t i = 0; i < s->n_cdf; ++i)
+                    if (s->starts[i + 1] <= s->starts[i]) throw std::runtime_error("BQ_GEN_BUCKETS: bucket starts must ascend");
+            d_cdf = static_cast<uint64_t*>(dev_alloc(ctx, (2 * s->n_cdf + 1) * 8));
             BQ_CUDA(cudaMemcpyAsync(d_cdf, s->cdf, s->n_cdf * 8, cudaMemcpyHostToDevice, ctx->stream));
+            if (buckets) BQ_CUDA(cudaMemcpyAsync(d_cdf + s->n_cdf, s->starts, (s->n_cdf + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
             p.cdf = d_cdf;
             p.n_cdf = s->n_cdf;
+            p.starts = d_cdf + s->n_cdf;
         }
         if (col->n) {
             int grid = grid_for(ctx, col->n, 8);

@@ -18,6 +18,8 @@
 #include "bq_common.cuh"
 #include "bq_internal.cuh"
 
+#include <algorithm>
+
 namespace bq {
 
 struct BuildParams {
@@ -214,6 +216,56 @@ __global__ void __launch_bounds__(kBlock) k_probe_fill(const __grid_constant__ P
     for (unsigned a = 0; a < m; ++a) pr[a] = static_cast<unsigned>(i);
 }
 
+// ---- semi-join probe in key-range passes (bitmaps beyond L2) ----------------------------------------------------------
+struct ProbeBitsParams {
+    const void* key;
+    int key_kind;
+    size_t row_begin, row_end;
+    long long key_min;
+    unsigned long long slice_lo, slice_len;      // this pass tests keys with slice_lo <= key - key_min < slice_lo + slice_len
+    const unsigned* bitmap;
+    unsigned* out;                               // bit i = row i
+    int first;                                   // first pass stores every word, later passes OR into the words they hit
+};
+
+// A warp owns 128 consecutive rows per trip (row_begin is a multiple of 128): lane t tests rows t, 32+t, 64+t, 96+t, so the key
+// column is read with fully coalesced 256-byte requests and each ballot is one finished word of the output.  Only rows
+// whose key lies in the pass's slice touch the bitmap, so the slice (tens of MB) is what the L2 keeps hot.
+__global__ void __launch_bounds__(kBlock) k_probe_bits(const __grid_constant__ ProbeBitsParams p) {
+    const int lane = threadIdx.x & 31;
+    const size_t warps = static_cast<size_t>(gridDim.x) * (kBlock / 32);
+    const size_t warp = static_cast<size_t>(blockIdx.x) * (kBlock / 32) + (threadIdx.x >> 5);
+    const size_t n_chunks = (p.row_end - p.row_begin + 127) / 128;
+    for (size_t c = warp; c < n_chunks; c += warps) {
+        const size_t base = p.row_begin + c * 128;
+        long long k[4];
+        bool in[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const size_t i = base + 32 * r + lane;
+            in[r] = i < p.row_end;
+            k[r] = in[r] ? load_raw(p.key, p.key_kind, i) : 0;
+        }
+        unsigned hit[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const unsigned long long idx = static_cast<unsigned long long>(k[r] - p.key_min) - p.slice_lo;
+            const bool mine = in[r] && idx < p.slice_len;
+            const unsigned long long g = idx + p.slice_lo;
+            hit[r] = mine ? (__ldg(p.bitmap + (g >> 5)) >> (g & 31)) & 1u : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const unsigned word = __ballot_sync(0xffffffffu, hit[r] != 0);
+            if (lane == r) {
+                unsigned* dst = p.out + (base >> 5) + r;
+                if (p.first) *dst = word;
+                else if (word) *dst |= word;
+            }
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kBlock) k_popcount_words(const unsigned* __restrict__ w, size_t n, unsigned long long* __restrict__ out) {
     unsigned long long c = 0;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c += __popc(w[i]);
@@ -383,6 +435,61 @@ int bq_join_bitmap_popcount(bq_ctx* ctx, const bq_join* j, uint64_t* out) {
 void* bq_join_bitmap_ptr(const bq_join* j, size_t* n_words) {
     if (n_words) *n_words = j->bitmap_words;
     return j->bitmap;
+}
+
+int bq_join_probe_bits(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, size_t row_begin, size_t row_end,
+                       size_t slice_bytes, bq_col** out_bits) {
+    return guarded([&] {
+        if (j->kind != BQ_JOIN_BITMAP) throw std::runtime_error("key-range probe passes need a bitmap join");
+        if (probe_key->type == BQ_DOUBLE) throw std::runtime_error("bitmap joins have integer keys");
+        if (row_end < row_begin || row_end > probe_key->n) throw std::runtime_error("bad probe row range");
+        if (row_begin % 128) throw std::runtime_error("probe passes need a row range starting at a multiple of 128");
+        if (slice_bytes < (1u << 20)) slice_bytes = 1u << 20;
+        const unsigned long long domain = static_cast<unsigned long long>(j->key_max - j->key_min) + 1ULL;
+        // whole 32-bit words per slice, equal slices
+        unsigned long long passes = (j->bytes + slice_bytes - 1) / slice_bytes;
+        if (passes < 1) passes = 1;
+        unsigned long long slice_keys = ((domain + passes - 1) / passes + 31) / 32 * 32;
+        const size_t words = (row_end + 31) / 32;
+        bq_col* bits = new_col(ctx, BQ_STRING, (words + 3) / 4 * 4);       // whole 16-byte groups: the scan loads four words at once
+        try {
+            BQ_CUDA(cudaMemsetAsync(bits->ptr, 0, bits->n * 4, ctx->stream));
+            if (row_end > row_begin) {
+                ProbeBitsParams p{};
+                p.key = probe_key->ptr;
+                p.key_kind = probe_key->type;
+                p.row_begin = row_begin;
+                p.row_end = row_end;
+                p.key_min = j->key_min;
+                p.bitmap = j->bitmap;
+                p.out = static_cast<unsigned*>(bits->ptr);
+                const int grid = grid_for(ctx, row_end - row_begin, 8);
+                int pass = 0;
+                for (unsigned long long lo = 0; lo < domain; lo += slice_keys, ++pass) {
+                    p.slice_lo = lo;
+                    p.slice_len = std::min(slice_keys, domain - lo);
+                    p.first = pass == 0;
+                    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+                    if (ctx->profile) {
+                        BQ_CUDA(cudaEventCreate(&ev0));
+                        BQ_CUDA(cudaEventCreate(&ev1));
+                        BQ_CUDA(cudaEventRecord(ev0, ctx->stream));
+                    }
+                    k_probe_bits<<<grid, kBlock, 0, ctx->stream>>>(p);
+                    if (ctx->profile) {
+                        BQ_CUDA(cudaEventRecord(ev1, ctx->stream));
+                        ctx->profile_events.emplace_back(ev0, ev1);
+                    }
+                    ctx->launches++;
+                    BQ_CUDA(cudaGetLastError());
+                }
+            }
+        } catch (...) {
+            free_col(bits);
+            throw;
+        }
+        *out_bits = bits;
+    });
 }
 
 int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const bq_col* probe_rowids,

@@ -51,6 +51,7 @@ struct ScanParams {
     size_t vec_begin;          // first row of the vector region (multiple of 4)
     size_t n_chunks;           // 128-row chunks in the vector region
     const long long* mask;     // optional 0/1 per row
+    const unsigned* row_bits;  // BQ_JOIN_ROWBITS: bit i = row i joins (bq_join_probe_bits); row_begin is a multiple of 128
     // group state
     long long key_min;
     unsigned long long key_domain;     // G_SMEM / G_DENSE: number of slots
@@ -125,6 +126,41 @@ BQ_D void load_quad(const void* ptr, int kind, size_t base, int lane, long long 
         const int2* q = reinterpret_cast<const int2*>(static_cast<const char*>(ptr) + (base + 2 * lane) * 4);
         int2 a = ldg_stream2(q);
         int2 b = ldg_stream2(q + 32);
+        if (kind == BQ_STRING) {
+            raw[0] = static_cast<unsigned>(a.x);
+            raw[1] = static_cast<unsigned>(a.y);
+            raw[2] = static_cast<unsigned>(b.x);
+            raw[3] = static_cast<unsigned>(b.y);
+        } else {
+            raw[0] = a.x;
+            raw[1] = a.y;
+            raw[2] = b.x;
+            raw[3] = b.y;
+        }
+    }
+}
+
+// The same with each half predicated: a lane whose two rows of a half were ruled out beforehand (join-match bits) does not
+// issue that load, so a 32-byte sector none of whose four rows survive is never fetched from HBM.
+BQ_D void load_quad_pred(const void* ptr, int kind, size_t base, int lane, bool lo_half, bool hi_half, long long (&raw)[4]) {
+    raw[0] = raw[1] = raw[2] = raw[3] = 0;
+    if (kind == BQ_INT64 || kind == BQ_DOUBLE) {
+        const int4* q = reinterpret_cast<const int4*>(static_cast<const char*>(ptr) + (base + 2 * lane) * 8);
+        if (lo_half) {
+            int4 a = ldg_stream(q);
+            raw[0] = pack64(a.x, a.y);
+            raw[1] = pack64(a.z, a.w);
+        }
+        if (hi_half) {
+            int4 b = ldg_stream(q + 32);
+            raw[2] = pack64(b.x, b.y);
+            raw[3] = pack64(b.z, b.w);
+        }
+    } else {
+        const int2* q = reinterpret_cast<const int2*>(static_cast<const char*>(ptr) + (base + 2 * lane) * 4);
+        int2 a = make_int2(0, 0), b = make_int2(0, 0);
+        if (lo_half) a = ldg_stream2(q);
+        if (hi_half) b = ldg_stream2(q + 32);
         if (kind == BQ_STRING) {
             raw[0] = static_cast<unsigned>(a.x);
             raw[1] = static_cast<unsigned>(a.y);
@@ -347,7 +383,7 @@ struct RowSink {
 
     // a row that passed every streamed range (scalar head/tail path and staged flushes)
     BQ_D void row(long long key_raw, long long a, long long b, long long jk) {
-        if (Xs::jmode(p) == 0) {
+        if (Xs::jmode(p) == 0 || Xs::jmode(p) == BQ_JOIN_ROWBITS) {      // (match bits were tested by the caller)
             add(key_raw, a, b);
         } else if (Xs::jmode(p) == BQ_JOIN_HASH) {
             probe_hash(key_raw, a, b, jk);
@@ -464,14 +500,28 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
         const size_t base = p.vec_begin + c * 128;
         long long raw[N_SLOTS][4];
         long long mk[4] = {1, 1, 1, 1};
-        // phase 1: issue every load of the chunk
+        bool pass[4] = {true, true, true, true};
+        if (Xs::jmode(p) == BQ_JOIN_ROWBITS) {
+            // join-match bits of the chunk's 128 rows: one 16-byte broadcast load, then only the halves with a match are read
+            const uint4 w = __ldg(reinterpret_cast<const uint4*>(p.row_bits + (base >> 5)));
+            const unsigned lo_w = lane < 16 ? w.x : w.y, hi_w = lane < 16 ? w.z : w.w;
+            const int sh = (2 * lane) & 31;
+            pass[0] = (lo_w >> sh) & 1u;
+            pass[1] = (lo_w >> (sh + 1)) & 1u;
+            pass[2] = (hi_w >> sh) & 1u;
+            pass[3] = (hi_w >> (sh + 1)) & 1u;
 #pragma unroll
-        for (int s = 0; s < N_SLOTS; ++s) {
-            if (Sh::streamed(p, s)) load_quad(p.s[s].ptr, Sh::kind(p, s), base, lane, raw[s]);
+            for (int s = 0; s < N_SLOTS; ++s)
+                if (Sh::streamed(p, s)) load_quad_pred(p.s[s].ptr, Sh::kind(p, s), base, lane, pass[0] || pass[1], pass[2] || pass[3], raw[s]);
+        } else {
+            // phase 1: issue every load of the chunk
+#pragma unroll
+            for (int s = 0; s < N_SLOTS; ++s) {
+                if (Sh::streamed(p, s)) load_quad(p.s[s].ptr, Sh::kind(p, s), base, lane, raw[s]);
+            }
         }
         if (mask) load_quad(mask, BQ_INT64, base, lane, mk);
         // phase 2: range tests
-        bool pass[4] = {true, true, true, true};
 #pragma unroll
         for (int s = 0; s < N_SLOTS; ++s) {
             if (Sh::streamed(p, s) && nr_of(s) > 0) {
@@ -546,6 +596,7 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
                 }
             }
             if (mask && __ldg(mask + i) == 0) ok = false;
+            if (Xs::jmode(p) == BQ_JOIN_ROWBITS && !((__ldg(p.row_bits + (i >> 5)) >> (i & 31)) & 1u)) ok = false;
             if (ok) sink.row(val[S_KEY], val[S_A], val[S_B], val[S_JK]);
         }
     }
@@ -698,6 +749,7 @@ constexpr uint32_t kX_A = xshape(0, 1, BQ_V_A);                                 
 constexpr uint32_t kX_AB = xshape(0, 2, BQ_V_A, 0, 0, BQ_V_B);                    // SUM(a), SUM(b), no join
 constexpr uint32_t kX_Q2 = xshape(BQ_JOIN_BITMAP, 1, BQ_V_MUL, BQ_L_A, BQ_R_B);   // bitmap probe, SUM(a * b)
 constexpr uint32_t kX_J5 = xshape(BQ_JOIN_DIRECT, 1, BQ_V_MUL, BQ_L_A, BQ_R_B);   // direct probe, SUM(a * b.w)
+constexpr uint32_t kX_Q2B = xshape(BQ_JOIN_ROWBITS, 1, BQ_V_MUL, BQ_L_A, BQ_R_B); // precomputed match bits, SUM(a * b)
 constexpr uint32_t kR_Q1 = rshape_bits(S_KEY, 1) | rshape_bits(S_P0, 1);     // one (merged) range on the date, one on status
 constexpr uint32_t kR_P0 = rshape_bits(S_P0, 1);                             // filter sweep: one range on the predicate column
 constexpr uint32_t kR_A = rshape_bits(S_A, 1);
@@ -722,6 +774,9 @@ constexpr uint32_t kShapeQ2 = shape_bits(S_KEY, BQ_INT64, false) | shape_bits(S_
                               shape_bits(S_B, BQ_DOUBLE, false) | shape_bits(S_JK, BQ_INT64, false);
 constexpr uint32_t kShapeQ2S = shape_bits(S_KEY, BQ_STRING, false) | shape_bits(S_A, BQ_INT64, false) |
                                shape_bits(S_B, BQ_DOUBLE, false) | shape_bits(S_JK, BQ_INT64, false);
+// Q2 after bq_join_probe_bits: the probe key is no longer read
+constexpr uint32_t kShapeQ2B = shape_bits(S_KEY, BQ_INT64, false) | shape_bits(S_A, BQ_INT64, false) | shape_bits(S_B, BQ_DOUBLE, false);
+constexpr uint32_t kShapeQ2SB = shape_bits(S_KEY, BQ_STRING, false) | shape_bits(S_A, BQ_INT64, false) | shape_bits(S_B, BQ_DOUBLE, false);
 // high-cardinality GROUP BY k (INT64) SUM/COUNT/AVG(v DOUBLE)
 constexpr uint32_t kShapeGB = shape_bits(S_KEY, BQ_INT64, false) | shape_bits(S_A, BQ_DOUBLE, false);
 // skewed join: probe p.k, SUM(p.v * b.w) with b.w from the build side
@@ -737,6 +792,7 @@ static const ShapeEntry kShapes[] = {
     BQ_SHAPE(kShapeA_F64, kR_A, kX_A, G_NONE, false),
     BQ_SHAPE(kShapeQ2, kR_NONE, kX_Q2, G_DENSE, false),   BQ_SHAPE(kShapeQ2, kR_NONE, kX_Q2, G_HASH, true),
     BQ_SHAPE(kShapeQ2S, kR_NONE, kX_Q2, G_DENSE, false),  BQ_SHAPE(kShapeQ2S, kR_NONE, kX_Q2, G_SMEM, true),
+    BQ_SHAPE(kShapeQ2B, kR_NONE, kX_Q2B, G_DENSE, false), BQ_SHAPE(kShapeQ2SB, kR_NONE, kX_Q2B, G_DENSE, false),
     BQ_SHAPE(kShapeGB, kR_NONE, kX_A, G_HASH, true),      BQ_SHAPE(kShapeGB, kR_NONE, kX_A, G_DENSE, false),
     BQ_SHAPE(kShapeJ5, kR_NONE, kX_J5, G_NONE, false),
     // any other slot / range / argument layout, join kind or a mask column: same source, run-time flags
@@ -886,6 +942,13 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st, bool n
     } else if (spec->jkey.col) {
         throw std::runtime_error("probe key slot without a join");
     }
+    if (spec->row_bits) {
+        if (spec->join) throw std::runtime_error("row bits replace the join probe: pass one or the other");
+        if (spec->row_bits->type != BQ_STRING || spec->row_bits->n * 32 < spec->row_end) throw std::runtime_error("row bits must be a uint32 column with one bit per row");
+        if (spec->row_begin % 128) throw std::runtime_error("row bits need a row range starting at a multiple of 128");
+        p.jmode = BQ_JOIN_ROWBITS;
+        p.row_bits = static_cast<const unsigned*>(spec->row_bits->ptr);
+    }
 
     // ---- group state ----
     st.has_key = spec->group_mode != BQ_GROUP_NONE;
@@ -951,12 +1014,12 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st, bool n
     if (blocks_per_sm < 1) blocks_per_sm = 1;
     int grid = grid_for(ctx, rows, blocks_per_sm);      // a whole number of resident CTAs per SM: one wave
 
-    // one allocation: cnt | sum0 | sum1 | keys | part_cnt | part_sum | ticket | err
+    // one allocation: cnt | sum0 | sum1 | ticket err | keys | part_cnt | part_sum   (the first four are what ranks exchange)
     size_t n = st.slots;
-    size_t off_cnt = 0, off_s0 = off_cnt + n * 8, off_s1 = off_s0 + n * 8, off_keys = off_s1 + n * 8;
+    size_t off_cnt = 0, off_s0 = off_cnt + n * 8, off_s1 = off_s0 + n * 8, off_tk = off_s1 + n * 8, off_keys = off_tk + 16;
     size_t off_pc = off_keys + (st.gmode == G_HASH ? n * 8 : 0);
-    size_t off_ps = off_pc + static_cast<size_t>(grid) * 8, off_tk = off_ps + static_cast<size_t>(grid) * 16;
-    size_t total = off_tk + 16;
+    size_t off_ps = off_pc + static_cast<size_t>(grid) * 8;
+    size_t total = off_ps + static_cast<size_t>(grid) * 16;
     st.ctx = ctx;
     st.block = dev_alloc(ctx, total);
     char* base = static_cast<char*>(st.block);
@@ -1122,11 +1185,79 @@ __global__ void __launch_bounds__(kBlock) k_merge_partial(const __grid_constant_
     atomicAdd(m.g_sum1 + idx, m.s1[i]);
 }
 
+// Dense states of all ranks, gathered back to back (block r = rank r's cnt | sum0 | sum1 | ticket err), folded into this
+// rank's state: counts add up, sums are added in rank order (the same bits on every rank), error flags are OR-ed.
+__global__ void __launch_bounds__(kBlock) k_fold_dense(const unsigned char* __restrict__ gathered, size_t block_bytes, int world, size_t n,
+                                                       unsigned long long* __restrict__ cnt, double* __restrict__ sum0,
+                                                       double* __restrict__ sum1, int* __restrict__ err) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n) {
+        unsigned long long c = 0;
+        double s0 = 0.0, s1 = 0.0;
+        for (int r = 0; r < world; ++r) {
+            const unsigned char* b = gathered + static_cast<size_t>(r) * block_bytes;
+            c += reinterpret_cast<const unsigned long long*>(b)[i];
+            s0 = __dadd_rn(s0, reinterpret_cast<const double*>(b + n * 8)[i]);
+            s1 = __dadd_rn(s1, reinterpret_cast<const double*>(b + n * 16)[i]);
+        }
+        cnt[i] = c;
+        sum0[i] = s0;
+        sum1[i] = s1;
+    }
+    if (i == 0) {
+        int e = 0;
+        for (int r = 0; r < world; ++r) e |= *reinterpret_cast<const int*>(gathered + static_cast<size_t>(r) * block_bytes + n * 24 + 8);
+        *err = e;
+    }
+}
+
 }  // namespace bq
 
 using namespace bq;
 
+struct bq_agg_state {
+    AggState st;
+};
+
 extern "C" {
+
+int bq_scan_state(bq_ctx* ctx, const bq_scan_spec* spec, bq_agg_state** out) {
+    return guarded([&] {
+        auto* s = new bq_agg_state();
+        try {
+            run_scan(ctx, spec, s->st, true);
+        } catch (...) {
+            delete s;
+            throw;
+        }
+        *out = s;
+    });
+}
+
+int bq_agg_state_dense(const bq_agg_state* s, void** ptr, size_t* bytes) {
+    const bool dense = s->st.gmode != G_HASH;
+    if (ptr) *ptr = dense ? s->st.block : nullptr;
+    if (bytes) *bytes = dense ? s->st.slots * 24 + 16 : 0;
+    return 0;
+}
+
+int bq_agg_state_fold(bq_ctx* ctx, bq_agg_state* s, const void* gathered, int world) {
+    return guarded([&] {
+        if (s->st.gmode == G_HASH) throw std::runtime_error("only dense aggregate states are exchanged as they are");
+        const size_t n = s->st.slots;
+        k_fold_dense<<<(unsigned)((n + kBlock - 1) / kBlock), kBlock, 0, ctx->stream>>>(static_cast<const unsigned char*>(gathered), n * 24 + 16, world, n,
+                                                                                   s->st.cnt, s->st.sum0, s->st.sum1, s->st.err);
+        ctx->launches++;
+        BQ_CUDA(cudaGetLastError());
+        s->st.presence = 0;
+    });
+}
+
+int bq_agg_state_emit(bq_ctx* ctx, bq_agg_state* s, const bq_agg_out* outs, int n_out, bq_rel** out) {
+    return guarded([&] { *out = emit_state(ctx, s->st, outs, n_out, false); });
+}
+
+void bq_agg_state_free(bq_agg_state* s) { delete s; }
 
 int bq_scan_aggregate(bq_ctx* ctx, const bq_scan_spec* spec, bq_rel** out) {
     return guarded([&] {

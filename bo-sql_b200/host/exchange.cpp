@@ -213,6 +213,19 @@ void gather_partials(const DeviceRelation* local, int error_flags, bool has_key,
     // `send` may be released here: the allocator is stream ordered, and the collective was enqueued on the same stream
 }
 
+void all_gather_fold_state(bq_agg_state* state) {
+    Exchange& x = exchange();
+    bq_ctx* ctx = context();
+    void* mine = nullptr;
+    size_t bytes = 0;
+    check(bq_agg_state_dense(state, &mine, &bytes));
+    if (!mine) throw std::runtime_error("internal: a hash-table state cannot be exchanged as a dense block");
+    DevColPtr all = alloc_bytes(bytes * static_cast<size_t>(x.world()));
+    xcheck(x.fn.all_gather(x.fn.user, mine, ptr_of(all), bytes, bq_ctx_stream(ctx)), "all_gather");
+    check(bq_agg_state_fold(ctx, state, ptr_of(all), x.world()));
+    // `all` may be released here: the allocator is stream ordered and the fold was enqueued on the same stream
+}
+
 // Partition count shared by both shuffle implementations: a power of two >= world (x8 when world is not a power of two, so
 // the contiguous runs handed to the ranks stay balanced); hash bits [40, 40 + log2 P) are disjoint from the bits the local
 // tables use (top bits: L2 partition, bottom bits: slot).

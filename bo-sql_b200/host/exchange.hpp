@@ -51,6 +51,10 @@ struct GatheredPartials {
 void gather_partials(const DeviceRelation* local, int error_flags, bool has_key, TypeId key_type, int64_t capacity,
                      GatheredPartials& out);
 
+// Dense / global aggregate states (bq_scan_state): every rank's raw state block is all-gathered (same size everywhere: the
+// key domain comes from catalog statistics) and folded in rank order by one launch - no compaction, no size exchange.
+void all_gather_fold_state(bq_agg_state* state);
+
 // Hash-partitions rows [0, rows) of key + payload by rank and exchanges them all-to-all; returns the rows this rank owns.
 struct Shuffled {
     DevColPtr key;

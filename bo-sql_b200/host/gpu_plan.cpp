@@ -7,6 +7,7 @@
 #include "exchange.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <limits>
@@ -761,6 +762,23 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         break;
     }
 
+    // A semi-join bitmap far beyond the L2 (a 2-billion-key domain is 250 MB; across GPUs the bitmap spans the GLOBAL key
+    // domain) is probed in key-range passes: each pass streams the probe key once and tests only the keys of one L2-sized
+    // slice, leaving one match bit per row; the fused scan then reads those bits instead of probing (and skips the sectors
+    // of rows that did not match).  $BOSQL_BITMAP_SLICE_MB sets the slice size (default 40; 0 = always probe fused).
+    DevColPtr row_bits;
+    if (join && bq_join_kind(join) == BQ_JOIN_BITMAP && p.rows > 0) {
+        size_t slice_mb = 40;
+        if (const char* e = std::getenv("BOSQL_BITMAP_SLICE_MB")) slice_mb = static_cast<size_t>(std::atoll(e));
+        if (slice_mb > 0 && bq_join_bytes(join) > (slice_mb << 20) + (slice_mb << 18)) {
+            PhaseTrace ptrace;
+            bq_col* b = nullptr;
+            check(bq_join_probe_bits(ctx, join, p.cols[p.probe_key].dev->h, 0, p.rows, slice_mb << 20, &b));
+            row_bits = adopt(b);
+            ptrace.mark("probe in key-range passes");
+        }
+    }
+
     // ---- run the passes ---------------------------------------------------------------------------------------------------
     bool groups_stay_sharded = false;
     std::vector<DeviceRelationPtr> pass_results;
@@ -789,6 +807,11 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         s.row_begin = 0;
         s.row_end = p.rows;
         s.join = join;
+        if (row_bits && s.jkey.n_ranges == 0) {        // (a range riding on the probe key keeps the fused probe)
+            s.join = nullptr;
+            s.jkey = bq_slot{};
+            s.row_bits = row_bits->h;
+        }
         s.n_v = static_cast<int32_t>(ps.vals.size());
         for (size_t k = 0; k < ps.vals.size(); ++k) {
             const ValueForm& f = values[ps.vals[k]].form;
@@ -972,6 +995,22 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             // local scan (division by zero, stale bounds) travels as a poisoned partial, so every rank's merge fails alike.
             const TypeId key_type = has_key ? p.cols[key_col].type : TypeId::INT64;
             auto attempt = [&]() {
+                // dense / global states travel as they are: one all-gather of the raw count | sum arrays, one fold launch
+                const bool dense_state = s.group_mode == BQ_GROUP_NONE ||
+                                         (s.group_mode == BQ_GROUP_DENSE && static_cast<uint64_t>(s.key_max - s.key_min) < (1ull << 18));
+                if (dense_state) {
+                    bq_agg_state* st = nullptr;
+                    check(bq_scan_state(ctx, &s, &st));
+                    struct StateGuard {
+                        bq_agg_state* s;
+                        ~StateGuard() { bq_agg_state_free(s); }
+                    } state_guard{st};
+                    all_gather_fold_state(st);
+                    bq_rel* fin = nullptr;
+                    int rc2 = bq_agg_state_emit(ctx, st, s.out, s.n_out, &fin);
+                    if (!rc2) r = relation_from(fin);
+                    return rc2;
+                }
                 bq_rel* rel = nullptr;
                 int rc = bq_scan_partial(ctx, &s, &rel);
                 int flags = 0;

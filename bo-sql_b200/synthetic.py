@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import numpy as np
 
-GEN_SEQ, GEN_UNIFORM, GEN_UNIFORM_DIV, GEN_DATE, GEN_TABLE, GEN_HASHED = range(6)
+GEN_SEQ, GEN_UNIFORM, GEN_UNIFORM_DIV, GEN_DATE, GEN_TABLE, GEN_HASHED, GEN_BUCKETS = range(7)
 INT64, DOUBLE, STRING, DATE32 = 0, 1, 2, 3
 
 STATUS_DICT = ["COMPLETE", "PENDING", "CANCELLED", "RETURNED"]     # ids 0..3 (first-seen order)
@@ -56,3 +56,34 @@ def zipf_cdf(n_keys: int, s: float = 1.1) -> np.ndarray:
     t = np.floor(c * float(1 << 53)).astype(np.uint64)
     t[-1] = np.uint64(1 << 53)
     return t
+
+
+def zipf_buckets(n_keys: int, s: float = 1.1, head: int = 1 << 16, per_octave: int = 64):
+    """Zipf(s) over ALL n_keys ranks for GEN_BUCKETS: (cdf thresholds, bucket starts).
+
+    One bucket per rank for the first `head` ranks (exact masses k^-s); beyond, `per_octave` buckets per doubling of the rank,
+    each carrying the mass of its ranks (midpoint rule on t^-s, relative error < 1e-9 at these ranks) and spreading it
+    uniformly inside - the density changes by 2^(1/64) across a bucket, about 1 %.  Every key of the domain can be drawn."""
+    head = min(head, n_keys)
+    k = np.arange(1, head + 1, dtype=np.float64)
+    mass = [1.0 / np.power(k, s)]
+    starts = [np.arange(head, dtype=np.uint64)]
+    if n_keys > head:
+        edges = [head]
+        x = float(head)
+        step = 2.0 ** (1.0 / per_octave)
+        while edges[-1] < n_keys:
+            x *= step
+            e = min(n_keys, max(edges[-1] + 1, int(x)))
+            edges.append(e)
+        e = np.asarray(edges, dtype=np.float64)          # bucket i covers ranks e[i]+1 .. e[i+1]  (offsets e[i] .. e[i+1]-1)
+        a, b = e[:-1] + 0.5, e[1:] + 0.5
+        mass.append((np.power(a, 1.0 - s) - np.power(b, 1.0 - s)) / (s - 1.0))
+        starts.append(np.asarray(edges[:-1], dtype=np.uint64))
+    m = np.concatenate(mass)
+    c = np.cumsum(m)
+    c /= c[-1]
+    t = np.floor(c * float(1 << 53)).astype(np.uint64)
+    t[-1] = np.uint64(1 << 53)
+    st = np.concatenate(starts + [np.asarray([n_keys], dtype=np.uint64)])
+    return t, st

@@ -91,7 +91,10 @@ enum {
     BQ_GEN_UNIFORM_DIV = 2,/* (double)(lo + hash % (hi-lo+1)) / div             (DOUBLE, k/div)          */
     BQ_GEN_DATE = 3,       /* base_year*10000 + 100*m + d, m in 1..12, d in 1..28, uniform over years    */
     BQ_GEN_TABLE = 4,      /* inverse-CDF lookup: smallest i with cdf[i] > hash>>11 (53-bit), value lo+i */
-    BQ_GEN_HASHED = 5      /* lo + mix(hash % (hi-lo+1)) % modulus: sparse keys drawn from hi-lo+1 ids   */
+    BQ_GEN_HASHED = 5,     /* lo + mix(hash % (hi-lo+1)) % modulus: sparse keys drawn from hi-lo+1 ids   */
+    BQ_GEN_BUCKETS = 6     /* inverse-CDF over n_cdf buckets, then uniform inside the bucket:
+                              i as BQ_GEN_TABLE, value lo + starts[i] + mix(hash) % (starts[i+1] - starts[i]).
+                              Heavy-tailed keys over a domain too large for one threshold per key (Zipf over 5e8 ids) */
 };
 typedef struct bq_gen_spec {
     int dist;
@@ -104,6 +107,7 @@ typedef struct bq_gen_spec {
     const uint64_t* cdf;   /* BQ_GEN_TABLE: HOST pointer to n_cdf ascending 53-bit thresholds */
     size_t n_cdf;
     uint64_t modulus;      /* BQ_GEN_HASHED */
+    const uint64_t* starts; /* BQ_GEN_BUCKETS: HOST pointer to n_cdf + 1 ascending offsets */
 } bq_gen_spec;
 int bq_col_generate(bq_ctx* ctx, bq_col* col, const bq_gen_spec* spec, uint64_t global_row0);
 
@@ -192,6 +196,8 @@ typedef struct bq_scan_spec {
     int64_t key_min, key_max;
     size_t ndv_hint;         /* HASH: table capacity = next pow2 >= 2*ndv_hint               */
     const bq_join* join;     /* optional: inner-join probe on jkey                          */
+    const bq_col* row_bits;  /* optional, instead of join: per-row match bits from bq_join_probe_bits (semi-join already
+                              * probed in key-range passes); needs row_begin % 128 == 0                             */
     int32_t n_out;
     bq_agg_out out[BQ_MAX_AGG_OUT];
     /* HASH grouping over rows that bq_partition has ordered by partition = (hash(key) >> hash_part_shift) & (2^log2 - 1):
@@ -212,6 +218,17 @@ int bq_scan_partial(bq_ctx* ctx, const bq_scan_spec* spec, bq_rel** out);
 /* Merge `n_parts` partial relations (equal keys combined, parts added in index order) and emit final outputs. */
 int bq_agg_finish(bq_ctx* ctx, const bq_rel* const* parts, int n_parts, int has_key, int key_type,
                   const bq_agg_out* outs, int n_out, bq_rel** out);
+
+/* The same exchange for DENSE / global states without compaction: the state stays on the device as it is (count | sum0 |
+ * sum1 arrays over the key domain + the error word), ranks all-gather the raw blocks - same size on every rank, because
+ * the domain comes from catalog statistics - and ONE launch folds them in rank order.  bq_agg_state_dense returns a NULL
+ * pointer for a hash-table state (use bq_scan_partial / bq_agg_finish for those). */
+typedef struct bq_agg_state bq_agg_state;
+int bq_scan_state(bq_ctx* ctx, const bq_scan_spec* spec, bq_agg_state** out);
+int bq_agg_state_dense(const bq_agg_state* s, void** device_ptr, size_t* bytes);
+int bq_agg_state_fold(bq_ctx* ctx, bq_agg_state* s, const void* gathered_blocks, int world);
+int bq_agg_state_emit(bq_ctx* ctx, bq_agg_state* s, const bq_agg_out* outs, int n_out, bq_rel** out);
+void bq_agg_state_free(bq_agg_state* s);
 
 /* ---- selection vectors: Selection::next + copy_selected (src/exec/operator.cpp:403-429, 11-49) ------
  * Rows of [row_begin,row_end) passing all slot ranges (and mask), in scan order, as a STRING-typed (uint32)
@@ -234,7 +251,7 @@ int bq_slice(bq_ctx* ctx, const bq_col* col, size_t begin, size_t end, bq_col** 
  * duplicate keys kept) otherwise.  Rows failing the build-side ranges / mask are not inserted — the
  * reference evaluates such predicates above the join (src/logical/planner.cpp:110-117); for an inner join the
  * row set is the same. */
-enum { BQ_JOIN_AUTO = 0, BQ_JOIN_BITMAP = 1, BQ_JOIN_DIRECT = 2, BQ_JOIN_HASH = 3 };
+enum { BQ_JOIN_AUTO = 0, BQ_JOIN_BITMAP = 1, BQ_JOIN_DIRECT = 2, BQ_JOIN_HASH = 3, BQ_JOIN_ROWBITS = 4 /* scan-side only */ };
 typedef struct bq_join_spec {
     const bq_col* key;
     bq_slot pred[3];
@@ -256,6 +273,13 @@ void* bq_join_bitmap_ptr(const bq_join* j, size_t* n_words);
 /* number of set bits (after ranks merged their bitmaps by summing words: must equal the rows they inserted, or two ranks
  * held the same key and the sum was not an OR) */
 int bq_join_bitmap_popcount(bq_ctx* ctx, const bq_join* j, uint64_t* out);
+/* Semi-join probe in KEY-RANGE PASSES for bitmaps larger than L2 (a 2-billion-key domain is 250 MB): the bitmap is cut into
+ * slices of about slice_bytes; pass j streams the probe key once and tests only the rows whose key falls into slice j, so the
+ * slice stays L2-resident while it is hot (a probe into an HBM-resident bitmap costs a 32-byte DRAM sector per row instead).
+ * Result: a uint32 column of ceil((row_end-row_begin)/32) words (+ padding), bit i = row row_begin+i has a match.  The fused
+ * scan then takes it as bq_scan_spec.row_bits and no longer reads the probe key. */
+int bq_join_probe_bits(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, size_t row_begin, size_t row_end,
+                       size_t slice_bytes, bq_col** out_bits);
 /* Materialising probe (HashJoin::next, src/exec/operator.cpp:764-837): all (probe row, build row) pairs in probe
  * order, matches of one probe row in build insertion order. `probe_rowids` (optional) restricts/ordering the probe rows. */
 int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const bq_col* probe_rowids,

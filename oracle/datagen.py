@@ -12,7 +12,7 @@ import numpy as np
 U64 = np.uint64
 MASK = (1 << 64) - 1
 
-GEN_SEQ, GEN_UNIFORM, GEN_UNIFORM_DIV, GEN_DATE, GEN_TABLE, GEN_HASHED = range(6)
+GEN_SEQ, GEN_UNIFORM, GEN_UNIFORM_DIV, GEN_DATE, GEN_TABLE, GEN_HASHED, GEN_BUCKETS = range(7)
 INT64, DOUBLE, STRING, DATE32 = 0, 1, 2, 3
 NP_DTYPES = {INT64: np.int64, DOUBLE: np.float64, STRING: np.uint32, DATE32: np.int32}
 
@@ -39,11 +39,11 @@ def row_hash(seed: int, stream: int, rows: np.ndarray) -> np.ndarray:
         return _mix64_arr(U64(base) + rows.astype(U64))
 
 
-def generate(typ, n, dist, seed, stream, lo=0, hi=0, div=1.0, base_year=2024, n_years=1, cdf=None, modulus=0, row0=0):
+def generate(typ, n, dist, seed, stream, lo=0, hi=0, div=1.0, base_year=2024, n_years=1, cdf=None, modulus=0, row0=0, starts=None):
     """Rows [row0, row0+n) of a synthetic column, as the device kernel k_generate produces them."""
     rows = np.arange(row0, row0 + n, dtype=U64)
     h = row_hash(seed, stream, rows)
-    rng = U64((hi - lo + 1) & MASK) if dist not in (GEN_SEQ, GEN_DATE, GEN_TABLE) else U64(1)
+    rng = U64((hi - lo + 1) & MASK) if dist not in (GEN_SEQ, GEN_DATE, GEN_TABLE, GEN_BUCKETS) else U64(1)
     f = None
     if dist == GEN_SEQ:
         v = np.int64(lo) + rows.astype(np.int64)
@@ -64,6 +64,13 @@ def generate(typ, n, dist, seed, stream, lo=0, hi=0, div=1.0, base_year=2024, n_
         idx = np.searchsorted(c, u, side="right")      # first i with cdf[i] > u
         idx = np.minimum(idx, len(c) - 1)
         v = np.int64(lo) + idx.astype(np.int64)
+    elif dist == GEN_BUCKETS:
+        c = np.ascontiguousarray(cdf, dtype=U64)
+        st = np.ascontiguousarray(starts, dtype=U64)
+        u = h >> U64(11)
+        idx = np.minimum(np.searchsorted(c, u, side="right"), len(c) - 1)
+        width = st[idx + 1] - st[idx]
+        v = np.int64(lo) + (st[idx] + _mix64_arr(h) % width).astype(np.int64)
     elif dist == GEN_HASHED:
         ident = h % rng
         with np.errstate(over="ignore"):
@@ -95,6 +102,7 @@ orders_schema = _defs.orders_schema
 lineitem_schema = _defs.lineitem_schema
 sweep_schema = _defs.sweep_schema
 zipf_cdf = _defs.zipf_cdf
+zipf_buckets = _defs.zipf_buckets
 
 
 def host_table(schema, n, seed, row0=0):

@@ -37,6 +37,12 @@ def test_generator_table_and_hashed(bq, ctx):
     want = datagen.generate(INT64, n, datagen.GEN_HASHED, 5, 4, lo=0, hi=9999, modulus=1 << 61)
     assert np.array_equal(col.to_numpy(), want)
     assert len(np.unique(want)) <= 10000
+    # Zipf(1.1) over a whole 50 M-key domain: exact head, geometric buckets in the tail, uniform inside a bucket
+    cdf, starts = datagen.zipf_buckets(50_000_000, 1.1, head=1 << 12)
+    col = ctx.alloc(INT64, n).generate(dist=bq.GEN_BUCKETS, seed=5, stream=5, lo=1, cdf=cdf, starts=starts, row0=12345)
+    want = datagen.generate(INT64, n, datagen.GEN_BUCKETS, 5, 5, lo=1, cdf=cdf, starts=starts, row0=12345)
+    assert np.array_equal(col.to_numpy(), want)
+    assert want.min() >= 1 and want.max() <= 50_000_000 and want.max() > 1 << 20
 
 
 def test_minmax_and_f64_key(bq, ctx):
@@ -356,6 +362,52 @@ def test_q2_kernel_vs_reference(bq, ctx, ref, sku_type):
         s.join = j2.h
         top2 = ctx.rel_sort(ctx.scan_aggregate(s), [1], [0], limit=20).to_numpy()
         assert_same_rows(top2, r.cols, ordered_by=[(1, False)], what=f"Q2 join kind {kind}")
+
+
+@pytest.mark.parametrize("sku_type", [INT64, STRING])
+@pytest.mark.parametrize("n_line", [0, 100, 128, 150_007])
+def test_q2_probe_in_key_range_passes(bq, ctx, sku_type, n_line):
+    """bq_join_probe_bits (the bitmap cut into slices, one streaming pass over the probe key per slice) followed by the fused
+    scan over row bits must equal the single fused probe - at any slice count, incl. ragged tails and an empty probe side."""
+    n_orders, n_sku = 200_000, 300
+    orders = datagen.host_table(datagen.orders_schema(n_orders, prefix="o."), n_orders, seed=11)
+    line = datagen.host_table(datagen.lineitem_schema(n_orders, n_sku, sku_type=sku_type), max(n_line, 1), seed=12)
+    o = {name: ctx.upload(t, a) for name, t, a in orders}
+    l = {name: ctx.upload(t, a[:n_line]) for name, t, a in line}
+    j = ctx.join_build(o["o.order_id"], preds=[bq.make_slot(o["o.status"], [(0, 0, 0)])], unique=True, key_min=1, key_max=n_orders)
+    assert j.kind == bq.JOIN_BITMAP and j.popcount() == j.build_rows
+
+    def spec():
+        s = bq.ScanSpec()
+        s.key = bq.make_slot(l["l.sku"])
+        s.a = bq.make_slot(l["l.qty"])
+        s.b = bq.make_slot(l["l.price"])
+        s.row_begin, s.row_end = 0, n_line
+        s.n_v = 1
+        s.v[0] = bq.VExpr(op=bq.V_MUL)
+        s.group_mode = bq.GROUP_DENSE
+        s.key_min, s.key_max = 0, n_sku - 1
+        s.n_out = 2
+        s.out[0] = bq.AggOut(func=bq.AGG_SUM, v=0)
+        s.out[1] = bq.AggOut(func=bq.AGG_COUNT)
+        return s
+    fused = spec()
+    fused.jkey = bq.make_slot(l["l.order_id"])
+    fused.join = j.h
+    want = ctx.scan_aggregate(fused).to_numpy()
+    key = line[0][2][:n_line]
+    status = orders[1][2]
+    expect_bits = status[key - 1] == 0
+    for slice_bytes in (1 << 30, 8 << 10, 1 << 10):            # 1, 4 and 25 passes over the 25 KB bitmap (slices are >= 1 MB
+        bits = j.probe_bits(l["l.order_id"], 0, n_line, slice_bytes=slice_bytes)      # unless forced: see below)
+        words = bits.to_numpy()
+        got_bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:n_line].astype(bool)
+        assert np.array_equal(got_bits, expect_bits), f"slice {slice_bytes}"
+        assert not np.unpackbits(words.view(np.uint8), bitorder="little")[n_line:].any(), "bits beyond the last row must be clear"
+        s = spec()
+        s.row_bits = bits.h
+        got = ctx.scan_aggregate(s).to_numpy()
+        assert_same_rows(got, want, what=f"row bits, slice {slice_bytes}")
 
 
 def test_join_payload_from_build_side(bq, ctx):
