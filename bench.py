@@ -199,11 +199,26 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-class CudaArray:
-    """__cuda_array_interface__ over a raw device pointer so torch can view a bq column without copying."""
+C2_TYPES = ("INT64", "DOUBLE", "STRING", "DATE32")
+TRAFFIC_FILES = {"q1": "q1_scan_traffic.json", "q2": "q2_scan_traffic.json"}
 
-    def __init__(self, ptr, n, typestr):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+def stamped_traffic(which, lib_path):
+    """DRAM bytes per launch from the committed ncu capture - only while the kernel's SASS still hashes to the value
+    recorded with that capture (scripts/sass_hash.py); a changed kernel drops the number instead of repeating it."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILES[which])))
+    except Exception:  # noqa: BLE001
+        return None, "no ncu capture committed for this kernel"
+    want = rec.get("sass_sha256")
+    if not want:
+        return None, "capture carries no SASS stamp"
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    from sass_hash import kernel_sass_hash
+    have = kernel_sass_hash(lib_path, rec["kernel_regex"])
+    if have != want:
+        return None, f"stale: kernel SASS changed since the capture ({rec.get('source')})"
+    return rec["dram_bytes_per_launch"], f"ncu --set full, {rec.get('source')}; SASS stamp matches the built library"
 
 
 def run_ours(args):
@@ -214,7 +229,7 @@ def run_ours(args):
     from __graft_entry__ import load_package
 
     bq = load_package()
-    from bosql_b200 import synthetic as datagen        # workload definitions only; the oracle is imported in the cpu_baseline leg
+    from bosql_b200 import synthetic as datagen        # workload definitions only; the oracle is imported in the checker legs
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -229,8 +244,17 @@ def run_ours(args):
     stream = torch.cuda.Stream()
     ctx.set_stream(stream.cuda_stream)
     rows = int(args.rows)
-    row0 = rank * rows                      # this rank's shard of the N*R-row table
     peak, peak_src = measured_peak()
+    NVLINK_PEAK = 770.0            # GB/s per direction per GPU, measured peer copy on this pool (B200_PROFILING.md; 900 nominal)
+    t_start = time.perf_counter()
+
+    # One code path for every N: the SQL statement through the operator layer.  With N > 1 every rank holds a row shard of
+    # each table (statistics describe the whole table) and the library's own NCCL exchange (bq_comm_*, no Python between a
+    # plan and its collectives) runs at the plan's exchange points; every rank ends up with the full result.
+    exchange = None
+    if world > 1:
+        from bosql_b200 import distributed as DIST
+        exchange = DIST.install_native(xl)
 
     def barrier():
         torch.cuda.synchronize()
@@ -244,14 +268,23 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(step, steps, warmup, profile=False):
-        sampler = ClockSampler(local)
-        if rank == 0:
+    def sum_over_ranks(x):
+        if world == 1:
+            return int(x)
+        t = torch.tensor([int(x)], dtype=torch.int64, device="cuda")
+        dist.all_reduce(t)
+        return int(t.item())
+
+    def timed(step, steps, warmup, profile=False, clocks=False):
+        """W warm-up steps, then K steps between barriers, CUDA events on the launching stream, max over ranks."""
+        sampler = ClockSampler(local) if (clocks and rank == 0) else None
+        if sampler:
             sampler.start()
         for _ in range(warmup):
             step()
         barrier()
-        sampler.mark_begin()
+        if sampler:
+            sampler.mark_begin()
         l0 = ctx.launches
         if profile:
             ctx.profile_read()
@@ -262,16 +295,15 @@ def run_ours(args):
             step()
         e1.record(stream)
         barrier()
-        sampler.mark_end()
+        if sampler:
+            sampler.mark_end()
         ms = max_over_ranks(e0.elapsed_time(e1))
         kern = None
         if profile:
             ctx.profile(False)
             kern = ctx.profile_read()
-        clocks = sampler.stop() if rank == 0 else None
-        return ms / steps, ctx.launches - l0, kern, clocks
+        return ms / steps, (ctx.launches - l0) // steps, kern, (sampler.stop() if sampler else None)
 
-    # ---- synthetic tables, generated in HBM --------------------------------------------------------------------------
     def gen_table(schema, n, seed, r0):
         cols = {}
         for i, (name, typ, spec) in enumerate(schema):
@@ -279,157 +311,557 @@ def run_ours(args):
         ctx.sync()
         return cols
 
-    t0 = time.perf_counter()
-    orders = gen_table(datagen.orders_schema(rows), rows, SEED, row0)
-    log(f"[rank {rank}] generated orders ({rows} rows) in {time.perf_counter() - t0:.2f}s")
+    def free_table(cols):
+        for c in cols.values():
+            c.free()
+
+    def exchange_counters():
+        return (dict(exchange.calls), exchange.bytes_sent) if exchange else ({}, 0)
+
+    def exchange_delta(before, runs):
+        if not exchange:
+            return None
+        calls0, sent0 = before
+        calls1, sent1 = exchange_counters()
+        return {"collectives_per_step": {k: (calls1[k] - calls0.get(k, 0)) // runs for k in calls1 if calls1[k] != calls0.get(k, 0)},
+                "collective_bytes_sent_per_gpu_per_step": (sent1 - sent0) // runs}
+
     DATE_MIN, DATE_MAX = 20240101, 20241228
 
-    eng = bq.Engine()
-    sdict = eng.new_dict(datagen.STATUS_DICT)
-    q1_cols = [("status", bq.STRING, orders["status"]), ("order_date", bq.DATE32, orders["order_date"]),
-               ("total", bq.DOUBLE, orders["total"])]
-    eng.add_table("orders", q1_cols, sdict, stats={"order_date": (DATE_MIN, DATE_MAX, 336), "total": (1.0, 1000.0, 99901)})
-    q1_plan = eng.plan(Q1_SQL)
-    result = {}
+    # ---- workloads: (tables, statistics, SQL) as functions of the global size, so that the full-size run, the strong-
+    # scaling run and the small parity sample are THE SAME statements over the same generator -----------------------------
+    def q1_tables(n_all, n_local, r0):
+        o = gen_table(datagen.orders_schema(n_all), n_local, SEED, r0)
+        cols = [("status", bq.STRING, o["status"]), ("order_date", bq.DATE32, o["order_date"]), ("total", bq.DOUBLE, o["total"])]
+        o["order_id"].free()
+        return {"orders": (cols, {"order_date": (DATE_MIN, DATE_MAX, 336), "total": (1.0, 1000.0, 99901)})}
 
-    # One code path for every N: the SQL statement through the operator layer.  With N > 1 every rank holds a row shard
-    # of `orders` (statistics describe the whole table) and the installed exchange makes HashAggregate all-gather and
-    # merge the partial states in rank order (bo-sql_b200/host/exchange.cpp); every rank ends up with the full result.
-    exchange = None
-    if world > 1:
-        from bosql_b200 import distributed as DIST
-        exchange = DIST.install(xl, device="cuda")
+    def q2_tables(n_line_all, n_line, line_r0, n_ord_all, n_ord, ord_r0):
+        o = gen_table(datagen.orders_schema(n_ord_all, prefix="o.")[:2], n_ord, SEED + 1, ord_r0)
+        li = gen_table(datagen.lineitem_schema(n_ord_all, N_SKU), n_line, SEED + 2, line_r0)
+        return {"orders": ([("o.order_id", bq.INT64, o["o.order_id"]), ("o.status", bq.STRING, o["o.status"])],
+                           {"o.order_id": (1, n_ord_all, n_ord_all)}),
+                "lineitem": ([(n, t, li[n]) for n, t, _ in datagen.lineitem_schema(n_ord_all, N_SKU)],
+                             {"l.sku": (0, N_SKU - 1, N_SKU), "l.order_id": (1, n_ord_all, n_ord_all)})}
 
-    def q1_step():
-        result["q1"] = q1_plan.run()
+    def c2_tables(n_all, n_local, r0):
+        s = gen_table(datagen.sweep_schema_c2(), n_local, SEED + 3, r0)
+        return {"sweep": ([(n, t, s[n]) for n, t, _ in datagen.sweep_schema_c2()], {})}
 
-    ms_step, launches, kern, clocks = timed(q1_step, args.steps, max(3, args.warmup), profile=True)
-    total_rows = rows * world
-    value = total_rows / (ms_step * 1e-3)
-    k_launches, k_ms = kern
-    k_avg_ms = k_ms / max(1, k_launches)
-    achieved = Q1_BYTES_PER_ROW * rows / (k_avg_ms * 1e-3) / 1e9 if k_launches else None
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "q1_scan_traffic.json")))["dram_bytes_per_launch"]
-    except Exception:
-        pass
-    out = {
-        "metric": "q1_rows_per_sec", "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "Q1 revenue-by-day (status = 'COMPLETE' AND order_date range, GROUP BY order_date SUM(total), ORDER BY) "
-                               f"on {rows} synthetic orders rows per GPU",
-                   "rows_per_gpu": rows, "sql": Q1_SQL, "parallelism": f"row-range x{world}",
-                   "l2": "inputs (16 GB per GPU) exceed the 126 MB L2; no flush needed", "seed": SEED,
-                   "algorithmic_bytes_per_row": Q1_BYTES_PER_ROW},
-        "gbs_whole_query": Q1_BYTES_PER_ROW * total_rows / (ms_step * 1e-3) / 1e9,
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "bq::k_scan (fused scan+selection+dense GROUP BY)", "achieved": achieved,
-                     "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
-                     "traffic": traffic, "launches_timed": int(k_launches), "avg_launch_ms": k_avg_ms,
-                     "algorithmic_bytes_per_launch": Q1_BYTES_PER_ROW * rows},
-    }
+    def c4_tables(n_all, n_local, r0, ids=None):
+        ids = ids or max(16, n_all // 20)                # 100 M distinct keys over 2 B rows
+        k = ctx.alloc(bq.INT64, n_local).generate(dist=bq.GEN_HASHED, seed=SEED + 4, stream=0, lo=0, hi=ids - 1, modulus=1 << 61, row0=r0)
+        v = ctx.alloc(bq.DOUBLE, n_local).generate(dist=bq.GEN_UNIFORM_DIV, seed=SEED + 4, stream=1, lo=1, hi=6400, div=64.0, row0=r0)
+        ctx.sync()
+        return {"t": ([("k", bq.INT64, k), ("v", bq.DOUBLE, v)], {"k": (0, (1 << 61) - 1, ids)})}
 
-    # ---- parity + cpu_baseline on a bounded sample (rank 0, N = 1 only) -------------------------------------------
-    if world == 1 and not args.no_cpu:
-        from oracle import ref_engine
-        from tests.parity import assert_same_rows
-        sample = int(min(rows, args.ref_rows))
-        host = [(name, typ, col.to_numpy(0, sample)) for name, typ, col in q1_cols]
-        geng = bq.Engine()
-        geng.add_table("orders", host, geng.new_dict(datagen.STATUS_DICT))
-        got = geng.query(Q1_SQL)
-        if ref_engine.available():
-            reng = ref_engine.RefEngine()
-            reng.add_table("orders", host, reng.new_dict(datagen.STATUS_DICT))
-            runs = [reng.query(Q1_SQL) for _ in range(3)]
-            sec = statistics.median(r.seconds for r in runs)
-            assert_same_rows(got.cols, runs[0].cols, ordered_by=[(0, True)], what="bench Q1 sample vs reference")
-            out["cpu_baseline"] = {"value": sample / sec, "unit": "rows/s", "cores": 1, "kind": "reference",
-                                   "sample": f"first {sample} rows of the same table, reference open..close median of 3 = {sec:.3f}s",
-                                   "parity_on_sample": "ok (keys exact, SUM within 1e-12)"}
-        else:
-            out["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref not built"}
-        del geng, host
+    def c5_tables(n_probe_all, n_probe, probe_r0, n_build_all, n_build, build_r0):
+        bk = ctx.alloc(bq.INT64, n_build).generate(dist=bq.GEN_SEQ, seed=SEED + 5, stream=0, lo=1, row0=build_r0)
+        bw = ctx.alloc(bq.DOUBLE, n_build).generate(dist=bq.GEN_UNIFORM_DIV, seed=SEED + 5, stream=1, lo=1, hi=64, div=4.0, row0=build_r0)
+        cdf, starts = datagen.zipf_buckets(n_build_all, 1.1)           # Zipf(1.1) over the WHOLE build-key domain
+        pk = ctx.alloc(bq.INT64, n_probe).generate(dist=bq.GEN_BUCKETS, seed=SEED + 6, stream=0, lo=1, cdf=cdf, starts=starts, row0=probe_r0)
+        pv = ctx.alloc(bq.DOUBLE, n_probe).generate(dist=bq.GEN_UNIFORM_DIV, seed=SEED + 6, stream=1, lo=1, hi=64, div=4.0, row0=probe_r0)
+        ctx.sync()
+        return {"build": ([("b.k", bq.INT64, bk), ("b.w", bq.DOUBLE, bw)], {"b.k": (1, n_build_all, n_build_all)}),
+                "probe": ([("p.k", bq.INT64, pk), ("p.v", bq.DOUBLE, pv)], {"p.k": (1, n_build_all, n_build_all)})}
 
-    # ---- e2e: the same query with HOST-resident columns; every step pays the host->device copy ----------------------
-    if not args.no_e2e:
-        e2e_rows = rows
-        widths = {bq.STRING: 4, bq.DATE32: 4, bq.DOUBLE: 8, bq.INT64: 8}
-        bufs = []
+    C4_SQL = "SELECT k, SUM(v), COUNT(*), AVG(v) FROM t GROUP BY k"
+    C5_SQL = "SELECT COUNT(*), SUM(p.v * b.w) FROM probe p JOIN build b ON p.k = b.k"
+
+    def c2_queries():
+        """(type, nominal selectivity, SQL): COUNT(*) + SUM(v) under one predicate on a column of each physical type."""
+        qs = []
+        for sel in (0.01, 0.10, 0.50, 0.90, 0.99):
+            qs.append(("INT64", sel, f"SELECT COUNT(*), SUM(v) FROM sweep WHERE c_i64 < {int(sel * 1_000_000)}"))
+            qs.append(("DOUBLE", sel, f"SELECT COUNT(*), SUM(v) FROM sweep WHERE c_f64 < {int(sel * 10_000)}"))
+        for sel, pred in ((1 / 64, "c_str = 's5'"), (0.125, "c_str = 's2'"), (0.5, "c_str = 's0'"), (0.875, "c_str != 's2'"), (63 / 64, "c_str != 's5'")):
+            qs.append(("STRING", sel, f"SELECT COUNT(*), SUM(v) FROM sweep WHERE {pred}"))
+        for sel, lit in ((1 / 120, 20150201), (0.1, 20160101), (0.5, 20200101), (0.9, 20240101), (119 / 120, 20241201)):
+            qs.append(("DATE32", sel, f"SELECT COUNT(*), SUM(v) FROM sweep WHERE c_date < {lit}"))
+        return qs
+
+    def make_engine(tables, dicts=None):
+        eng = bq.Engine()
+        d = eng.new_dict(dicts if dicts is not None else datagen.STATUS_DICT)
+        for name, (cols, stats) in tables.items():
+            eng.add_table(name, cols, d, stats=stats)
+        return eng
+
+    def drop(tables):
+        for cols, _ in tables.values():
+            for _n, _t, c in cols:
+                c.free()
+
+    out = {}
+    errors = {}
+
+    def section(name, fn):
         try:
-            host_cols = []
-            for name, typ, col in q1_cols:
-                p = ctx.host_alloc(widths[typ] * e2e_rows)
+            t0 = time.perf_counter()
+            fn()
+            log(f"[rank {rank}] {name}: {time.perf_counter() - t0:.1f}s")
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            errors[name] = str(e)[:300]
+            log(f"[rank {rank}] {name} FAILED: {traceback.format_exc()[-1500:]}")
+        barrier()
+
+    # =================================================================================================================
+    # Q1 (the headline): weak scaling, R rows per GPU
+    # =================================================================================================================
+    steps, warmup = args.steps, max(3, args.warmup)
+    q1 = {}
+
+    def run_q1():
+        tabs = q1_tables(rows * world, rows, rank * rows)
+        q1["tabs"] = tabs
+        eng = make_engine(tabs)
+        plan = eng.plan(Q1_SQL)
+        res = {}
+
+        def step():
+            res["r"] = plan.run()
+        before = exchange_counters()
+        ms_step, launches, kern, clocks = timed(step, steps, warmup, profile=True, clocks=True)
+        total_rows = rows * world
+        k_launches, k_ms = kern
+        k_avg_ms = k_ms / max(1, k_launches)
+        achieved = Q1_BYTES_PER_ROW * rows / (k_avg_ms * 1e-3) / 1e9 if k_launches else None
+        traffic, traffic_note = stamped_traffic("q1", bq.KERNEL_LIB) if rank == 0 else (None, None)
+        out.update({
+            "metric": "q1_rows_per_sec", "value": total_rows / (ms_step * 1e-3), "unit": "rows/s", "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "Q1 revenue-by-day (status = 'COMPLETE' AND order_date range, GROUP BY order_date SUM(total), ORDER BY) "
+                                   f"on {rows} synthetic orders rows per GPU",
+                       "rows_per_gpu": rows, "sql": Q1_SQL, "parallelism": f"row-range x{world}",
+                       "l2": "inputs (16 GB per GPU) exceed the 126 MB L2; no flush needed", "seed": SEED,
+                       "algorithmic_bytes_per_row": Q1_BYTES_PER_ROW,
+                       "exchange": "native NCCL inside libbosql_b200.so (bq_comm_*)" if world > 1 else "none (one GPU)"},
+            "gbs_whole_query": Q1_BYTES_PER_ROW * total_rows / (ms_step * 1e-3) / 1e9,
+            "gpu_launches": int(launches) * steps,
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "bq::k_scan (fused scan+selection+dense GROUP BY)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": (achieved / peak) if achieved else None, "peak_source": peak_src,
+                         "traffic": traffic, "traffic_source": traffic_note, "launches_timed": int(k_launches), "avg_launch_ms": k_avg_ms,
+                         "algorithmic_bytes_per_launch": Q1_BYTES_PER_ROW * rows},
+        })
+        if exchange:
+            out["exchange"] = exchange_delta(before, steps + warmup)
+        q1["rows_result"] = res["r"].rows
+        del plan, eng
+
+    section("q1", run_q1)
+
+    # ---- e2e: the same query with HOST-resident columns; every step pays the host->device copy ----------------------------
+    def run_q1_e2e():
+        import ctypes as C
+        widths = {bq.STRING: 4, bq.DATE32: 4, bq.DOUBLE: 8, bq.INT64: 8}
+        cols, _ = q1["tabs"]["orders"]
+        bufs, host_cols = [], []
+        try:
+            for name, typ, col in cols:
+                p = ctx.host_alloc(widths[typ] * rows)
                 bufs.append(p)
-                import ctypes as C
-                if bq.kernel_lib().bq_col_read(ctx.h, col.h, 0, e2e_rows, C.c_void_p(p)):
+                if bq.kernel_lib().bq_col_read(ctx.h, col.h, 0, rows, C.c_void_p(p)):
                     raise RuntimeError(bq.kernel_lib().bq_last_error().decode())
-                host_cols.append((name, typ, (p, e2e_rows)))
+                host_cols.append((name, typ, (p, rows)))
             heng = bq.Engine()
-            heng.add_table("orders", host_cols, heng.new_dict(datagen.STATUS_DICT),
-                           stats={"order_date": (DATE_MIN, DATE_MAX, 336)})
+            heng.add_table("orders", host_cols, heng.new_dict(datagen.STATUS_DICT), stats={"order_date": (DATE_MIN, DATE_MAX, 336)})
             hplan = heng.plan(Q1_SQL)
             res = {}
 
             def e2e_step():
                 heng.evict_device("orders")
                 res["r"] = hplan.run()
-            e2e_steps = max(1, min(args.steps, args.e2e_steps))
+            e2e_steps = max(1, min(steps, args.e2e_steps))
             ms_e2e, _, _, _ = timed(e2e_step, e2e_steps, 1)
             d2h = sum(c.nbytes for c in res["r"].cols)
-            out["e2e"] = {"value": e2e_rows * world / (ms_e2e * 1e-3), "unit": "rows/s",
-                          "h2d_bytes_per_step": Q1_BYTES_PER_ROW * e2e_rows, "d2h_bytes_per_step": int(d2h),
-                          "ms_per_step": ms_e2e, "steps": e2e_steps,
+            out["e2e"] = {"value": rows * world / (ms_e2e * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": Q1_BYTES_PER_ROW * rows,
+                          "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e, "steps": e2e_steps,
                           "path": "Engine over pinned host columns (bqx_table_add_borrowed_column); mirrors evicted before every step"}
             del hplan, heng
-        except Exception as e:  # noqa: BLE001
-            out["e2e"] = {"value": None, "unit": "rows/s", "error": str(e)[:200]}
         finally:
             for p in bufs:
                 ctx.host_free(p)
 
-    # ---- Q2 (N = 1): lineitem(R) JOIN orders(R/4) ------------------------------------------------------------------------
-    if not args.no_q2:
+    if not args.no_e2e:
+        section("q1_e2e", run_q1_e2e)
+        if "q1_e2e" in errors:
+            out["e2e"] = {"value": None, "unit": "rows/s", "error": errors["q1_e2e"]}
+    if "tabs" in q1:
+        drop(q1.pop("tabs"))
+
+    # =================================================================================================================
+    # Q2: lineitem JOIN orders.  weak = R lineitem + R/4 orders rows PER GPU (the key domain, and with it the join bitmap,
+    # grows with N); strong = R + R/4 rows IN TOTAL, sharded N ways (N > 1 only)
+    # =================================================================================================================
+    def run_q2(key, n_line_all, n_line, line_r0, n_ord_all, n_ord, ord_r0, e2e=False):
+        tabs = q2_tables(n_line_all, n_line, line_r0, n_ord_all, n_ord, ord_r0)
         try:
-            del q1_plan, eng
-            for c in ("total", "order_date"):
-                orders[c].free()
-            n_orders = max(1, rows // 4)                  # per GPU; both tables are sharded by row range
-            n_orders_all = n_orders * world
-            o2 = gen_table(datagen.orders_schema(n_orders_all, prefix="o.")[:2], n_orders, SEED + 1, rank * n_orders)
-            li = gen_table(datagen.lineitem_schema(n_orders_all, N_SKU), rows, SEED + 2, row0)
-            e2 = bq.Engine()
-            d2 = e2.new_dict(datagen.STATUS_DICT)
-            e2.add_table("orders", [("o.order_id", bq.INT64, o2["o.order_id"]), ("o.status", bq.STRING, o2["o.status"])], d2,
-                         stats={"o.order_id": (1, n_orders_all, n_orders_all)})
-            e2.add_table("lineitem", [(n, t, li[n]) for n, t, _ in datagen.lineitem_schema(n_orders_all, N_SKU)], d2,
-                         stats={"l.sku": (0, N_SKU - 1, N_SKU), "l.order_id": (1, n_orders_all, n_orders_all)})
-            p2 = e2.plan(Q2_SQL)
-            r2 = {}
+            eng = make_engine(tabs)
+            plan = eng.plan(Q2_SQL)
+            res = {}
 
-            def q2_step():
-                r2["r"] = p2.run()
-            ms2, l2, kern2, _ = timed(q2_step, max(3, args.steps // 2), 3, profile=True)
-            q2_bytes = Q2_BYTES_PER_PROBE_ROW * rows + Q2_BYTES_PER_BUILD_ROW * n_orders
+            def step():
+                res["r"] = plan.run()
+            before = exchange_counters()
+            q2_steps = max(3, steps // 2)
+            ms2, l2, kern2, _ = timed(step, q2_steps, 3, profile=True)
+            q2_bytes = Q2_BYTES_PER_PROBE_ROW * n_line + Q2_BYTES_PER_BUILD_ROW * n_ord
             k2n, k2ms = kern2
-            k2avg = k2ms / max(1, k2n)
-            out["q2"] = {"metric": "q2_rows_per_sec", "value": (rows + n_orders) * world / (ms2 * 1e-3), "unit": "rows/s (probe + build)",
-                         "ms_per_step": ms2, "gbs_whole_query": q2_bytes * world / (ms2 * 1e-3) / 1e9, "gpu_launches": int(l2),
-                         "rows": {"lineitem_per_gpu": rows, "orders_per_gpu": n_orders, "sku": N_SKU}, "sql": Q2_SQL,
-                         "join": "bitmap over the global o.order_id domain" + (", per-rank bitmaps summed over NVLink" if world > 1 else ""),
-                         "roofline": {"bound": "hbm", "kernel": "bq::k_scan (probe + GROUP BY sku)",
-                                      "achieved": Q2_BYTES_PER_PROBE_ROW * rows / (k2avg * 1e-3) / 1e9 if k2n else None,
-                                      "peak": peak, "unit": "GB/s", "avg_launch_ms": k2avg,
-                                      "frac": (Q2_BYTES_PER_PROBE_ROW * rows / (k2avg * 1e-3) / 1e9 / peak) if k2n else None},
-                         "top": [int(x) for x in r2["r"].cols[0][:5]]}
-        except Exception as e:  # noqa: BLE001
-            out["q2"] = {"error": str(e)[:300]}
+            probe_ms = k2ms / q2_steps              # all probe-side launches of one step (key-range passes + fused scan)
+            bitmap_mb = (n_ord_all + 7) // 8 / 1e6
+            traffic, traffic_note = (stamped_traffic("q2", bq.KERNEL_LIB) if (rank == 0 and key == "q2" and world == 1) else (None, "captured at N = 1 only"))
+            rec = {"metric": "q2_rows_per_sec", "value": (n_line_all + n_ord_all) / (ms2 * 1e-3), "unit": "rows/s (probe + build)",
+                   "ms_per_step": ms2, "steps": q2_steps, "gbs_whole_query": q2_bytes * world / (ms2 * 1e-3) / 1e9, "gpu_launches": int(l2) * q2_steps,
+                   "rows": {"lineitem_per_gpu": n_line, "orders_per_gpu": n_ord, "lineitem_total": n_line_all, "orders_total": n_ord_all, "sku": N_SKU},
+                   "sql": Q2_SQL,
+                   "join": f"bitmap over the global o.order_id domain ({bitmap_mb:.0f} MB)" +
+                           (", per-rank bitmaps summed over NVLink and verified by popcount" if world > 1 else "") +
+                           (", probed in key-range passes" if k2n // q2_steps > 1 else ", probed inside the fused scan"),
+                   "roofline": {"bound": "hbm", "kernel": "probe side: bq::k_probe_bits passes + bq::k_scan (GROUP BY sku)" if k2n // q2_steps > 1
+                                else "bq::k_scan (probe + GROUP BY sku)",
+                                "achieved": Q2_BYTES_PER_PROBE_ROW * n_line / (probe_ms * 1e-3) / 1e9 if k2n else None,
+                                "peak": peak, "unit": "GB/s", "probe_ms_per_step": probe_ms, "probe_launches_per_step": k2n // q2_steps,
+                                "frac": (Q2_BYTES_PER_PROBE_ROW * n_line / (probe_ms * 1e-3) / 1e9 / peak) if k2n else None,
+                                "algorithmic_bytes_per_step": Q2_BYTES_PER_PROBE_ROW * n_line, "traffic": traffic, "traffic_source": traffic_note},
+                   "roofline_whole_query": {"achieved": q2_bytes / (ms2 * 1e-3) / 1e9, "frac": q2_bytes / (ms2 * 1e-3) / 1e9 / peak,
+                                            "frac_of_8TBs": q2_bytes / (ms2 * 1e-3) / 1e9 / 8000.0},
+                   "top": [int(x) for x in res["r"].cols[0][:5]]}
+            if exchange:
+                rec["exchange"] = exchange_delta(before, q2_steps + 3)
+            out[key] = rec
+            del plan, eng
+            if e2e:
+                run_q2_e2e(tabs, n_line, n_ord, n_ord_all, rec)
+        finally:
+            drop(tabs)
 
-    if exchange is not None:
-        out["exchange"] = {"calls": exchange.calls, "bytes_sent_per_rank": int(exchange.bytes_sent), "error": exchange.error}
+    def run_q2_e2e(tabs, n_line, n_ord, n_ord_all, rec):
+        """Q2 from pinned HOST columns: 32 B x lineitem + 12 B x orders cross PCIe inside every step."""
+        import ctypes as C
+        widths = {bq.STRING: 4, bq.DATE32: 4, bq.DOUBLE: 8, bq.INT64: 8}
+        bufs = []
+        try:
+            host_tabs = {}
+            h2d = 0
+            for tname, (cols, stats) in tabs.items():
+                hc = []
+                for name, typ, col in cols:
+                    n = col.n
+                    p = ctx.host_alloc(widths[typ] * n)
+                    bufs.append(p)
+                    if bq.kernel_lib().bq_col_read(ctx.h, col.h, 0, n, C.c_void_p(p)):
+                        raise RuntimeError(bq.kernel_lib().bq_last_error().decode())
+                    hc.append((name, typ, (p, n)))
+                    h2d += widths[typ] * n
+                host_tabs[tname] = (hc, stats)
+            heng = make_engine(host_tabs)
+            hplan = heng.plan(Q2_SQL)
+            res = {}
+
+            def step():
+                heng.evict_device("orders")
+                heng.evict_device("lineitem")
+                res["r"] = hplan.run()
+            ms, _, _, _ = timed(step, 2, 1)
+            rec["e2e"] = {"value": (n_line + n_ord) / (ms * 1e-3), "unit": "rows/s (probe + build)", "h2d_bytes_per_step": int(h2d),
+                          "d2h_bytes_per_step": int(sum(c.nbytes for c in res["r"].cols)), "ms_per_step": ms, "steps": 2,
+                          "path": "Engine over pinned host columns; both tables' mirrors evicted before every step"}
+            del hplan, heng
+        except Exception as e:  # noqa: BLE001
+            rec["e2e"] = {"value": None, "error": str(e)[:200]}
+        finally:
+            for p in bufs:
+                ctx.host_free(p)
+
+    if not args.no_q2:
+        n_ord = max(1, rows // 4)
+        section("q2", lambda: run_q2("q2", rows * world, rows, rank * rows, n_ord * world, n_ord, rank * n_ord,
+                                     e2e=(world == 1 and not args.no_e2e)))
+
+    # ---- strong scaling: the 1 B-row tables IN TOTAL, sharded N ways --------------------------------------------------------
+    def run_q1_strong():
+        n_local = rows // world
+        tabs = q1_tables(rows, n_local, rank * n_local)
+        try:
+            eng = make_engine(tabs)
+            plan = eng.plan(Q1_SQL)
+            ms, launches, kern, _ = timed(lambda: plan.run(), steps, warmup, profile=True)
+            kn, kms = kern
+            out["q1_strong"] = {"metric": "q1_rows_per_sec", "scaling": "strong", "value": n_local * world / (ms * 1e-3), "unit": "rows/s",
+                                "rows_total": n_local * world, "rows_per_gpu": n_local, "ms_per_step": ms, "steps": steps,
+                                "kernel_ms": kms / max(1, kn), "gbs_whole_query": Q1_BYTES_PER_ROW * n_local * world / (ms * 1e-3) / 1e9}
+            del plan, eng
+        finally:
+            drop(tabs)
+
+    if world > 1 and not args.no_strong:
+        section("q1_strong", run_q1_strong)
+        if not args.no_q2:
+            nl, no = rows // world, max(1, rows // 4 // world)
+            section("q2_strong", lambda: run_q2("q2_strong", nl * world, nl, rank * nl, no * world, no, rank * no))
+            if "q2_strong" in out:
+                out["q2_strong"]["scaling"] = "strong"
+
+    # =================================================================================================================
+    # C2: filter-only sweep, COUNT(*) + SUM(v) under one predicate per physical type, 1 % .. 99 %
+    # =================================================================================================================
+    def run_c2():
+        tabs = c2_tables(rows * world, rows, rank * rows)
+        try:
+            eng = make_engine(tabs, dicts=datagen.C2_STR_DICT)
+            per_type = {t: [] for t in C2_TYPES}
+            for typ, sel, sql in c2_queries():
+                plan = eng.plan(sql)
+                res = {}
+
+                def step():
+                    res["r"] = plan.run()
+                ms, launches, kern, _ = timed(step, 5, 2, profile=True)
+                kn, kms = kern
+                width = 16 if typ in ("INT64", "DOUBLE") else 12
+                cnt = int(res["r"].cols[0][0]) if res["r"].rows else 0         # a global aggregate: every rank holds the merged count
+                per_type[typ].append({"selectivity_nominal": round(sel, 4), "selectivity_measured": cnt / (rows * world), "ms_per_step": ms,
+                                      "kernel_ms": kms / max(1, kn), "rows_per_sec": rows * world / (ms * 1e-3),
+                                      "gbs": width * rows * world / (ms * 1e-3) / 1e9,
+                                      "kernel_frac_of_peak": width * rows / (kms / max(1, kn) * 1e-3) / 1e9 / peak, "sql": sql})
+                del plan
+            worst = min(p["kernel_frac_of_peak"] for v in per_type.values() for p in v)
+            out["c2"] = {"config": "filter-only scan selectivity sweep, COUNT(*) + SUM(v)", "rows_per_gpu": rows, "n_gpus": world,
+                         "algorithmic_bytes_per_row": {"INT64": 16, "DOUBLE": 16, "STRING": 12, "DATE32": 12},
+                         "sweep": per_type, "roofline": {"bound": "hbm", "kernel": "bq::k_scan (global aggregate)", "worst_kernel_frac": worst,
+                                                         "peak": peak, "unit": "GB/s"}}
+            del eng
+        finally:
+            drop(tabs)
+
+    if not args.no_stress:
+        section("c2", run_c2)
+
+    # =================================================================================================================
+    # C4: high-cardinality GROUP BY (100 M distinct keys over 2 B rows on 8 GPUs = 250 M rows per GPU), key-hash shuffle
+    # =================================================================================================================
+    def run_c4():
+        n = max(1024, rows // 4)
+        tabs = c4_tables(n * world, n, rank * n)
+        try:
+            if exchange:
+                exchange.keep_sharded(True)
+            eng = make_engine(tabs)
+            plan = eng.plan(C4_SQL)
+            before = exchange_counters()
+
+            def step_dev():
+                plan.run_device().free()
+            ms_dev, launches, _, _ = timed(step_dev, 5, 2)
+            res = {}
+
+            def step_host():
+                res["r"] = plan.run()
+            ms_host, _, _, _ = timed(step_host, 2, 1)
+            r = res["r"]
+            groups = sum_over_ranks(r.rows)
+            rows_seen = sum_over_ranks(int(r.cols[2].sum()))
+            ids = max(16, n * world // 20)
+            alg = 16 * n + 32 * (groups // world)
+            rec = {"config": "C4 high-cardinality GROUP BY: SUM / COUNT / AVG per key", "n_gpus": world, "rows_per_gpu": n, "distinct_keys": groups,
+                   "sql": C4_SQL, "ms_per_step": ms_dev, "rows_per_sec": n * world / (ms_dev * 1e-3),
+                   "result": "groups left in HBM, each rank holding the keys it owns" if world > 1 else "groups left in HBM",
+                   "ms_per_step_result_paged_to_host": ms_host, "result_bytes_to_host_per_gpu": int(sum(c.nbytes for c in r.cols)),
+                   "gpu_launches_per_step": int(launches),
+                   "roofline": {"bound": "hbm", "achieved": alg / (ms_dev * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                                "frac": alg / (ms_dev * 1e-3) / 1e9 / peak, "algorithmic_bytes_per_gpu_per_step": alg},
+                   "invariants_at_full_size": "ok" if (rows_seen == n * world and ids * 0.99 < groups <= ids) else
+                                              f"FAILED: rows {rows_seen} of {n * world}, groups {groups} of {ids}"}
+            if world > 1:
+                moved = 16 * n * (world - 1) // world
+                rec["nvlink"] = {"bytes_stored_per_gpu_per_step": moved, "note": "rows are written straight into the owning rank's buffer by the partition kernel",
+                                 "gbs_if_the_whole_step_were_the_shuffle": moved / (ms_dev * 1e-3) / 1e9, "peak": NVLINK_PEAK,
+                                 "floor_ms": moved / NVLINK_PEAK / 1e6}
+                rec["exchange"] = exchange_delta(before, 10)
+            out["c4"] = rec
+            del plan, eng, r, res
+        finally:
+            if exchange:
+                exchange.keep_sharded(False)
+            drop(tabs)
+
+    if not args.no_stress:
+        section("c4", run_c4)
+
+    # =================================================================================================================
+    # C5: Zipf(1.1) equi-join, 2 B probe x 500 M build rows on 8 GPUs = 250 M x 62.5 M per GPU
+    # =================================================================================================================
+    def run_c5():
+        n, nb = max(1024, rows // 4), max(256, rows // 16)
+        tabs = c5_tables(n * world, n, rank * n, nb * world, nb, rank * nb)
+        try:
+            eng = make_engine(tabs)
+            plan = eng.plan(C5_SQL)
+            res = {}
+
+            def step():
+                res["r"] = plan.run()
+            before = exchange_counters()
+            ms, launches, _, _ = timed(step, 5, 2)
+            r = res["r"]
+            alg = 16 * (n + nb)
+            rec = {"config": "C5 skewed equi-join: probe key Zipf(1.1) over the whole build domain", "n_gpus": world, "probe_rows_per_gpu": n,
+                   "build_rows_per_gpu": nb, "sql": C5_SQL, "ms_per_step": ms, "rows_per_sec": (n + nb) * world / (ms * 1e-3),
+                   "gpu_launches_per_step": int(launches),
+                   "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                                "algorithmic_bytes_per_gpu_per_step": alg},
+                   "invariants_at_full_size": "ok" if int(r.cols[0][0]) == n * world else f"FAILED: COUNT(*) {int(r.cols[0][0])} of {n * world}"}
+            if exchange:
+                d = exchange_delta(before, 7)
+                rec["exchange"] = d
+                sent = d["collective_bytes_sent_per_gpu_per_step"]
+                rec["nvlink"] = {"collective_bytes_sent_per_gpu_per_step": sent, "peak": NVLINK_PEAK,
+                                 "note": "broadcast join: the build side is all-gathered; a co-partitioned join would move "
+                                         f"{16 * (n + nb) * (world - 1) // world} bytes per GPU instead"}
+            out["c5"] = rec
+            del plan, eng
+        finally:
+            drop(tabs)
+
+    if not args.no_stress:
+        section("c5", run_c5)
+
+    # =================================================================================================================
+    # Parity on samples, at EVERY N: the same statements over small tables of the same generator, sharded over the ranks
+    # and run through the same (NCCL) path; rank 0 regenerates the whole small table on the host, runs the compiled
+    # reference on it and compares.  At N = 1 the reference's timings are the cpu_baseline of each configuration.
+    # =================================================================================================================
+    def run_parity():
+        have_ref = False
+        if rank == 0:
+            from oracle import datagen as odg, ref_engine
+            from tests.parity import assert_same_rows
+            have_ref = ref_engine.available()
+        S = int(min(rows, args.ref_rows))
+
+        def shard(n):
+            lo = rank * n // world
+            return lo, (rank + 1) * n // world - lo
+
+        def compare(name, sqls, gpu_tables, host_tables_fn, dicts, sample_desc, sample_rows, ordered=None, env=None):
+            """gpu_tables: this rank's shard in HBM; host_tables_fn(): the whole sample as numpy (rank 0 only)."""
+            rec = {"sample": sample_desc}
+            old_env = {}
+            for k, v in (env or {}).items():
+                old_env[k] = os.environ.get(k)
+                os.environ[k] = v
+            try:
+                eng = make_engine(gpu_tables, dicts=dicts)
+                got = [eng.query(sql) for sql in sqls]
+                del eng
+            finally:
+                for k, v in old_env.items():
+                    if v is None:
+                        os.environ.pop(k, None)
+                    else:
+                        os.environ[k] = v
+                drop(gpu_tables)
+            if rank == 0:
+                if not have_ref:
+                    rec["parity_on_sample"] = "not checked: oracle/_ref was not built"
+                else:
+                    reng = ref_engine.RefEngine()
+                    d = reng.new_dict(dicts if dicts is not None else odg.STATUS_DICT)
+                    for tname, cols in host_tables_fn().items():
+                        reng.add_table(tname, cols, d)
+                    secs = 0.0
+                    for sql, g in zip(sqls, got):
+                        w = reng.query(sql)
+                        secs += w.seconds
+                        assert_same_rows(g.cols, w.cols, ordered_by=ordered, what=f"bench {name} sample vs reference: {sql[:60]}")
+                    rec["parity_on_sample"] = (f"ok: {len(sqls)} statement(s), N = {world}, integers / keys / order exact, DOUBLE SUM / AVG within 1e-12, "
+                                               "against the compiled reference (oracle/_ref)")
+                    rec["reference_seconds"] = secs
+                    if world == 1:
+                        rec["cpu_baseline"] = {"value": sample_rows * len(sqls) / secs, "unit": "rows/s", "cores": 1, "kind": "reference",
+                                               "sample": sample_desc + f"; reference open..close {secs:.2f}s for {len(sqls)} statement(s)"}
+            return rec
+
+        results = {}
+        # Q1
+        lo, n = shard(S)
+        results["q1"] = compare("Q1", [Q1_SQL], q1_tables(S, n, lo),
+                                lambda: {"orders": [c for c in odg.host_table(odg.orders_schema(S), S, SEED) if c[0] != "order_id"]},
+                                None, f"{S} orders rows of the same generator", S, ordered=[(0, True)])
+        # Q2: fused probe, and the key-range passes forced by a tiny slice size
+        SL, SO = max(1024, S // 2), max(256, S // 8)
+        lo, n = shard(SL)
+        olo, on = shard(SO)
+
+        def q2_host():
+            return {"orders": odg.host_table(odg.orders_schema(SO, prefix="o.")[:2], SO, SEED + 1),
+                    "lineitem": odg.host_table(odg.lineitem_schema(SO, N_SKU), SL, SEED + 2)}
+        results["q2"] = compare("Q2", [Q2_SQL], q2_tables(SL, n, lo, SO, on, olo), q2_host, None,
+                                f"{SL} lineitem x {SO} orders rows of the same generator", SL + SO, ordered=[(1, False)])
+        if rank == 0 and "cpu_baseline" in results["q2"]:
+            results["q2"]["cpu_baseline"]["note"] = "rows = probe + build"
+        r2 = compare("Q2 key-range passes", [Q2_SQL], q2_tables(SL, n, lo, SO, on, olo), q2_host, None, "same sample, bitmap cut into 16 KB slices",
+                     SL + SO, ordered=[(1, False)], env={"BOSQL_BITMAP_SLICE_KB": "16"})
+        results["q2"]["parity_on_sample_key_range_passes"] = r2.get("parity_on_sample")
+        # C2: one statement per type and selectivity
+        S2 = max(1024, S // 2)
+        lo, n = shard(S2)
+        results["c2"] = compare("C2", [q[2] for q in c2_queries()], c2_tables(S2, n, lo),
+                                lambda: {"sweep": odg.host_table(odg.sweep_schema_c2(), S2, SEED + 3)}, datagen.C2_STR_DICT,
+                                f"{S2} rows of the sweep table", S2)
+        # C4: 3.3 M distinct keys, so that the N > 1 run takes the key-hash shuffle (more than 96 MB of group state)
+        S4 = max(1024, min(S, 4_000_000))
+        ids4 = max(16, S4 * 5 // 6)
+        lo, n = shard(S4)
+
+        def c4_host():
+            return {"t": [("k", bq.INT64, odg.generate(bq.INT64, S4, odg.GEN_HASHED, SEED + 4, 0, lo=0, hi=ids4 - 1, modulus=1 << 61)),
+                          ("v", bq.DOUBLE, odg.generate(bq.DOUBLE, S4, odg.GEN_UNIFORM_DIV, SEED + 4, 1, lo=1, hi=6400, div=64.0))]}
+        results["c4"] = compare("C4", [C4_SQL], c4_tables(S4, n, lo, ids=ids4), c4_host, None, f"{S4} rows, up to {ids4} distinct keys", S4)
+        # C5
+        SP, SB = max(1024, S // 4), max(256, S // 16)
+        lo, n = shard(SP)
+        blo, bn = shard(SB)
+
+        def c5_host():
+            cdf, starts = odg.zipf_buckets(SB, 1.1)
+            return {"build": [("b.k", bq.INT64, odg.generate(bq.INT64, SB, odg.GEN_SEQ, SEED + 5, 0, lo=1)),
+                              ("b.w", bq.DOUBLE, odg.generate(bq.DOUBLE, SB, odg.GEN_UNIFORM_DIV, SEED + 5, 1, lo=1, hi=64, div=4.0))],
+                    "probe": [("p.k", bq.INT64, odg.generate(bq.INT64, SP, odg.GEN_BUCKETS, SEED + 6, 0, lo=1, cdf=cdf, starts=starts)),
+                              ("p.v", bq.DOUBLE, odg.generate(bq.DOUBLE, SP, odg.GEN_UNIFORM_DIV, SEED + 6, 1, lo=1, hi=64, div=4.0))]}
+        results["c5"] = compare("C5", [C5_SQL], c5_tables(SP, n, lo, SB, bn, blo), c5_host, None, f"{SP} probe x {SB} build rows, Zipf(1.1) probe keys", SP + SB)
+        if world > 1:
+            r5 = compare("C5 co-partitioned", [C5_SQL], c5_tables(SP, n, lo, SB, bn, blo), c5_host, None, "same sample, join forced to the key-hash shuffle",
+                         SP + SB, env={"BOSQL_JOIN": "shuffle"})
+            results["c5"]["parity_on_sample_shuffle_join"] = r5.get("parity_on_sample")
+        return results
+
+    if not args.no_cpu:
+        parity = {}
+
+        def go():
+            parity.update(run_parity())
+        section("parity", go)
+        if rank == 0:
+            for key, rec in parity.items():
+                target = out if key == "q1" else out.get(key)
+                if target is None:
+                    out[key] = target = {}
+                for k, v in rec.items():
+                    if key == "q1" and k == "sample":
+                        continue
+                    target[k] = v
+            if "cpu_baseline" not in out and world == 1:
+                out["cpu_baseline"] = {"value": None, "unit": "rows/s", "cores": 1, "kind": "reference", "sample": "oracle/_ref not built or the check failed"}
+            if "cpu_baseline" in out and "parity_on_sample" in out:
+                out["cpu_baseline"]["parity_on_sample"] = out["parity_on_sample"]
+
+    if errors:
+        out["errors"] = errors
+    out["bench_wall_s"] = time.perf_counter() - t_start
     if rank == 0:
         emit(out)
     if world > 1:
@@ -447,7 +879,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-q2", action="store_true")
-    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the parity samples / cpu_baseline (reference executor on rank 0)")
+    ap.add_argument("--no-stress", action="store_true", help="skip the C2 / C4 / C5 configurations")
+    ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling variants (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

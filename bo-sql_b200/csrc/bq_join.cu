@@ -444,7 +444,7 @@ int bq_join_probe_bits(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, s
         if (probe_key->type == BQ_DOUBLE) throw std::runtime_error("bitmap joins have integer keys");
         if (row_end < row_begin || row_end > probe_key->n) throw std::runtime_error("bad probe row range");
         if (row_begin % 128) throw std::runtime_error("probe passes need a row range starting at a multiple of 128");
-        if (slice_bytes < (1u << 20)) slice_bytes = 1u << 20;
+        if (slice_bytes < 1024) slice_bytes = 1024;
         const unsigned long long domain = static_cast<unsigned long long>(j->key_max - j->key_min) + 1ULL;
         // whole 32-bit words per slice, equal slices
         unsigned long long passes = (j->bytes + slice_bytes - 1) / slice_bytes;

@@ -768,12 +768,13 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
     // of rows that did not match).  $BOSQL_BITMAP_SLICE_MB sets the slice size (default 40; 0 = always probe fused).
     DevColPtr row_bits;
     if (join && bq_join_kind(join) == BQ_JOIN_BITMAP && p.rows > 0) {
-        size_t slice_mb = 40;
-        if (const char* e = std::getenv("BOSQL_BITMAP_SLICE_MB")) slice_mb = static_cast<size_t>(std::atoll(e));
-        if (slice_mb > 0 && bq_join_bytes(join) > (slice_mb << 20) + (slice_mb << 18)) {
+        size_t slice_bytes = 40u << 20;
+        if (const char* e = std::getenv("BOSQL_BITMAP_SLICE_MB")) slice_bytes = static_cast<size_t>(std::atoll(e)) << 20;
+        if (const char* e = std::getenv("BOSQL_BITMAP_SLICE_KB")) slice_bytes = static_cast<size_t>(std::atoll(e)) << 10;      // tests: force passes on small tables
+        if (slice_bytes > 0 && bq_join_bytes(join) > slice_bytes + slice_bytes / 4) {
             PhaseTrace ptrace;
             bq_col* b = nullptr;
-            check(bq_join_probe_bits(ctx, join, p.cols[p.probe_key].dev->h, 0, p.rows, slice_mb << 20, &b));
+            check(bq_join_probe_bits(ctx, join, p.cols[p.probe_key].dev->h, 0, p.rows, slice_bytes, &b));
             row_bits = adopt(b);
             ptrace.mark("probe in key-range passes");
         }

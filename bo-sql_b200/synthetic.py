@@ -48,6 +48,22 @@ def sweep_schema(div=100.0):
     ]
 
 
+C2_STR_DICT = [f"s{i}" for i in range(16)]
+
+
+def sweep_schema_c2(div=100.0):
+    """Configuration 2's table: like sweep_schema, but c_str is GEOMETRIC over 16 ids (id i with probability 2^-(i+1)), so that
+    `c_str = 's<i>'` selects 50 %, 25 %, ... 1.6 % of the rows and `!=` the complements (STRING supports only = and !=)."""
+    w = np.power(0.5, np.arange(1, 17, dtype=np.float64))
+    c = np.cumsum(w)
+    c /= c[-1]
+    t = np.floor(c * float(1 << 53)).astype(np.uint64)
+    t[-1] = np.uint64(1 << 53)
+    schema = sweep_schema(div)
+    schema[2] = ("c_str", STRING, dict(dist=GEN_TABLE, lo=0, cdf=t))
+    return schema
+
+
 def zipf_cdf(n_keys: int, s: float = 1.1) -> np.ndarray:
     """53-bit integer thresholds of a Zipf(s) distribution over n_keys ranks (for GEN_TABLE)."""
     w = 1.0 / np.power(np.arange(1, n_keys + 1, dtype=np.float64), s)

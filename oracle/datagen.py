@@ -101,6 +101,8 @@ STATUS_DICT = _defs.STATUS_DICT
 orders_schema = _defs.orders_schema
 lineitem_schema = _defs.lineitem_schema
 sweep_schema = _defs.sweep_schema
+sweep_schema_c2 = _defs.sweep_schema_c2
+C2_STR_DICT = _defs.C2_STR_DICT
 zipf_cdf = _defs.zipf_cdf
 zipf_buckets = _defs.zipf_buckets
 

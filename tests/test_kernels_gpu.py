@@ -398,8 +398,8 @@ def test_q2_probe_in_key_range_passes(bq, ctx, sku_type, n_line):
     key = line[0][2][:n_line]
     status = orders[1][2]
     expect_bits = status[key - 1] == 0
-    for slice_bytes in (1 << 30, 8 << 10, 1 << 10):            # 1, 4 and 25 passes over the 25 KB bitmap (slices are >= 1 MB
-        bits = j.probe_bits(l["l.order_id"], 0, n_line, slice_bytes=slice_bytes)      # unless forced: see below)
+    for slice_bytes in (1 << 30, 8 << 10, 1 << 10):            # 1, 4 and 25 passes over the 25 KB bitmap
+        bits = j.probe_bits(l["l.order_id"], 0, n_line, slice_bytes=slice_bytes)
         words = bits.to_numpy()
         got_bits = np.unpackbits(words.view(np.uint8), bitorder="little")[:n_line].astype(bool)
         assert np.array_equal(got_bits, expect_bits), f"slice {slice_bytes}"
