@@ -79,6 +79,47 @@ BQ_D int4 ldg_stream(const int4* p) {
     return r;
 }
 
+// L2 residency hints (createpolicy + ld ... L2::cache_hint).  A kernel that streams tens of GB past a table it probes at
+// random (a join bitmap, a direct-address table) marks the stream evict-first and the table evict-last, so the table is
+// what the 126 MB L2 keeps: without the hints the stream keeps pushing table lines out.
+BQ_D uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+BQ_D uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+BQ_D int4 ldg_stream_hint(const int4* p, uint64_t policy) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.s32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+BQ_D int2 ldg_stream2_hint(const int2* p, uint64_t policy) {
+    int2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.s32 {%0,%1}, [%2], %3;" : "=r"(r.x), "=r"(r.y) : "l"(p), "l"(policy));
+    return r;
+}
+BQ_D long long ldg_stream_i64_hint(const long long* p, uint64_t policy) {
+    long long r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(r) : "l"(p), "l"(policy));
+    return r;
+}
+BQ_D int ldg_stream_i32_hint(const int* p, uint64_t policy) {
+    int r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy));
+    return r;
+}
+BQ_D unsigned ldg_keep_u32(const unsigned* p, uint64_t policy) {
+    unsigned r;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(policy));
+    return r;
+}
+
 // Widen one element of `kind` at row i to its 8-byte slot value (what BQ_OP_COL pushes).
 BQ_D int64_t load_raw(const void* base, int kind, size_t i) {
     switch (kind) {

@@ -222,46 +222,77 @@ struct ProbeBitsParams {
     int key_kind;
     size_t row_begin, row_end;
     long long key_min;
+    unsigned long long domain;
     unsigned long long slice_lo, slice_len;      // this pass tests keys with slice_lo <= key - key_min < slice_lo + slice_len
     const unsigned* bitmap;
     unsigned* out;                               // bit i = row i
+    unsigned* idx32;                             // key - key_min per row (0xFFFFFFFF = outside the domain): written by the
+                                                 // first pass, read by the later ones (4 bytes per row instead of 8)
     int first;                                   // first pass stores every word, later passes OR into the words they hit
 };
 
-// A warp owns 128 consecutive rows per trip (row_begin is a multiple of 128): lane t tests rows t, 32+t, 64+t, 96+t, so the key
-// column is read with fully coalesced 256-byte requests and each ballot is one finished word of the output.  Only rows
-// whose key lies in the pass's slice touch the bitmap, so the slice (tens of MB) is what the L2 keeps hot.
+// A warp owns 32 * ROWS consecutive rows per trip (row_begin is a multiple of 128): lane t tests rows t, 32+t, 64+t, ..., so
+// the key column is read with fully coalesced requests, ROWS of them in flight per lane before the first use, and each
+// ballot is one finished word of the output.  Only rows whose key lies in the pass's slice touch the bitmap; the key stream
+// is marked L2 evict-first and the bitmap evict-last, so the slice (64-96 MB) is what the L2 keeps.
+// FIRST: reads the key column itself and leaves key - key_min as a uint32 per row for the passes that follow.
+template <bool FIRST, int ROWS>
 __global__ void __launch_bounds__(kBlock) k_probe_bits(const __grid_constant__ ProbeBitsParams p) {
     const int lane = threadIdx.x & 31;
     const size_t warps = static_cast<size_t>(gridDim.x) * (kBlock / 32);
     const size_t warp = static_cast<size_t>(blockIdx.x) * (kBlock / 32) + (threadIdx.x >> 5);
-    const size_t n_chunks = (p.row_end - p.row_begin + 127) / 128;
+    constexpr size_t per = 32 * ROWS;
+    const size_t n_chunks = (p.row_end - p.row_begin + per - 1) / per;
+    const size_t n_words = (p.row_end + 31) / 32;
+    const uint64_t stream_policy = l2_policy_evict_first(), keep_policy = l2_policy_evict_last();
     for (size_t c = warp; c < n_chunks; c += warps) {
-        const size_t base = p.row_begin + c * 128;
-        long long k[4];
-        bool in[4];
+        const size_t base = p.row_begin + c * per;
+        unsigned idx[ROWS];
+        if (FIRST) {
+            long long k[ROWS];
+            bool in[ROWS];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const size_t i = base + 32 * r + lane;
-            in[r] = i < p.row_end;
-            k[r] = in[r] ? load_raw(p.key, p.key_kind, i) : 0;
-        }
-        unsigned hit[4];
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const unsigned long long idx = static_cast<unsigned long long>(k[r] - p.key_min) - p.slice_lo;
-            const bool mine = in[r] && idx < p.slice_len;
-            const unsigned long long g = idx + p.slice_lo;
-            hit[r] = mine ? (__ldg(p.bitmap + (g >> 5)) >> (g & 31)) & 1u : 0u;
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const unsigned word = __ballot_sync(0xffffffffu, hit[r] != 0);
-            if (lane == r) {
-                unsigned* dst = p.out + (base >> 5) + r;
-                if (p.first) *dst = word;
-                else if (word) *dst |= word;
+            for (int r = 0; r < ROWS; ++r) {
+                const size_t i = base + 32 * r + lane;
+                in[r] = i < p.row_end;
+                k[r] = 0;
+                if (in[r]) {
+                    if (p.key_kind == BQ_INT64) k[r] = ldg_stream_i64_hint(static_cast<const long long*>(p.key) + i, stream_policy);
+                    else if (p.key_kind == BQ_STRING) k[r] = static_cast<unsigned>(ldg_stream_i32_hint(static_cast<const int*>(p.key) + i, stream_policy));
+                    else k[r] = ldg_stream_i32_hint(static_cast<const int*>(p.key) + i, stream_policy);
+                }
             }
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const unsigned long long d = static_cast<unsigned long long>(k[r] - p.key_min);
+                idx[r] = (in[r] && d < p.domain) ? static_cast<unsigned>(d) : 0xFFFFFFFFu;
+                if (in[r] && p.idx32) p.idx32[base + 32 * r + lane] = idx[r];
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const size_t i = base + 32 * r + lane;
+                idx[r] = i < p.row_end ? static_cast<unsigned>(ldg_stream_i32_hint(reinterpret_cast<const int*>(p.idx32) + i, stream_policy)) : 0xFFFFFFFFu;
+            }
+        }
+        unsigned hit[ROWS];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const unsigned long long s = static_cast<unsigned long long>(idx[r]) - p.slice_lo;
+            const bool mine = idx[r] != 0xFFFFFFFFu && s < p.slice_len;
+            hit[r] = mine ? (ldg_keep_u32(p.bitmap + (idx[r] >> 5), keep_policy) >> (idx[r] & 31)) & 1u : 0u;
+        }
+        unsigned mine_word = 0;
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const unsigned word = __ballot_sync(0xffffffffu, hit[r] != 0);
+            if (lane == r) mine_word = word;
+        }
+        // lanes 0..ROWS-1 hold the words of the chunk: one coalesced store (or read-modify-write in later passes)
+        const size_t w = (base >> 5) + lane;
+        if (lane < ROWS && w < n_words) {
+            if (p.first) p.out[w] = mine_word;
+            else if (mine_word) p.out[w] |= mine_word;
         }
     }
 }
@@ -437,59 +468,84 @@ void* bq_join_bitmap_ptr(const bq_join* j, size_t* n_words) {
     return j->bitmap;
 }
 
+static void probe_bits_impl(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, size_t row_begin, size_t row_end, size_t slice_bytes,
+                            bool but_last, bq_col** out_bits, uint64_t* last_lo, uint64_t* last_len) {
+    if (j->kind != BQ_JOIN_BITMAP) throw std::runtime_error("key-range probe passes need a bitmap join");
+    if (probe_key->type == BQ_DOUBLE) throw std::runtime_error("bitmap joins have integer keys");
+    if (row_end < row_begin || row_end > probe_key->n) throw std::runtime_error("bad probe row range");
+    if (row_begin % 128) throw std::runtime_error("probe passes need a row range starting at a multiple of 128");
+    if (slice_bytes < 1024) slice_bytes = 1024;
+    const unsigned long long domain = static_cast<unsigned long long>(j->key_max - j->key_min) + 1ULL;
+    // whole 32-bit words per slice, equal slices
+    unsigned long long passes = (j->bytes + slice_bytes - 1) / slice_bytes;
+    if (passes < 1) passes = 1;
+    const unsigned long long slice_keys = ((domain + passes - 1) / passes + 31) / 32 * 32;
+    passes = (domain + slice_keys - 1) / slice_keys;
+    if (but_last) {
+        *last_lo = (passes - 1) * slice_keys;
+        *last_len = domain - *last_lo;
+        if (passes == 1) {
+            *out_bits = nullptr;           // one slice: the fused scan probes it all, no bits needed
+            return;
+        }
+    }
+    const unsigned long long run = but_last ? passes - 1 : passes;
+    const size_t words = (row_end + 31) / 32;
+    bq_col* bits = new_col(ctx, BQ_STRING, (words + 31) / 32 * 32);       // whole groups of words (scan: four at once; passes: up to 16)
+    unsigned* idx32 = nullptr;
+    try {
+        BQ_CUDA(cudaMemsetAsync(bits->ptr, 0, bits->n * 4, ctx->stream));
+        if (row_end > row_begin) {
+            // with several passes the first one leaves key - key_min as 4 bytes per row: the later passes read half the bytes
+            if (run > 1 && domain <= 0xFFFFFFFFull) idx32 = static_cast<unsigned*>(dev_alloc(ctx, row_end * 4));
+            ProbeBitsParams p{};
+            p.key = probe_key->ptr;
+            p.key_kind = probe_key->type;
+            p.row_begin = row_begin;
+            p.row_end = row_end;
+            p.key_min = j->key_min;
+            p.domain = domain;
+            p.bitmap = j->bitmap;
+            p.out = static_cast<unsigned*>(bits->ptr);
+            p.idx32 = idx32;
+            const int grid = grid_for(ctx, row_end - row_begin, 8);
+            for (unsigned long long pass = 0; pass < run; ++pass) {
+                p.slice_lo = pass * slice_keys;
+                p.slice_len = std::min(slice_keys, domain - p.slice_lo);
+                p.first = pass == 0;
+                cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+                if (ctx->profile) {
+                    BQ_CUDA(cudaEventCreate(&ev0));
+                    BQ_CUDA(cudaEventCreate(&ev1));
+                    BQ_CUDA(cudaEventRecord(ev0, ctx->stream));
+                }
+                if (pass == 0 || !idx32) k_probe_bits<true, 8><<<grid, kBlock, 0, ctx->stream>>>(p);
+                else k_probe_bits<false, 16><<<grid, kBlock, 0, ctx->stream>>>(p);
+                if (ctx->profile) {
+                    BQ_CUDA(cudaEventRecord(ev1, ctx->stream));
+                    ctx->profile_events.emplace_back(ev0, ev1);
+                }
+                ctx->launches++;
+                BQ_CUDA(cudaGetLastError());
+            }
+        }
+        dev_free(ctx, idx32);
+    } catch (...) {
+        dev_free(ctx, idx32);
+        free_col(bits);
+        throw;
+    }
+    *out_bits = bits;
+}
+
 int bq_join_probe_bits(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, size_t row_begin, size_t row_end,
                        size_t slice_bytes, bq_col** out_bits) {
-    return guarded([&] {
-        if (j->kind != BQ_JOIN_BITMAP) throw std::runtime_error("key-range probe passes need a bitmap join");
-        if (probe_key->type == BQ_DOUBLE) throw std::runtime_error("bitmap joins have integer keys");
-        if (row_end < row_begin || row_end > probe_key->n) throw std::runtime_error("bad probe row range");
-        if (row_begin % 128) throw std::runtime_error("probe passes need a row range starting at a multiple of 128");
-        if (slice_bytes < 1024) slice_bytes = 1024;
-        const unsigned long long domain = static_cast<unsigned long long>(j->key_max - j->key_min) + 1ULL;
-        // whole 32-bit words per slice, equal slices
-        unsigned long long passes = (j->bytes + slice_bytes - 1) / slice_bytes;
-        if (passes < 1) passes = 1;
-        unsigned long long slice_keys = ((domain + passes - 1) / passes + 31) / 32 * 32;
-        const size_t words = (row_end + 31) / 32;
-        bq_col* bits = new_col(ctx, BQ_STRING, (words + 3) / 4 * 4);       // whole 16-byte groups: the scan loads four words at once
-        try {
-            BQ_CUDA(cudaMemsetAsync(bits->ptr, 0, bits->n * 4, ctx->stream));
-            if (row_end > row_begin) {
-                ProbeBitsParams p{};
-                p.key = probe_key->ptr;
-                p.key_kind = probe_key->type;
-                p.row_begin = row_begin;
-                p.row_end = row_end;
-                p.key_min = j->key_min;
-                p.bitmap = j->bitmap;
-                p.out = static_cast<unsigned*>(bits->ptr);
-                const int grid = grid_for(ctx, row_end - row_begin, 8);
-                int pass = 0;
-                for (unsigned long long lo = 0; lo < domain; lo += slice_keys, ++pass) {
-                    p.slice_lo = lo;
-                    p.slice_len = std::min(slice_keys, domain - lo);
-                    p.first = pass == 0;
-                    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-                    if (ctx->profile) {
-                        BQ_CUDA(cudaEventCreate(&ev0));
-                        BQ_CUDA(cudaEventCreate(&ev1));
-                        BQ_CUDA(cudaEventRecord(ev0, ctx->stream));
-                    }
-                    k_probe_bits<<<grid, kBlock, 0, ctx->stream>>>(p);
-                    if (ctx->profile) {
-                        BQ_CUDA(cudaEventRecord(ev1, ctx->stream));
-                        ctx->profile_events.emplace_back(ev0, ev1);
-                    }
-                    ctx->launches++;
-                    BQ_CUDA(cudaGetLastError());
-                }
-            }
-        } catch (...) {
-            free_col(bits);
-            throw;
-        }
-        *out_bits = bits;
-    });
+    return guarded([&] { probe_bits_impl(ctx, j, probe_key, row_begin, row_end, slice_bytes, false, out_bits, nullptr, nullptr); });
+}
+
+int bq_join_probe_bits_but_last(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, size_t row_begin, size_t row_end,
+                                size_t slice_bytes, bq_col** out_bits, uint64_t* last_lo, uint64_t* last_len) {
+    return guarded([&] { probe_bits_impl(ctx, j, probe_key, row_begin, row_end, slice_bytes, true, out_bits, last_lo, last_len); });
 }
 
 int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const bq_col* probe_rowids,

@@ -762,13 +762,16 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         break;
     }
 
-    // A semi-join bitmap far beyond the L2 (a 2-billion-key domain is 250 MB; across GPUs the bitmap spans the GLOBAL key
-    // domain) is probed in key-range passes: each pass streams the probe key once and tests only the keys of one L2-sized
-    // slice, leaving one match bit per row; the fused scan then reads those bits instead of probing (and skips the sectors
-    // of rows that did not match).  $BOSQL_BITMAP_SLICE_MB sets the slice size (default 40; 0 = always probe fused).
+    // A semi-join bitmap beyond the L2 (a 2-billion-key domain is 250 MB; across GPUs the bitmap spans the GLOBAL key domain)
+    // is probed in key-range passes: each pass streams the probe key once (8 bytes per row the first time, 4 afterwards) and
+    // tests only the keys of one L2-sized slice, leaving one match bit per row; the fused scan then reads the bits instead of
+    // probing, and not the probe key at all.  The kernels mark their streams L2 evict-first and the bitmap evict-last, which
+    // is what lets a slice be most of the 126 MB L2.  (Leaving the last slice to the scan - bq_join_probe_bits_but_last -
+    // measured slower: the scan is bound by its group updates, not by the probe.)
+    // $BOSQL_BITMAP_SLICE_MB sets the slice size (0 = always one fused probe).
     DevColPtr row_bits;
     if (join && bq_join_kind(join) == BQ_JOIN_BITMAP && p.rows > 0) {
-        size_t slice_bytes = 40u << 20;
+        size_t slice_bytes = 64u << 20;
         if (const char* e = std::getenv("BOSQL_BITMAP_SLICE_MB")) slice_bytes = static_cast<size_t>(std::atoll(e)) << 20;
         if (const char* e = std::getenv("BOSQL_BITMAP_SLICE_KB")) slice_bytes = static_cast<size_t>(std::atoll(e)) << 10;      // tests: force passes on small tables
         if (slice_bytes > 0 && bq_join_bytes(join) > slice_bytes + slice_bytes / 4) {
@@ -808,10 +811,10 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         s.row_begin = 0;
         s.row_end = p.rows;
         s.join = join;
-        if (row_bits && s.jkey.n_ranges == 0) {        // (a range riding on the probe key keeps the fused probe)
+        if (row_bits) {
             s.join = nullptr;
-            s.jkey = bq_slot{};
             s.row_bits = row_bits->h;
+            if (s.jkey.n_ranges == 0) s.jkey = bq_slot{};      // a range riding on the probe key keeps the column as a predicate slot
         }
         s.n_v = static_cast<int32_t>(ps.vals.size());
         for (size_t k = 0; k < ps.vals.size(); ++k) {

@@ -1,0 +1,2 @@
+#pragma once
+#include "bosql_sql.hpp"
