@@ -75,8 +75,7 @@ class ScanSpec(C.Structure):
                 ("row_begin", C.c_size_t), ("row_end", C.c_size_t), ("mask", C.c_void_p),
                 ("n_v", C.c_int32), ("v", VExpr * 2), ("group_mode", C.c_int32),
                 ("key_min", C.c_int64), ("key_max", C.c_int64), ("ndv_hint", C.c_size_t),
-                ("join", C.c_void_p), ("row_bits", C.c_void_p), ("join_slice_lo", C.c_uint64), ("join_slice_len", C.c_uint64),
-                ("n_out", C.c_int32), ("out", AggOut * 8),
+                ("join", C.c_void_p), ("row_bits", C.c_void_p), ("n_out", C.c_int32), ("out", AggOut * 8),
                 ("hash_part_log2", C.c_int32), ("hash_part_shift", C.c_int32)]
 
 
@@ -186,7 +185,6 @@ def kernel_lib():
         "bq_join_bitmap_popcount": ([vp, vp, P(C.c_uint64)], C.c_int),
         "bq_join_probe": ([vp, vp, vp, vp, sz, sz, P(vp), P(vp)], C.c_int),
         "bq_join_probe_bits": ([vp, vp, vp, sz, sz, sz, P(vp)], C.c_int),
-        "bq_join_probe_bits_but_last": ([vp, vp, vp, sz, sz, sz, P(vp), P(C.c_uint64), P(C.c_uint64)], C.c_int),
         "bq_rel_sort": ([vp, vp, C.c_int, P(C.c_int), P(C.c_int), i64, P(vp)], C.c_int),
         "bq_rel_create": ([vp, P(vp), C.c_int, P(vp)], C.c_int),
         "bq_rel_rows": ([vp], sz),
@@ -338,14 +336,6 @@ class Join:
         end = probe_key.n if row_end is None else row_end
         _check(kernel_lib().bq_join_probe_bits(self.ctx.h, self.h, probe_key.h, row_begin, end, slice_bytes, C.byref(out)))
         return Column(self.ctx, out.value)
-
-    def probe_bits_but_last(self, probe_key, row_begin=0, row_end=None, slice_bytes=48 << 20):
-        """The same, leaving the last slice to the fused scan: (bits column or None, last_lo, last_len)."""
-        out, lo, ln = C.c_void_p(), C.c_uint64(), C.c_uint64()
-        end = probe_key.n if row_end is None else row_end
-        _check(kernel_lib().bq_join_probe_bits_but_last(self.ctx.h, self.h, probe_key.h, row_begin, end, slice_bytes, C.byref(out),
-                                                         C.byref(lo), C.byref(ln)))
-        return (Column(self.ctx, out.value) if out.value else None), int(lo.value), int(ln.value)
 
     def free(self):
         if self.h:

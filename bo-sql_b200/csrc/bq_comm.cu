@@ -13,11 +13,58 @@
 //   bq_comm_host_all_gather_i64        n int64 per rank through a device staging buffer, one stream synchronisation
 #include "bq_common.cuh"
 
+#include <dlfcn.h>
 #include <nccl.h>
 
 #include <cstring>
 
 namespace bq {
+
+// NCCL is bound at run time, when the first communicator is made: the library has no link-time dependency on libnccl, so
+// loading it never decides which NCCL a host process ends up with (PyTorch bundles its own, newer libnccl.so.2; an older
+// copy loaded first would leave torch's symbols unresolved).  dlopen by soname returns the copy the process already has.
+struct NcclApi {
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+};
+
+static const NcclApi& nccl() {
+    static NcclApi api;
+    static bool loaded = false;
+    if (loaded) return api;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
+    if (!h) throw std::runtime_error(std::string("cannot load NCCL (libnccl.so.2): ") + dlerror());
+    auto bind = [&](auto& fn, const char* name) {
+        void* sym = dlsym(h, name);
+        if (!sym) throw std::runtime_error(std::string("NCCL symbol missing: ") + name);
+        fn = reinterpret_cast<std::remove_reference_t<decltype(fn)>>(sym);
+    };
+    bind(api.GetUniqueId, "ncclGetUniqueId");
+    bind(api.CommInitRank, "ncclCommInitRank");
+    bind(api.CommDestroy, "ncclCommDestroy");
+    bind(api.CommAbort, "ncclCommAbort");
+    bind(api.GetErrorString, "ncclGetErrorString");
+    bind(api.AllGather, "ncclAllGather");
+    bind(api.AllReduce, "ncclAllReduce");
+    bind(api.Broadcast, "ncclBroadcast");
+    bind(api.Send, "ncclSend");
+    bind(api.Recv, "ncclRecv");
+    bind(api.GroupStart, "ncclGroupStart");
+    bind(api.GroupEnd, "ncclGroupEnd");
+    loaded = true;
+    return api;
+}
 
 struct Comm {
     ncclComm_t comm = nullptr;
@@ -35,7 +82,7 @@ constexpr size_t kStageWords = 512;    // int64 per rank per host exchange
     do {                                                                                                \
         ncclResult_t _r = (expr);                                                                       \
         if (_r != ncclSuccess) {                                                                        \
-            throw std::runtime_error(std::string("NCCL error: ") + ncclGetErrorString(_r) + " at " +    \
+            throw std::runtime_error(std::string("NCCL error: ") + nccl().GetErrorString(_r) + " at " +    \
                                      __FILE__ + ":" + std::to_string(__LINE__) + " (" #expr ")");       \
         }                                                                                               \
     } while (0)
@@ -56,7 +103,7 @@ int bq_comm_unique_id(void* id128) {
     return guarded([&] {
         static_assert(sizeof(ncclUniqueId) == BQ_COMM_ID_BYTES, "unique id size");
         ncclUniqueId id;
-        BQ_NCCL(ncclGetUniqueId(&id));
+        BQ_NCCL(nccl().GetUniqueId(&id));
         std::memcpy(id128, &id, sizeof id);
     });
 }
@@ -72,12 +119,12 @@ int bq_comm_init(bq_ctx* ctx, int world, int rank, const void* id128) {
             c->rank = rank;
             ncclUniqueId id;
             std::memcpy(&id, id128, sizeof id);
-            BQ_NCCL(ncclCommInitRank(&c->comm, world, id, rank));
+            BQ_NCCL(nccl().CommInitRank(&c->comm, world, id, rank));
             c->stage_words = kStageWords * (static_cast<size_t>(world) + 1);
             BQ_CUDA(cudaMalloc(&c->dev_stage, c->stage_words * 8));
             BQ_CUDA(cudaMallocHost(&c->host_stage, c->stage_words * 8));
         } catch (...) {
-            if (c->comm) ncclCommAbort(c->comm);
+            if (c->comm) nccl().CommAbort(c->comm);
             if (c->dev_stage) cudaFree(c->dev_stage);
             if (c->host_stage) cudaFreeHost(c->host_stage);
             delete c;
@@ -91,7 +138,7 @@ void bq_comm_destroy(bq_ctx* ctx) {
     if (!ctx || !ctx->comm) return;
     auto* c = static_cast<Comm*>(ctx->comm);
     cudaStreamSynchronize(ctx->stream);
-    if (c->comm) ncclCommDestroy(c->comm);
+    if (c->comm) nccl().CommDestroy(c->comm);
     if (c->dev_stage) cudaFree(c->dev_stage);
     if (c->host_stage) cudaFreeHost(c->host_stage);
     delete c;
@@ -115,7 +162,7 @@ int bq_comm_all_gather(bq_ctx* ctx, const void* send, void* recv, size_t bytes) 
         Comm* c = comm_of(ctx);
         c->calls[0]++;
         c->bytes_sent += bytes;
-        if (bytes) BQ_NCCL(ncclAllGather(send, recv, bytes, ncclUint8, c->comm, ctx->stream));
+        if (bytes) BQ_NCCL(nccl().AllGather(send, recv, bytes, ncclUint8, c->comm, ctx->stream));
     });
 }
 
@@ -127,25 +174,25 @@ int bq_comm_all_gather_v(bq_ctx* ctx, const void* send, void* recv, const int64_
         bool equal = true;
         for (int r = 1; r < c->world; ++r) equal = equal && bytes_by_rank[r] == bytes_by_rank[0];
         if (equal) {
-            if (bytes_by_rank[0]) BQ_NCCL(ncclAllGather(send, recv, static_cast<size_t>(bytes_by_rank[0]), ncclUint8, c->comm, ctx->stream));
+            if (bytes_by_rank[0]) BQ_NCCL(nccl().AllGather(send, recv, static_cast<size_t>(bytes_by_rank[0]), ncclUint8, c->comm, ctx->stream));
             return;
         }
         // one broadcast per contributing rank, straight into its slot of the output (no padding, no staging copy)
-        BQ_NCCL(ncclGroupStart());
+        BQ_NCCL(nccl().GroupStart());
         size_t off = 0;
         for (int r = 0; r < c->world; ++r) {
             const size_t n = static_cast<size_t>(bytes_by_rank[r]);
             if (n) {
                 char* slot = static_cast<char*>(recv) + off;
-                ncclResult_t rc = ncclBroadcast(r == c->rank ? send : slot, slot, n, ncclUint8, r, c->comm, ctx->stream);
+                ncclResult_t rc = nccl().Broadcast(r == c->rank ? send : slot, slot, n, ncclUint8, r, c->comm, ctx->stream);
                 if (rc != ncclSuccess) {
-                    ncclGroupEnd();
+                    nccl().GroupEnd();
                     BQ_NCCL(rc);
                 }
             }
             off += n;
         }
-        BQ_NCCL(ncclGroupEnd());
+        BQ_NCCL(nccl().GroupEnd());
     });
 }
 
@@ -153,18 +200,18 @@ int bq_comm_all_to_all_v(bq_ctx* ctx, const void* send, const int64_t* send_byte
     return guarded([&] {
         Comm* c = comm_of(ctx);
         c->calls[2]++;
-        BQ_NCCL(ncclGroupStart());
+        BQ_NCCL(nccl().GroupStart());
         size_t so = 0, ro = 0;
         ncclResult_t rc = ncclSuccess;
         for (int r = 0; r < c->world && rc == ncclSuccess; ++r) {
             const size_t sn = static_cast<size_t>(send_bytes[r]), rn = static_cast<size_t>(recv_bytes[r]);
             if (r != c->rank) c->bytes_sent += sn;
-            if (sn) rc = ncclSend(static_cast<const char*>(send) + so, sn, ncclUint8, r, c->comm, ctx->stream);
-            if (rn && rc == ncclSuccess) rc = ncclRecv(static_cast<char*>(recv) + ro, rn, ncclUint8, r, c->comm, ctx->stream);
+            if (sn) rc = nccl().Send(static_cast<const char*>(send) + so, sn, ncclUint8, r, c->comm, ctx->stream);
+            if (rn && rc == ncclSuccess) rc = nccl().Recv(static_cast<char*>(recv) + ro, rn, ncclUint8, r, c->comm, ctx->stream);
             so += sn;
             ro += rn;
         }
-        ncclResult_t end = ncclGroupEnd();
+        ncclResult_t end = nccl().GroupEnd();
         BQ_NCCL(rc);
         BQ_NCCL(end);
     });
@@ -175,7 +222,7 @@ int bq_comm_all_reduce_sum_u32(bq_ctx* ctx, void* buf, size_t words) {
         Comm* c = comm_of(ctx);
         c->calls[3]++;
         c->bytes_sent += words * 4;
-        if (words) BQ_NCCL(ncclAllReduce(buf, buf, words, ncclUint32, ncclSum, c->comm, ctx->stream));
+        if (words) BQ_NCCL(nccl().AllReduce(buf, buf, words, ncclUint32, ncclSum, c->comm, ctx->stream));
     });
 }
 
@@ -188,7 +235,7 @@ int bq_comm_host_all_gather_i64(bq_ctx* ctx, const int64_t* mine, int32_t n, int
         const size_t w = static_cast<size_t>(n);
         std::memcpy(c->host_stage, mine, w * 8);
         BQ_CUDA(cudaMemcpyAsync(c->dev_stage, c->host_stage, w * 8, cudaMemcpyHostToDevice, ctx->stream));
-        BQ_NCCL(ncclAllGather(c->dev_stage, c->dev_stage + kStageWords, w, ncclInt64, c->comm, ctx->stream));
+        BQ_NCCL(nccl().AllGather(c->dev_stage, c->dev_stage + kStageWords, w, ncclInt64, c->comm, ctx->stream));
         BQ_CUDA(cudaMemcpyAsync(c->host_stage + kStageWords, c->dev_stage + kStageWords, w * 8 * static_cast<size_t>(c->world),
                                 cudaMemcpyDeviceToHost, ctx->stream));
         BQ_CUDA(cudaStreamSynchronize(ctx->stream));

@@ -19,6 +19,7 @@
 #include "bq_internal.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace bq {
 
@@ -232,47 +233,61 @@ struct ProbeBitsParams {
 };
 
 // A warp owns 32 * ROWS consecutive rows per trip (row_begin is a multiple of 128): lane t tests rows t, 32+t, 64+t, ..., so
-// the key column is read with fully coalesced requests, ROWS of them in flight per lane before the first use, and each
-// ballot is one finished word of the output.  Only rows whose key lies in the pass's slice touch the bitmap; the key stream
-// is marked L2 evict-first and the bitmap evict-last, so the slice (64-96 MB) is what the L2 keeps.
+// the key column is read with fully coalesced requests and each ballot is one finished word of the output.  The loads of
+// the NEXT trip are issued before the current trip probes (two trips of loads in flight per warp), later passes merge
+// their words with red.or (no read-modify-write on the critical path), and the kernel is held to 48 registers so that
+// eight CTAs stay resident: the pass is a latency chain (key load -> bitmap probe -> word), and bytes in flight are what
+// hide it.  Only rows whose key lies in the pass's slice touch the bitmap; with $BOSQL_PROBE_HINTS=1 the key stream is
+// marked L2 evict-first and the bitmap evict-last.
 // FIRST: reads the key column itself and leaves key - key_min as a uint32 per row for the passes that follow.
-template <bool FIRST, int ROWS>
-__global__ void __launch_bounds__(kBlock) k_probe_bits(const __grid_constant__ ProbeBitsParams p) {
+template <bool FIRST, int ROWS, bool HINTS>
+__global__ void __launch_bounds__(kBlock, 6) k_probe_bits(const __grid_constant__ ProbeBitsParams p) {
     const int lane = threadIdx.x & 31;
     const size_t warps = static_cast<size_t>(gridDim.x) * (kBlock / 32);
     const size_t warp = static_cast<size_t>(blockIdx.x) * (kBlock / 32) + (threadIdx.x >> 5);
     constexpr size_t per = 32 * ROWS;
     const size_t n_chunks = (p.row_end - p.row_begin + per - 1) / per;
     const size_t n_words = (p.row_end + 31) / 32;
-    const uint64_t stream_policy = l2_policy_evict_first(), keep_policy = l2_policy_evict_last();
-    for (size_t c = warp; c < n_chunks; c += warps) {
+    uint64_t stream_policy = 0, keep_policy = 0;
+    if (HINTS) {
+        stream_policy = l2_policy_evict_first();
+        keep_policy = l2_policy_evict_last();
+    }
+    // raw loads of one trip: FIRST reads 8-byte keys (4-byte kinds widened), later passes the 4-byte offsets
+    auto load_trip = [&](size_t c, long long (&raw)[ROWS]) {
         const size_t base = p.row_begin + c * per;
-        unsigned idx[ROWS];
-        if (FIRST) {
-            long long k[ROWS];
-            bool in[ROWS];
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                const size_t i = base + 32 * r + lane;
-                in[r] = i < p.row_end;
-                k[r] = 0;
-                if (in[r]) {
-                    if (p.key_kind == BQ_INT64) k[r] = ldg_stream_i64_hint(static_cast<const long long*>(p.key) + i, stream_policy);
-                    else if (p.key_kind == BQ_STRING) k[r] = static_cast<unsigned>(ldg_stream_i32_hint(static_cast<const int*>(p.key) + i, stream_policy));
-                    else k[r] = ldg_stream_i32_hint(static_cast<const int*>(p.key) + i, stream_policy);
+        for (int r = 0; r < ROWS; ++r) {
+            const size_t i = base + 32 * r + lane;
+            raw[r] = -1;
+            if (i < p.row_end) {
+                if (FIRST) {
+                    if (p.key_kind == BQ_INT64)
+                        raw[r] = HINTS ? ldg_stream_i64_hint(static_cast<const long long*>(p.key) + i, stream_policy) : __ldg(static_cast<const long long*>(p.key) + i);
+                    else if (p.key_kind == BQ_STRING) raw[r] = static_cast<unsigned>(__ldg(static_cast<const int*>(p.key) + i));
+                    else raw[r] = __ldg(static_cast<const int*>(p.key) + i);
+                } else {
+                    raw[r] = static_cast<unsigned>(HINTS ? ldg_stream_i32_hint(reinterpret_cast<const int*>(p.idx32) + i, stream_policy)
+                                                         : __ldg(reinterpret_cast<const int*>(p.idx32) + i));
                 }
             }
+        }
+    };
+    long long cur[ROWS], nxt[ROWS];
+    if (warp < n_chunks) load_trip(warp, cur);
+    for (size_t c = warp; c < n_chunks; c += warps) {
+        const size_t base = p.row_begin + c * per;
+        if (c + warps < n_chunks) load_trip(c + warps, nxt);
+        unsigned idx[ROWS];
 #pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                const unsigned long long d = static_cast<unsigned long long>(k[r] - p.key_min);
-                idx[r] = (in[r] && d < p.domain) ? static_cast<unsigned>(d) : 0xFFFFFFFFu;
-                if (in[r] && p.idx32) p.idx32[base + 32 * r + lane] = idx[r];
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < ROWS; ++r) {
-                const size_t i = base + 32 * r + lane;
-                idx[r] = i < p.row_end ? static_cast<unsigned>(ldg_stream_i32_hint(reinterpret_cast<const int*>(p.idx32) + i, stream_policy)) : 0xFFFFFFFFu;
+        for (int r = 0; r < ROWS; ++r) {
+            const bool in = base + 32 * r + lane < p.row_end;
+            if (FIRST) {
+                const unsigned long long d = static_cast<unsigned long long>(cur[r] - p.key_min);
+                idx[r] = (in && d < p.domain) ? static_cast<unsigned>(d) : 0xFFFFFFFFu;
+                if (in && p.idx32) p.idx32[base + 32 * r + lane] = idx[r];
+            } else {
+                idx[r] = in ? static_cast<unsigned>(cur[r]) : 0xFFFFFFFFu;
             }
         }
         unsigned hit[ROWS];
@@ -280,7 +295,11 @@ __global__ void __launch_bounds__(kBlock) k_probe_bits(const __grid_constant__ P
         for (int r = 0; r < ROWS; ++r) {
             const unsigned long long s = static_cast<unsigned long long>(idx[r]) - p.slice_lo;
             const bool mine = idx[r] != 0xFFFFFFFFu && s < p.slice_len;
-            hit[r] = mine ? (ldg_keep_u32(p.bitmap + (idx[r] >> 5), keep_policy) >> (idx[r] & 31)) & 1u : 0u;
+            hit[r] = 0u;
+            if (mine) {
+                const unsigned w = HINTS ? ldg_keep_u32(p.bitmap + (idx[r] >> 5), keep_policy) : __ldg(p.bitmap + (idx[r] >> 5));
+                hit[r] = (w >> (idx[r] & 31)) & 1u;
+            }
         }
         unsigned mine_word = 0;
 #pragma unroll
@@ -288,12 +307,14 @@ __global__ void __launch_bounds__(kBlock) k_probe_bits(const __grid_constant__ P
             const unsigned word = __ballot_sync(0xffffffffu, hit[r] != 0);
             if (lane == r) mine_word = word;
         }
-        // lanes 0..ROWS-1 hold the words of the chunk: one coalesced store (or read-modify-write in later passes)
+        // lanes 0..ROWS-1 hold the words of the chunk: one coalesced store, or a red.or into the earlier passes' words
         const size_t w = (base >> 5) + lane;
         if (lane < ROWS && w < n_words) {
             if (p.first) p.out[w] = mine_word;
-            else if (mine_word) p.out[w] |= mine_word;
+            else if (mine_word) atomicOr(p.out + w, mine_word);
         }
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) cur[r] = nxt[r];
     }
 }
 
@@ -468,84 +489,72 @@ void* bq_join_bitmap_ptr(const bq_join* j, size_t* n_words) {
     return j->bitmap;
 }
 
-static void probe_bits_impl(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, size_t row_begin, size_t row_end, size_t slice_bytes,
-                            bool but_last, bq_col** out_bits, uint64_t* last_lo, uint64_t* last_len) {
-    if (j->kind != BQ_JOIN_BITMAP) throw std::runtime_error("key-range probe passes need a bitmap join");
-    if (probe_key->type == BQ_DOUBLE) throw std::runtime_error("bitmap joins have integer keys");
-    if (row_end < row_begin || row_end > probe_key->n) throw std::runtime_error("bad probe row range");
-    if (row_begin % 128) throw std::runtime_error("probe passes need a row range starting at a multiple of 128");
-    if (slice_bytes < 1024) slice_bytes = 1024;
-    const unsigned long long domain = static_cast<unsigned long long>(j->key_max - j->key_min) + 1ULL;
-    // whole 32-bit words per slice, equal slices
-    unsigned long long passes = (j->bytes + slice_bytes - 1) / slice_bytes;
-    if (passes < 1) passes = 1;
-    const unsigned long long slice_keys = ((domain + passes - 1) / passes + 31) / 32 * 32;
-    passes = (domain + slice_keys - 1) / slice_keys;
-    if (but_last) {
-        *last_lo = (passes - 1) * slice_keys;
-        *last_len = domain - *last_lo;
-        if (passes == 1) {
-            *out_bits = nullptr;           // one slice: the fused scan probes it all, no bits needed
-            return;
-        }
-    }
-    const unsigned long long run = but_last ? passes - 1 : passes;
-    const size_t words = (row_end + 31) / 32;
-    bq_col* bits = new_col(ctx, BQ_STRING, (words + 31) / 32 * 32);       // whole groups of words (scan: four at once; passes: up to 16)
-    unsigned* idx32 = nullptr;
-    try {
-        BQ_CUDA(cudaMemsetAsync(bits->ptr, 0, bits->n * 4, ctx->stream));
-        if (row_end > row_begin) {
-            // with several passes the first one leaves key - key_min as 4 bytes per row: the later passes read half the bytes
-            if (run > 1 && domain <= 0xFFFFFFFFull) idx32 = static_cast<unsigned*>(dev_alloc(ctx, row_end * 4));
-            ProbeBitsParams p{};
-            p.key = probe_key->ptr;
-            p.key_kind = probe_key->type;
-            p.row_begin = row_begin;
-            p.row_end = row_end;
-            p.key_min = j->key_min;
-            p.domain = domain;
-            p.bitmap = j->bitmap;
-            p.out = static_cast<unsigned*>(bits->ptr);
-            p.idx32 = idx32;
-            const int grid = grid_for(ctx, row_end - row_begin, 8);
-            for (unsigned long long pass = 0; pass < run; ++pass) {
-                p.slice_lo = pass * slice_keys;
-                p.slice_len = std::min(slice_keys, domain - p.slice_lo);
-                p.first = pass == 0;
-                cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-                if (ctx->profile) {
-                    BQ_CUDA(cudaEventCreate(&ev0));
-                    BQ_CUDA(cudaEventCreate(&ev1));
-                    BQ_CUDA(cudaEventRecord(ev0, ctx->stream));
-                }
-                if (pass == 0 || !idx32) k_probe_bits<true, 8><<<grid, kBlock, 0, ctx->stream>>>(p);
-                else k_probe_bits<false, 16><<<grid, kBlock, 0, ctx->stream>>>(p);
-                if (ctx->profile) {
-                    BQ_CUDA(cudaEventRecord(ev1, ctx->stream));
-                    ctx->profile_events.emplace_back(ev0, ev1);
-                }
-                ctx->launches++;
-                BQ_CUDA(cudaGetLastError());
-            }
-        }
-        dev_free(ctx, idx32);
-    } catch (...) {
-        dev_free(ctx, idx32);
-        free_col(bits);
-        throw;
-    }
-    *out_bits = bits;
-}
-
 int bq_join_probe_bits(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, size_t row_begin, size_t row_end,
                        size_t slice_bytes, bq_col** out_bits) {
-    return guarded([&] { probe_bits_impl(ctx, j, probe_key, row_begin, row_end, slice_bytes, false, out_bits, nullptr, nullptr); });
-}
-
-int bq_join_probe_bits_but_last(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, size_t row_begin, size_t row_end,
-                                size_t slice_bytes, bq_col** out_bits, uint64_t* last_lo, uint64_t* last_len) {
-    return guarded([&] { probe_bits_impl(ctx, j, probe_key, row_begin, row_end, slice_bytes, true, out_bits, last_lo, last_len); });
+    return guarded([&] {
+        if (j->kind != BQ_JOIN_BITMAP) throw std::runtime_error("key-range probe passes need a bitmap join");
+        if (probe_key->type == BQ_DOUBLE) throw std::runtime_error("bitmap joins have integer keys");
+        if (row_end < row_begin || row_end > probe_key->n) throw std::runtime_error("bad probe row range");
+        if (row_begin % 128) throw std::runtime_error("probe passes need a row range starting at a multiple of 128");
+        if (slice_bytes < 1024) slice_bytes = 1024;
+        const unsigned long long domain = static_cast<unsigned long long>(j->key_max - j->key_min) + 1ULL;
+        // whole 32-bit words per slice, equal slices
+        unsigned long long passes = (j->bytes + slice_bytes - 1) / slice_bytes;
+        if (passes < 1) passes = 1;
+        const unsigned long long slice_keys = ((domain + passes - 1) / passes + 31) / 32 * 32;
+        passes = (domain + slice_keys - 1) / slice_keys;
+        const size_t words = (row_end + 31) / 32;
+        bq_col* bits = new_col(ctx, BQ_STRING, (words + 31) / 32 * 32);       // whole groups of words (scan: four at once; passes: up to 16)
+        unsigned* idx32 = nullptr;
+        const char* hint_env = std::getenv("BOSQL_PROBE_HINTS");
+        const bool hints = hint_env && *hint_env == '1';
+        try {
+            BQ_CUDA(cudaMemsetAsync(bits->ptr, 0, bits->n * 4, ctx->stream));
+            if (row_end > row_begin) {
+                // with several passes the first one leaves key - key_min as 4 bytes per row: the later passes read half the bytes
+                if (passes > 1 && domain <= 0xFFFFFFFFull) idx32 = static_cast<unsigned*>(dev_alloc(ctx, row_end * 4));
+                ProbeBitsParams p{};
+                p.key = probe_key->ptr;
+                p.key_kind = probe_key->type;
+                p.row_begin = row_begin;
+                p.row_end = row_end;
+                p.key_min = j->key_min;
+                p.domain = domain;
+                p.bitmap = j->bitmap;
+                p.out = static_cast<unsigned*>(bits->ptr);
+                p.idx32 = idx32;
+                const int grid = grid_for(ctx, row_end - row_begin, 6);
+                for (unsigned long long pass = 0; pass < passes; ++pass) {
+                    p.slice_lo = pass * slice_keys;
+                    p.slice_len = std::min(slice_keys, domain - p.slice_lo);
+                    p.first = pass == 0;
+                    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+                    if (ctx->profile) {
+                        BQ_CUDA(cudaEventCreate(&ev0));
+                        BQ_CUDA(cudaEventCreate(&ev1));
+                        BQ_CUDA(cudaEventRecord(ev0, ctx->stream));
+                    }
+                    const bool first_kind = pass == 0 || !idx32;
+                    if (first_kind && hints) k_probe_bits<true, 4, true><<<grid, kBlock, 0, ctx->stream>>>(p);
+                    else if (first_kind) k_probe_bits<true, 4, false><<<grid, kBlock, 0, ctx->stream>>>(p);
+                    else if (hints) k_probe_bits<false, 8, true><<<grid, kBlock, 0, ctx->stream>>>(p);
+                    else k_probe_bits<false, 8, false><<<grid, kBlock, 0, ctx->stream>>>(p);
+                    if (ctx->profile) {
+                        BQ_CUDA(cudaEventRecord(ev1, ctx->stream));
+                        ctx->profile_events.emplace_back(ev0, ev1);
+                    }
+                    ctx->launches++;
+                    BQ_CUDA(cudaGetLastError());
+                }
+            }
+            dev_free(ctx, idx32);
+        } catch (...) {
+            dev_free(ctx, idx32);
+            free_col(bits);
+            throw;
+        }
+        *out_bits = bits;
+    });
 }
 
 int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const bq_col* probe_rowids,

@@ -54,10 +54,6 @@ struct ScanParams {
     const long long* mask;     // optional 0/1 per row
     const unsigned* row_bits;  // BQ_JOIN_ROWBITS: bit i = row i joins (bq_join_probe_bits); row_begin is a multiple of 128
     int rowbits_skip;          // 1: loads of halves without a matching row are not issued (sector skipping)
-    // BQ_JOIN_BITMAP with row_bits: the scan probes only keys of [j_slice_lo, j_slice_lo + j_slice_len) (the last key-range
-    // slice, L2-resident); rows whose key lies in an earlier slice take their match bit from row_bits
-    unsigned long long j_slice_lo, j_slice_len;
-    int l2_hints;              // join table beyond ~40 MB: streams are marked L2 evict-first, the table evict-last
     // group state
     long long key_min;
     unsigned long long key_domain;     // G_SMEM / G_DENSE: number of slots
@@ -132,34 +128,6 @@ BQ_D void load_quad(const void* ptr, int kind, size_t base, int lane, long long 
         const int2* q = reinterpret_cast<const int2*>(static_cast<const char*>(ptr) + (base + 2 * lane) * 4);
         int2 a = ldg_stream2(q);
         int2 b = ldg_stream2(q + 32);
-        if (kind == BQ_STRING) {
-            raw[0] = static_cast<unsigned>(a.x);
-            raw[1] = static_cast<unsigned>(a.y);
-            raw[2] = static_cast<unsigned>(b.x);
-            raw[3] = static_cast<unsigned>(b.y);
-        } else {
-            raw[0] = a.x;
-            raw[1] = a.y;
-            raw[2] = b.x;
-            raw[3] = b.y;
-        }
-    }
-}
-
-// The same with an L2 eviction policy on every load (streams next to a probed table are marked evict-first)
-BQ_D void load_quad_hint(const void* ptr, int kind, size_t base, int lane, uint64_t policy, long long (&raw)[4]) {
-    if (kind == BQ_INT64 || kind == BQ_DOUBLE) {
-        const int4* q = reinterpret_cast<const int4*>(static_cast<const char*>(ptr) + (base + 2 * lane) * 8);
-        int4 a = ldg_stream_hint(q, policy);
-        int4 b = ldg_stream_hint(q + 32, policy);
-        raw[0] = pack64(a.x, a.y);
-        raw[1] = pack64(a.z, a.w);
-        raw[2] = pack64(b.x, b.y);
-        raw[3] = pack64(b.z, b.w);
-    } else {
-        const int2* q = reinterpret_cast<const int2*>(static_cast<const char*>(ptr) + (base + 2 * lane) * 4);
-        int2 a = ldg_stream2_hint(q, policy);
-        int2 b = ldg_stream2_hint(q + 32, policy);
         if (kind == BQ_STRING) {
             raw[0] = static_cast<unsigned>(a.x);
             raw[1] = static_cast<unsigned>(a.y);
@@ -314,7 +282,6 @@ struct RowSink {
     unsigned long long cnt = 0;
     double sum0 = 0.0, sum1 = 0.0;
     int err = 0;
-    uint64_t keep_policy = 0;      // L2 evict-last: the probed join table
 
     BQ_D RowSink(const ScanParams& pp, double* a, double* b, unsigned* c) : p(pp), s_sum0(a), s_sum1(b), s_cnt(c) {}
 
@@ -387,8 +354,7 @@ struct RowSink {
     }
 
     // bitmap / direct-address probe: true = the row joins (brow = matched build row for DIRECT)
-    // prior: the row's match bit from earlier key-range passes (only read when the key lies outside the scan's slice)
-    BQ_D bool probe_dense(long long jk, unsigned& brow, bool prior = false) {
+    BQ_D bool probe_dense(long long jk, unsigned& brow) {
         brow = 0;
         if (Sh::kind(p, S_JK) == BQ_DOUBLE) {
             if (jk == INT64_MIN) jk = 0;                                         // -0.0 == 0.0 (KeyEqual, :657)
@@ -396,12 +362,8 @@ struct RowSink {
         }
         unsigned long long idx = static_cast<unsigned long long>(jk - p.jk_min);
         if (idx >= p.jk_domain) return false;
-        if (Xs::jmode(p) == BQ_JOIN_BITMAP) {
-            if (p.row_bits && idx - p.j_slice_lo >= p.j_slice_len) return prior;
-            const unsigned w = p.l2_hints ? ldg_keep_u32(p.j_bitmap + (idx >> 5), keep_policy) : __ldg(p.j_bitmap + (idx >> 5));
-            return (w >> (idx & 31)) & 1u;
-        }
-        unsigned e = p.l2_hints ? ldg_keep_u32(p.j_direct + idx, keep_policy) : __ldg(p.j_direct + idx);
+        if (Xs::jmode(p) == BQ_JOIN_BITMAP) return (__ldg(p.j_bitmap + (idx >> 5)) >> (idx & 31)) & 1u;
+        unsigned e = __ldg(p.j_direct + idx);
         brow = e - 1;
         return e != 0;
     }
@@ -422,14 +384,14 @@ struct RowSink {
     }
 
     // a row that passed every streamed range (scalar head/tail path and staged flushes)
-    BQ_D void row(long long key_raw, long long a, long long b, long long jk, bool prior = false) {
+    BQ_D void row(long long key_raw, long long a, long long b, long long jk) {
         if (Xs::jmode(p) == 0 || Xs::jmode(p) == BQ_JOIN_ROWBITS) {      // (match bits were tested by the caller)
             add(key_raw, a, b);
         } else if (Xs::jmode(p) == BQ_JOIN_HASH) {
             probe_hash(key_raw, a, b, jk);
         } else {
             unsigned brow;
-            if (probe_dense(jk, brow, prior)) build_add(key_raw, a, b, brow);
+            if (probe_dense(jk, brow)) build_add(key_raw, a, b, brow);
         }
     }
 };
@@ -504,12 +466,6 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
     __syncthreads();
 
     RowSink<SHAPE, XSHAPE, GMODE> sink(p, s_sum0, s_sum1, s_cnt);
-    uint64_t stream_policy = 0;
-    const bool hinted = (Xs::jmode(p) == BQ_JOIN_BITMAP || Xs::jmode(p) == BQ_JOIN_DIRECT) && p.l2_hints;
-    if (hinted) {
-        stream_policy = l2_policy_evict_first();
-        sink.keep_policy = l2_policy_evict_last();
-    }
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -542,9 +498,8 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
     };
 
     // match bits are fetched one trip ahead, so that the (predicated) column loads never wait for them
-    const bool use_bits = Xs::jmode(p) == BQ_JOIN_ROWBITS || (Xs::jmode(p) == BQ_JOIN_BITMAP && p.row_bits != nullptr);
     uint4 bits_next = make_uint4(0, 0, 0, 0);
-    if (use_bits && warp_global < p.n_chunks)
+    if (Xs::jmode(p) == BQ_JOIN_ROWBITS && warp_global < p.n_chunks)
         bits_next = __ldg(reinterpret_cast<const uint4*>(p.row_bits + ((p.vec_begin + warp_global * 128) >> 5)));
 
     // ---- vector region: whole 128-row chunks -----------------------------------------------------
@@ -553,22 +508,17 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
         long long raw[N_SLOTS][4];
         long long mk[4] = {1, 1, 1, 1};
         bool pass[4] = {true, true, true, true};
-        bool prior[4] = {false, false, false, false};
-        if (use_bits) {
-            // join-match bits of the chunk's 128 rows (fetched one trip ahead): one 16-byte broadcast load
+        if (Xs::jmode(p) == BQ_JOIN_ROWBITS) {
+            // join-match bits of the chunk's 128 rows (fetched one trip ahead): one 16-byte broadcast load; the bits ARE
+            // the join, and only the halves with a match are read
             const uint4 w = bits_next;
             if (c + warps_total < p.n_chunks) bits_next = __ldg(reinterpret_cast<const uint4*>(p.row_bits + ((base + warps_total * 128) >> 5)));
             const unsigned lo_w = lane < 16 ? w.x : w.y, hi_w = lane < 16 ? w.z : w.w;
             const int sh = (2 * lane) & 31;
-            prior[0] = (lo_w >> sh) & 1u;
-            prior[1] = (lo_w >> (sh + 1)) & 1u;
-            prior[2] = (hi_w >> sh) & 1u;
-            prior[3] = (hi_w >> (sh + 1)) & 1u;
-        }
-        if (Xs::jmode(p) == BQ_JOIN_ROWBITS) {
-            // the bits ARE the join: only the halves with a match are read
-#pragma unroll
-            for (int r = 0; r < 4; ++r) pass[r] = prior[r];
+            pass[0] = (lo_w >> sh) & 1u;
+            pass[1] = (lo_w >> (sh + 1)) & 1u;
+            pass[2] = (hi_w >> sh) & 1u;
+            pass[3] = (hi_w >> (sh + 1)) & 1u;
             const bool all = p.rowbits_skip == 0;
 #pragma unroll
             for (int s = 0; s < N_SLOTS; ++s)
@@ -577,10 +527,7 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
             // phase 1: issue every load of the chunk
 #pragma unroll
             for (int s = 0; s < N_SLOTS; ++s) {
-                if (Sh::streamed(p, s)) {
-                    if (hinted) load_quad_hint(p.s[s].ptr, Sh::kind(p, s), base, lane, stream_policy, raw[s]);
-                    else load_quad(p.s[s].ptr, Sh::kind(p, s), base, lane, raw[s]);
-                }
+                if (Sh::streamed(p, s)) load_quad(p.s[s].ptr, Sh::kind(p, s), base, lane, raw[s]);
             }
         }
         if (mask) load_quad(mask, BQ_INT64, base, lane, mk);
@@ -601,7 +548,7 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
         if (dense_join) {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
-                if (pass[r]) pass[r] = sink.probe_dense(raw[S_JK][r], brow[r], prior[r]);
+                if (pass[r]) pass[r] = sink.probe_dense(raw[S_JK][r], brow[r]);
         }
         // phase 3: aggregate the survivors
 #pragma unroll
@@ -659,9 +606,8 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
                 }
             }
             if (mask && __ldg(mask + i) == 0) ok = false;
-            const bool row_bit = use_bits && ((__ldg(p.row_bits + (i >> 5)) >> (i & 31)) & 1u);
-            if (Xs::jmode(p) == BQ_JOIN_ROWBITS && !row_bit) ok = false;
-            if (ok) sink.row(val[S_KEY], val[S_A], val[S_B], val[S_JK], row_bit);
+            if (Xs::jmode(p) == BQ_JOIN_ROWBITS && !((__ldg(p.row_bits + (i >> 5)) >> (i & 31)) & 1u)) ok = false;
+            if (ok) sink.row(val[S_KEY], val[S_A], val[S_B], val[S_JK]);
         }
     }
 
@@ -1000,8 +946,6 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st, bool n
         p.jh_keys = j->h_keys;
         p.jh_rows = j->h_rows;
         p.jh_mask = j->h_mask;
-        // a table that fits the L2 next to the streams needs no help (and the hinted loads cost about 8 % there, measured)
-        p.l2_hints = (j->kind == BQ_JOIN_BITMAP || j->kind == BQ_JOIN_DIRECT) && j->bytes > (40u << 20);
         if (j->kind == BQ_JOIN_BITMAP)
             for (int s = 0; s < N_SLOTS; ++s)
                 if (p.s[s].from_build) throw std::runtime_error("a bitmap join carries no build columns");
@@ -1011,16 +955,9 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st, bool n
     if (spec->row_bits) {
         if (spec->row_bits->type != BQ_STRING || spec->row_bits->n * 32 < spec->row_end) throw std::runtime_error("row bits must be a uint32 column with one bit per row");
         if (spec->row_begin % 128) throw std::runtime_error("row bits need a row range starting at a multiple of 128");
+        if (spec->join) throw std::runtime_error("row bits replace the join probe: pass one or the other");
         p.row_bits = static_cast<const unsigned*>(spec->row_bits->ptr);
-        if (spec->join) {
-            // the scan probes the LAST key-range slice itself; rows of earlier slices bring their bit
-            if (spec->join->kind != BQ_JOIN_BITMAP) throw std::runtime_error("row bits combine with a bitmap join only");
-            if (spec->join_slice_len == 0) throw std::runtime_error("row bits next to a join need the slice the scan is to probe");
-            p.j_slice_lo = spec->join_slice_lo;
-            p.j_slice_len = spec->join_slice_len;
-        } else {
-            p.jmode = BQ_JOIN_ROWBITS;
-        }
+        p.jmode = BQ_JOIN_ROWBITS;
         const char* skip = std::getenv("BOSQL_ROWBITS_SKIP");
         p.rowbits_skip = (skip && *skip == '0') ? 0 : 1;
     }

@@ -168,6 +168,8 @@ struct OrderBy : public Operator {
     // Limit above an OrderBy asks for the first k rows only (top-k instead of a full sort)
     std::shared_ptr<gpu::DeviceRelation> sorted_prefix(int64_t limit);
     std::shared_ptr<gpu::DeviceRelation> sort_relation(const std::shared_ptr<gpu::DeviceRelation>& in, int64_t limit);
+    // across GPUs, no LIMIT: this rank's rows exchanged so that it holds one key range of the first sort key
+    std::shared_ptr<gpu::DeviceRelation> range_partition(const std::shared_ptr<gpu::DeviceRelation>& in);
 private:
     std::unique_ptr<Operator> input_;
     std::vector<SortKey> sort_keys;

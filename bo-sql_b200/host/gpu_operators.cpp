@@ -757,10 +757,177 @@ DeviceRelationPtr OrderBy::sorted_prefix(int64_t limit) {
     // Across GPUs the input is this rank's share of the rows: a local top-k first when there is a LIMIT (each rank's k
     // best rows are the only candidates), one all-gather, then the same sort on the gathered candidates - every rank ends
     // up with the complete ordered result (ORDER BY ... LIMIT k).  Without a LIMIT everything is gathered.
+    if (limit < 0) {
+        // no LIMIT: range-partition the rows by sampled splitters of the first sort key, exchange them all-to-all and sort
+        // locally - rank r ends up with the r-th range of the ordered result (ORDER BY without LIMIT).  Small
+        // inputs (and $BOSQL_SORT=gather) are gathered and sorted on every rank instead, which leaves the complete result
+        // everywhere.
+        const char* mode = std::getenv("BOSQL_SORT");
+        const bool force_gather = mode && std::string(mode) == "gather", force_range = mode && std::string(mode) == "range";
+        const int64_t total = gpu::exchange().host_sum(static_cast<int64_t>(in->rows));
+        if (!force_gather && (force_range || total > (1 << 22)) && gpu::exchange().world() <= 16) {
+            DeviceRelationPtr mine = range_partition(in);
+            DeviceRelationPtr out = sort_relation(mine, -1);
+            out->replicated = false;
+            return out;
+        }
+    }
     DeviceRelationPtr local = limit >= 0 ? sort_relation(in, limit) : in;
     DeviceRelationPtr all = gpu::all_gather_relation(local, types_);
     DeviceRelationPtr out = sort_relation(all, limit);
     out->replicated = true;
+    return out;
+}
+
+// Rows of this rank's shard redistributed so that rank r holds the r-th key range of the first sort key (all rows with equal
+// first key land on one rank, so the later keys order them locally).  Splitters: every rank contributes 128 keys sampled at a
+// regular stride; the pooled sample's quantiles cut the key space into one range per rank.
+DeviceRelationPtr OrderBy::range_partition(const DeviceRelationPtr& in) {
+    gpu::Exchange& x = gpu::exchange();
+    bq_ctx* ctx = context();
+    const int W = x.world();
+    std::vector<PipeCol> cols = pipe_cols(names_, types_, *in);
+    // the first sort key as a column (a plain reference, or evaluated - its outcome exchange runs on every rank)
+    const SortKey& k0 = sort_keys.front();
+    DevColPtr key;
+    TypeId key_type;
+    if (k0.expr->type == ExprType::COLUMN_REF) {
+        auto it = bindings.name_to_index.find(k0.expr->str_val);
+        if (it == bindings.name_to_index.end()) throw std::runtime_error("Unknown column: " + k0.expr->str_val);
+        key = in->cols[it->second];
+        key_type = types_[it->second];
+    } else {
+        key_type = gpu::value_type(k0.expr.get(), gpu::lookup_for(cols));
+        key = gpu::eval_to_column(k0.expr.get(), cols, in->rows, dict_, key_type, false);
+    }
+    const bool fp = key_type == TypeId::DOUBLE;
+    // ---- sample ----
+    constexpr size_t kSample = 128;
+    std::vector<int64_t> mine(kSample + 1, 0);
+    const size_t take = std::min(kSample, in->rows);
+    mine[kSample] = static_cast<int64_t>(take);
+    if (take) {
+        const int64_t stride = static_cast<int64_t>(in->rows / take);
+        bq_col* iota = nullptr;
+        check(bq_col_alloc(ctx, BQ_INT64, take, &iota));
+        DevColPtr seq = gpu::adopt(iota);
+        bq_gen_spec g{};
+        g.dist = BQ_GEN_SEQ;
+        check(bq_col_generate(ctx, seq->h, &g, 0));
+        bq_insn prog[3] = {{BQ_OP_COL, 0, {0}}, {BQ_OP_IMM_I, 0, {stride}}, {BQ_OP_MUL_I, 0, {0}}};
+        const bq_col* pc[1] = {seq->h};
+        bq_col* ids = nullptr;
+        check(bq_eval(ctx, prog, 3, pc, 1, 0, take, BQ_STRING, &ids));
+        DevColPtr rowids = gpu::adopt(ids);
+        bq_col* sampled = nullptr;
+        check(bq_gather(ctx, key->h, rowids->h, &sampled));
+        DevColPtr sk = gpu::adopt(sampled);
+        if (type_width(key_type) == 8) {
+            check(bq_col_read(ctx, sk->h, 0, take, mine.data()));          // INT64, or the bits of a DOUBLE
+        } else {
+            std::vector<int32_t> narrow(take);
+            check(bq_col_read(ctx, sk->h, 0, take, narrow.data()));
+            for (size_t i = 0; i < take; ++i)
+                mine[i] = key_type == TypeId::STRING ? static_cast<int64_t>(static_cast<uint32_t>(narrow[i])) : static_cast<int64_t>(narrow[i]);
+        }
+    }
+    auto all = x.host_gather(mine);
+    std::vector<int64_t> pool;
+    for (int r = 0; r < W; ++r) {
+        const int64_t n = all[static_cast<size_t>(r) * (kSample + 1) + kSample];
+        for (int64_t i = 0; i < n; ++i) pool.push_back(all[static_cast<size_t>(r) * (kSample + 1) + static_cast<size_t>(i)]);
+    }
+    auto as_f = [](int64_t b) {
+        double d;
+        std::memcpy(&d, &b, 8);
+        return d;
+    };
+    // order of the OUTPUT: ascending keys go to rank 0 first; for DESC the largest do
+    std::sort(pool.begin(), pool.end(), [&](int64_t a, int64_t b) {
+        const bool lt = fp ? as_f(a) < as_f(b) : a < b;
+        const bool gt = fp ? as_f(a) > as_f(b) : a > b;
+        return k0.asc ? lt : gt;
+    });
+    std::vector<int64_t> split;                          // W - 1 splitters, in output order
+    for (int r = 1; r < W && !pool.empty(); ++r) split.push_back(pool[std::min(pool.size() - 1, pool.size() * static_cast<size_t>(r) / static_cast<size_t>(W))]);
+    // ---- destination rank of every row: how many splitters lie at or before its key (in output order) ----
+    std::vector<bq_insn> code;
+    for (size_t i = 0; i < split.size(); ++i) {
+        code.push_back({BQ_OP_COL, 0, {0}});
+        bq_insn imm{};
+        imm.op = fp ? BQ_OP_IMM_F : BQ_OP_IMM_I;
+        imm.imm.i = split[i];                            // (the bits of the double for IMM_F: same union)
+        code.push_back(imm);
+        const int ge = fp ? BQ_OP_GE_F : BQ_OP_GE_I, le = fp ? BQ_OP_LE_F : BQ_OP_LE_I;
+        code.push_back({k0.asc ? ge : le, 0, {0}});
+        if (i) code.push_back({BQ_OP_ADD_I, 0, {0}});
+    }
+    if (code.empty()) code.push_back({BQ_OP_IMM_I, 0, {0}});
+    const bq_col* kc[1] = {key->h};
+    bq_col* dest_h = nullptr;
+    check(bq_eval(ctx, code.data(), static_cast<int>(code.size()), kc, 1, 0, in->rows, BQ_INT64, &dest_h));
+    DevColPtr dest = gpu::adopt(dest_h);
+    // ---- stable reorder by destination, sizes, all-to-all per column ----
+    std::vector<int64_t> send_rows(static_cast<size_t>(W), 0);
+    DeviceRelationPtr ordered = in;
+    if (in->rows) {
+        std::vector<bq_col*> hs;
+        for (auto& c : in->cols) hs.push_back(c->h);
+        hs.push_back(dest->h);
+        bq_rel* shell = nullptr;
+        check(bq_rel_create(ctx, hs.data(), static_cast<int>(hs.size()), &shell));
+        const int by = static_cast<int>(hs.size()) - 1, asc = 1;
+        bq_rel* sorted = nullptr;
+        int rc = bq_rel_sort(ctx, shell, 1, &by, &asc, -1, &sorted);
+        std::vector<bq_col*> back(hs.size());
+        bq_rel_release(shell, back.data());
+        check(rc);
+        ordered = gpu::relation_from(sorted);
+        // rows per destination: a dense COUNT over the (sorted) destination column
+        bq_scan_spec cs{};
+        cs.key = gpu::make_slot(ordered->cols.back(), {});
+        cs.row_begin = 0;
+        cs.row_end = in->rows;
+        cs.group_mode = BQ_GROUP_DENSE;
+        cs.key_min = 0;
+        cs.key_max = W - 1;
+        cs.n_out = 1;
+        cs.out[0].func = BQ_AGG_COUNT;
+        bq_rel* counted = nullptr;
+        check(bq_scan_aggregate(ctx, &cs, &counted));
+        DeviceRelationPtr cr = gpu::relation_from(counted);
+        std::vector<int64_t> dk(cr->rows), dn(cr->rows);
+        if (cr->rows) {
+            check(bq_col_read(ctx, cr->cols[0]->h, 0, cr->rows, dk.data()));
+            check(bq_col_read(ctx, cr->cols[1]->h, 0, cr->rows, dn.data()));
+        }
+        for (size_t i = 0; i < dk.size(); ++i) send_rows[static_cast<size_t>(dk[i])] = dn[i];
+    }
+    auto matrix = x.host_gather(send_rows);              // matrix[s*W + d] = rows rank s sends to rank d
+    std::vector<int64_t> recv_rows(static_cast<size_t>(W));
+    size_t total = 0;
+    for (int s2 = 0; s2 < W; ++s2) {
+        recv_rows[static_cast<size_t>(s2)] = matrix[static_cast<size_t>(s2) * W + static_cast<size_t>(x.rank())];
+        total += static_cast<size_t>(recv_rows[static_cast<size_t>(s2)]);
+    }
+    if (total > 0xFFFFFFFFull) throw std::runtime_error("a rank would own more than 2^32 rows after the range partition");
+    auto out = std::make_shared<DeviceRelation>();
+    out->rows = total;
+    for (size_t c = 0; c < types_.size(); ++c) {
+        const size_t w = type_width(types_[c]);
+        std::vector<int64_t> sb(static_cast<size_t>(W)), rb(static_cast<size_t>(W));
+        for (int r = 0; r < W; ++r) {
+            sb[static_cast<size_t>(r)] = send_rows[static_cast<size_t>(r)] * static_cast<int64_t>(w);
+            rb[static_cast<size_t>(r)] = recv_rows[static_cast<size_t>(r)] * static_cast<int64_t>(w);
+        }
+        bq_col* recv = nullptr;
+        check(bq_col_alloc(ctx, static_cast<int>(types_[c]), total, &recv));
+        DevColPtr dst = gpu::adopt(recv);
+        if (x.fn.all_to_all_v(x.fn.user, bq_col_ptr(ordered->cols[c]->h), sb.data(), bq_col_ptr(dst->h), rb.data(), bq_ctx_stream(ctx)))
+            throw std::runtime_error("exchange callback failed: all_to_all_v");
+        out->cols.push_back(dst);
+    }
+    check(bq_ctx_sync(ctx));          // `ordered` (the send side) is released when this returns
     return out;
 }
 

@@ -196,12 +196,8 @@ typedef struct bq_scan_spec {
     int64_t key_min, key_max;
     size_t ndv_hint;         /* HASH: table capacity = next pow2 >= 2*ndv_hint               */
     const bq_join* join;     /* optional: inner-join probe on jkey                          */
-    const bq_col* row_bits;  /* optional: per-row match bits from bq_join_probe_bits (a semi-join probed in key-range
-                              * passes); needs row_begin % 128 == 0.  Without `join` the bits ARE the join and the probe
-                              * key is not read; with a BITMAP `join` the scan itself probes the keys of the last slice,
-                              * [join_slice_lo, join_slice_lo + join_slice_len) relative to the join's key_min, and rows of
-                              * earlier slices take their bit                                                       */
-    uint64_t join_slice_lo, join_slice_len;
+    const bq_col* row_bits;  /* optional, instead of join: per-row match bits from bq_join_probe_bits (a semi-join already
+                              * probed in key-range passes); needs row_begin % 128 == 0.  jkey may stay bound for its ranges */
     int32_t n_out;
     bq_agg_out out[BQ_MAX_AGG_OUT];
     /* HASH grouping over rows that bq_partition has ordered by partition = (hash(key) >> hash_part_shift) & (2^log2 - 1):
@@ -284,10 +280,6 @@ int bq_join_bitmap_popcount(bq_ctx* ctx, const bq_join* j, uint64_t* out);
  * scan then takes it as bq_scan_spec.row_bits and no longer reads the probe key. */
 int bq_join_probe_bits(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, size_t row_begin, size_t row_end,
                        size_t slice_bytes, bq_col** out_bits);
-/* The same, leaving the LAST slice to the fused scan (one pass over the probe key fewer): *last_lo / *last_len receive that
- * slice for bq_scan_spec.join_slice_*.  With a single slice nothing is launched and *out_bits is NULL: probe fused. */
-int bq_join_probe_bits_but_last(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, size_t row_begin, size_t row_end,
-                                size_t slice_bytes, bq_col** out_bits, uint64_t* last_lo, uint64_t* last_len);
 /* Materialising probe (HashJoin::next, src/exec/operator.cpp:764-837): all (probe row, build row) pairs in probe
  * order, matches of one probe row in build insertion order. `probe_rowids` (optional) restricts/ordering the probe rows. */
 int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const bq_col* probe_rowids,

@@ -62,25 +62,15 @@ for n_orders in (n // 4, 2 * n):
     ms, k = kernel_ms(lambda: ctx.scan_aggregate(s).free())
     res[tag]["fused_ms"] = ms
     print(tag, "fused probe", ms, flush=True)
-    for slice_mb in (32, 64, 96, 128):
-        if (slice_mb << 20) * 1.25 >= j.bytes:
-            continue
-        ms_p, k = kernel_ms(lambda: j.probe_bits(li["l.order_id"], 0, n, slice_bytes=slice_mb << 20).free())
-        res[tag][f"all_passes_slice{slice_mb}_ms"] = ms_p
-        print(tag, "key-range passes (all slices), slice", slice_mb, "MB:", ms_p, "ms in", k, "launches", flush=True)
-
-        def hybrid():
-            part, lo, ln = j.probe_bits_but_last(li["l.order_id"], 0, n, slice_bytes=slice_mb << 20)
-            h = scan_spec(li)
-            h.jkey = bq.make_slot(li["l.order_id"])
-            h.join = j.h
-            h.row_bits = part.h
-            h.join_slice_lo, h.join_slice_len = lo, ln
-            ctx.scan_aggregate(h).free()
-            part.free()
-        ms_h, k = kernel_ms(hybrid)
-        res[tag][f"hybrid_slice{slice_mb}_ms"] = ms_h
-        print(tag, "passes but the last + hybrid scan, slice", slice_mb, "MB:", ms_h, "ms in", k, "launches", flush=True)
+    for hints in ("0", "1"):
+        os.environ["BOSQL_PROBE_HINTS"] = hints
+        for slice_mb in (32, 48, 64, 80, 96, 128):
+            if (slice_mb << 20) * 1.25 >= j.bytes:
+                continue
+            ms_p, k = kernel_ms(lambda: j.probe_bits(li["l.order_id"], 0, n, slice_bytes=slice_mb << 20).free())
+            res[tag][f"passes_slice{slice_mb}_hints{hints}_ms"] = ms_p
+            print(tag, "key-range passes, slice", slice_mb, "MB, L2 hints", hints, ":", ms_p, "ms in", k, "launches", flush=True)
+    os.environ["BOSQL_PROBE_HINTS"] = "0"
     bits = j.probe_bits(li["l.order_id"], 0, n, slice_bytes=96 << 20)
     s2 = scan_spec(li)
     s2.row_bits = bits.h

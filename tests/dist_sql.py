@@ -242,6 +242,32 @@ def run_rank(rank, world, backend, results):
         os.environ.pop("BOSQL_SHUFFLE", None)
     except Exception:  # noqa: BLE001
         results.append(("shuffle_groupby", traceback.format_exc()[-1500:]))
+    # ---- ORDER BY without LIMIT, range-partitioned: rank r ends up with the r-th key range of the ordered result ----------
+    try:
+        reinstall()
+        os.environ["BOSQL_SORT"] = "range"
+        for skew in (False, True):
+            eng = engine(skew, "stats")
+            for sql, order in (("SELECT l.order_id, l.sku, l.qty FROM lineitem l WHERE l.qty > 40 ORDER BY l.order_id, l.sku, l.qty", [(0, True), (1, True), (2, True)]),
+                               ("SELECT o.order_id, o.total FROM orders o ORDER BY o.total DESC, o.order_id", [(1, False), (0, True)]),
+                               ("SELECT l.sku, l.price * 2 AS p2 FROM lineitem l WHERE l.sku < 3 ORDER BY p2 DESC", [(1, False)])):
+                tag = f"range_sort[{'skew' if skew else 'even'}] {sql[7:40]}"
+                try:
+                    got, want = eng.query(sql), ora.query(sql)
+                    parts = [None] * world
+                    dist.all_gather_object(parts, [c.copy() for c in got.cols])
+                    # concatenation in RANK order must be the ordered result
+                    cols = [np.concatenate([pp[i] for pp in parts]) for i in range(len(got.cols))]
+                    assert_same_rows(cols, want.cols, ordered_by=order, what=tag)
+                    if world > 1 and not skew:
+                        assert sum(1 for pp in parts if len(pp[0])) > 1, "every row ended up on one rank: was the range partition taken?"
+                    results.append((tag, "ok"))
+                except Exception:  # noqa: BLE001
+                    results.append((tag, traceback.format_exc()[-1200:]))
+            del eng
+        os.environ.pop("BOSQL_SORT", None)
+    except Exception:  # noqa: BLE001
+        results.append(("range_sort", traceback.format_exc()[-1500:]))
     if not native:
         D.uninstall(xl)
     if ex.error:

@@ -408,19 +408,6 @@ def test_q2_probe_in_key_range_passes(bq, ctx, sku_type, n_line):
         s.row_bits = bits.h
         got = ctx.scan_aggregate(s).to_numpy()
         assert_same_rows(got, want, what=f"row bits, slice {slice_bytes}")
-        # the last slice left to the fused scan: earlier slices' rows bring their bit, the scan probes the rest
-        part, last_lo, last_len = j.probe_bits_but_last(l["l.order_id"], 0, n_line, slice_bytes=slice_bytes)
-        if slice_bytes >= 1 << 30:
-            assert part is None and last_lo == 0 and last_len == n_orders
-            continue
-        assert last_lo > 0 and last_lo + last_len == n_orders
-        h = spec()
-        h.jkey = bq.make_slot(l["l.order_id"])
-        h.join = j.h
-        h.row_bits = part.h
-        h.join_slice_lo, h.join_slice_len = last_lo, last_len
-        got = ctx.scan_aggregate(h).to_numpy()
-        assert_same_rows(got, want, what=f"hybrid probe, slice {slice_bytes}")
 
 
 def test_join_payload_from_build_side(bq, ctx):
