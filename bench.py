@@ -336,13 +336,15 @@ def run_ours(args):
         o["order_id"].free()
         return {"orders": (cols, {"order_date": (DATE_MIN, DATE_MAX, 336), "total": (1.0, 1000.0, 99901)})}
 
-    def q2_tables(n_line_all, n_line, line_r0, n_ord_all, n_ord, ord_r0):
-        o = gen_table(datagen.orders_schema(n_ord_all, prefix="o.")[:2], n_ord, SEED + 1, ord_r0)
-        li = gen_table(datagen.lineitem_schema(n_ord_all, N_SKU), n_line, SEED + 2, line_r0)
+    def q2_tables(n_line_all, n_line, line_r0, n_ord_all, n_ord, ord_r0, key_stride=1):
+        """key_stride > 1: order ids 1, 1 + s, 1 + 2s, ... - a sparse domain, so the join needs a real hash table"""
+        o = gen_table(datagen.orders_schema(n_ord_all, prefix="o.", key_stride=key_stride)[:2], n_ord, SEED + 1, ord_r0)
+        li = gen_table(datagen.lineitem_schema(n_ord_all, N_SKU, key_stride=key_stride), n_line, SEED + 2, line_r0)
+        key_max = 1 + (n_ord_all - 1) * key_stride
         return {"orders": ([("o.order_id", bq.INT64, o["o.order_id"]), ("o.status", bq.STRING, o["o.status"])],
-                           {"o.order_id": (1, n_ord_all, n_ord_all)}),
+                           {"o.order_id": (1, key_max, n_ord_all)}),
                 "lineitem": ([(n, t, li[n]) for n, t, _ in datagen.lineitem_schema(n_ord_all, N_SKU)],
-                             {"l.sku": (0, N_SKU - 1, N_SKU), "l.order_id": (1, n_ord_all, n_ord_all)})}
+                             {"l.sku": (0, N_SKU - 1, N_SKU), "l.order_id": (1, key_max, n_ord_all)})}
 
     def c2_tables(n_all, n_local, r0):
         s = gen_table(datagen.sweep_schema_c2(), n_local, SEED + 3, r0)
@@ -496,8 +498,8 @@ def run_ours(args):
     # Q2: lineitem JOIN orders.  weak = R lineitem + R/4 orders rows PER GPU (the key domain, and with it the join bitmap,
     # grows with N); strong = R + R/4 rows IN TOTAL, sharded N ways (N > 1 only)
     # =================================================================================================================
-    def run_q2(key, n_line_all, n_line, line_r0, n_ord_all, n_ord, ord_r0, e2e=False):
-        tabs = q2_tables(n_line_all, n_line, line_r0, n_ord_all, n_ord, ord_r0)
+    def run_q2(key, n_line_all, n_line, line_r0, n_ord_all, n_ord, ord_r0, e2e=False, key_stride=1):
+        tabs = q2_tables(n_line_all, n_line, line_r0, n_ord_all, n_ord, ord_r0, key_stride)
         try:
             eng = make_engine(tabs)
             plan = eng.plan(Q2_SQL)
@@ -517,9 +519,10 @@ def run_ours(args):
                    "ms_per_step": ms2, "steps": q2_steps, "gbs_whole_query": q2_bytes * world / (ms2 * 1e-3) / 1e9, "gpu_launches": int(l2) * q2_steps,
                    "rows": {"lineitem_per_gpu": n_line, "orders_per_gpu": n_ord, "lineitem_total": n_line_all, "orders_total": n_ord_all, "sku": N_SKU},
                    "sql": Q2_SQL,
-                   "join": f"bitmap over the global o.order_id domain ({bitmap_mb:.0f} MB)" +
-                           (", per-rank bitmaps summed over NVLink and verified by popcount" if world > 1 else "") +
-                           (", probed in key-range passes" if k2n // q2_steps > 1 else ", probed inside the fused scan"),
+                   "join": ("open-addressing hash table (sparse key domain: 16-byte slots, capacity 2 x build rows)" if key_stride > 1 else
+                            f"bitmap over the global o.order_id domain ({bitmap_mb:.0f} MB)" +
+                            (", per-rank bitmaps summed over NVLink and verified by popcount" if world > 1 else "") +
+                            (", probed in key-range passes" if k2n // q2_steps > 1 else ", probed inside the fused scan")),
                    "roofline": {"bound": "hbm", "kernel": "probe side: bq::k_probe_bits passes + bq::k_scan (GROUP BY sku)" if k2n // q2_steps > 1
                                 else "bq::k_scan (probe + GROUP BY sku)",
                                 "achieved": Q2_BYTES_PER_PROBE_ROW * n_line / (probe_ms * 1e-3) / 1e9 if k2n else None,
@@ -580,6 +583,11 @@ def run_ours(args):
         n_ord = max(1, rows // 4)
         section("q2", lambda: run_q2("q2", rows * world, rows, rank * rows, n_ord * world, n_ord, rank * n_ord,
                                      e2e=(world == 1 and not args.no_e2e)))
+
+    # ---- the same query over SPARSE order ids: no bitmap, no direct-address table - the open-addressing hash join (N = 1) ----
+    if not args.no_q2 and world == 1 and not args.no_stress:
+        n_ord = max(1, rows // 4)
+        section("q2_hash", lambda: run_q2("q2_hash", rows, rows, 0, n_ord, n_ord, 0, key_stride=7919))
 
     # ---- strong scaling: the 1 B-row tables IN TOTAL, sharded N ways --------------------------------------------------------
     def run_q1_strong():
@@ -806,6 +814,12 @@ def run_ours(args):
         r2 = compare("Q2 key-range passes", [Q2_SQL], q2_tables(SL, n, lo, SO, on, olo), q2_host, None, "same sample, bitmap cut into 16 KB slices",
                      SL + SO, ordered=[(1, False)], env={"BOSQL_BITMAP_SLICE_KB": "16"})
         results["q2"]["parity_on_sample_key_range_passes"] = r2.get("parity_on_sample")
+        if world == 1:
+            def q2h_host():
+                return {"orders": odg.host_table(odg.orders_schema(SO, prefix="o.", key_stride=7919)[:2], SO, SEED + 1),
+                        "lineitem": odg.host_table(odg.lineitem_schema(SO, N_SKU, key_stride=7919), SL, SEED + 2)}
+            results["q2_hash"] = compare("Q2 hash join", [Q2_SQL], q2_tables(SL, n, lo, SO, on, olo, key_stride=7919), q2h_host, None,
+                                         f"{SL} lineitem x {SO} orders rows, sparse order ids", SL + SO, ordered=[(1, False)])
         # C2: one statement per type and selectivity
         S2 = max(1024, S // 2)
         lo, n = shard(S2)

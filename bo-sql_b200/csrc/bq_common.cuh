@@ -194,6 +194,26 @@ struct bq_rel {
     size_t rows = 0;
 };
 
+namespace bq {
+// One slot of the open-addressing join table: key and build row id + 1 (0 = empty) side by side, so a probe step is ONE
+// 16-byte load (the first-generation layout kept keys and rows in two arrays: two random sectors per step).
+struct alignas(16) JoinSlot {
+    long long key;
+    unsigned row;
+    unsigned pad;
+};
+#if defined(__CUDACC__)
+BQ_D JoinSlot load_join_slot(const JoinSlot* p) {
+    const int4 v = __ldg(reinterpret_cast<const int4*>(p));
+    JoinSlot s;
+    s.key = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(v.y)) << 32) | static_cast<unsigned>(v.x));
+    s.row = static_cast<unsigned>(v.z);
+    s.pad = 0;
+    return s;
+}
+#endif
+}  // namespace bq
+
 struct bq_join {
     bq_ctx* ctx = nullptr;
     int kind = BQ_JOIN_HASH;
@@ -201,8 +221,7 @@ struct bq_join {
     unsigned* bitmap = nullptr;           // BITMAP: bit (key-key_min)
     size_t bitmap_words = 0;
     unsigned* direct = nullptr;           // DIRECT: build row id + 1 at [key-key_min], 0 = absent
-    long long* h_keys = nullptr;          // HASH: open addressing, linear probing
-    unsigned* h_rows = nullptr;           //       build row id + 1, 0 = empty slot
+    bq::JoinSlot* h_slots = nullptr;      // HASH: open addressing, linear probing over 16-byte slots
     uint64_t h_mask = 0;
     size_t build_rows = 0;                // rows inserted
     size_t bytes = 0;

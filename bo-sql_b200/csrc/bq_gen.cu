@@ -28,8 +28,8 @@ BQ_D int64_t gen_value(const GenParams& p, uint64_t row, double* as_f) {
     uint64_t h = row_hash(p.seed, p.stream, row);
     int64_t v = 0;
     switch (p.dist) {
-        case BQ_GEN_SEQ: v = p.lo + static_cast<int64_t>(row); break;
-        case BQ_GEN_UNIFORM: v = p.lo + static_cast<int64_t>(h % p.range); break;
+        case BQ_GEN_SEQ: v = p.lo + static_cast<int64_t>(row * p.modulus); break;             // modulus = stride (1 unless given)
+        case BQ_GEN_UNIFORM: v = p.lo + static_cast<int64_t>((h % p.range) * p.modulus); break;
         case BQ_GEN_UNIFORM_DIV:
             v = p.lo + static_cast<int64_t>(h % p.range);
             *as_f = static_cast<double>(v) / p.div;

@@ -33,8 +33,7 @@ struct BuildParams {
     unsigned long long domain;
     unsigned* bitmap;
     unsigned* direct;
-    long long* h_keys;
-    unsigned* h_rows;
+    JoinSlot* h_slots;
     unsigned long long h_mask;
     unsigned long long* n_inserted;
     int* flags;   // 1 = duplicate key seen (BITMAP/DIRECT), 2 = key outside [min,max], 4 = table full
@@ -56,87 +55,106 @@ BQ_D bool fast_pass(const DSlot& s, long long raw) {
     return ok;
 }
 
+__global__ void __launch_bounds__(kBlock) k_popcount_words(const unsigned* __restrict__ w, size_t n, unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c += __popc(w[i]);
+    c = warp_sum(c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
 // KEYK: key kind known at compile time (-1: read it from the parameters); NPRED: number of predicate slots in use
-// (-1: test all three at run time).  The loop is one row per lane per trip, kept light enough (about 30 instructions
-// per 32 rows in the common instance) that the kernel is bound by its 12 B/row of reads, with 8 CTAs per SM in flight.
+// (-1: test all three at run time).  A warp takes 128 consecutive rows per trip, four per lane, with all loads of the trip
+// issued before the first use.  BITMAP inserts are reductions (red.or: nothing comes back, so no lane waits on the L2);
+// duplicate keys are found afterwards by comparing the bitmap's popcount with the rows inserted (build_kind).
 template <int KIND, int KEYK, int NPRED>
 __global__ void __launch_bounds__(kBlock) k_join_build(const __grid_constant__ BuildParams p) {
     unsigned long long local = 0;
     const size_t n = p.row_end - p.row_begin;
     const int lane = threadIdx.x & 31;
-    const size_t stride = (size_t)gridDim.x * blockDim.x;
     const int key_kind = KEYK >= 0 ? KEYK : p.key_kind;
-    // warp-uniform trip count (the bitmap path uses warp collectives)
-    for (size_t base = blockIdx.x * (size_t)blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
-        const size_t t = base + lane;
-        bool ok = t < n;
-        const size_t i = p.row_begin + (ok ? t : 0);
-        long long k = load_raw(p.key, key_kind, i);
-        if (NPRED < 0) {
+    constexpr int R = 4;
+    const size_t warps = static_cast<size_t>(gridDim.x) * (kBlock / 32);
+    const size_t warp = static_cast<size_t>(blockIdx.x) * (kBlock / 32) + (threadIdx.x >> 5);
+    const size_t n_chunks = (n + 32 * R - 1) / (32 * R);
+    for (size_t c = warp; c < n_chunks; c += warps) {
+        long long k[R];
+        bool ok[R];
+        size_t row[R];
 #pragma unroll
-            for (int s = 0; s < 3; ++s)
-                if (p.s[s].ptr && p.s[s].nr) ok = ok && fast_pass(p.s[s], load_raw(p.s[s].ptr, p.s[s].kind, i));
-            if (p.mask && __ldg(p.mask + i) == 0) ok = false;
-        } else {
-#pragma unroll
-            for (int s = 0; s < 3; ++s)
-                if (s < NPRED) ok = ok && fast_pass(p.s[s], load_raw(p.s[s].ptr, p.s[s].kind, i));
+        for (int r = 0; r < R; ++r) {
+            const size_t t = c * (32 * R) + 32 * r + lane;
+            ok[r] = t < n;
+            row[r] = p.row_begin + (ok[r] ? t : 0);
+            k[r] = load_raw(p.key, key_kind, row[r]);
         }
-        ok = ok && canon_join_key(k, key_kind);
-        if (KIND == BQ_JOIN_BITMAP) {
-            unsigned long long idx = static_cast<unsigned long long>(k - p.key_min);
-            if (ok && idx >= p.domain) {
-                atomicOr(p.flags, 2);
-                ok = false;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const size_t i = row[r];
+            if (NPRED < 0) {
+#pragma unroll
+                for (int s = 0; s < 3; ++s)
+                    if (p.s[s].ptr && p.s[s].nr) ok[r] = ok[r] && fast_pass(p.s[s], load_raw(p.s[s].ptr, p.s[s].kind, i));
+                if (p.mask && __ldg(p.mask + i) == 0) ok[r] = false;
+            } else {
+#pragma unroll
+                for (int s = 0; s < 3; ++s)
+                    if (s < NPRED) ok[r] = ok[r] && fast_pass(p.s[s], load_raw(p.s[s].ptr, p.s[s].kind, i));
             }
-            // Build keys usually arrive clustered (o.order_id = row + 1): when every inserting lane of the warp hits
-            // the same bitmap word, the warp combines its bits and issues ONE atomicOr instead of up to 32 that
-            // would serialise on one L2 address.  Otherwise each lane inserts on its own.
-            const unsigned word = static_cast<unsigned>(idx >> 5);
-            const unsigned bit = ok ? 1u << (idx & 31) : 0u;
-            const unsigned active = __ballot_sync(0xffffffffu, ok);
-            if (active) {
-                const int first = __ffs(active) - 1;
-                const unsigned w0 = __shfl_sync(0xffffffffu, word, first);
-                const bool same = __all_sync(0xffffffffu, !ok || word == w0);
-                if (same) {
-                    const unsigned bits = __reduce_or_sync(0xffffffffu, bit);
-                    if (lane == first) {
-                        if (__popc(bits) != __popc(active)) atomicOr(p.flags, 1);      // one key twice inside the warp
-                        unsigned old = atomicOr(p.bitmap + w0, bits);
-                        if (old & bits) atomicOr(p.flags, 1);
-                    }
-                } else if (ok) {
-                    unsigned old = atomicOr(p.bitmap + word, bit);
-                    if (old & bit) atomicOr(p.flags, 1);
-                }
-                local += ok ? 1 : 0;
-            }
-        } else if (KIND == BQ_JOIN_DIRECT) {
-            if (ok) {
-                unsigned long long idx = static_cast<unsigned long long>(k - p.key_min);
-                if (idx >= p.domain) {
+            ok[r] = ok[r] && canon_join_key(k[r], key_kind);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const size_t i = row[r];
+            if (KIND == BQ_JOIN_BITMAP) {
+                unsigned long long idx = static_cast<unsigned long long>(k[r] - p.key_min);
+                if (ok[r] && idx >= p.domain) {
                     atomicOr(p.flags, 2);
-                } else {
-                    unsigned old = atomicCAS(p.direct + idx, 0u, static_cast<unsigned>(i) + 1u);
-                    if (old) atomicOr(p.flags, 1);
-                    local++;
+                    ok[r] = false;
                 }
-            }
-        } else if (ok) {
-            unsigned long long h = key_hash(static_cast<uint64_t>(k)) & p.h_mask;
-            bool placed = false;
-            for (unsigned long long probes = 0; probes <= p.h_mask; ++probes) {
-                unsigned old = atomicCAS(p.h_rows + h, 0u, static_cast<unsigned>(i) + 1u);
-                if (old == 0u) {
-                    p.h_keys[h] = k;
-                    placed = true;
-                    break;
+                // Build keys usually arrive clustered (o.order_id = row + 1): when every inserting lane of the warp hits
+                // the same bitmap word, the warp combines its bits into ONE reduction instead of up to 32 on one address.
+                const unsigned word = static_cast<unsigned>(idx >> 5);
+                const unsigned bit = ok[r] ? 1u << (idx & 31) : 0u;
+                const unsigned active = __ballot_sync(0xffffffffu, ok[r]);
+                if (active) {
+                    const int first = __ffs(active) - 1;
+                    const unsigned w0 = __shfl_sync(0xffffffffu, word, first);
+                    const bool same = __all_sync(0xffffffffu, !ok[r] || word == w0);
+                    if (same) {
+                        const unsigned bits = __reduce_or_sync(0xffffffffu, bit);
+                        if (lane == first) atomicOr(p.bitmap + w0, bits);
+                    } else if (ok[r]) {
+                        atomicOr(p.bitmap + word, bit);
+                    }
+                    local += ok[r] ? 1 : 0;
                 }
-                h = (h + 1) & p.h_mask;
+            } else if (KIND == BQ_JOIN_DIRECT) {
+                if (ok[r]) {
+                    unsigned long long idx = static_cast<unsigned long long>(k[r] - p.key_min);
+                    if (idx >= p.domain) {
+                        atomicOr(p.flags, 2);
+                    } else {
+                        unsigned old = atomicCAS(p.direct + idx, 0u, static_cast<unsigned>(i) + 1u);
+                        if (old) atomicOr(p.flags, 1);
+                        local++;
+                    }
+                }
+            } else if (ok[r]) {
+                // open addressing over 16-byte slots {key, build row + 1}: the row word is claimed, then the key is stored
+                unsigned long long h = key_hash(static_cast<uint64_t>(k[r])) & p.h_mask;
+                bool placed = false;
+                for (unsigned long long probes = 0; probes <= p.h_mask; ++probes) {
+                    unsigned old = atomicCAS(&p.h_slots[h].row, 0u, static_cast<unsigned>(i) + 1u);
+                    if (old == 0u) {
+                        p.h_slots[h].key = k[r];
+                        placed = true;
+                        break;
+                    }
+                    h = (h + 1) & p.h_mask;
+                }
+                if (!placed) atomicOr(p.flags, 4);
+                local++;
             }
-            if (!placed) atomicOr(p.flags, 4);
-            local++;
         }
     }
     local = warp_sum(local);
@@ -155,8 +173,7 @@ struct ProbeParams {
     unsigned long long domain;
     const unsigned* bitmap;
     const unsigned* direct;
-    const long long* h_keys;
-    const unsigned* h_rows;
+    const JoinSlot* h_slots;
     unsigned long long h_mask;
 };
 
@@ -174,10 +191,10 @@ BQ_D unsigned probe_matches(const ProbeParams& p, long long k, unsigned* out, un
     unsigned m = 0;
     unsigned long long h = key_hash(static_cast<uint64_t>(k)) & p.h_mask;
     for (unsigned long long probes = 0; probes <= p.h_mask; ++probes) {
-        unsigned e = __ldg(p.h_rows + h);
-        if (!e) break;
-        if (__ldg(p.h_keys + h) == k) {
-            if (out && m < cap_out) out[m] = e - 1;
+        const JoinSlot e = load_join_slot(p.h_slots + h);         // one 16-byte load: key and row together
+        if (!e.row) break;
+        if (e.key == k) {
+            if (out && m < cap_out) out[m] = e.row - 1;
             ++m;
         }
         h = (h + 1) & p.h_mask;
@@ -233,15 +250,15 @@ struct ProbeBitsParams {
 };
 
 // A warp owns 32 * ROWS consecutive rows per trip (row_begin is a multiple of 128): lane t tests rows t, 32+t, 64+t, ..., so
-// the key column is read with fully coalesced requests and each ballot is one finished word of the output.  The loads of
-// the NEXT trip are issued before the current trip probes (two trips of loads in flight per warp), later passes merge
-// their words with red.or (no read-modify-write on the critical path), and the kernel is held to 48 registers so that
-// eight CTAs stay resident: the pass is a latency chain (key load -> bitmap probe -> word), and bytes in flight are what
-// hide it.  Only rows whose key lies in the pass's slice touch the bitmap; with $BOSQL_PROBE_HINTS=1 the key stream is
-// marked L2 evict-first and the bitmap evict-last.
+// the key column is read with fully coalesced requests, ROWS of them in flight per lane before the first use, and each
+// ballot is one finished word of the output; later passes merge their words with red.or (no read-modify-write on the
+// critical path).  The pass is a latency chain (key load -> bitmap probe -> word) hidden by resident warps: five CTAs per
+// SM.  Only rows whose key lies in the pass's slice touch the bitmap; the key stream is marked L2 evict-first and the
+// bitmap evict-last ($BOSQL_PROBE_HINTS=0 switches the hints off): ncu shows the slice competing with the stream for L2
+// (half of a 64 MB slice's probes went to DRAM without them).
 // FIRST: reads the key column itself and leaves key - key_min as a uint32 per row for the passes that follow.
 template <bool FIRST, int ROWS, bool HINTS>
-__global__ void __launch_bounds__(kBlock, 6) k_probe_bits(const __grid_constant__ ProbeBitsParams p) {
+__global__ void __launch_bounds__(kBlock, 5) k_probe_bits(const __grid_constant__ ProbeBitsParams p) {
     const int lane = threadIdx.x & 31;
     const size_t warps = static_cast<size_t>(gridDim.x) * (kBlock / 32);
     const size_t warp = static_cast<size_t>(blockIdx.x) * (kBlock / 32) + (threadIdx.x >> 5);
@@ -253,58 +270,50 @@ __global__ void __launch_bounds__(kBlock, 6) k_probe_bits(const __grid_constant_
         stream_policy = l2_policy_evict_first();
         keep_policy = l2_policy_evict_last();
     }
-    // raw loads of one trip: FIRST reads 8-byte keys (4-byte kinds widened), later passes the 4-byte offsets
-    auto load_trip = [&](size_t c, long long (&raw)[ROWS]) {
-        const size_t base = p.row_begin + c * per;
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const size_t i = base + 32 * r + lane;
-            raw[r] = -1;
-            if (i < p.row_end) {
-                if (FIRST) {
-                    if (p.key_kind == BQ_INT64)
-                        raw[r] = HINTS ? ldg_stream_i64_hint(static_cast<const long long*>(p.key) + i, stream_policy) : __ldg(static_cast<const long long*>(p.key) + i);
-                    else if (p.key_kind == BQ_STRING) raw[r] = static_cast<unsigned>(__ldg(static_cast<const int*>(p.key) + i));
-                    else raw[r] = __ldg(static_cast<const int*>(p.key) + i);
-                } else {
-                    raw[r] = static_cast<unsigned>(HINTS ? ldg_stream_i32_hint(reinterpret_cast<const int*>(p.idx32) + i, stream_policy)
-                                                         : __ldg(reinterpret_cast<const int*>(p.idx32) + i));
-                }
-            }
-        }
-    };
-    long long cur[ROWS], nxt[ROWS];
-    if (warp < n_chunks) load_trip(warp, cur);
     for (size_t c = warp; c < n_chunks; c += warps) {
         const size_t base = p.row_begin + c * per;
-        if (c + warps < n_chunks) load_trip(c + warps, nxt);
         unsigned idx[ROWS];
+        if (FIRST) {
+            long long k[ROWS];
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const bool in = base + 32 * r + lane < p.row_end;
-            if (FIRST) {
-                const unsigned long long d = static_cast<unsigned long long>(cur[r] - p.key_min);
+            for (int r = 0; r < ROWS; ++r) {
+                const size_t i = base + 32 * r + lane;
+                k[r] = 0;
+                if (i < p.row_end) {
+                    if (p.key_kind == BQ_INT64)
+                        k[r] = HINTS ? ldg_stream_i64_hint(static_cast<const long long*>(p.key) + i, stream_policy) : __ldg(static_cast<const long long*>(p.key) + i);
+                    else if (p.key_kind == BQ_STRING) k[r] = static_cast<unsigned>(__ldg(static_cast<const int*>(p.key) + i));
+                    else k[r] = __ldg(static_cast<const int*>(p.key) + i);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const bool in = base + 32 * r + lane < p.row_end;
+                const unsigned long long d = static_cast<unsigned long long>(k[r] - p.key_min);
                 idx[r] = (in && d < p.domain) ? static_cast<unsigned>(d) : 0xFFFFFFFFu;
                 if (in && p.idx32) p.idx32[base + 32 * r + lane] = idx[r];
-            } else {
-                idx[r] = in ? static_cast<unsigned>(cur[r]) : 0xFFFFFFFFu;
             }
-        }
-        unsigned hit[ROWS];
+        } else {
 #pragma unroll
-        for (int r = 0; r < ROWS; ++r) {
-            const unsigned long long s = static_cast<unsigned long long>(idx[r]) - p.slice_lo;
-            const bool mine = idx[r] != 0xFFFFFFFFu && s < p.slice_len;
-            hit[r] = 0u;
-            if (mine) {
-                const unsigned w = HINTS ? ldg_keep_u32(p.bitmap + (idx[r] >> 5), keep_policy) : __ldg(p.bitmap + (idx[r] >> 5));
-                hit[r] = (w >> (idx[r] & 31)) & 1u;
+            for (int r = 0; r < ROWS; ++r) {
+                const size_t i = base + 32 * r + lane;
+                idx[r] = 0xFFFFFFFFu;
+                if (i < p.row_end)
+                    idx[r] = static_cast<unsigned>(HINTS ? ldg_stream_i32_hint(reinterpret_cast<const int*>(p.idx32) + i, stream_policy)
+                                                         : __ldg(reinterpret_cast<const int*>(p.idx32) + i));
             }
         }
         unsigned mine_word = 0;
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) {
-            const unsigned word = __ballot_sync(0xffffffffu, hit[r] != 0);
+            const unsigned long long s = static_cast<unsigned long long>(idx[r]) - p.slice_lo;
+            const bool mine = idx[r] != 0xFFFFFFFFu && s < p.slice_len;
+            bool hit = false;
+            if (mine) {
+                const unsigned w = HINTS ? ldg_keep_u32(p.bitmap + (idx[r] >> 5), keep_policy) : __ldg(p.bitmap + (idx[r] >> 5));
+                hit = (w >> (idx[r] & 31)) & 1u;
+            }
+            const unsigned word = __ballot_sync(0xffffffffu, hit);
             if (lane == r) mine_word = word;
         }
         // lanes 0..ROWS-1 hold the words of the chunk: one coalesced store, or a red.or into the earlier passes' words
@@ -313,16 +322,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_probe_bits(const __grid_constant_
             if (p.first) p.out[w] = mine_word;
             else if (mine_word) atomicOr(p.out + w, mine_word);
         }
-#pragma unroll
-        for (int r = 0; r < ROWS; ++r) cur[r] = nxt[r];
     }
-}
-
-__global__ void __launch_bounds__(kBlock) k_popcount_words(const unsigned* __restrict__ w, size_t n, unsigned long long* __restrict__ out) {
-    unsigned long long c = 0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) c += __popc(w[i]);
-    c = warp_sum(c);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
 }
 
 static size_t next_pow2(size_t v) {
@@ -334,10 +334,9 @@ static size_t next_pow2(size_t v) {
 static void free_tables(bq_join* j) {
     dev_free(j->ctx, j->bitmap);
     dev_free(j->ctx, j->direct);
-    dev_free(j->ctx, j->h_keys);
-    dev_free(j->ctx, j->h_rows);
-    j->bitmap = j->direct = j->h_rows = nullptr;
-    j->h_keys = nullptr;
+    dev_free(j->ctx, j->h_slots);
+    j->bitmap = j->direct = nullptr;
+    j->h_slots = nullptr;
 }
 
 // Builds one table kind; returns the kernel's flag word.
@@ -383,12 +382,10 @@ static int build_kind(bq_ctx* ctx, const bq_join_spec* spec, int kind, bq_join* 
     } else {
         size_t cap = next_pow2(n * 2 < 1024 ? 1024 : n * 2);
         j->h_mask = cap - 1;
-        j->bytes = cap * 12;
-        j->h_keys = static_cast<long long*>(dev_alloc(ctx, cap * 8));
-        j->h_rows = static_cast<unsigned*>(dev_alloc(ctx, cap * 4));
-        BQ_CUDA(cudaMemsetAsync(j->h_rows, 0, cap * 4, ctx->stream));
-        p.h_keys = j->h_keys;
-        p.h_rows = j->h_rows;
+        j->bytes = cap * sizeof(JoinSlot);
+        j->h_slots = static_cast<JoinSlot*>(dev_alloc(ctx, cap * sizeof(JoinSlot)));
+        BQ_CUDA(cudaMemsetAsync(j->h_slots, 0, cap * sizeof(JoinSlot), ctx->stream));
+        p.h_slots = j->h_slots;
         p.h_mask = j->h_mask;
     }
     auto* d = static_cast<unsigned long long*>(scratch(ctx, 16));
@@ -413,7 +410,19 @@ static int build_kind(bq_ctx* ctx, const bq_join_spec* spec, int kind, bq_join* 
     BQ_CUDA(cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, ctx->stream));
     BQ_CUDA(cudaStreamSynchronize(ctx->stream));
     j->build_rows = static_cast<size_t>(h[0]);
-    return static_cast<int>(h[1] & 0xFFFFFFFFull);
+    int flags = static_cast<int>(h[1] & 0xFFFFFFFFull);
+    if (kind == BQ_JOIN_BITMAP && !(flags & 2) && j->build_rows) {
+        // the inserts were reductions: a key inserted twice shows as a bitmap with fewer bits than rows
+        auto* dc = static_cast<unsigned long long*>(scratch(ctx, 16));
+        BQ_CUDA(cudaMemsetAsync(dc, 0, 8, ctx->stream));
+        k_popcount_words<<<grid_for(ctx, j->bitmap_words, 8), kBlock, 0, ctx->stream>>>(j->bitmap, j->bitmap_words, dc);
+        ctx->launches++;
+        BQ_CUDA(cudaGetLastError());
+        BQ_CUDA(cudaMemcpyAsync(h, dc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h[0] != j->build_rows) flags |= 1;
+    }
+    return flags;
 }
 
 }  // namespace bq
@@ -507,7 +516,7 @@ int bq_join_probe_bits(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, s
         bq_col* bits = new_col(ctx, BQ_STRING, (words + 31) / 32 * 32);       // whole groups of words (scan: four at once; passes: up to 16)
         unsigned* idx32 = nullptr;
         const char* hint_env = std::getenv("BOSQL_PROBE_HINTS");
-        const bool hints = hint_env && *hint_env == '1';
+        const bool hints = !(hint_env && *hint_env == '0');
         try {
             BQ_CUDA(cudaMemsetAsync(bits->ptr, 0, bits->n * 4, ctx->stream));
             if (row_end > row_begin) {
@@ -523,7 +532,7 @@ int bq_join_probe_bits(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, s
                 p.bitmap = j->bitmap;
                 p.out = static_cast<unsigned*>(bits->ptr);
                 p.idx32 = idx32;
-                const int grid = grid_for(ctx, row_end - row_begin, 6);
+                const int grid = grid_for(ctx, row_end - row_begin, 5);
                 for (unsigned long long pass = 0; pass < passes; ++pass) {
                     p.slice_lo = pass * slice_keys;
                     p.slice_len = std::min(slice_keys, domain - p.slice_lo);
@@ -535,10 +544,10 @@ int bq_join_probe_bits(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, s
                         BQ_CUDA(cudaEventRecord(ev0, ctx->stream));
                     }
                     const bool first_kind = pass == 0 || !idx32;
-                    if (first_kind && hints) k_probe_bits<true, 4, true><<<grid, kBlock, 0, ctx->stream>>>(p);
-                    else if (first_kind) k_probe_bits<true, 4, false><<<grid, kBlock, 0, ctx->stream>>>(p);
-                    else if (hints) k_probe_bits<false, 8, true><<<grid, kBlock, 0, ctx->stream>>>(p);
-                    else k_probe_bits<false, 8, false><<<grid, kBlock, 0, ctx->stream>>>(p);
+                    if (first_kind && hints) k_probe_bits<true, 8, true><<<grid, kBlock, 0, ctx->stream>>>(p);
+                    else if (first_kind) k_probe_bits<true, 8, false><<<grid, kBlock, 0, ctx->stream>>>(p);
+                    else if (hints) k_probe_bits<false, 16, true><<<grid, kBlock, 0, ctx->stream>>>(p);
+                    else k_probe_bits<false, 16, false><<<grid, kBlock, 0, ctx->stream>>>(p);
                     if (ctx->profile) {
                         BQ_CUDA(cudaEventRecord(ev1, ctx->stream));
                         ctx->profile_events.emplace_back(ev0, ev1);
@@ -574,8 +583,7 @@ int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const 
         p.domain = static_cast<unsigned long long>(j->key_max - j->key_min) + 1ULL;
         p.bitmap = j->bitmap;
         p.direct = j->direct;
-        p.h_keys = j->h_keys;
-        p.h_rows = j->h_rows;
+        p.h_slots = j->h_slots;
         p.h_mask = j->h_mask;
         bq_col *op = nullptr, *ob = nullptr;
         unsigned* counts = nullptr;

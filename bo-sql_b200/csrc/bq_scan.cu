@@ -69,8 +69,7 @@ struct ScanParams {
     unsigned long long jk_domain;
     const unsigned* j_bitmap;
     const unsigned* j_direct;
-    const long long* jh_keys;
-    const unsigned* jh_rows;
+    const JoinSlot* jh_slots;
     unsigned long long jh_mask;
     // G_NONE partials: [grid] x {cnt, sum0, sum1}
     unsigned long long* part_cnt;
@@ -376,9 +375,9 @@ struct RowSink {
         }
         unsigned long long h = key_hash(static_cast<uint64_t>(jk)) & p.jh_mask;
         for (unsigned long long probes = 0; probes <= p.jh_mask; ++probes) {
-            unsigned e = __ldg(p.jh_rows + h);
-            if (!e) return;
-            if (__ldg(p.jh_keys + h) == jk) build_add(key_raw, a, b, e - 1);
+            const JoinSlot e = load_join_slot(p.jh_slots + h);
+            if (!e.row) return;
+            if (e.key == jk) build_add(key_raw, a, b, e.row - 1);
             h = (h + 1) & p.jh_mask;
         }
     }
@@ -943,8 +942,7 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st, bool n
         p.jk_domain = static_cast<unsigned long long>(j->key_max - j->key_min) + 1ULL;
         p.j_bitmap = j->bitmap;
         p.j_direct = j->direct;
-        p.jh_keys = j->h_keys;
-        p.jh_rows = j->h_rows;
+        p.jh_slots = j->h_slots;
         p.jh_mask = j->h_mask;
         if (j->kind == BQ_JOIN_BITMAP)
             for (int s = 0; s < N_SLOTS; ++s)

@@ -5,12 +5,16 @@
 // layout (src/exec/formatter.cpp, src/exec/execution.cpp:8-61: cells through std::to_string, DOUBLE with six decimals,
 // dictionary ids decoded through the base table's dictionary).  Header names follow get_output_schema
 // (src/logical/planner.cpp:167-270): alias, else the column name, else "expr".  The REPL is not reproduced.
+#include <thread>
+#include <cstdlib>
+#include <chrono>
 #include <algorithm>
 #include <iomanip>
 #include <iostream>
 #include <sstream>
 
 #include "bosql_operator.hpp"
+#include "gpu_device.hpp"
 #include "bosql_types.hpp"
 
 using namespace bosql;
@@ -170,15 +174,47 @@ int main(int argc, char** argv) {
         std::cerr << "bq_b200 runs one statement: bq_b200 [file.csv] --sql \"SELECT ...\" [--output-format markdown|csv]\n";
         return 1;
     }
+    // The CUDA context (driver initialisation, primary context, stream-ordered pool) takes longer than parsing a million-row
+    // file: it is created on a second thread while the CSV loads, and the statement waits for whichever finishes last.
+    // $BOSQL_TRACE=1 prints where the wall time went.
+    const bool trace = std::getenv("BOSQL_TRACE") && *std::getenv("BOSQL_TRACE") == '1';
+    const auto t0 = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    if (!std::getenv("CUDA_VISIBLE_DEVICES")) {
+        // one process uses one GPU: initialising the driver for the other seven of a full box costs about as much again
+        const char* dev = std::getenv("BOSQL_DEVICE") ? std::getenv("BOSQL_DEVICE") : (std::getenv("LOCAL_RANK") ? std::getenv("LOCAL_RANK") : "0");
+        setenv("CUDA_VISIBLE_DEVICES", dev, 1);
+        setenv("BOSQL_DEVICE", "0", 1);
+        unsetenv("LOCAL_RANK");
+    }
+    std::string context_error;
+    double context_s = 0.0;
+    std::thread warm([&] {
+        try {
+            gpu::context();
+        } catch (const std::exception& e) {
+            context_error = e.what();          // reported by the first operator that needs the device, as before
+        }
+        context_s = since();
+    });
     Catalog catalog;
+    double load_s = 0.0;
     try {
         auto [table, meta] = csv_file.empty() ? load_csv(std::cin) : load_csv(csv_file);
         table.name = "table";
         meta.name = "table";
         catalog.register_table(std::move(table), std::move(meta));
+        load_s = since();
     } catch (const std::exception& e) {
+        warm.join();
         std::cerr << "Error loading CSV" << (csv_file.empty() ? " from stdin" : "") << ": " << e.what() << "\n";
         return 1;
     }
-    return run(sql, catalog, format);
+    warm.join();
+    const double ready_s = since();
+    const int rc = run(sql, catalog, format);
+    if (trace)
+        std::cerr << "[bosql trace] csv load " << load_s << " s | cuda context (concurrent) " << context_s << " s | both ready " << ready_s
+                  << " s | statement " << since() - ready_s << " s | total " << since() << " s\n";
+    return rc;
 }

@@ -771,7 +771,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
     // $BOSQL_BITMAP_SLICE_MB sets the slice size (0 = always one fused probe).
     DevColPtr row_bits;
     if (join && bq_join_kind(join) == BQ_JOIN_BITMAP && p.rows > 0) {
-        size_t slice_bytes = 64u << 20;
+        size_t slice_bytes = 80u << 20;
         if (const char* e = std::getenv("BOSQL_BITMAP_SLICE_MB")) slice_bytes = static_cast<size_t>(std::atoll(e)) << 20;
         if (const char* e = std::getenv("BOSQL_BITMAP_SLICE_KB")) slice_bytes = static_cast<size_t>(std::atoll(e)) << 10;      // tests: force passes on small tables
         if (slice_bytes > 0 && bq_join_bytes(join) > slice_bytes + slice_bytes / 4) {
@@ -866,14 +866,17 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             resolve_stats(kc, force_device_stats);
             if (dist && kc.stats.measured) xch.minmax(kc.stats.min_key, kc.stats.max_key);
             Domain d{kc.stats.min_key, kc.stats.max_key};
-            const uint64_t est_rows = p.rows;
+            // every rank must choose the same table kind (the partial states are exchanged in the form the kind implies):
+            // across GPUs the row count that the choice weighs is the global one, not this shard's
+            uint64_t est_rows = p.rows;
+            if (dist && d.size() > 4096 && d.size() <= (1ULL << 26)) est_rows = static_cast<uint64_t>(xch.host_sum(static_cast<int64_t>(p.rows)));
             if (d.size() > 0 && d.size() <= (1ULL << 26) && d.size() <= 4 * est_rows + 4096) {
                 s.group_mode = BQ_GROUP_DENSE;
                 s.key_min = d.lo;
                 s.key_max = d.hi;
             } else {
                 s.group_mode = BQ_GROUP_HASH;
-                uint64_t hint = kc.stats.ndv ? kc.stats.ndv : std::min<uint64_t>(est_rows, d.size() ? d.size() : est_rows);
+                uint64_t hint = kc.stats.ndv ? kc.stats.ndv : std::min<uint64_t>(std::max<uint64_t>(p.rows, 1), d.size() ? d.size() : std::max<uint64_t>(p.rows, 1));
                 s.ndv_hint = static_cast<size_t>(hint);
             }
         };

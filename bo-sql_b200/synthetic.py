@@ -15,21 +15,22 @@ INT64, DOUBLE, STRING, DATE32 = 0, 1, 2, 3
 STATUS_DICT = ["COMPLETE", "PENDING", "CANCELLED", "RETURNED"]     # ids 0..3 (first-seen order)
 
 
-def orders_schema(n_orders, prefix="", div=100.0):
-    """o.order_id unique dense 1..N; o.status uniform over 4 ids; o.order_date 2024 days; o.total k/div."""
+def orders_schema(n_orders, prefix="", div=100.0, key_stride=1):
+    """o.order_id unique, 1 + row * key_stride (dense for stride 1; a large stride makes the domain sparse, so that a join
+    on it needs a real hash table); o.status uniform over 4 ids; o.order_date 2024 days; o.total k/div."""
     p = prefix
     return [
-        (p + "order_id", INT64, dict(dist=GEN_SEQ, lo=1)),
+        (p + "order_id", INT64, dict(dist=GEN_SEQ, lo=1, modulus=key_stride)),
         (p + "status", STRING, dict(dist=GEN_UNIFORM, lo=0, hi=3)),
         (p + "order_date", DATE32, dict(dist=GEN_DATE, base_year=2024, n_years=1)),
         (p + "total", DOUBLE, dict(dist=GEN_UNIFORM_DIV, lo=100, hi=100000, div=div)),
     ]
 
 
-def lineitem_schema(n_orders, n_sku=100000, prefix="l.", div=100.0, sku_type=INT64):
+def lineitem_schema(n_orders, n_sku=100000, prefix="l.", div=100.0, sku_type=INT64, key_stride=1):
     p = prefix
     return [
-        (p + "order_id", INT64, dict(dist=GEN_UNIFORM, lo=1, hi=n_orders)),
+        (p + "order_id", INT64, dict(dist=GEN_UNIFORM, lo=1, hi=n_orders, modulus=key_stride)),
         (p + "sku", sku_type, dict(dist=GEN_UNIFORM, lo=0, hi=n_sku - 1)),
         (p + "qty", INT64, dict(dist=GEN_UNIFORM, lo=1, hi=50)),
         (p + "price", DOUBLE, dict(dist=GEN_UNIFORM_DIV, lo=100, hi=10000, div=div)),

@@ -86,8 +86,8 @@ void bq_host_free(void* p);
  * value(row) = f(seed, stream, global_row) with a counter-based hash, so any slice can be regenerated
  * on the host (oracle/datagen.py restates the same arithmetic in numpy). */
 enum {
-    BQ_GEN_SEQ = 0,        /* lo + global_row                                   (unique dense keys)      */
-    BQ_GEN_UNIFORM = 1,    /* lo + hash % (hi-lo+1)                             (ints, ids)              */
+    BQ_GEN_SEQ = 0,        /* lo + global_row * stride                          (unique keys; dense when stride = 1) */
+    BQ_GEN_UNIFORM = 1,    /* lo + (hash % (hi-lo+1)) * stride                  (ints, ids; stride = modulus, default 1) */
     BQ_GEN_UNIFORM_DIV = 2,/* (double)(lo + hash % (hi-lo+1)) / div             (DOUBLE, k/div)          */
     BQ_GEN_DATE = 3,       /* base_year*10000 + 100*m + d, m in 1..12, d in 1..28, uniform over years    */
     BQ_GEN_TABLE = 4,      /* inverse-CDF lookup: smallest i with cdf[i] > hash>>11 (53-bit), value lo+i */
@@ -106,7 +106,7 @@ typedef struct bq_gen_spec {
     int32_t n_years;       /* BQ_GEN_DATE */
     const uint64_t* cdf;   /* BQ_GEN_TABLE: HOST pointer to n_cdf ascending 53-bit thresholds */
     size_t n_cdf;
-    uint64_t modulus;      /* BQ_GEN_HASHED */
+    uint64_t modulus;      /* BQ_GEN_HASHED; BQ_GEN_SEQ / BQ_GEN_UNIFORM: stride between values (0 = 1) */
     const uint64_t* starts; /* BQ_GEN_BUCKETS: HOST pointer to n_cdf + 1 ascending offsets */
 } bq_gen_spec;
 int bq_col_generate(bq_ctx* ctx, bq_col* col, const bq_gen_spec* spec, uint64_t global_row0);

@@ -45,10 +45,11 @@ def generate(typ, n, dist, seed, stream, lo=0, hi=0, div=1.0, base_year=2024, n_
     h = row_hash(seed, stream, rows)
     rng = U64((hi - lo + 1) & MASK) if dist not in (GEN_SEQ, GEN_DATE, GEN_TABLE, GEN_BUCKETS) else U64(1)
     f = None
+    stride = np.int64(modulus if modulus else 1)
     if dist == GEN_SEQ:
-        v = np.int64(lo) + rows.astype(np.int64)
+        v = np.int64(lo) + rows.astype(np.int64) * stride
     elif dist == GEN_UNIFORM:
-        v = np.int64(lo) + (h % rng).astype(np.int64)
+        v = np.int64(lo) + (h % rng).astype(np.int64) * stride
     elif dist == GEN_UNIFORM_DIV:
         v = np.int64(lo) + (h % rng).astype(np.int64)
         f = v.astype(np.float64) / np.float64(div)
