@@ -224,6 +224,7 @@ struct bq_join {
     bq::JoinSlot* h_slots = nullptr;      // HASH: open addressing, linear probing over 16-byte slots
     uint64_t h_mask = 0;
     size_t build_rows = 0;                // rows inserted
+    uint64_t bitmap_bits = 0;             // BITMAP: bits set when the build finished (== build_rows unless a key repeats)
     size_t bytes = 0;
 };
 

@@ -400,6 +400,16 @@ int bq_col_read(bq_ctx* ctx, const bq_col* col, size_t offset, size_t n, void* h
     });
 }
 
+int bq_col_read_async(bq_ctx* ctx, const bq_col* col, size_t offset, size_t n, void* host) {
+    return guarded([&] {
+        if (offset + n > col->n) throw std::runtime_error("bq_col_read out of range");
+        if (!n) return;
+        size_t w = width_of(col->type);
+        BQ_CUDA(cudaMemcpyAsync(host, static_cast<const char*>(col->ptr) + offset * w, n * w, cudaMemcpyDeviceToHost,
+                                ctx->stream));
+    });
+}
+
 void bq_col_free(bq_ctx* ctx, bq_col* col) {
     (void)ctx;          // the column remembers its owner; release is stream-ordered, no synchronisation
     free_col(col);

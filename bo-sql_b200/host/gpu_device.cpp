@@ -117,7 +117,10 @@ struct PinnedPool {
         for (auto& b : free_list) bq_host_free(b.p);
     }
     void* take(size_t& bytes) {
-        bytes = (bytes + (2u << 20) - 1) & ~static_cast<size_t>((2u << 20) - 1);
+        // small results (a few groups) share 64 KB buffers, large ones are rounded to 2 MB: either way the next query
+        // finds its buffer in the free list and no page is pinned on the query path
+        const size_t grain = bytes <= (64u << 10) ? (64u << 10) : (2u << 20);
+        bytes = (bytes + grain - 1) / grain * grain;
         size_t best = free_list.size();
         for (size_t i = 0; i < free_list.size(); ++i)
             if (free_list[i].bytes >= bytes && free_list[i].bytes <= 2 * bytes &&
@@ -149,11 +152,9 @@ PinnedPool& pinned_pool() {
 }  // namespace
 
 std::shared_ptr<void> host_buffer(size_t bytes) {
-    if (bytes < (256u << 10)) {
-        auto v = std::make_shared<std::vector<unsigned char>>(bytes);
-        return std::shared_ptr<void>(v, v->data());
-    }
-    size_t got = bytes;
+    // always pinned: a copy into pageable memory is staged by the driver and blocks the calling thread (0.17 ms measured for
+    // a 20-row result); pinned buffers let all columns of a result be enqueued and waited for once
+    size_t got = bytes ? bytes : 1;
     void* p = pinned_pool().take(got);
     return std::shared_ptr<void>(p, [got](void* q) { pinned_pool().give(q, got); });
 }

@@ -103,7 +103,7 @@ gpu::KeyStats stats_from_meta(const ColumnMeta& m, size_t table_rows) {
 template <typename T>
 std::shared_ptr<void> download(const DevColPtr& col, size_t rows) {
     std::shared_ptr<void> buf = gpu::host_buffer(rows * sizeof(T));
-    if (rows) check(bq_col_read(context(), col->h, 0, rows, buf.get()));
+    if (rows) check(bq_col_read_async(context(), col->h, 0, rows, buf.get()));      // page_out waits once for all columns
     return buf;
 }
 
@@ -131,6 +131,7 @@ bool Operator::page_out(ExecBatch& out) {
                 case TypeId::DATE32: host_cols_.push_back(download<int32_t>(result_->cols[c], result_->rows)); break;
             }
         }
+        check(bq_ctx_sync(context()));
         trace.mark("result to host");
         emit_offset_ = 0;
         paged_ = true;

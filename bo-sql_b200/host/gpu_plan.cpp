@@ -408,6 +408,26 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
     // on a condition only this rank sees (an empty shard still takes part in the collectives).
     Exchange& xch = exchange();
     const bool dist = xch.active;
+    // Row counts over all ranks, fetched with ONE host exchange the first time a decision needs them (every rank reaches
+    // that point together: the decisions that lead there depend only on catalog statistics and on these counts).  They
+    // stay valid when rows are shuffled between ranks later on - a shuffle moves rows, it does not change their number.
+    struct GlobalRows {
+        bool have = false;
+        uint64_t probe = 0, build = 0;
+        std::vector<int64_t> build_by_rank;
+    } global_rows;
+    auto fetch_global_rows = [&]() -> const GlobalRows& {
+        if (!global_rows.have) {
+            auto all = xch.host_gather({static_cast<int64_t>(p.rows), static_cast<int64_t>(p.build_rows)});
+            for (int r = 0; r < xch.world(); ++r) {
+                global_rows.probe += static_cast<uint64_t>(all[2 * static_cast<size_t>(r)]);
+                global_rows.build += static_cast<uint64_t>(all[2 * static_cast<size_t>(r) + 1]);
+                global_rows.build_by_rank.push_back(all[2 * static_cast<size_t>(r) + 1]);
+            }
+            global_rows.have = true;
+        }
+        return global_rows;
+    };
     auto not_fusable = [&](const char* why) -> DeviceRelationPtr {
         if (dist) throw std::runtime_error(std::string("not supported across GPUs: ") + why);
         return nullptr;
@@ -633,9 +653,8 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         bool dist_bitmap = false;
         uint64_t shuffled_global_build = 0;      // > 0: both sides were co-partitioned; the key domain is still the global one
         if (dist) {
-            auto rows_by_rank = xch.host_gather({static_cast<int64_t>(p.build_rows)});
-            uint64_t global_build = 0;
-            for (int64_t r : rows_by_rank) global_build += static_cast<uint64_t>(r);
+            const std::vector<int64_t> rows_by_rank = fetch_global_rows().build_by_rank;
+            const uint64_t global_build = global_rows.build;
             if (bk.type != TypeId::DOUBLE && !need_rows) {
                 resolve_stats(bk);
                 if (bk.stats.measured) xch.minmax(bk.stats.min_key, bk.stats.max_key);
@@ -666,7 +685,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
                     return b;
                 };
                 const uint64_t W = static_cast<uint64_t>(xch.world());
-                const uint64_t global_probe = static_cast<uint64_t>(xch.host_sum(static_cast<int64_t>(p.rows)));
+                const uint64_t global_probe = fetch_global_rows().probe;
                 const uint64_t broadcast_in = global_build * row_bytes(build_refs) * (W - 1) / W;                  // per rank
                 const uint64_t shuffle_out = (global_probe * row_bytes(probe_refs) + global_build * row_bytes(build_refs)) / W * (W - 1) / W;
                 const char* force = std::getenv("BOSQL_JOIN");
@@ -741,11 +760,20 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         check(bq_join_build(ctx, &js, &join));
         if (dist_bitmap) {
             // a duplicate key inside one shard makes that rank fall back to a hash table: agree before summing
-            if (!xch.host_all(bq_join_kind(join) == BQ_JOIN_BITMAP))
+            // (kind, rows inserted) of every rank in one exchange
+            uint64_t inserted = 0;
+            bool all_bitmaps = true;
+            {
+                auto all = xch.host_gather({bq_join_kind(join) == BQ_JOIN_BITMAP ? 1 : 0, static_cast<int64_t>(bq_join_build_rows(join))});
+                for (int r = 0; r < xch.world(); ++r) {
+                    all_bitmaps = all_bitmaps && all[2 * static_cast<size_t>(r)] != 0;
+                    inserted += static_cast<uint64_t>(all[2 * static_cast<size_t>(r) + 1]);
+                }
+            }
+            if (!all_bitmaps)
                 throw std::runtime_error("join key statistics claim unique keys (ndv == row count) but a shard holds duplicates");
             size_t words = 0;
             void* bits = bq_join_bitmap_ptr(join, &words);
-            const uint64_t inserted = static_cast<uint64_t>(xch.host_sum(static_cast<int64_t>(bq_join_build_rows(join))));
             xch.sum_words(bits, words);
             // The sum of the ranks' words equals their OR only while no key was inserted by two ranks (statistics that call
             // the key unique may be stale, or a dimension table may be partly replicated): a doubly set bit would carry into
@@ -869,7 +897,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             // every rank must choose the same table kind (the partial states are exchanged in the form the kind implies):
             // across GPUs the row count that the choice weighs is the global one, not this shard's
             uint64_t est_rows = p.rows;
-            if (dist && d.size() > 4096 && d.size() <= (1ULL << 26)) est_rows = static_cast<uint64_t>(xch.host_sum(static_cast<int64_t>(p.rows)));
+            if (dist && d.size() > 4096 && d.size() <= (1ULL << 26)) est_rows = fetch_global_rows().probe;
             if (d.size() > 0 && d.size() <= (1ULL << 26) && d.size() <= 4 * est_rows + 4096) {
                 s.group_mode = BQ_GROUP_DENSE;
                 s.key_min = d.lo;
@@ -897,8 +925,8 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             if (!groups) {
                 groups = d.size();
                 if (groups == 0 || groups * 32 > (96ull << 20)) {
-                    const uint64_t global_rows = static_cast<uint64_t>(xch.host_sum(static_cast<int64_t>(p.rows)));
-                    groups = groups ? std::min(groups, global_rows) : global_rows;
+                    const uint64_t all_rows = fetch_global_rows().probe;
+                    groups = groups ? std::min(groups, all_rows) : all_rows;
                 }
             }
             if (groups * 32 > (96ull << 20)) {

@@ -62,6 +62,9 @@ int bq_col_upload(bq_ctx* ctx, int type, const void* host, size_t n, bq_col** ou
 int bq_col_write(bq_ctx* ctx, bq_col* col, size_t offset, const void* host, size_t n);
 /* synchronous D2H of rows [offset, offset+n) */
 int bq_col_read(bq_ctx* ctx, const bq_col* col, size_t offset, size_t n, void* host);
+/* the same copy enqueued on the context's stream without waiting (host must be pinned: bq_host_alloc); the bytes are there
+ * after the next bq_ctx_sync - several result columns cost one synchronisation instead of one each */
+int bq_col_read_async(bq_ctx* ctx, const bq_col* col, size_t offset, size_t n, void* host);
 void bq_col_free(bq_ctx* ctx, bq_col* col);
 /* non-owning column over device memory the caller manages (e.g. a buffer filled by an NCCL collective) */
 int bq_col_wrap(bq_ctx* ctx, int type, void* device_ptr, size_t n, bq_col** out);
@@ -219,9 +222,11 @@ int bq_scan_partial(bq_ctx* ctx, const bq_scan_spec* spec, bq_rel** out);
 int bq_agg_finish(bq_ctx* ctx, const bq_rel* const* parts, int n_parts, int has_key, int key_type,
                   const bq_agg_out* outs, int n_out, bq_rel** out);
 
-/* The same exchange for DENSE / global states without compaction: the state stays on the device as it is (count | sum0 |
- * sum1 arrays over the key domain + the error word), ranks all-gather the raw blocks - same size on every rank, because
- * the domain comes from catalog statistics - and ONE launch folds them in rank order.  bq_agg_state_dense returns a NULL
+/* The same exchange for DENSE / global states without compaction: the state stays on the device as it is (a 16-byte
+ * header with the error word, then the sum0 | count | sum1 arrays over the key domain, of which only the prefix in use is
+ * exchanged: 8 bytes per slot for a SUM-only state, whose untouched slots are marked by -0.0), ranks all-gather the raw
+ * blocks - same size on every rank, because the domain comes from catalog statistics and every rank runs the same plan -
+ * and ONE launch folds them in rank order.  bq_agg_state_dense returns a NULL
  * pointer for a hash-table state (use bq_scan_partial / bq_agg_finish for those). */
 typedef struct bq_agg_state bq_agg_state;
 int bq_scan_state(bq_ctx* ctx, const bq_scan_spec* spec, bq_agg_state** out);

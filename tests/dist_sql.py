@@ -75,7 +75,7 @@ class _Log(list):
     def append(self, item):
         super().append(item)
         if self.f:
-            self.f.write(f"{item[0]}: {item[1][:300]}\n")
+            self.f.write(f"{item[0]}: {item[1][-500:]}\n")
             self.f.flush()
 
 
