@@ -542,4 +542,4 @@ def wrap_context(handle) -> "Context":
     return c
 
 
-from .engine import PARSE_BETWEEN, PARSE_DECIMALS, Engine, exec_lib  # noqa: E402,F401
+from .engine import PARSE_ANY_CASE, PARSE_BETWEEN, PARSE_DECIMALS, PARSE_NEGATIVE, Engine, exec_lib  # noqa: E402,F401

@@ -161,65 +161,81 @@ __global__ void __launch_bounds__(kBlock) k_join_build(const __grid_constant__ B
     if (lane == 0 && local) atomicAdd(p.n_inserted, local);
 }
 
-// Bitmap build for the common shape (INT64 key, at most one predicate column, no mask; row_begin a multiple of 4).
-// A lane owns FOUR CONSECUTIVE rows of a 128-row chunk, so a chunk is two 128-bit key loads and one 128-bit (4-byte
-// predicate column) or two 128-bit (8-byte) predicate loads per lane, all issued before the first use.  The four bits of a
-// lane almost always fall into one bitmap word; lanes whose neighbours hit the same word fold their bits with five
+// Bitmap build for the common shape (INT64 key, at most one predicate column, no mask; row_begin a multiple of 8).
+// A lane owns EIGHT CONSECUTIVE rows of a 256-row chunk, so a chunk is four 128-bit key loads and two (4-byte predicate
+// column) or four (8-byte) 128-bit predicate loads per lane, all issued before the first use.  The eight bits of a lane
+// almost always fall into one bitmap word; lanes whose neighbours hit the same word fold their bits with five
 // shuffle steps (a segmented OR: folding is only ever done between lanes that name the SAME word, so it is correct for
 // any key order and optimal for clustered keys such as o.order_id = row + 1), and only the first lane of each run issues
-// the reduction: 4 red.or per 128 sequential rows instead of one per inserted row.  Nothing comes back from the L2, so no
+// the reduction: 8 red.or per 256 sequential rows instead of one per inserted row.  Nothing comes back from the L2, so no
 // lane waits on it; duplicates are found afterwards by popcount (build_kind).
 // PW: width of the predicate column in bytes (0 = no predicate).
 template <int PW>
 __global__ void __launch_bounds__(kBlock) k_bitmap_build4(const __grid_constant__ BuildParams p) {
+    constexpr int R = 8;                       // consecutive rows per lane: 64 B of keys + 32 / 64 B of predicate values in flight
     unsigned long long local = 0;
     const size_t n = p.row_end - p.row_begin;
     const int lane = threadIdx.x & 31;
     const size_t warps = static_cast<size_t>(gridDim.x) * (kBlock / 32);
     const size_t warp = static_cast<size_t>(blockIdx.x) * (kBlock / 32) + (threadIdx.x >> 5);
-    const size_t n_chunks = (n + 127) / 128;
+    const size_t n_chunks = (n + 32 * R - 1) / (32 * R);
     const DSlot& s0 = p.s[0];
     bool out_of_domain = false;
+    auto i64_of = [](int lo, int hi) { return static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(hi)) << 32) | static_cast<unsigned>(lo)); };
     for (size_t c = warp; c < n_chunks; c += warps) {
-        const size_t t0 = c * 128 + 4 * static_cast<size_t>(lane);       // first of this lane's four rows, relative to row_begin
+        const size_t t0 = c * (32 * R) + R * static_cast<size_t>(lane);       // first of this lane's rows, relative to row_begin
         const size_t i0 = p.row_begin + t0;
-        long long k[4];
-        long long pv[4];
-        bool ok[4];
-        if (t0 + 4 <= n) {
+        long long k[R];
+        long long pv[R];
+        bool ok[R];
+        if (t0 + R <= n) {
             const int4* kp = reinterpret_cast<const int4*>(static_cast<const long long*>(p.key) + i0);
-            const int4 a = ldg_stream(kp), b = ldg_stream(kp + 1);
-            k[0] = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(a.y)) << 32) | static_cast<unsigned>(a.x));
-            k[1] = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(a.w)) << 32) | static_cast<unsigned>(a.z));
-            k[2] = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(b.y)) << 32) | static_cast<unsigned>(b.x));
-            k[3] = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(b.w)) << 32) | static_cast<unsigned>(b.z));
-            if (PW == 4) {
-                const int4 q = ldg_stream(reinterpret_cast<const int4*>(static_cast<const int*>(s0.ptr) + i0));
-                const int v[4] = {q.x, q.y, q.z, q.w};
+            int4 kv[R / 2];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) pv[r] = s0.kind == BQ_STRING ? static_cast<long long>(static_cast<unsigned>(v[r])) : static_cast<long long>(v[r]);
+            for (int v = 0; v < R / 2; ++v) kv[v] = ldg_stream(kp + v);
+            if (PW == 4) {
+                const int4* qp = reinterpret_cast<const int4*>(static_cast<const int*>(s0.ptr) + i0);
+                int4 q[R / 4];
+#pragma unroll
+                for (int v = 0; v < R / 4; ++v) q[v] = ldg_stream(qp + v);
+#pragma unroll
+                for (int v = 0; v < R / 4; ++v) {
+                    const int w4[4] = {q[v].x, q[v].y, q[v].z, q[v].w};
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+                        pv[4 * v + r] = s0.kind == BQ_STRING ? static_cast<long long>(static_cast<unsigned>(w4[r])) : static_cast<long long>(w4[r]);
+                }
             } else if (PW == 8) {
                 const int4* qp = reinterpret_cast<const int4*>(static_cast<const long long*>(s0.ptr) + i0);
-                const int4 qa = ldg_stream(qp), qb = ldg_stream(qp + 1);
-                pv[0] = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(qa.y)) << 32) | static_cast<unsigned>(qa.x));
-                pv[1] = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(qa.w)) << 32) | static_cast<unsigned>(qa.z));
-                pv[2] = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(qb.y)) << 32) | static_cast<unsigned>(qb.x));
-                pv[3] = static_cast<long long>((static_cast<unsigned long long>(static_cast<unsigned>(qb.w)) << 32) | static_cast<unsigned>(qb.z));
+                int4 q[R / 2];
+#pragma unroll
+                for (int v = 0; v < R / 2; ++v) q[v] = ldg_stream(qp + v);
+#pragma unroll
+                for (int v = 0; v < R / 2; ++v) {
+                    pv[2 * v] = i64_of(q[v].x, q[v].y);
+                    pv[2 * v + 1] = i64_of(q[v].z, q[v].w);
+                }
             }
 #pragma unroll
-            for (int r = 0; r < 4; ++r) ok[r] = true;
+            for (int v = 0; v < R / 2; ++v) {
+                k[2 * v] = i64_of(kv[v].x, kv[v].y);
+                k[2 * v + 1] = i64_of(kv[v].z, kv[v].w);
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) ok[r] = true;
         } else {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
+            for (int r = 0; r < R; ++r) {
                 ok[r] = t0 + r < n;
                 const size_t i = ok[r] ? i0 + r : p.row_begin;
                 k[r] = __ldg(static_cast<const long long*>(p.key) + i);
                 if (PW) pv[r] = load_raw(s0.ptr, s0.kind, i);
             }
         }
-        unsigned w[4], b[4];
+        unsigned w[R], b[R];
+        bool one_word = true;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < R; ++r) {
             if (PW) ok[r] = ok[r] && fast_pass(s0, pv[r]);
             const unsigned long long idx = static_cast<unsigned long long>(k[r] - p.key_min);
             if (ok[r] && idx >= p.domain) {
@@ -229,16 +245,17 @@ __global__ void __launch_bounds__(kBlock) k_bitmap_build4(const __grid_constant_
             w[r] = static_cast<unsigned>(idx >> 5);
             b[r] = ok[r] ? 1u << (idx & 31) : 0u;
             local += ok[r] ? 1 : 0;
+            one_word = one_word && w[r] == w[0];
         }
         // fold inside the lane, then across lanes that name the same word
-        const bool one_word = w[0] == w[1] && w[0] == w[2] && w[0] == w[3];
         unsigned W = 0xF0000000u | static_cast<unsigned>(lane), B = 0;      // a word index no bitmap has (domain <= 2^32 keys)
         if (one_word) {
             W = w[0];
-            B = b[0] | b[1] | b[2] | b[3];
+#pragma unroll
+            for (int r = 0; r < R; ++r) B |= b[r];
         } else {
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
+            for (int r = 0; r < R; ++r)
                 if (b[r]) atomicOr(p.bitmap + w[r], b[r]);
         }
 #pragma unroll
@@ -495,7 +512,7 @@ static int build_kind(bq_ctx* ctx, const bq_join_spec* spec, int kind, bq_join* 
         if (lean && n_pred == 0) k_join_build<KIND, BQ_INT64, 0><<<grid, kBlock, 0, ctx->stream>>>(p);         \
         else if (lean) k_join_build<KIND, BQ_INT64, 1><<<grid, kBlock, 0, ctx->stream>>>(p);                   \
         else k_join_build<KIND, -1, -1><<<grid, kBlock, 0, ctx->stream>>>(p);
-        if (kind == BQ_JOIN_BITMAP && lean && p.row_begin % 4 == 0) {
+        if (kind == BQ_JOIN_BITMAP && lean && p.row_begin % 8 == 0) {
             if (pw == 0) k_bitmap_build4<0><<<grid, kBlock, 0, ctx->stream>>>(p);
             else if (pw == 4) k_bitmap_build4<4><<<grid, kBlock, 0, ctx->stream>>>(p);
             else k_bitmap_build4<8><<<grid, kBlock, 0, ctx->stream>>>(p);

@@ -14,7 +14,7 @@ import numpy as np
 
 from . import EXEC_LIB, NP_DTYPES, BqError, kernel_lib
 
-PARSE_BETWEEN, PARSE_DECIMALS = 1, 2
+PARSE_BETWEEN, PARSE_DECIMALS, PARSE_NEGATIVE, PARSE_ANY_CASE = 1, 2, 4, 8
 
 _xlib = None
 

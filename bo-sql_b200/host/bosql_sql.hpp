@@ -82,6 +82,9 @@ struct SelectStmt {
 struct ParseOptions {
     bool between = false;           // col BETWEEN a AND b  ->  (col >= a) AND (col <= b)
     bool decimal_literals = false;  // 1.5 -> LITERAL_DOUBLE
+    bool negative_literals = false; // -5 / -1.5 where an operand is expected -> a literal (the reference lexes '-' as MINUS only
+                                    // and its primary() rejects it, src/parser/parser.cpp:278-331)
+    bool keywords_any_case = false; // select / Select / SELECT (the reference matches keywords exactly, :82-103)
 };
 
 SelectStmt parse_sql(const std::string& sql);

@@ -237,5 +237,10 @@ public:
 // ndv recorded in the TableMeta.
 std::pair<Table, TableMeta> load_csv(std::istream& stream);
 std::pair<Table, TableMeta> load_csv(const std::string& filename);
+// The same loader appending to a dictionary that other tables already use: string ids stay comparable
+// across tables, so a join whose two sides both carry STRING columns decodes correctly - the reference gives every table a
+// dictionary of its own and HashJoin keeps only the left one (src/exec/operator.cpp:694-704).
+std::pair<Table, TableMeta> load_csv(std::istream& stream, std::shared_ptr<Dictionary> shared_dict);
+std::pair<Table, TableMeta> load_csv(const std::string& filename, std::shared_ptr<Dictionary> shared_dict);
 
 }  // namespace bosql

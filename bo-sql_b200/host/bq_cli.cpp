@@ -92,9 +92,9 @@ void print_markdown(const std::vector<std::string>& headers, const std::vector<s
     for (const auto& r : rows) line(r);
 }
 
-int run(const std::string& sql, const Catalog& catalog, const std::string& format) {
+int run(const std::string& sql, const Catalog& catalog, const std::string& format, const ParseOptions& parse_opts) {
     try {
-        SelectStmt stmt = parse_sql(sql);
+        SelectStmt stmt = parse_sql(sql, parse_opts);
         LogicalPlanner planner;
         auto logical = planner.build_logical_plan(stmt);
         auto root = build_physical_plan(logical.get(), catalog);
@@ -142,8 +142,23 @@ int run(const std::string& sql, const Catalog& catalog, const std::string& forma
 int main(int argc, char** argv) {
     std::vector<std::string> args(argv + 1, argv + argc);
     std::string csv_file, sql, format = "markdown";
+    std::vector<std::pair<std::string, std::string>> named_tables;      // --table name=file.csv (repeatable): LOAD TABLE without a REPL
+    ParseOptions parse_opts;                                             // --extended-sql: BETWEEN, 1.5, -5, keywords in any case
     bool have_sql = false;
     for (size_t i = 0; i < args.size(); ++i) {
+        if (args[i] == "--extended-sql") {
+            parse_opts.between = parse_opts.decimal_literals = parse_opts.negative_literals = parse_opts.keywords_any_case = true;
+            continue;
+        }
+        if (args[i] == "--table") {
+            if (i + 1 >= args.size() || args[i + 1].find('=') == std::string::npos) {
+                std::cerr << "--table requires name=file.csv\n";
+                return 1;
+            }
+            const std::string& spec = args[++i];
+            named_tables.emplace_back(spec.substr(0, spec.find('=')), spec.substr(spec.find('=') + 1));
+            continue;
+        }
         if (args[i] == "--sql" || args[i] == "--output-format") {
             if (i + 1 >= args.size()) {
                 std::cerr << args[i] << " requires an argument\n";
@@ -171,7 +186,8 @@ int main(int argc, char** argv) {
         return 1;
     }
     if (!have_sql) {
-        std::cerr << "bq_b200 runs one statement: bq_b200 [file.csv] --sql \"SELECT ...\" [--output-format markdown|csv]\n";
+        std::cerr << "bq_b200 runs one statement: bq_b200 [file.csv] [--table name=file.csv ...] --sql \"SELECT ...\" "
+                     "[--extended-sql] [--output-format markdown|csv]\n";
         return 1;
     }
     // The CUDA context (driver initialisation, primary context, stream-ordered pool) takes longer than parsing a million-row
@@ -200,10 +216,23 @@ int main(int argc, char** argv) {
     Catalog catalog;
     double load_s = 0.0;
     try {
-        auto [table, meta] = csv_file.empty() ? load_csv(std::cin) : load_csv(csv_file);
-        table.name = "table";
-        meta.name = "table";
-        catalog.register_table(std::move(table), std::move(meta));
+        // All tables of one invocation share ONE dictionary, so string ids compare across tables.  With a
+        // single table this is exactly the reference's per-table dictionary.
+        std::shared_ptr<Dictionary> dict;
+        if (!csv_file.empty() || named_tables.empty()) {
+            auto [table, meta] = csv_file.empty() ? load_csv(std::cin) : load_csv(csv_file);
+            dict = table.dict;
+            table.name = "table";                 // src/cli/main.cpp:105
+            meta.name = "table";
+            catalog.register_table(std::move(table), std::move(meta));
+        }
+        for (const auto& [name, path] : named_tables) {
+            auto [table, meta] = load_csv(path, dict);
+            dict = table.dict;
+            table.name = name;                    // LOAD TABLE <name> FROM '<file>' (src/cli/main.cpp:152-168)
+            meta.name = name;
+            catalog.register_table(std::move(table), std::move(meta));
+        }
         load_s = since();
     } catch (const std::exception& e) {
         warm.join();
@@ -212,7 +241,7 @@ int main(int argc, char** argv) {
     }
     warm.join();
     const double ready_s = since();
-    const int rc = run(sql, catalog, format);
+    const int rc = run(sql, catalog, format, parse_opts);
     if (trace)
         std::cerr << "[bosql trace] csv load " << load_s << " s | cuda context (concurrent) " << context_s << " s | both ready " << ready_s
                   << " s | statement " << since() - ready_s << " s | total " << since() << " s\n";

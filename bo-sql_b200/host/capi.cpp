@@ -63,6 +63,8 @@ ParseOptions parse_options(unsigned flags) {
     ParseOptions o;
     o.between = flags & 1u;
     o.decimal_literals = flags & 2u;
+    o.negative_literals = flags & 4u;
+    o.keywords_any_case = flags & 8u;
     return o;
 }
 

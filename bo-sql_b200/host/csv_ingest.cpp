@@ -115,7 +115,9 @@ bool stod_like(const char* s, double& out) {
 
 }  // namespace
 
-std::pair<Table, TableMeta> load_csv(std::istream& stream) {
+std::pair<Table, TableMeta> load_csv(std::istream& stream) { return load_csv(stream, nullptr); }
+
+std::pair<Table, TableMeta> load_csv(std::istream& stream, std::shared_ptr<Dictionary> shared_dict) {
     std::string buf;
     {
         std::ostringstream all;                       // one bulk copy through the stream buffer (not a per-character iterator)
@@ -123,7 +125,7 @@ std::pair<Table, TableMeta> load_csv(std::istream& stream) {
         buf = std::move(all).str();
     }
     Table table;
-    table.dict = std::make_shared<Dictionary>();
+    table.dict = shared_dict ? std::move(shared_dict) : std::make_shared<Dictionary>();
     std::vector<ColumnMeta> metas;
 
     // ---- split into lines and cells in place ----------------------------------------------------------------
@@ -271,10 +273,12 @@ std::pair<Table, TableMeta> load_csv(std::istream& stream) {
     return {std::move(table), std::move(table_meta)};
 }
 
-std::pair<Table, TableMeta> load_csv(const std::string& filename) {
+std::pair<Table, TableMeta> load_csv(const std::string& filename) { return load_csv(filename, nullptr); }
+
+std::pair<Table, TableMeta> load_csv(const std::string& filename, std::shared_ptr<Dictionary> shared_dict) {
     std::ifstream file(filename, std::ios::binary);
     if (!file.is_open()) throw std::runtime_error("Cannot open file: " + filename);
-    return load_csv(file);
+    return load_csv(file, std::move(shared_dict));
 }
 
 }  // namespace bosql

@@ -46,6 +46,9 @@ struct DeviceRelation {
     // Across GPUs: false = these are the rows THIS rank produced from its shard (scan, selection, join, a GROUP BY whose
     // groups stay with their owner); true = every rank holds the same complete relation (merged aggregates).
     bool replicated = false;
+    // The rows are in ascending order of column 0 and column 0 holds distinct values (the groups of a dense aggregate
+    // state are emitted in key order): an ORDER BY on that column alone has nothing left to do.
+    bool ordered_by_first = false;
 };
 using DeviceRelationPtr = std::shared_ptr<DeviceRelation>;
 DeviceRelationPtr relation_from(bq_rel* rel);     // consumes the bq_rel shell, keeps its columns

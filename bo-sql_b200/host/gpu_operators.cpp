@@ -956,6 +956,13 @@ DeviceRelationPtr OrderBy::sort_relation(const DeviceRelationPtr& in, int64_t li
         asc.push_back(k.asc ? 1 : 0);
     }
     if (in->rows == 0 || limit == 0) return gpu::empty_relation(types_);
+    // Groups of a dense aggregate arrive in key order with distinct keys: ORDER BY <that key> [ASC] is the input itself
+    // (the reference sorts regardless, src/exec/operator.cpp:1115; its result is this order - distinct keys leave no ties)
+    if (in->ordered_by_first && key_cols.size() == 1 && key_cols[0] == 0 && asc[0] == 1 && rel_cols.size() == in->cols.size() &&
+        (limit < 0 || static_cast<size_t>(limit) >= in->rows)) {
+        auto same = std::make_shared<DeviceRelation>(*in);
+        return same;
+    }
     std::vector<bq_col*> hs;
     for (auto& c : rel_cols) hs.push_back(c->h);
     bq_rel* shell = nullptr;

@@ -813,6 +813,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
 
     // ---- run the passes ---------------------------------------------------------------------------------------------------
     bool groups_stay_sharded = false;
+    bool groups_in_key_order = true;
     std::vector<DeviceRelationPtr> pass_results;
     std::vector<std::vector<size_t>> pass_aggs;      // which aggregates each pass produced, in column order
     for (const Pass& ps : passes) {
@@ -1101,6 +1102,10 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             r = relation_from(sorted);
         }
         trace.mark("aggregate (+ exchange)");
+        // dense states (local, or all-gathered and folded) emit their groups in ascending key order; so does the re-sort above
+        const bool dense_emit = s.group_mode == BQ_GROUP_DENSE && !shuffled &&
+                                (!dist || static_cast<uint64_t>(s.key_max - s.key_min) < (1ull << 18));
+        if (!(dense_emit || (passes.size() > 1 && key_col >= 0))) groups_in_key_order = false;
         pass_results.push_back(r);
         pass_aggs.push_back(agg_index);
     }
@@ -1108,6 +1113,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
     // ---- stitch: [keys] then aggregates in declaration order ----------------------------------------------------
     auto out = std::make_shared<DeviceRelation>();
     out->replicated = dist && !groups_stay_sharded;
+    out->ordered_by_first = key_col >= 0 && packed_domains.empty() && groups_in_key_order;
     out->rows = pass_results.front()->rows;
     for (auto& pr : pass_results)
         if (pr->rows != out->rows) throw std::runtime_error("internal: aggregate passes disagree on the group count");

@@ -3,6 +3,7 @@
 // Behavioural contract = the reference's src/parser/parser.cpp and src/logical/planner.cpp (file:line cited per
 // function); written from that behaviour, not from its text.  It feeds the GPU operators the same Expr trees and
 // plan shapes the reference feeds its CPU operators, so one SQL string drives both in the differential tests.
+#include <algorithm>
 #include <cctype>
 #include <charconv>
 #include <set>
@@ -97,8 +98,10 @@ struct Token {
     std::string text;
 };
 
-Tok keyword_or_identifier(const std::string& s) {
-    // exact, case-sensitive (src/parser/parser.cpp:82-103)
+Tok keyword_or_identifier(const std::string& word, bool any_case) {
+    // exact, case-sensitive (src/parser/parser.cpp:82-103) unless the extension flag folds the word to upper case first
+    std::string s = word;
+    if (any_case) std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return static_cast<char>(std::toupper(c)); });
     static const std::pair<const char*, Tok> kw[] = {
         {"SELECT", Tok::SELECT}, {"FROM", Tok::FROM}, {"WHERE", Tok::WHERE}, {"INNER", Tok::INNER}, {"JOIN", Tok::JOIN},
         {"ON", Tok::ON}, {"GROUP", Tok::GROUP}, {"BY", Tok::BY}, {"HAVING", Tok::HAVING}, {"ORDER", Tok::ORDER},
@@ -122,7 +125,7 @@ std::vector<Token> lex(const std::string& sql, const ParseOptions& opts) {
             size_t j = i + 1;
             while (j < n && (std::isalnum(uc(j)) || sql[j] == '_')) ++j;
             std::string word = sql.substr(i, j - i);
-            out.push_back({keyword_or_identifier(word), word});
+            out.push_back({keyword_or_identifier(word, opts.keywords_any_case), word});
             i = j;
             continue;
         }
@@ -281,7 +284,7 @@ private:
                                                       {Tok::LE, BinaryOp::LE}, {Tok::GT, BinaryOp::GT}, {Tok::GE, BinaryOp::GE}};
         for (const auto& [tok, op] : ops)
             if (accept(tok)) return binary(op, std::move(l), sum());
-        if (opts_.between && at(Tok::IDENTIFIER) && cur().text == "BETWEEN") {      // extension, off by default
+        if (opts_.between && at(Tok::IDENTIFIER) && is_word(cur().text, "BETWEEN")) {      // extension, off by default
             ++pos_;
             auto lo = sum();
             expect(Tok::AND);
@@ -310,7 +313,22 @@ private:
         }
         return l;
     }
+    bool is_word(const std::string& text, const char* upper) const {
+        if (!opts_.keywords_any_case) return text == upper;
+        std::string s = text;
+        std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return static_cast<char>(std::toupper(c)); });
+        return s == upper;
+    }
     std::unique_ptr<Expr> factor() {
+        // extension, off by default: a minus sign directly in front of a number where an operand is expected is part of the literal
+        if (opts_.negative_literals && at(Tok::MINUS) && pos_ + 1 < toks_.size() &&
+            (toks_[pos_ + 1].type == Tok::NUMBER || toks_[pos_ + 1].type == Tok::DECIMAL)) {
+            ++pos_;
+            auto e = primary();
+            if (e->type == ExprType::LITERAL_INT) e->i64_val = -e->i64_val;
+            else e->f64_val = -e->f64_val;
+            return e;
+        }
         if (accept(Tok::LPAREN)) {
             auto e = expr();
             expect(Tok::RPAREN);
@@ -327,6 +345,8 @@ private:
         switch (t.type) {
             case Tok::IDENTIFIER: case Tok::SUM: case Tok::COUNT: case Tok::AVG: {
                 std::string name = t.text;
+                if (opts_.keywords_any_case && t.type != Tok::IDENTIFIER)      // Sum(...) / sum(...) name the aggregate SUM
+                    std::transform(name.begin(), name.end(), name.begin(), [](unsigned char c) { return static_cast<char>(std::toupper(c)); });
                 if (at(Tok::IDENTIFIER) && cur().text == ".") {     // "l" "." "sku" -> the literal name "l.sku"
                     ++pos_;
                     name += "." + cur().text;

@@ -71,7 +71,8 @@ const char* bqx_catalog_dict_get(bqx_catalog* c, const char* name, uint32_t id);
  * end-to-end leg pays the host->device copy inside every timed step this way). */
 int bqx_catalog_evict_device(bqx_catalog* c, const char* table);
 
-/* extensions of the SQL front end, off by default: bit 0 BETWEEN, bit 1 decimal literals */
+/* extensions of the SQL front end, off by default: bit 0 BETWEEN, bit 1 decimal literals,
+ * bit 2 negative literals (-5, -1.5), bit 3 keywords in any case */
 int bqx_plan_create(bqx_catalog* c, const char* sql, unsigned parse_flags, bqx_plan** out);
 void bqx_plan_destroy(bqx_plan* p);
 size_t bqx_plan_columns(const bqx_plan* p);

@@ -45,6 +45,10 @@ def main():
             times.append(time.perf_counter() - t0)
             assert r.returncode == 0 and r.stdout.count("\n") > 5, r.stderr[-500:]
         texts[name] = r.stdout
+        if name == "ours":      # where the wall time went: load / CUDA context (concurrent) / statement, printed by the binary itself
+            tr = subprocess.run([binary, path, "--sql", SQL, "--output-format", "csv"], capture_output=True, text=True, timeout=300,
+                                env=dict(os.environ, BOSQL_TRACE="1"))
+            out["ours_phases"] = [ln for ln in tr.stderr.splitlines() if "bosql trace" in ln][-1:]
         out[name + "_wall_s"] = statistics.median(times)
         out[name + "_wall_all"] = times
     if len(texts) == 2:

@@ -93,3 +93,56 @@ def test_cli_argument_errors(orders_csv):
         r = subprocess.run([OURS] + args, capture_output=True, text=True, timeout=60)
         q = subprocess.run([REF] + args, capture_output=True, text=True, timeout=60)
         assert r.returncode == q.returncode == 1, (args, r.returncode, q.returncode)
+
+
+def _rows(markdown):
+    """cells of a markdown table (both command lines print one), header and rule dropped"""
+    lines = [ln for ln in markdown.splitlines() if ln.startswith("|")]
+    return [[c.strip() for c in ln.strip("|").split("|")] for ln in lines[2:]]
+
+
+def test_cli_two_tables_join_like_the_reference_repl(tmp_path):
+    """the README's Q2 through the command line.  The reference can only do this from its REPL
+    (LOAD TABLE ... twice, src/cli/main.cpp:152-168); ours takes --table name=file.csv.  lineitem has no STRING column, so
+    the reference's left-else-right dictionary choice (operator.cpp:694-704) is well defined and both must agree."""
+    from oracle import datagen
+    n_o, n_l = 3000, 20000
+    o = {name: arr for name, _, arr in datagen.host_table(datagen.orders_schema(n_o, prefix="o."), n_o, seed=11)}
+    li = {name: arr for name, _, arr in datagen.host_table(datagen.lineitem_schema(n_o, 50), n_l, seed=12)}
+    op, lp = tmp_path / "orders.csv", tmp_path / "lineitem.csv"
+    with open(op, "w") as f:
+        f.write("o.order_id,o.status,o.total\n")
+        for i in range(n_o):
+            f.write(f"{int(o['o.order_id'][i])},{datagen.STATUS_DICT[int(o['o.status'][i])]},{float(o['o.total'][i])!r}\n")
+    with open(lp, "w") as f:
+        f.write("l.order_id,l.sku,l.qty,l.price\n")
+        for i in range(n_l):
+            f.write(f"{int(li['l.order_id'][i])},{int(li['l.sku'][i])},{int(li['l.qty'][i])},{float(li['l.price'][i])!r}\n")
+    sql = ("SELECT l.sku, SUM(l.qty * l.price) AS rev FROM lineitem l JOIN orders o ON l.order_id = o.order_id "
+           "WHERE o.status = 'COMPLETE' GROUP BY l.sku ORDER BY rev DESC LIMIT 20")
+    r = subprocess.run([OURS, "--table", f"lineitem={lp}", "--table", f"orders={op}", "--sql", sql], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    ours = _rows(r.stdout)
+    assert len(ours) == 20
+    if not os.path.exists(REF):
+        pytest.skip("oracle/_ref/bq_ref was not built")
+    repl = f"LOAD TABLE lineitem FROM '{lp}'\nLOAD TABLE orders FROM '{op}'\n{sql}\nEXIT\n"
+    q = subprocess.run([REF], input=repl, capture_output=True, text=True, timeout=120)
+    ref = _rows(q.stdout)
+    assert len(ref) == 20, q.stdout[-500:]
+    for a, b in zip(ours, ref):
+        assert a[0] == b[0] and abs(float(a[1]) - float(b[1])) <= 2e-6 + 1e-12 * abs(float(b[1])), (a, b)
+
+
+def test_cli_shared_dictionary_and_extended_sql(tmp_path):
+    """Both sides of the join carry STRING columns: with one dictionary for all tables of an invocation the right side's
+    strings decode correctly (the reference would read them through the left table's dictionary).  --extended-sql turns on
+    BETWEEN, decimal / negative literals and keywords in any case."""
+    a, b = tmp_path / "a.csv", tmp_path / "b.csv"
+    a.write_text("a.id,a.colour,a.v\n1,red,-1.5\n2,green,2.5\n3,blue,4.0\n")
+    b.write_text("b.id,b.shape\n1,square\n2,circle\n3,square\n")
+    sql = "select a.colour, b.shape, a.v from a join b on a.id = b.id where a.v between -2.0 and 2.5 order by a.id"
+    r = subprocess.run([OURS, "--table", f"a={a}", "--table", f"b={b}", "--extended-sql", "--output-format", "csv", "--sql", sql],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip().splitlines() == ["a.colour,b.shape,a.v", "red,square,-1.500000", "green,circle,2.500000"], r.stdout

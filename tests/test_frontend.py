@@ -57,6 +57,34 @@ def test_front_end_extensions_are_opt_in(bq):
     assert "(x > 1.5)" in buf.value.decode()
 
 
+def test_negative_literals_and_keyword_case_are_opt_in(bq):
+    """The rest of SURVEY.md 8f N4: -5 / -1.5 as literals and keywords in any case, behind parse flags; without the flags
+    the reference's behaviour stays (its primary() rejects a leading '-', its keywords match exactly: parser.cpp:82-103,278-331)."""
+    L = bq.exec_lib()
+    buf = C.create_string_buffer(8192)
+
+    def explain(sql, flags):
+        rc = L.bqx_explain(sql.encode(), flags, buf, 8192)
+        return rc, (buf.value.decode() if rc == 0 else L.bqx_last_error().decode())
+
+    rc, text = explain("SELECT a FROM t WHERE x > -5", 0)
+    assert rc != 0 and text == "Unexpected token in expression"
+    rc, text = explain("SELECT a FROM t WHERE x > -5 AND y = 3 - -2", bq.PARSE_NEGATIVE)
+    assert rc == 0 and "((x > -5) AND (y = (3 - -2)))" in text
+    rc, text = explain("SELECT a FROM t WHERE x > -1.5", bq.PARSE_NEGATIVE | bq.PARSE_DECIMALS)
+    assert rc == 0 and "(x > -1.5)" in text
+    rc, text = explain("SELECT a - 1 FROM t", bq.PARSE_NEGATIVE)            # a binary minus is still a binary minus
+    assert rc == 0 and "(a - 1)" in text
+    rc, text = explain("select a from t where x > 1", 0)
+    assert rc != 0 and text == "Expected 0 got 13"                          # "select" is an identifier to the reference
+    rc, text = explain("select a, Sum(b) as s from t where x > 1 group by a order by s desc limit 3", bq.PARSE_ANY_CASE)
+    want = explain("SELECT a, SUM(b) AS s FROM t WHERE x > 1 GROUP BY a ORDER BY s DESC LIMIT 3", 0)
+    assert rc == 0 and want[0] == 0
+    assert text == want[1]
+    rc, text = explain("select a from t where d between 1 and 2", bq.PARSE_ANY_CASE | bq.PARSE_BETWEEN)
+    assert rc == 0 and "((d >= 1) AND (d <= 2))" in text
+
+
 def test_plan_construction_errors_need_no_gpu(bq):
     """Constructor-time validation (unknown table / column / join key) happens before any kernel could run."""
     eng = bq.Engine()
