@@ -738,6 +738,68 @@ def run_ours(args):
         section("c5", run_c5)
 
     # =================================================================================================================
+    # ORDER BY <double> DESC without LIMIT (BASELINE.md lists it as a measured reference row: 0.52 Mrows/s): rows / 10 rows
+    # per GPU (10^8), result left in HBM.  N = 1: LSD radix sort of (64-bit key, row id) pairs, then one gather per column.
+    # N > 1: sampled splitters, all-to-all by key range, local sort - rank r ends up holding the r-th range.
+    # =================================================================================================================
+    SORT_SQL = "SELECT k, v FROM s ORDER BY v DESC"
+
+    def sort_tables(n_all, n_local, r0):
+        k = ctx.alloc(bq.INT64, n_local).generate(dist=bq.GEN_UNIFORM, seed=SEED + 7, stream=0, lo=0, hi=(1 << 40), row0=r0)
+        v = ctx.alloc(bq.DOUBLE, n_local).generate(dist=bq.GEN_UNIFORM_DIV, seed=SEED + 7, stream=1, lo=1, hi=(1 << 52), div=4096.0, row0=r0)
+        ctx.sync()
+        return {"s": ([("k", bq.INT64, k), ("v", bq.DOUBLE, v)], {})}
+
+    def run_sort():
+        n = max(4096, rows // 10)
+        tabs = sort_tables(n * world, n, rank * n)
+        try:
+            eng = make_engine(tabs)
+            plan = eng.plan(SORT_SQL)
+            keep = {}
+
+            def step():
+                if "r" in keep:
+                    keep["r"].free()
+                keep["r"] = plan.run_device()
+            before = exchange_counters()
+            ms, launches, kern, _ = timed(step, 5, 2, profile=True)
+            rel = keep["r"]
+            mine = rel.rows
+            total = sum_over_ranks(mine)
+            # invariants at full size: every row is somewhere, each rank's rows descend, and the ranks' ranges descend too
+            head = rel.col(1).to_numpy(0, min(mine, 1 << 20)) if mine else np.empty(0)
+            tail = rel.col(1).to_numpy(max(0, mine - (1 << 20)), min(mine, 1 << 20)) if mine else np.empty(0)
+            ok = total == n * world and bool(np.all(head[:-1] >= head[1:])) and bool(np.all(tail[:-1] >= tail[1:]))
+            if world > 1:
+                ends = torch.tensor([float(head[0]) if mine else float("inf"), float(tail[-1]) if mine else float("inf")], dtype=torch.float64, device="cuda")
+                allends = [torch.empty_like(ends) for _ in range(world)]
+                dist.all_gather(allends, ends)
+                e = [t.tolist() for t in allends]
+                ok = ok and all(e[r][1] >= e[r + 1][0] for r in range(world - 1))
+            kn, kms = kern
+            passes = kn // 5 if kn else 0
+            alg = (16 + 16) * n + passes * 24 * n          # keys made + columns gathered once, 24 B per row per radix pass
+            rec = {"config": "ORDER BY a DOUBLE column DESC, no LIMIT; result left in HBM", "n_gpus": world, "rows_per_gpu": n, "sql": SORT_SQL,
+                   "ms_per_step": ms, "rows_per_sec": n * world / (ms * 1e-3), "gpu_launches_per_step": int(launches),
+                   "radix_passes_per_step": passes, "radix_ms_per_step": kms / 5 if kn else None,
+                   "roofline": {"bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                                "algorithmic_bytes_per_gpu_per_step": alg,
+                                "note": "24 B per row per 8-bit pass (key + row id read and written) + 32 B per row to make the keys and gather two columns"},
+                   "rows_after_the_exchange_on_rank_0": mine,
+                   "invariants_at_full_size": "ok" if ok else f"FAILED: {total} of {n * world} rows, or an order violation"}
+            if exchange:
+                rec["exchange"] = exchange_delta(before, 7)
+            out["sort"] = rec
+            keep["r"].free()
+            del plan, eng
+        finally:
+            drop(tabs)
+
+    if not args.no_stress:
+        section("sort", run_sort)
+
+    # =================================================================================================================
     # Parity on samples, at EVERY N: the same statements over small tables of the same generator, sharded over the ranks
     # and run through the same (NCCL) path; rank 0 regenerates the whole small table on the host, runs the compiled
     # reference on it and compares.  At N = 1 the reference's timings are the cpu_baseline of each configuration.
@@ -847,6 +909,14 @@ def run_ours(args):
                     "probe": [("p.k", bq.INT64, odg.generate(bq.INT64, SP, odg.GEN_BUCKETS, SEED + 6, 0, lo=1, cdf=cdf, starts=starts)),
                               ("p.v", bq.DOUBLE, odg.generate(bq.DOUBLE, SP, odg.GEN_UNIFORM_DIV, SEED + 6, 1, lo=1, hi=64, div=4.0))]}
         results["c5"] = compare("C5", [C5_SQL], c5_tables(SP, n, lo, SB, bn, blo), c5_host, None, f"{SP} probe x {SB} build rows, Zipf(1.1) probe keys", SP + SB)
+        # ORDER BY DESC over a DOUBLE column (the whole sample ends up on every rank: it is below the range-sort threshold)
+        SS = max(1024, min(S, 2_000_000))
+        lo, n = shard(SS)
+
+        def sort_host():
+            return {"s": [("k", bq.INT64, odg.generate(bq.INT64, SS, odg.GEN_UNIFORM, SEED + 7, 0, lo=0, hi=(1 << 40))),
+                          ("v", bq.DOUBLE, odg.generate(bq.DOUBLE, SS, odg.GEN_UNIFORM_DIV, SEED + 7, 1, lo=1, hi=(1 << 52), div=4096.0))]}
+        results["sort"] = compare("ORDER BY", [SORT_SQL], sort_tables(SS, n, lo), sort_host, None, f"{SS} rows of the same generator", SS, ordered=[(1, False)])
         if world > 1:
             r5 = compare("C5 co-partitioned", [C5_SQL], c5_tables(SP, n, lo, SB, bn, blo), c5_host, None, "same sample, join forced to the key-hash shuffle",
                          SP + SB, env={"BOSQL_JOIN": "shuffle"})

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kBlock) k_u32_block_scan(const unsigned* __res
 }
 
 // offsets[i] = sum_{j<i} counts[j]; returns the total (host sync). `offsets` must hold n entries.
-size_t exclusive_scan_u32(bq_ctx* ctx, const unsigned* counts, size_t n, unsigned long long* offsets) {
+size_t exclusive_scan_u32(bq_ctx* ctx, const unsigned* counts, size_t n, unsigned long long* offsets, bool want_total) {
     if (n == 0) return 0;
     size_t n_blocks = (n + kBlock - 1) / kBlock;
     DevBuf sums_buf(ctx, (n_blocks + 1) * sizeof(unsigned long long));
@@ -189,6 +189,7 @@ size_t exclusive_scan_u32(bq_ctx* ctx, const unsigned* counts, size_t n, unsigne
         k_u32_block_scan<<<(unsigned)n_blocks, kBlock, 0, ctx->stream>>>(counts, n, sums, offsets);
         ctx->launches += 3;
         BQ_CUDA(cudaGetLastError());
+        if (!want_total) return 0;           // sums_buf is released in stream order, after the kernels above
         auto* h = static_cast<unsigned long long*>(pinned(ctx, 8));
         BQ_CUDA(cudaMemcpyAsync(h, sums + n_blocks, 8, cudaMemcpyDeviceToHost, ctx->stream));
         BQ_CUDA(cudaStreamSynchronize(ctx->stream));

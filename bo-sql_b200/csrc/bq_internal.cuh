@@ -8,7 +8,8 @@ namespace bq {
 // dev_flag (optional): a device int fetched in the same host round trip as the count
 size_t compact_bits(bq_ctx* ctx, const unsigned* bits, size_t n_bits, unsigned base_index, bq_col** out_rowids,
                     const int* dev_flag = nullptr, int* host_flag = nullptr);
-size_t exclusive_scan_u32(bq_ctx* ctx, const unsigned* counts, size_t n, unsigned long long* offsets);
+// want_total = false: nothing is read back and the host does not wait (the caller does not need the grand total)
+size_t exclusive_scan_u32(bq_ctx* ctx, const unsigned* counts, size_t n, unsigned long long* offsets, bool want_total = true);
 
 // ---- device view of a predicate slot (bq_slot resolved to raw pointers) ------------------------
 struct DSlot {

@@ -133,8 +133,17 @@ __global__ void __launch_bounds__(kBlock) k_compose(const unsigned* __restrict__
 }
 
 // ---- radix sort passes ---------------------------------------------------------------------------
-constexpr int kRadixRounds = 8;
-constexpr int kRadixTile = kBlock * kRadixRounds;
+// LSD, 8 bits per pass, (uint64 key, uint32 row id) pairs, stable.  One pass = k_radix_hist (digit counts per 4096-key
+// tile, 8 B/row read) -> exclusive scan of the [digit][tile] counts -> k_radix_scatter (12 B/row read, 12 B/row written).
+// The scatter sorts its tile by digit INSIDE shared memory first and then writes it out in that order, so neighbouring
+// threads store to neighbouring addresses of the same digit's run (runs average 16 keys = 128 B for random digits); the
+// first generation stored every key straight from the thread that had loaded it - 32 different runs per warp store.
+// Ranking inside the tile is match-based and needs no block-wide barrier per round: a warp owns 512 consecutive keys and
+// keeps its own running count per digit (one writer per counter, no atomics); (warp, round, lane) IS the input order, so
+// digit_base[d] + the earlier warps' counts + the running count + rank-in-group is the stable position.
+constexpr int kSortItems = 16;                        // keys per thread
+constexpr int kSortTile = kBlock * kSortItems;        // 4096 keys per CTA
+constexpr size_t kSortSmem = static_cast<size_t>(kSortTile) * 12;      // the tile's keys and row ids in digit order: 48 KB, three CTAs per SM
 
 __global__ void __launch_bounds__(kBlock) k_diff_bits(const unsigned long long* __restrict__ keys, size_t n,
                                                       unsigned long long* __restrict__ out) {
@@ -147,59 +156,122 @@ __global__ void __launch_bounds__(kBlock) k_diff_bits(const unsigned long long* 
 }
 
 __global__ void __launch_bounds__(kBlock) k_radix_hist(const unsigned long long* __restrict__ keys, size_t n, int shift,
-                                                       unsigned* __restrict__ hist, unsigned n_blocks) {
-    __shared__ unsigned h[256];
-    h[threadIdx.x] = 0;
-    __syncthreads();
-    size_t base = blockIdx.x * (size_t)kRadixTile;
+                                                       unsigned* __restrict__ hist /* [256][n_tiles] */, unsigned n_tiles) {
+    __shared__ unsigned h[kBlock / 32][256];          // one copy per warp: same-digit collisions stay inside a warp
+    const int warp = threadIdx.x >> 5;
 #pragma unroll
-    for (int r = 0; r < kRadixRounds; ++r) {
-        size_t i = base + r * kBlock + threadIdx.x;
-        if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
-    }
+    for (int w = 0; w < kBlock / 32; ++w) h[w][threadIdx.x] = 0;
     __syncthreads();
-    hist[threadIdx.x * (size_t)n_blocks + blockIdx.x] = h[threadIdx.x];
+    const size_t base = blockIdx.x * (size_t)kSortTile;
+    unsigned long long k[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const size_t i = base + r * kBlock + threadIdx.x;
+        k[r] = i < n ? keys[i] : 0ULL;
+    }
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r)
+        if (base + r * kBlock + threadIdx.x < n) atomicAdd(&h[warp][(k[r] >> shift) & 255u], 1u);
+    __syncthreads();
+    unsigned t = 0;
+#pragma unroll
+    for (int w = 0; w < kBlock / 32; ++w) t += h[w][threadIdx.x];
+    hist[threadIdx.x * (size_t)n_tiles + blockIdx.x] = t;
 }
 
-__global__ void __launch_bounds__(kBlock) k_radix_scatter(const unsigned long long* __restrict__ keys_in,
-                                                          const unsigned* __restrict__ vals_in,
-                                                          unsigned long long* __restrict__ keys_out,
-                                                          unsigned* __restrict__ vals_out, size_t n, int shift,
-                                                          const unsigned long long* __restrict__ offsets, unsigned n_blocks) {
-    __shared__ unsigned running[256];
-    __shared__ unsigned wc[kBlock / 32][256];
+__global__ void __launch_bounds__(kBlock, 3) k_radix_scatter(const unsigned long long* __restrict__ keys_in,
+                                                             const unsigned* __restrict__ vals_in,
+                                                             unsigned long long* __restrict__ keys_out,
+                                                             unsigned* __restrict__ vals_out, size_t n, int shift,
+                                                             const unsigned long long* __restrict__ offsets /* [256][n_tiles] */,
+                                                             unsigned n_tiles) {
+    extern __shared__ __align__(16) unsigned char sort_smem[];
+    auto* skey = reinterpret_cast<unsigned long long*>(sort_smem);                          // tile in digit order
+    auto* sval = reinterpret_cast<unsigned*>(sort_smem + kSortTile * 8);
+    __shared__ unsigned short cnt[kBlock / 32][256];                                        // per warp: keys of digit d seen so far
+    __shared__ unsigned digit_base[256];
+    __shared__ unsigned long long goff[256];                                                // global offset of a digit's run minus its tile-local base
+    __shared__ unsigned warp_tot[kBlock / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    running[threadIdx.x] = 0;
-    size_t base = blockIdx.x * (size_t)kRadixTile;
-    for (int r = 0; r < kRadixRounds; ++r) {
+    const size_t base = blockIdx.x * (size_t)kSortTile;
+    const unsigned tile_n = static_cast<unsigned>((n - base) < (size_t)kSortTile ? (n - base) : (size_t)kSortTile);
+    constexpr unsigned kWarpKeys = kSortItems * 32;                                         // a warp owns 512 consecutive keys of the tile
+
 #pragma unroll
-        for (int w = 0; w < kBlock / 32; ++w) wc[w][threadIdx.x] = 0;
-        __syncthreads();
-        size_t i = base + r * kBlock + threadIdx.x;
-        bool valid = i < n;
-        unsigned long long key = valid ? keys_in[i] : 0ULL;
-        unsigned d = static_cast<unsigned>((key >> shift) & 255u);
-        unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 256u + lane);
-        unsigned rank_in_warp = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rank_in_warp == 0) wc[warp][d] = __popc(peers);
-        __syncthreads();
-        if (valid) {
-            unsigned pre = 0;
-            for (int w = 0; w < warp; ++w) pre += wc[w][d];
-            unsigned long long pos = offsets[d * (size_t)n_blocks + blockIdx.x] + running[d] + pre + rank_in_warp;
-            keys_out[pos] = key;
-            vals_out[pos] = vals_in[i];
+    for (int w = 0; w < kBlock / 32; ++w) cnt[w][threadIdx.x] = 0;
+    unsigned long long k[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const unsigned x = warp * kWarpKeys + r * 32 + lane;
+        k[r] = x < tile_n ? keys_in[base + x] : 0ULL;
+    }
+    __syncthreads();
+    // Ranking.  Input order inside the tile is (warp, round, lane); a warp walks its rounds in order, so the running count
+    // of digit d in cnt[warp][d] is touched by one warp only - no block-wide barrier per round.  Lanes holding the same
+    // digit find each other with match.any; each of them reads the running count, the first of them adds the group size.
+    unsigned short off_in_warp[kSortItems];
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const bool valid = warp * kWarpKeys + r * 32 + lane < tile_n;
+        const unsigned d = static_cast<unsigned>((k[r] >> shift) & 255u);
+        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 256u + lane);
+        const unsigned rk = __popc(peers & ((1u << lane) - 1u));
+        unsigned before = 0;
+        if (valid) before = cnt[warp][d];
+        __syncwarp();
+        if (valid && rk == 0) cnt[warp][d] = static_cast<unsigned short>(before + __popc(peers));
+        __syncwarp();
+        off_in_warp[r] = static_cast<unsigned short>(before + rk);
+    }
+    __syncthreads();
+    {   // thread d: digit d's counts over the warps -> exclusive offsets per warp; then the digits' bases
+        unsigned run = 0;
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; ++w) {
+            const unsigned c = cnt[w][threadIdx.x];
+            cnt[w][threadIdx.x] = static_cast<unsigned short>(run);
+            run += c;
         }
-        __syncthreads();
-        unsigned add = 0;
+        unsigned incl = run;
 #pragma unroll
-        for (int w = 0; w < kBlock / 32; ++w) add += wc[w][threadIdx.x];
-        running[threadIdx.x] += add;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
         __syncthreads();
+        unsigned pre = 0;
+        for (int w = 0; w < warp; ++w) pre += warp_tot[w];
+        const unsigned excl = pre + incl - run;
+        digit_base[threadIdx.x] = excl;
+        goff[threadIdx.x] = offsets[threadIdx.x * (size_t)n_tiles + blockIdx.x] - excl;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const unsigned x = warp * kWarpKeys + r * 32 + lane;
+        if (x < tile_n) {
+            const unsigned d = static_cast<unsigned>((k[r] >> shift) & 255u);
+            const unsigned pos = digit_base[d] + cnt[warp][d] + off_in_warp[r];
+            skey[pos] = k[r];
+            sval[pos] = vals_in[base + x];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kSortItems; ++r) {
+        const unsigned j = r * kBlock + threadIdx.x;
+        if (j < tile_n) {
+            const unsigned long long key = skey[j];
+            const unsigned long long g = goff[(key >> shift) & 255u] + j;
+            keys_out[g] = key;
+            vals_out[g] = sval[j];
+        }
     }
 }
 
-// Stable sort of (keys, vals) by keys ascending; result left in keys/vals (buffers may swap).
+// Stable sort of (keys, vals) by keys ascending; result left in keys/vals (buffers may swap).  One host round trip per
+// sort: which of the eight key bytes vary at all (constant bytes are skipped - an int32-ranged key takes four passes).
 static void radix_sort_pairs(bq_ctx* ctx, unsigned long long*& keys, unsigned*& vals, unsigned long long*& keys_alt,
                              unsigned*& vals_alt, size_t n) {
     auto* d_diff = static_cast<unsigned long long*>(scratch(ctx, 16));
@@ -210,19 +282,30 @@ static void radix_sort_pairs(bq_ctx* ctx, unsigned long long*& keys, unsigned*& 
     BQ_CUDA(cudaMemcpyAsync(h, d_diff, 8, cudaMemcpyDeviceToHost, ctx->stream));
     BQ_CUDA(cudaStreamSynchronize(ctx->stream));
     const unsigned long long diff = *h;
-    const unsigned n_blocks = static_cast<unsigned>((n + kRadixTile - 1) / kRadixTile);
-    DevBuf hist(ctx, 256 * (size_t)n_blocks * 4), offs(ctx, 256 * (size_t)n_blocks * 8);
+    const unsigned n_tiles = static_cast<unsigned>((n + kSortTile - 1) / kSortTile);
+    DevBuf hist(ctx, 256 * (size_t)n_tiles * 4), offs(ctx, 256 * (size_t)n_tiles * 8);
+    BQ_CUDA(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSortSmem)));
     for (int byte = 0; byte < 8; ++byte) {
         if (((diff >> (8 * byte)) & 0xFFull) == 0) continue;
         const int shift = 8 * byte;
-        k_radix_hist<<<n_blocks, kBlock, 0, ctx->stream>>>(keys, n, shift, static_cast<unsigned*>(hist.p), n_blocks);
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        if (ctx->profile) {
+            BQ_CUDA(cudaEventCreate(&ev0));
+            BQ_CUDA(cudaEventCreate(&ev1));
+            BQ_CUDA(cudaEventRecord(ev0, ctx->stream));
+        }
+        k_radix_hist<<<n_tiles, kBlock, 0, ctx->stream>>>(keys, n, shift, static_cast<unsigned*>(hist.p), n_tiles);
         ctx->launches++;
         BQ_CUDA(cudaGetLastError());
-        exclusive_scan_u32(ctx, static_cast<unsigned*>(hist.p), 256 * (size_t)n_blocks, static_cast<unsigned long long*>(offs.p));
-        k_radix_scatter<<<n_blocks, kBlock, 0, ctx->stream>>>(keys, vals, keys_alt, vals_alt, n, shift,
-                                                              static_cast<unsigned long long*>(offs.p), n_blocks);
+        exclusive_scan_u32(ctx, static_cast<unsigned*>(hist.p), 256 * (size_t)n_tiles, static_cast<unsigned long long*>(offs.p), false);
+        k_radix_scatter<<<n_tiles, kBlock, kSortSmem, ctx->stream>>>(keys, vals, keys_alt, vals_alt, n, shift,
+                                                                   static_cast<unsigned long long*>(offs.p), n_tiles);
         ctx->launches++;
         BQ_CUDA(cudaGetLastError());
+        if (ctx->profile) {
+            BQ_CUDA(cudaEventRecord(ev1, ctx->stream));
+            ctx->profile_events.emplace_back(ev0, ev1);
+        }
         std::swap(keys, keys_alt);
         std::swap(vals, vals_alt);
     }

@@ -1,7 +1,7 @@
 """Development probe: the device timeline of one query step (kernels, copies, gaps), through torch.profiler's CUPTI
 activity records - they cover every launch in the process, the library's own kernels included.
 
-    python scripts/timeline.py q1|q2|c4 [rows_total] [--strong]          (also under torch.distributed.run)
+    python scripts/timeline.py q1|q2|c4|sort [rows_total] [--strong]          (also under torch.distributed.run)
 
 Prints, for the last profiled step, every device activity in start order with its duration and the idle gap before it,
 and the host-side runtime calls that synchronise.  Numbers taken under the profiler are for attribution only.
@@ -72,6 +72,12 @@ elif which == "q2":
     eng.add_table("lineitem", [(n, t, li[n]) for n, t, _ in datagen.lineitem_schema(n_ord_all, bench.N_SKU)], d,
                   stats={"l.sku": (0, bench.N_SKU - 1, bench.N_SKU), "l.order_id": (1, n_ord_all, n_ord_all)})
     sql = bench.Q2_SQL
+elif which == "sort":
+    k = ctx.alloc(bq.INT64, n_loc).generate(dist=bq.GEN_UNIFORM, seed=SEED + 7, stream=0, lo=0, hi=(1 << 40), row0=rank * n_loc)
+    v = ctx.alloc(bq.DOUBLE, n_loc).generate(dist=bq.GEN_UNIFORM_DIV, seed=SEED + 7, stream=1, lo=1, hi=(1 << 52), div=4096.0, row0=rank * n_loc)
+    ctx.sync()
+    eng.add_table("s", [("k", bq.INT64, k), ("v", bq.DOUBLE, v)], d)
+    sql = "SELECT k, v FROM s ORDER BY v DESC"
 else:
     ids = max(16, n_all // 20)
     k = ctx.alloc(bq.INT64, n_loc).generate(dist=bq.GEN_HASHED, seed=SEED + 4, stream=0, lo=0, hi=ids - 1, modulus=1 << 61, row0=rank * n_loc)
@@ -82,7 +88,11 @@ else:
     xl.bqx_exchange_keep_sharded(1)
 
 plan = eng.plan(sql)
-run = plan.run_device if which == "c4" and hasattr(plan, "run_device") else plan.run
+if which in ("c4", "sort"):
+    def run():
+        plan.run_device().free()
+else:
+    run = plan.run
 for _ in range(4):
     run()
 torch.cuda.synchronize()

@@ -457,6 +457,28 @@ def test_sort_multi_key(bq, ctx, n):
         assert np.array_equal(g, w[order])
 
 
+def test_radix_sort_wide_keys(bq, ctx):
+    """The LSD radix passes over keys that use all eight bytes: 64-bit integers (with a heavily repeated value: stability)
+    and doubles of both signs, ascending and descending, over several hundred 4096-key tiles with a ragged last one."""
+    n = 1_000_003
+    rng = np.random.default_rng(5)
+    k = rng.integers(-2**62, 2**62, size=n).astype(np.int64)
+    k[::7] = k[3]
+    f = rng.standard_normal(n) * 1e6
+    f[::11] = -f[5]
+    tag = np.arange(n, dtype=np.int32)
+    rel = ctx.rel_create([ctx.upload(INT64, k), ctx.upload(DOUBLE, f), ctx.upload(DATE32, tag)])
+    got = ctx.rel_sort(rel, [0], [1]).to_numpy()
+    order = np.argsort(k, kind="stable")
+    assert np.array_equal(got[0], k[order]) and np.array_equal(got[2], tag[order])
+    got = ctx.rel_sort(rel, [1], [0]).to_numpy()                   # DESC: ties keep input order
+    order = np.argsort(-f, kind="stable")
+    assert np.array_equal(got[1], f[order]) and np.array_equal(got[2], tag[order])
+    got = ctx.rel_sort(rel, [1, 0], [1, 0]).to_numpy()             # f ASC, then k DESC
+    order = np.lexsort((tag, -k, f))
+    assert np.array_equal(got[1], f[order]) and np.array_equal(got[0], k[order]) and np.array_equal(got[2], tag[order])
+
+
 # ---- expression programs -----------------------------------------------------------------------------
 def test_eval_programs(bq, ctx):
     n = 10_007
