@@ -909,6 +909,10 @@ def run_ours(args):
                     "probe": [("p.k", bq.INT64, odg.generate(bq.INT64, SP, odg.GEN_BUCKETS, SEED + 6, 0, lo=1, cdf=cdf, starts=starts)),
                               ("p.v", bq.DOUBLE, odg.generate(bq.DOUBLE, SP, odg.GEN_UNIFORM_DIV, SEED + 6, 1, lo=1, hi=64, div=4.0))]}
         results["c5"] = compare("C5", [C5_SQL], c5_tables(SP, n, lo, SB, bn, blo), c5_host, None, f"{SP} probe x {SB} build rows, Zipf(1.1) probe keys", SP + SB)
+        if world > 1:
+            r5 = compare("C5 co-partitioned", [C5_SQL], c5_tables(SP, n, lo, SB, bn, blo), c5_host, None, "same sample, join forced to the key-hash shuffle",
+                         SP + SB, env={"BOSQL_JOIN": "shuffle"})
+            results["c5"]["parity_on_sample_shuffle_join"] = r5.get("parity_on_sample")
         # ORDER BY DESC over a DOUBLE column (the whole sample ends up on every rank: it is below the range-sort threshold)
         SS = max(1024, min(S, 2_000_000))
         lo, n = shard(SS)
@@ -917,10 +921,6 @@ def run_ours(args):
             return {"s": [("k", bq.INT64, odg.generate(bq.INT64, SS, odg.GEN_UNIFORM, SEED + 7, 0, lo=0, hi=(1 << 40))),
                           ("v", bq.DOUBLE, odg.generate(bq.DOUBLE, SS, odg.GEN_UNIFORM_DIV, SEED + 7, 1, lo=1, hi=(1 << 52), div=4096.0))]}
         results["sort"] = compare("ORDER BY", [SORT_SQL], sort_tables(SS, n, lo), sort_host, None, f"{SS} rows of the same generator", SS, ordered=[(1, False)])
-        if world > 1:
-            r5 = compare("C5 co-partitioned", [C5_SQL], c5_tables(SP, n, lo, SB, bn, blo), c5_host, None, "same sample, join forced to the key-hash shuffle",
-                         SP + SB, env={"BOSQL_JOIN": "shuffle"})
-            results["c5"]["parity_on_sample_shuffle_join"] = r5.get("parity_on_sample")
         return results
 
     if not args.no_cpu:

@@ -184,6 +184,8 @@ def kernel_lib():
         "bq_join_bitmap_ptr": ([vp, P(sz)], vp),
         "bq_join_build_rows": ([vp], sz),
         "bq_join_bitmap_popcount": ([vp, vp, P(C.c_uint64)], C.c_int),
+        "bq_join_build_bitmap_nosync": ([vp, P(JoinSpec), P(vp)], C.c_int),
+        "bq_join_bitmap_verdict": ([vp, vp, P(C.c_uint64), P(C.c_uint64), P(C.c_int)], C.c_int),
         "bq_join_probe": ([vp, vp, vp, vp, sz, sz, P(vp), P(vp)], C.c_int),
         "bq_join_probe_bits": ([vp, vp, vp, sz, sz, sz, P(vp)], C.c_int),
         "bq_rel_sort": ([vp, vp, C.c_int, P(C.c_int), P(C.c_int), i64, P(vp)], C.c_int),

@@ -450,8 +450,22 @@ static void free_tables(bq_join* j) {
     j->h_slots = nullptr;
 }
 
-// Builds one table kind; returns the kernel's flag word.
-static int build_kind(bq_ctx* ctx, const bq_join_spec* spec, int kind, bq_join* j) {
+// A bitmap built for an exchange carries its build counters BEHIND the bitmap words, in a form that survives a word-wise
+// sum over ranks: the rows inserted as three 21-bit limbs and the number of ranks that saw a key outside the domain - so
+// one all-reduce merges the bitmaps AND tells every rank what all ranks inserted, with no host exchange in between.
+constexpr size_t kTrailerWords = BQ_JOIN_TRAILER_WORDS;
+__global__ void k_pack_trailer(const unsigned long long* __restrict__ counters /* [0] inserted, [1] flags */, unsigned* __restrict__ trailer) {
+    const unsigned long long ins = counters[0];
+    trailer[0] = static_cast<unsigned>(ins & 0x1FFFFFu);
+    trailer[1] = static_cast<unsigned>((ins >> 21) & 0x1FFFFFu);
+    trailer[2] = static_cast<unsigned>(ins >> 42);
+    trailer[3] = (counters[1] & 2ull) ? 1u : 0u;      // keys outside [key_min, key_max]: stale statistics
+    for (size_t i = 4; i < kTrailerWords; ++i) trailer[i] = 0;
+}
+
+// Builds one table kind; returns the kernel's flag word.  nosync (BITMAP only): nothing is read back - the counters are
+// packed behind the bitmap and 0 is returned; bq_join_bitmap_verdict reads them after the exchange.
+static int build_kind(bq_ctx* ctx, const bq_join_spec* spec, int kind, bq_join* j, bool nosync = false) {
     BuildParams p{};
     p.key = spec->key->ptr;
     p.key_kind = spec->key->type;
@@ -481,8 +495,8 @@ static int build_kind(bq_ctx* ctx, const bq_join_spec* spec, int kind, bq_join* 
         if (kind == BQ_JOIN_BITMAP) {
             j->bitmap_words = (p.domain + 31) / 32;
             j->bytes = j->bitmap_words * 4;
-            j->bitmap = static_cast<unsigned*>(dev_alloc(ctx, j->bytes + 4));
-            BQ_CUDA(cudaMemsetAsync(j->bitmap, 0, j->bytes + 4, ctx->stream));
+            j->bitmap = static_cast<unsigned*>(dev_alloc(ctx, j->bytes + 4 + kTrailerWords * 4));
+            BQ_CUDA(cudaMemsetAsync(j->bitmap, 0, j->bytes + 4 + kTrailerWords * 4, ctx->stream));
             p.bitmap = j->bitmap;
         } else {
             j->bytes = p.domain * 4;
@@ -523,12 +537,20 @@ static int build_kind(bq_ctx* ctx, const bq_join_spec* spec, int kind, bq_join* 
 #undef BQ_BUILD
         ctx->launches++;
         BQ_CUDA(cudaGetLastError());
-        if (kind == BQ_JOIN_BITMAP) {
+        if (kind == BQ_JOIN_BITMAP && !nosync) {
             // the inserts were reductions: a key inserted twice shows as a bitmap with fewer bits than rows
             k_popcount_words<<<grid_for(ctx, j->bitmap_words, 8), kBlock, 0, ctx->stream>>>(j->bitmap, j->bitmap_words, d + 2);
             ctx->launches++;
             BQ_CUDA(cudaGetLastError());
         }
+    }
+    if (nosync) {
+        k_pack_trailer<<<1, 1, 0, ctx->stream>>>(d, j->bitmap + j->bitmap_words);
+        ctx->launches++;
+        BQ_CUDA(cudaGetLastError());
+        j->build_rows = 0;
+        j->bitmap_bits = 0;
+        return 0;
     }
     auto* h = static_cast<unsigned long long*>(pinned(ctx, 32));
     BQ_CUDA(cudaMemcpyAsync(h, d, 24, cudaMemcpyDeviceToHost, ctx->stream));
@@ -605,6 +627,50 @@ int bq_join_bitmap_popcount(bq_ctx* ctx, const bq_join* j, uint64_t* out) {
         BQ_CUDA(cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
         BQ_CUDA(cudaStreamSynchronize(ctx->stream));
         *out = *h;
+    });
+}
+
+int bq_join_build_bitmap_nosync(bq_ctx* ctx, const bq_join_spec* spec, bq_join** out) {
+    return guarded([&] {
+        if (!spec->key) throw std::runtime_error("join build needs a key column");
+        if (spec->key->type == BQ_DOUBLE) throw std::runtime_error("bitmap joins have integer keys");
+        if (spec->row_end < spec->row_begin || spec->row_end > spec->key->n) throw std::runtime_error("bad build row range");
+        if (spec->key_max < spec->key_min || static_cast<unsigned long long>(spec->key_max - spec->key_min) >= (1ULL << 32))
+            throw std::runtime_error("a bitmap join needs a key domain of at most 2^32 keys");
+        auto* j = new bq_join();
+        j->ctx = ctx;
+        try {
+            build_kind(ctx, spec, BQ_JOIN_BITMAP, j, true);
+            *out = j;
+        } catch (...) {
+            free_tables(j);
+            delete j;
+            throw;
+        }
+    });
+}
+
+int bq_join_bitmap_verdict(bq_ctx* ctx, bq_join* j, uint64_t* set_bits, uint64_t* inserted, int* flags) {
+    return guarded([&] {
+        if (j->kind != BQ_JOIN_BITMAP) throw std::runtime_error("not a bitmap join");
+        auto* d = static_cast<unsigned long long*>(scratch(ctx, 16));
+        BQ_CUDA(cudaMemsetAsync(d, 0, 8, ctx->stream));
+        if (j->bitmap_words) {
+            k_popcount_words<<<grid_for(ctx, j->bitmap_words, 8), kBlock, 0, ctx->stream>>>(j->bitmap, j->bitmap_words, d);
+            ctx->launches++;
+            BQ_CUDA(cudaGetLastError());
+        }
+        auto* h = static_cast<unsigned long long*>(pinned(ctx, 8 + kTrailerWords * 4));
+        BQ_CUDA(cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        BQ_CUDA(cudaMemcpyAsync(h + 1, j->bitmap + j->bitmap_words, kTrailerWords * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        BQ_CUDA(cudaStreamSynchronize(ctx->stream));            // the one host round trip of a build that was exchanged
+        const auto* t = reinterpret_cast<const unsigned*>(h + 1);
+        const uint64_t ins = static_cast<uint64_t>(t[0]) + (static_cast<uint64_t>(t[1]) << 21) + (static_cast<uint64_t>(t[2]) << 42);
+        j->build_rows = static_cast<size_t>(ins);
+        j->bitmap_bits = h[0];
+        if (set_bits) *set_bits = h[0];
+        if (inserted) *inserted = ins;
+        if (flags) *flags = t[3] ? 2 : 0;
     });
 }
 

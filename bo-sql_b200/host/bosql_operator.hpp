@@ -156,6 +156,9 @@ private:
     ExprBindings child_bindings;
     std::vector<TypeId> group_types, agg_types, agg_arg_types;
     bool child_consumed = false;
+    // across GPUs: the row counts of every rank's shard, exchanged by the first run and reused by the next ones (a plan's
+    // tables do not change under it: ColumnarScan holds the Table it was built over)
+    std::shared_ptr<void> row_count_cache_;
 };
 
 struct OrderBy : public Operator {

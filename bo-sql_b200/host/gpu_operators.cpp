@@ -692,6 +692,8 @@ DeviceRelationPtr HashAggregate::device_result() {
     req.group_exprs = &group_exprs;
     req.group_types = group_types;
     req.dict = dict_;
+    if (!row_count_cache_) row_count_cache_ = std::make_shared<gpu::RowCountCache>();
+    req.row_cache = static_cast<gpu::RowCountCache*>(row_count_cache_.get());
     for (size_t i = 0; i < aggregates.size(); ++i) {
         const auto& a = aggregates[i];
         if (a.func_name != "COUNT" && a.func_name != "SUM" && a.func_name != "AVG")

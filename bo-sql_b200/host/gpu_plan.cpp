@@ -418,7 +418,14 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
     } global_rows;
     auto fetch_global_rows = [&]() -> const GlobalRows& {
         if (!global_rows.have) {
-            auto all = xch.host_gather({static_cast<int64_t>(p.rows), static_cast<int64_t>(p.build_rows)});
+            std::vector<int64_t> all;
+            RowCountCache* rc = req.row_cache;
+            if (rc && rc->have && rc->local_probe == static_cast<int64_t>(p.rows) && rc->local_build == static_cast<int64_t>(p.build_rows)) {
+                all = rc->all;                    // every rank ran this plan before, over the same tables: same answer, no exchange
+            } else {
+                all = xch.host_gather({static_cast<int64_t>(p.rows), static_cast<int64_t>(p.build_rows)});
+                if (rc) *rc = RowCountCache{true, static_cast<int64_t>(p.rows), static_cast<int64_t>(p.build_rows), all};
+            }
             for (int r = 0; r < xch.world(); ++r) {
                 global_rows.probe += static_cast<uint64_t>(all[2 * static_cast<size_t>(r)]);
                 global_rows.build += static_cast<uint64_t>(all[2 * static_cast<size_t>(r) + 1]);
@@ -757,35 +764,29 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             const uint64_t dom = static_cast<uint64_t>(js.key_max - js.key_min) + 1;
             if (dom <= (1ULL << 32) && dom <= 8 * shuffled_global_build + 1024) js.kind = need_rows ? BQ_JOIN_DIRECT : BQ_JOIN_BITMAP;
         }
-        check(bq_join_build(ctx, &js, &join));
         if (dist_bitmap) {
-            // a duplicate key inside one shard makes that rank fall back to a hash table: agree before summing
-            // (kind, rows inserted) of every rank in one exchange
-            uint64_t inserted = 0;
-            bool all_bitmaps = true;
-            {
-                auto all = xch.host_gather({bq_join_kind(join) == BQ_JOIN_BITMAP ? 1 : 0, static_cast<int64_t>(bq_join_build_rows(join))});
-                for (int r = 0; r < xch.world(); ++r) {
-                    all_bitmaps = all_bitmaps && all[2 * static_cast<size_t>(r)] != 0;
-                    inserted += static_cast<uint64_t>(all[2 * static_cast<size_t>(r) + 1]);
-                }
-            }
-            if (!all_bitmaps)
-                throw std::runtime_error("join key statistics claim unique keys (ndv == row count) but a shard holds duplicates");
+            // Each rank sets the bits of its own build rows over the GLOBAL key domain; nothing is read back.  The build
+            // counters ride behind the bitmap words through the same all-reduce, so the merged bitmap arrives together with
+            // the number of rows all ranks inserted: ONE collective and one host round trip for the whole distributed build.
+            // The sum of the ranks' words equals their OR only while no key was inserted twice - by one rank (a shard with
+            // duplicates) or by two (statistics that call the key unique may be stale, or a dimension table may be partly
+            // replicated): a doubly set bit would carry into its neighbour.  The merged bitmap must therefore hold exactly one
+            // bit per inserted row; if it does not (or a rank met a key outside the catalog's bounds), every rank sees the same
+            // numbers and the join is redone as a broadcast join.
+            check(bq_join_build_bitmap_nosync(ctx, &js, &join));
             size_t words = 0;
             void* bits = bq_join_bitmap_ptr(join, &words);
-            xch.sum_words(bits, words);
-            // The sum of the ranks' words equals their OR only while no key was inserted by two ranks (statistics that call
-            // the key unique may be stale, or a dimension table may be partly replicated): a doubly set bit would carry into
-            // its neighbour.  The merged bitmap must hold exactly one bit per inserted row; if it does not, every rank sees
-            // the same count and the join is redone as a broadcast join.
-            uint64_t set_bits = 0;
-            check(bq_join_bitmap_popcount(ctx, join, &set_bits));
-            if (set_bits != inserted) {
+            xch.sum_words(bits, words + BQ_JOIN_TRAILER_WORDS);
+            uint64_t set_bits = 0, inserted = 0;
+            int build_flags = 0;
+            check(bq_join_bitmap_verdict(ctx, join, &set_bits, &inserted, &build_flags));
+            if (build_flags || set_bits != inserted) {
                 bq_join_free(ctx, join);
                 join = nullptr;
                 continue;
             }
+        } else {
+            check(bq_join_build(ctx, &js, &join));
         }
         break;
     }

@@ -36,6 +36,13 @@ SlotPlan plan_slots(const std::vector<const Conjunct*>& conjuncts, const std::ve
 
 bq_slot make_slot(const DevColPtr& col, const std::vector<bq_range>& ranges, bool from_build = false);
 
+// What every rank's shard holds (rows scanned, build rows), as exchanged by an earlier run of the same plan.
+struct RowCountCache {
+    bool have = false;
+    int64_t local_probe = -1, local_build = -1;
+    std::vector<int64_t> all;       // [rank * 2] probe rows, [rank * 2 + 1] build rows
+};
+
 struct AggRequest {
     const std::vector<std::unique_ptr<Expr>>* group_exprs = nullptr;
     struct Agg {
@@ -46,6 +53,7 @@ struct AggRequest {
     std::vector<Agg> aggs;
     std::vector<TypeId> group_types;
     Dictionary* dict = nullptr;
+    RowCountCache* row_cache = nullptr;      // optional, owned by the operator that runs the plan repeatedly
 };
 // Runs the fused scan -> selection -> [join probe] -> aggregate pipeline.  Returns nullptr when the pipeline
 // cannot be fused as described (the caller materialises the child and calls again on the plain relation).

@@ -275,6 +275,14 @@ size_t bq_join_bytes(const bq_join* j);
 size_t bq_join_build_rows(const bq_join* j);               /* rows inserted (after the build-side predicates) */
 /* BITMAP joins: raw words, so ranks can exchange/OR partial bitmaps (multi-GPU broadcast join) */
 void* bq_join_bitmap_ptr(const bq_join* j, size_t* n_words);
+/* The same build for a bitmap that ranks are about to merge, WITHOUT a host round trip: the kernel is enqueued and its
+ * counters (rows inserted, out-of-domain flag) are packed into BQ_JOIN_TRAILER_WORDS uint32 words right behind the bitmap's
+ * words, in limbs that a word-wise SUM over up to 2048 ranks cannot overflow.  Sum n_words + BQ_JOIN_TRAILER_WORDS words
+ * across the ranks, then ask for the verdict: bits set in the merged bitmap, rows all ranks inserted, flags (2 = some rank
+ * saw a key outside [key_min, key_max]).  set_bits != inserted means a key was inserted twice (by one rank or by two). */
+#define BQ_JOIN_TRAILER_WORDS 8
+int bq_join_build_bitmap_nosync(bq_ctx* ctx, const bq_join_spec* spec, bq_join** out);
+int bq_join_bitmap_verdict(bq_ctx* ctx, bq_join* j, uint64_t* set_bits, uint64_t* inserted, int* flags);
 /* number of set bits (after ranks merged their bitmaps by summing words: must equal the rows they inserted, or two ranks
  * held the same key and the sum was not an OR) */
 int bq_join_bitmap_popcount(bq_ctx* ctx, const bq_join* j, uint64_t* out);
