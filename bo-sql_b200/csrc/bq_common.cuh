@@ -222,6 +222,8 @@ struct bq_join {
     size_t bitmap_words = 0;
     unsigned* direct = nullptr;           // DIRECT: build row id + 1 at [key-key_min], 0 = absent
     bq::JoinSlot* h_slots = nullptr;      // HASH: open addressing, linear probing over 16-byte slots
+    unsigned* h_occ = nullptr;            // HASH: one bit per slot, set when the slot holds a key (tables of <= 2^29 slots: the bits
+                                          // fit the L2, so a probe whose home slot is empty never touches the table in HBM)
     uint64_t h_mask = 0;
     size_t build_rows = 0;                // rows inserted
     uint64_t bitmap_bits = 0;             // BITMAP: bits set when the build finished (== build_rows unless a key repeats)

@@ -34,6 +34,7 @@ struct BuildParams {
     unsigned* bitmap;
     unsigned* direct;
     JoinSlot* h_slots;
+    unsigned* h_occ;
     unsigned long long h_mask;
     unsigned long long* n_inserted;
     int* flags;   // 1 = duplicate key seen (BITMAP/DIRECT), 2 = key outside [min,max], 4 = table full
@@ -105,7 +106,9 @@ __global__ void __launch_bounds__(kBlock) k_join_build(const __grid_constant__ B
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const size_t i = row[r];
-            if (KIND == BQ_JOIN_BITMAP) {
+            if (KIND == BQ_JOIN_AUTO) {
+                local += ok[r] ? 1 : 0;          // count only: how many rows the build-side predicates let through (sizes the hash table)
+            } else if (KIND == BQ_JOIN_BITMAP) {
                 unsigned long long idx = static_cast<unsigned long long>(k[r] - p.key_min);
                 if (ok[r] && idx >= p.domain) {
                     atomicOr(p.flags, 2);
@@ -147,6 +150,7 @@ __global__ void __launch_bounds__(kBlock) k_join_build(const __grid_constant__ B
                     unsigned old = atomicCAS(&p.h_slots[h].row, 0u, static_cast<unsigned>(i) + 1u);
                     if (old == 0u) {
                         p.h_slots[h].key = k[r];
+                        if (p.h_occ) atomicOr(p.h_occ + (h >> 5), 1u << (h & 31));
                         placed = true;
                         break;
                     }
@@ -446,6 +450,8 @@ static void free_tables(bq_join* j) {
     dev_free(j->ctx, j->bitmap);
     dev_free(j->ctx, j->direct);
     dev_free(j->ctx, j->h_slots);
+    dev_free(j->ctx, j->h_occ);
+    j->h_occ = nullptr;
     j->bitmap = j->direct = nullptr;
     j->h_slots = nullptr;
 }
@@ -505,12 +511,42 @@ static int build_kind(bq_ctx* ctx, const bq_join_spec* spec, int kind, bq_join* 
             p.direct = j->direct;
         }
     } else {
-        size_t cap = next_pow2(n * 2 < 1024 ? 1024 : n * 2);
+        // The table is sized from the rows that will be INSERTED, not from the rows scanned: with a selective build-side
+        // predicate (Q2: one order in four) a table sized for every scanned row is four times larger than needed - 8.6 GB
+        // for 250 M orders, which random probes cannot even keep in the TLBs.  One counting pass over the predicate columns
+        // (and one host round trip) buys a table of 2x the inserted rows.
+        size_t expect = n;
+        if (n && !never && (n_pred > 0 || p.mask)) {
+            auto* dcount = static_cast<unsigned long long*>(scratch(ctx, 32));
+            BQ_CUDA(cudaMemsetAsync(dcount, 0, 16, ctx->stream));
+            BuildParams pc = p;
+            pc.n_inserted = dcount;
+            pc.flags = reinterpret_cast<int*>(dcount + 1);
+            const int grid = grid_for(ctx, n, 8);
+            if (p.key_kind == BQ_INT64 && !p.mask && n_pred <= 1) k_join_build<BQ_JOIN_AUTO, BQ_INT64, 1><<<grid, kBlock, 0, ctx->stream>>>(pc);
+            else k_join_build<BQ_JOIN_AUTO, -1, -1><<<grid, kBlock, 0, ctx->stream>>>(pc);
+            ctx->launches++;
+            BQ_CUDA(cudaGetLastError());
+            auto* hc = static_cast<unsigned long long*>(pinned(ctx, 32));
+            BQ_CUDA(cudaMemcpyAsync(hc, dcount, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            BQ_CUDA(cudaStreamSynchronize(ctx->stream));
+            expect = static_cast<size_t>(hc[0]);
+        }
+        // load factor in (1/8, 1/4]: a probe of an absent key ends at its home slot three times out of four, and the
+        // occupancy bits (cap / 8 bytes, L2-resident up to 2^29 slots) answer those without touching the table
+        size_t cap = next_pow2(expect * 4 < 1024 ? 1024 : expect * 4);
+        if (cap * sizeof(JoinSlot) > (32ull << 30)) cap = next_pow2(expect * 2);      // very large builds: half the memory, longer probe chains
         j->h_mask = cap - 1;
         j->bytes = cap * sizeof(JoinSlot);
         j->h_slots = static_cast<JoinSlot*>(dev_alloc(ctx, cap * sizeof(JoinSlot)));
         BQ_CUDA(cudaMemsetAsync(j->h_slots, 0, cap * sizeof(JoinSlot), ctx->stream));
         p.h_slots = j->h_slots;
+        if (cap <= (1ull << 29)) {
+            j->h_occ = static_cast<unsigned*>(dev_alloc(ctx, cap / 8 + 4));
+            BQ_CUDA(cudaMemsetAsync(j->h_occ, 0, cap / 8 + 4, ctx->stream));
+            j->bytes += cap / 8;
+        }
+        p.h_occ = j->h_occ;
         p.h_mask = j->h_mask;
     }
     // [0] rows inserted, [1] flags, [2] bits set in the finished bitmap - fetched in ONE host round trip

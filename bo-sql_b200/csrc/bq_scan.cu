@@ -70,6 +70,7 @@ struct ScanParams {
     const unsigned* j_bitmap;
     const unsigned* j_direct;
     const JoinSlot* jh_slots;
+    const unsigned* jh_occ;            // optional: one bit per slot (occupied), L2-resident
     unsigned long long jh_mask;
     // G_NONE partials: [grid] x {cnt, sum0, sum1}
     unsigned long long* part_cnt;
@@ -382,6 +383,18 @@ struct RowSink {
         }
     }
 
+    // The same walk for a probe whose FIRST slot is already in registers: the vector loop issues the first-slot loads of a
+    // lane's four rows together (four random sectors in flight per lane instead of one), then finishes each row here.  At the
+    // tables' load factor (<= 0.5, usually far less) most probes end at that first slot: empty = no match.
+    BQ_D void probe_hash_from(long long key_raw, long long a, long long b, long long jk, unsigned long long h, JoinSlot e) {
+        for (unsigned long long probes = 0; probes <= p.jh_mask; ++probes) {
+            if (!e.row) return;
+            if (e.key == jk) build_add(key_raw, a, b, e.row - 1);
+            h = (h + 1) & p.jh_mask;
+            e = load_join_slot(p.jh_slots + h);
+        }
+    }
+
     // a row that passed every streamed range (scalar head/tail path and staged flushes)
     BQ_D void row(long long key_raw, long long a, long long b, long long jk) {
         if (Xs::jmode(p) == 0 || Xs::jmode(p) == BQ_JOIN_ROWBITS) {      // (match bits were tested by the caller)
@@ -548,6 +561,42 @@ __global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_sc
 #pragma unroll
             for (int r = 0; r < 4; ++r)
                 if (pass[r]) pass[r] = sink.probe_dense(raw[S_JK][r], brow[r]);
+        }
+        // phase 2c: hash-table probes straight from registers (dense / global aggregates: nothing to stage for)
+        if (Xs::jmode(p) == BQ_JOIN_HASH && !STAGED) {
+            JoinSlot first[4];
+            unsigned long long hh[4];
+            long long jkc[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                jkc[r] = raw[S_JK][r];
+                if (Sh::kind(p, S_JK) == BQ_DOUBLE) {
+                    if (jkc[r] == INT64_MIN) jkc[r] = 0;                                                  // -0.0 == 0.0 (KeyEqual, :657)
+                    if ((jkc[r] & 0x7FFFFFFFFFFFFFFFLL) > 0x7FF0000000000000LL) pass[r] = false;         // NaN never matches
+                }
+                hh[r] = key_hash(static_cast<uint64_t>(jkc[r])) & p.jh_mask;
+                first[r].row = 0;
+                first[r].key = 0;
+            }
+            if (p.jh_occ) {
+                // home slot empty = key absent (linear probing never skips an empty slot): answered from the L2-resident
+                // occupancy bits, four loads in flight, before any table sector is requested from HBM
+                unsigned occ[4];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) occ[r] = pass[r] ? __ldg(p.jh_occ + (hh[r] >> 5)) : 0u;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) pass[r] = pass[r] && ((occ[r] >> (hh[r] & 31)) & 1u);
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (pass[r]) first[r] = load_join_slot(p.jh_slots + hh[r]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if (pass[r] && first[r].row)
+                    sink.probe_hash_from(Sh::streamed(p, S_KEY) ? raw[S_KEY][r] : 0, Sh::streamed(p, S_A) ? raw[S_A][r] : 0,
+                                         Sh::streamed(p, S_B) ? raw[S_B][r] : 0, jkc[r], hh[r], first[r]);
+            }
+            continue;
         }
         // phase 3: aggregate the survivors
 #pragma unroll
@@ -758,6 +807,7 @@ constexpr uint32_t kX_A = xshape(0, 1, BQ_V_A);                                 
 constexpr uint32_t kX_AB = xshape(0, 2, BQ_V_A, 0, 0, BQ_V_B);                    // SUM(a), SUM(b), no join
 constexpr uint32_t kX_Q2 = xshape(BQ_JOIN_BITMAP, 1, BQ_V_MUL, BQ_L_A, BQ_R_B);   // bitmap probe, SUM(a * b)
 constexpr uint32_t kX_J5 = xshape(BQ_JOIN_DIRECT, 1, BQ_V_MUL, BQ_L_A, BQ_R_B);   // direct probe, SUM(a * b.w)
+constexpr uint32_t kX_Q2H = xshape(BQ_JOIN_HASH, 1, BQ_V_MUL, BQ_L_A, BQ_R_B);    // hash-table probe, SUM(a * b)
 constexpr uint32_t kX_Q2B = xshape(BQ_JOIN_ROWBITS, 1, BQ_V_MUL, BQ_L_A, BQ_R_B); // precomputed match bits, SUM(a * b)
 constexpr uint32_t kR_Q1 = rshape_bits(S_KEY, 1) | rshape_bits(S_P0, 1);     // one (merged) range on the date, one on status
 constexpr uint32_t kR_P0 = rshape_bits(S_P0, 1);                             // filter sweep: one range on the predicate column
@@ -801,6 +851,7 @@ static const ShapeEntry kShapes[] = {
     BQ_SHAPE(kShapeA_F64, kR_A, kX_A, G_NONE, false),
     BQ_SHAPE(kShapeQ2, kR_NONE, kX_Q2, G_DENSE, false),   BQ_SHAPE(kShapeQ2, kR_NONE, kX_Q2, G_HASH, true),
     BQ_SHAPE(kShapeQ2S, kR_NONE, kX_Q2, G_DENSE, false),  BQ_SHAPE(kShapeQ2S, kR_NONE, kX_Q2, G_SMEM, true),
+    BQ_SHAPE(kShapeQ2, kR_NONE, kX_Q2H, G_DENSE, false),  BQ_SHAPE(kShapeJ5, kR_NONE, xshape(BQ_JOIN_HASH, 1, BQ_V_MUL, BQ_L_A, BQ_R_B), G_NONE, false),
     BQ_SHAPE(kShapeQ2B, kR_NONE, kX_Q2B, G_DENSE, false), BQ_SHAPE(kShapeQ2SB, kR_NONE, kX_Q2B, G_DENSE, false),
     BQ_SHAPE(kShapeGB, kR_NONE, kX_A, G_HASH, true),      BQ_SHAPE(kShapeGB, kR_NONE, kX_A, G_DENSE, false),
     BQ_SHAPE(kShapeJ5, kR_NONE, kX_J5, G_NONE, false),
@@ -944,6 +995,7 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st, bool n
         p.j_bitmap = j->bitmap;
         p.j_direct = j->direct;
         p.jh_slots = j->h_slots;
+        p.jh_occ = j->h_occ;
         p.jh_mask = j->h_mask;
         if (j->kind == BQ_JOIN_BITMAP)
             for (int s = 0; s < N_SLOTS; ++s)
@@ -1008,7 +1060,8 @@ static void run_scan(bq_ctx* ctx, const bq_scan_spec* spec, AggState& st, bool n
     bool has_ranges = p.mask != nullptr;
     for (int s = 0; s < N_SLOTS; ++s) has_ranges = has_ranges || p.s[s].nr > 0;
     bool staged = false;
-    if (p.jmode == BQ_JOIN_HASH || st.gmode == G_SMEM || st.gmode == G_HASH) staged = true;
+    // (a hash-join probe into a dense / global aggregate runs from registers, four first-slot loads in flight per lane)
+    if (st.gmode == G_SMEM || st.gmode == G_HASH) staged = true;
     else if (st.gmode == G_DENSE) staged = has_ranges;
     p.staged = staged ? 1 : 0;
     bool specialised = false;

@@ -1,7 +1,7 @@
 """Development probe: the device timeline of one query step (kernels, copies, gaps), through torch.profiler's CUPTI
 activity records - they cover every launch in the process, the library's own kernels included.
 
-    python scripts/timeline.py q1|q2|c4|sort [rows_total] [--strong]          (also under torch.distributed.run)
+    python scripts/timeline.py q1|q2|q2hash|c4|sort [rows_total] [--strong]          (also under torch.distributed.run)
 
 Prints, for the last profiled step, every device activity in start order with its duration and the idle gap before it,
 and the host-side runtime calls that synchronise.  Numbers taken under the profiler are for attribution only.
@@ -63,14 +63,15 @@ if which == "q1":
     eng.add_table("orders", [("status", bq.STRING, o["status"]), ("order_date", bq.DATE32, o["order_date"]), ("total", bq.DOUBLE, o["total"])], d,
                   stats={"order_date": (20240101, 20241228, 336), "total": (1.0, 1000.0, 99901)})
     sql = bench.Q1_SQL
-elif which == "q2":
+elif which in ("q2", "q2hash"):
     n_ord_all, n_ord = n_all // 4, n_loc // 4
-    o = gen_table(datagen.orders_schema(n_ord_all, prefix="o.")[:2], n_ord, SEED + 1, rank * n_ord)
-    li = gen_table(datagen.lineitem_schema(n_ord_all, bench.N_SKU), n_loc, SEED + 2, rank * n_loc)
+    stride = 7919 if which == "q2hash" else 1           # sparse order ids: no bitmap, the open-addressing hash join
+    o = gen_table(datagen.orders_schema(n_ord_all, prefix="o.", key_stride=stride)[:2], n_ord, SEED + 1, rank * n_ord)
+    li = gen_table(datagen.lineitem_schema(n_ord_all, bench.N_SKU, key_stride=stride), n_loc, SEED + 2, rank * n_loc)
     eng.add_table("orders", [("o.order_id", bq.INT64, o["o.order_id"]), ("o.status", bq.STRING, o["o.status"])], d,
-                  stats={"o.order_id": (1, n_ord_all, n_ord_all)})
+                  stats={"o.order_id": (1, 1 + (n_ord_all - 1) * stride, n_ord_all)})
     eng.add_table("lineitem", [(n, t, li[n]) for n, t, _ in datagen.lineitem_schema(n_ord_all, bench.N_SKU)], d,
-                  stats={"l.sku": (0, bench.N_SKU - 1, bench.N_SKU), "l.order_id": (1, n_ord_all, n_ord_all)})
+                  stats={"l.sku": (0, bench.N_SKU - 1, bench.N_SKU), "l.order_id": (1, 1 + (n_ord_all - 1) * stride, n_ord_all)})
     sql = bench.Q2_SQL
 elif which == "sort":
     k = ctx.alloc(bq.INT64, n_loc).generate(dist=bq.GEN_UNIFORM, seed=SEED + 7, stream=0, lo=0, hi=(1 << 40), row0=rank * n_loc)
