@@ -788,6 +788,60 @@ __global__ void __launch_bounds__(kBlock) k_emit(const __grid_constant__ EmitPar
     }
 }
 
+// Small dense / global states (a date domain, a handful of statuses, a global aggregate): ONE CTA finds the groups that exist,
+// numbers them in slot order and writes the output columns - presence test, ordered compaction and emit in one launch, with
+// the group count and the scan's error word left for one host round trip.  The general path below spends four launches and
+// needs the count on the host BEFORE it can emit; for Q1's 31 groups that was most of the time after the scan.
+constexpr size_t kSmallState = 16384;
+__global__ void __launch_bounds__(1024) k_finish_small(const __grid_constant__ EmitParams p, size_t slots, int presence,
+                                                       unsigned long long* __restrict__ n_groups) {
+    __shared__ unsigned warp_tot[32];
+    __shared__ unsigned carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (size_t base = 0; base < slots; base += 1024) {
+        const size_t g = base + threadIdx.x;
+        bool present = false;
+        if (g < slots) present = presence == 1 ? (__double_as_longlong(p.sum0[g]) != INT64_MIN) : (p.cnt[g] != 0);
+        const unsigned ballot = __ballot_sync(0xffffffffu, present);
+        if (lane == 0) warp_tot[warp] = __popc(ballot);
+        __syncthreads();
+        unsigned pre = carry, total = 0;
+        for (int w = 0; w < 32; ++w) {
+            if (w < warp) pre += warp_tot[w];
+            total += warp_tot[w];
+        }
+        if (present) {
+            const size_t i = pre + __popc(ballot & ((1u << lane) - 1u));
+            if (p.out_key) {
+                const long long k = p.key_min + static_cast<long long>(g);
+                switch (p.key_type) {
+                    case BQ_INT64:
+                    case BQ_DOUBLE: static_cast<long long*>(p.out_key)[i] = k; break;
+                    case BQ_STRING: static_cast<unsigned*>(p.out_key)[i] = static_cast<unsigned>(k); break;
+                    default: static_cast<int*>(p.out_key)[i] = static_cast<int>(k); break;
+                }
+            }
+            const unsigned long long c = p.cnt[g];
+            for (int o = 0; o < p.n_out; ++o) {
+                const double sv = p.v[o] == 0 ? p.sum0[g] : p.sum1[g];
+                if (p.func[o] == BQ_AGG_COUNT) static_cast<long long*>(p.out[o])[i] = static_cast<long long>(c);
+                else if (p.func[o] == BQ_AGG_SUM) {
+                    if (p.as_int[o]) static_cast<long long*>(p.out[o])[i] = static_cast<long long>(sv);      // :1044
+                    else static_cast<double*>(p.out[o])[i] = sv;
+                } else {
+                    static_cast<double*>(p.out[o])[i] = c == 0 ? 0.0 : __ddiv_rn(sv, static_cast<double>(c));   // :1047
+                }
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *n_groups = carry;
+}
+
 __global__ void __launch_bounds__(kBlock) k_fill_keys(long long* __restrict__ keys, size_t n, long long v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) keys[i] = v;
 }
@@ -1147,6 +1201,61 @@ static void check_scan_flags(int flags) {
 
 // Turns the device state into a relation. partial = [key] count sum0 sum1, else [key] + outs.
 static bq_rel* emit_state(bq_ctx* ctx, AggState& st, const bq_agg_out* outs, int n_out, bool partial) {
+    bq_agg_out pouts[3] = {{BQ_AGG_COUNT, 0, 0, 0}, {BQ_AGG_SUM, 0, 0, 0}, {BQ_AGG_SUM, 1, 0, 0}};
+    if (partial) {
+        outs = pouts;
+        n_out = 3;
+    }
+    if (n_out < 0 || n_out > BQ_MAX_AGG_OUT) throw std::runtime_error("too many aggregate outputs");
+    if (st.gmode != G_HASH && st.slots <= kSmallState) {
+        // the columns are allocated for every slot (at most 16384 rows) and cut to the group count afterwards
+        std::vector<bq_col*> cols;
+        try {
+            EmitParams e{};
+            e.gmode = st.gmode;
+            e.key_type = st.key_type;
+            e.key_min = st.key_min;
+            e.cnt = st.cnt;
+            e.sum0 = st.sum0;
+            e.sum1 = st.sum1;
+            if (st.has_key) {
+                cols.push_back(new_col(ctx, st.key_type, st.slots));
+                e.out_key = cols.back()->ptr;
+            }
+            e.n_out = n_out;
+            for (int o = 0; o < n_out; ++o) {
+                int type = BQ_DOUBLE;
+                if (outs[o].func == BQ_AGG_COUNT) type = BQ_INT64;
+                else if (outs[o].func == BQ_AGG_SUM) type = outs[o].as_int ? BQ_INT64 : BQ_DOUBLE;
+                else if (outs[o].func != BQ_AGG_AVG) throw std::runtime_error("unknown aggregate function");
+                if (outs[o].v < 0 || outs[o].v > 1) throw std::runtime_error("bad aggregate argument index");
+                cols.push_back(new_col(ctx, type, st.slots));
+                e.func[o] = outs[o].func;
+                e.v[o] = outs[o].v;
+                e.as_int[o] = outs[o].as_int;
+                e.out[o] = cols.back()->ptr;
+            }
+            auto* d = static_cast<unsigned long long*>(scratch(ctx, 16));
+            k_finish_small<<<1, 1024, 0, ctx->stream>>>(e, st.slots, st.presence, d);
+            ctx->launches++;
+            BQ_CUDA(cudaGetLastError());
+            auto* h = static_cast<unsigned long long*>(pinned(ctx, 16));
+            BQ_CUDA(cudaMemcpyAsync(h, d, 8, cudaMemcpyDeviceToHost, ctx->stream));
+            BQ_CUDA(cudaMemcpyAsync(h + 1, st.err, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            BQ_CUDA(cudaStreamSynchronize(ctx->stream));          // the one host round trip: group count + the scan's error word
+            const int flags = static_cast<int>(h[1] & 0xFFFFFFFFull);
+            if (flags) check_scan_flags(flags);
+            const size_t n_groups = static_cast<size_t>(h[0]);
+            for (auto* c : cols) c->n = n_groups;
+            auto* rel = new bq_rel();
+            rel->cols = cols;
+            rel->rows = n_groups;
+            return rel;
+        } catch (...) {
+            for (auto* c : cols) free_col(c);
+            throw;
+        }
+    }
     bq_col* rowids = nullptr;
     size_t n_groups = 0;
     {
@@ -1182,12 +1291,6 @@ static bq_rel* emit_state(bq_ctx* ctx, AggState& st, const bq_agg_out* outs, int
             cols.push_back(new_col(ctx, st.key_type, n_groups));
             e.out_key = cols.back()->ptr;
         }
-        bq_agg_out pouts[3] = {{BQ_AGG_COUNT, 0, 0, 0}, {BQ_AGG_SUM, 0, 0, 0}, {BQ_AGG_SUM, 1, 0, 0}};
-        if (partial) {
-            outs = pouts;
-            n_out = 3;
-        }
-        if (n_out < 0 || n_out > BQ_MAX_AGG_OUT) throw std::runtime_error("too many aggregate outputs");
         e.n_out = n_out;
         for (int o = 0; o < n_out; ++o) {
             int type = BQ_DOUBLE;

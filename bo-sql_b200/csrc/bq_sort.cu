@@ -67,9 +67,16 @@ constexpr int kTopkTile = 2048;
 
 constexpr int kTopkThreads = 1024;      // one compare-exchange per thread per step: the network is a latency chain, so fill the SM
 
+struct TopkCols {              // the sort columns as they lie: the keys are made inside the kernel
+    const void* col[4];
+    int kind[4];
+    int asc[4];
+};
+
+// ids: the rows still in the running (nullptr = all rows, in order); out: the surviving ROW IDS, k per tile, in tile order
 template <int NK>
-__global__ void __launch_bounds__(kTopkThreads) k_tile_topk(const unsigned long long* __restrict__ keys, size_t n, unsigned k,
-                                                      unsigned* __restrict__ cand /* positions, k per tile */) {
+__global__ void __launch_bounds__(kTopkThreads) k_tile_topk(const __grid_constant__ TopkCols cols, const unsigned* __restrict__ ids, size_t n,
+                                                      unsigned k, unsigned* __restrict__ out) {
     extern __shared__ unsigned long long topk_smem[];
     unsigned long long* sk = topk_smem;                                       // [NK][kTopkTile]
     unsigned short* idx = reinterpret_cast<unsigned short*>(sk + NK * kTopkTile);
@@ -78,7 +85,14 @@ __global__ void __launch_bounds__(kTopkThreads) k_tile_topk(const unsigned long 
     const unsigned tn = static_cast<unsigned>((n - t0) < (size_t)kTopkTile ? (n - t0) : (size_t)kTopkTile);
 #pragma unroll
     for (int q = 0; q < NK; ++q)
-        for (unsigned x = threadIdx.x; x < (unsigned)kTopkTile; x += blockDim.x) sk[q * kTopkTile + x] = x < tn ? keys[q * n + t0 + x] : ~0ULL;
+        for (unsigned x = threadIdx.x; x < (unsigned)kTopkTile; x += blockDim.x) {
+            unsigned long long key = ~0ULL;
+            if (x < tn) {
+                const size_t row = ids ? ids[t0 + x] : t0 + x;
+                key = sort_key(load_raw(cols.col[q], cols.kind[q], row), cols.kind[q], cols.asc[q]);
+            }
+            sk[q * kTopkTile + x] = key;
+        }
     for (unsigned x = threadIdx.x; x < (unsigned)kTopkTile; x += blockDim.x) idx[x] = static_cast<unsigned short>(x);
     // a before b?  padding positions (>= tn) carry all-ones keys and the highest positions: they sort last
     auto before = [&](unsigned a, unsigned b) {
@@ -107,29 +121,24 @@ __global__ void __launch_bounds__(kTopkThreads) k_tile_topk(const unsigned long 
         }
     __syncthreads();
     const unsigned keep = k < tn ? k : tn;
-    for (unsigned r = threadIdx.x; r < keep; r += blockDim.x) cand[tile * k + r] = static_cast<unsigned>(t0 + idx[r]);
+    for (unsigned r = threadIdx.x; r < keep; r += blockDim.x) out[tile * k + r] = ids ? ids[t0 + idx[r]] : static_cast<unsigned>(t0 + idx[r]);
 }
 
-static void launch_tile_topk(bq_ctx* ctx, const unsigned long long* keys, int n_keys, size_t n, unsigned k, unsigned* cand) {
+static void launch_tile_topk(bq_ctx* ctx, const TopkCols& cols, int n_keys, const unsigned* ids, size_t n, unsigned k, unsigned* out) {
     const unsigned tiles = static_cast<unsigned>((n + kTopkTile - 1) / kTopkTile);
     const size_t smem = static_cast<size_t>(n_keys) * kTopkTile * 8 + kTopkTile * 2;
     switch (n_keys) {
-        case 1: k_tile_topk<1><<<tiles, kTopkThreads, smem, ctx->stream>>>(keys, n, k, cand); break;
-        case 2: k_tile_topk<2><<<tiles, kTopkThreads, smem, ctx->stream>>>(keys, n, k, cand); break;
+        case 1: k_tile_topk<1><<<tiles, kTopkThreads, smem, ctx->stream>>>(cols, ids, n, k, out); break;
+        case 2: k_tile_topk<2><<<tiles, kTopkThreads, smem, ctx->stream>>>(cols, ids, n, k, out); break;
         case 3:
             BQ_CUDA(cudaFuncSetAttribute(k_tile_topk<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));      // beyond the 48 KB default
-            k_tile_topk<3><<<tiles, kTopkThreads, smem, ctx->stream>>>(keys, n, k, cand); break;
+            k_tile_topk<3><<<tiles, kTopkThreads, smem, ctx->stream>>>(cols, ids, n, k, out); break;
         default:
             BQ_CUDA(cudaFuncSetAttribute(k_tile_topk<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            k_tile_topk<4><<<tiles, kTopkThreads, smem, ctx->stream>>>(keys, n, k, cand); break;
+            k_tile_topk<4><<<tiles, kTopkThreads, smem, ctx->stream>>>(cols, ids, n, k, out); break;
     }
-}
-
-// out[i] = src[idx[i]] (src == nullptr: identity)
-__global__ void __launch_bounds__(kBlock) k_compose(const unsigned* __restrict__ src, const unsigned* __restrict__ idx, size_t n,
-                                                    unsigned* __restrict__ out) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = src ? src[idx[i]] : idx[i];
+    ctx->launches++;
+    BQ_CUDA(cudaGetLastError());
 }
 
 // ---- radix sort passes ---------------------------------------------------------------------------
@@ -353,34 +362,30 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
                     ctx->launches++;
                     BQ_CUDA(cudaGetLastError());
                 } else if (m <= 256 && few_keys) {
-                    // top-k: tiles keep their first m rows until one tile is left
+                    // top-k: tiles keep their first m rows until one tile is left (one launch per round: keys are made from
+                    // the columns inside the kernel and the survivors leave as row ids)
                     const size_t max_cand = ((n + kTopkTile - 1) / kTopkTile) * m;
-                    DevBuf keys(ctx, static_cast<size_t>(n_keys) * n * 8), candB(ctx, max_cand * 4), idsA(ctx, max_cand * 4), idsB(ctx, max_cand * 4);
-                    auto* kbuf = static_cast<unsigned long long*>(keys.p);
-                    auto* cand = static_cast<unsigned*>(candB.p);
+                    DevBuf idsA(ctx, max_cand * 4), idsB(ctx, max_cand * 4);
+                    TopkCols tc{};
+                    for (int k = 0; k < n_keys; ++k) {
+                        const bq_col* c = rel->cols[key_cols[k]];
+                        tc.col[k] = c->ptr;
+                        tc.kind[k] = c->type;
+                        tc.asc[k] = asc[k];
+                    }
                     unsigned* ids = nullptr;                    // current survivors (global row ids); nullptr = all rows
                     auto* ids_next = static_cast<unsigned*>(idsA.p);
                     auto* ids_other = static_cast<unsigned*>(idsB.p);
                     size_t cur = n;
                     while (true) {
-                        for (int k = 0; k < n_keys; ++k) {
-                            const bq_col* c = rel->cols[key_cols[k]];
-                            k_make_keys<<<grid_for(ctx, cur, 8), kBlock, 0, ctx->stream>>>(c->ptr, c->type, asc[k], ids, cur, kbuf + k * cur);
-                            ctx->launches++;
-                        }
                         const size_t tiles = (cur + kTopkTile - 1) / kTopkTile;
-                        launch_tile_topk(ctx, kbuf, n_keys, cur, (unsigned)m, cand);
                         const size_t last = cur - (tiles - 1) * kTopkTile;
                         const size_t next = (tiles - 1) * m + (m < last ? m : last);
                         if (tiles == 1) {        // the last tile's first rows are the answer, already in order
-                            k_compose<<<grid_for(ctx, next, 8), kBlock, 0, ctx->stream>>>(ids, cand, next, perm);
-                            ctx->launches += 2;
-                            BQ_CUDA(cudaGetLastError());
+                            launch_tile_topk(ctx, tc, n_keys, ids, cur, (unsigned)m, perm);
                             break;
                         }
-                        k_compose<<<grid_for(ctx, next, 8), kBlock, 0, ctx->stream>>>(ids, cand, next, ids_next);
-                        ctx->launches += 2;
-                        BQ_CUDA(cudaGetLastError());
+                        launch_tile_topk(ctx, tc, n_keys, ids, cur, (unsigned)m, ids_next);
                         ids = ids_next;
                         std::swap(ids_next, ids_other);
                         cur = next;
