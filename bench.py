@@ -63,6 +63,44 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
 
 
+def bind_host_memory_near_gpu(device_index):
+    """Pinned host buffers of the end-to-end leg should live on the NUMA node the GPU hangs off: with eight ranks copying
+    16 GB each at once, buffers that all landed on one socket share that socket's memory controllers and the inter-socket
+    link (round 1: 290 ms per step on one GPU, 693 ms on eight).  Sets this process's memory policy to PREFER the GPU's node
+    and its CPU affinity to that node's cores; returns what it did (for the JSON line) or why it could not."""
+    import ctypes
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        index = device_index
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            index = int(vis.split(",")[device_index])
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{int(dom, 16):04x}:{rest.lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return {"bound": False, "why": f"{path} reports no NUMA node"}
+        mask = ctypes.c_ulong(1 << node)
+        libc = ctypes.CDLL("libc.so.6", use_errno=True)
+        rc = libc.syscall(238, 1, ctypes.byref(mask), ctypes.c_ulong(64))          # set_mempolicy(MPOL_PREFERRED, {node})
+        if rc != 0:
+            return {"bound": False, "why": f"set_mempolicy failed (errno {ctypes.get_errno()})"}
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        try:
+            os.sched_setaffinity(0, set(cpus) & os.sched_getaffinity(0) or os.sched_getaffinity(0))
+        except OSError:
+            pass
+        return {"bound": True, "numa_node": node, "gpu_pci": bus, "policy": "MPOL_PREFERRED + CPU affinity to the node"}
+    except Exception as e:  # noqa: BLE001
+        return {"bound": False, "why": str(e)[:120]}
+
+
 class ClockSampler:
     """SM clock and throttle reasons while the timed region runs: NVML polled every 5 ms from a thread (the timed region of
     the default run is ~50 ms), or `nvidia-smi -lms 50` when NVML cannot be loaded."""
@@ -237,6 +275,7 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    host_numa = bind_host_memory_near_gpu(local) if not args.no_numa else {"bound": False, "why": "--no-numa"}
     xl = bq.exec_lib()
     if xl.bqx_init(local):
         raise RuntimeError(xl.bqx_last_error().decode())
@@ -481,7 +520,8 @@ def run_ours(args):
             d2h = sum(c.nbytes for c in res["r"].cols)
             out["e2e"] = {"value": rows * world / (ms_e2e * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": Q1_BYTES_PER_ROW * rows,
                           "d2h_bytes_per_step": int(d2h), "ms_per_step": ms_e2e, "steps": e2e_steps,
-                          "path": "Engine over pinned host columns (bqx_table_add_borrowed_column); mirrors evicted before every step"}
+                          "path": "Engine over pinned host columns (bqx_table_add_borrowed_column); mirrors evicted before every step",
+                          "host_memory": host_numa}
             del hplan, heng
         finally:
             for p in bufs:
@@ -962,6 +1002,7 @@ def main():
     ap.add_argument("--ref-rows", type=float, default=2e7, help="sample size for the CPU reference")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-numa", action="store_true", help="leave the host buffers of the end-to-end leg wherever the kernel puts them")
     ap.add_argument("--no-q2", action="store_true")
     ap.add_argument("--no-cpu", action="store_true", help="skip the parity samples / cpu_baseline (reference executor on rank 0)")
     ap.add_argument("--no-stress", action="store_true", help="skip the C2 / C4 / C5 configurations")

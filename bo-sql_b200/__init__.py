@@ -132,6 +132,7 @@ def kernel_lib():
         "bq_col_write": ([vp, vp, sz, vp, sz], C.c_int),
         "bq_col_read": ([vp, vp, sz, sz, vp], C.c_int),
         "bq_col_read_async": ([vp, vp, sz, sz, vp], C.c_int),
+        "bq_col_owns": ([vp], C.c_int),
         "bq_col_free": ([vp, vp], None),
         "bq_col_size": ([vp], sz),
         "bq_col_type": ([vp], C.c_int),

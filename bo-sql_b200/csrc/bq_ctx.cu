@@ -416,6 +416,7 @@ void bq_col_free(bq_ctx* ctx, bq_col* col) {
 }
 
 size_t bq_col_size(const bq_col* col) { return col->n; }
+int bq_col_owns(const bq_col* col) { return col->owns && col->ptr ? 1 : 0; }
 int bq_col_type(const bq_col* col) { return col->type; }
 void* bq_col_ptr(const bq_col* col) { return col->ptr; }
 

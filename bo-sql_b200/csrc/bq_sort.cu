@@ -13,6 +13,8 @@
 #include "bq_common.cuh"
 #include "bq_internal.cuh"
 
+#include <memory>
+
 namespace bq {
 
 BQ_D unsigned long long sort_key(long long raw, int kind, int asc) {
@@ -22,12 +24,32 @@ BQ_D unsigned long long sort_key(long long raw, int kind, int asc) {
 }
 
 // keys[i] = sort_key(col[perm ? perm[i] : i])
+// neg_zero (optional): set when a DOUBLE column holds -0.0, the one value whose bits the key does not keep (it sorts as +0.0)
 __global__ void __launch_bounds__(kBlock) k_make_keys(const void* __restrict__ col, int kind, int asc,
                                                       const unsigned* __restrict__ perm, size_t n,
-                                                      unsigned long long* __restrict__ keys) {
+                                                      unsigned long long* __restrict__ keys, int* __restrict__ neg_zero = nullptr) {
+    bool seen = false;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         size_t r = perm ? perm[i] : i;
-        keys[i] = sort_key(load_raw(col, kind, r), kind, asc);
+        const long long raw = load_raw(col, kind, r);
+        seen = seen || (kind == BQ_DOUBLE && raw == INT64_MIN);
+        keys[i] = sort_key(raw, kind, asc);
+    }
+    if (neg_zero && seen) atomicOr(neg_zero, 1);
+}
+
+// The inverse: a sorted key array IS the sorted column (unless the column held -0.0), so the first sort column of a full sort
+// is written back from its keys in one streaming pass instead of being gathered through the permutation - a random 8-byte
+// gather costs a 32-byte sector per row (2.6 ms per 10^8 rows against 0.25 ms).
+__global__ void __launch_bounds__(kBlock) k_unmake_keys(const unsigned long long* __restrict__ keys, int kind, int asc, size_t n,
+                                                        void* __restrict__ out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long u = asc ? keys[i] : ~keys[i];
+        const long long k = static_cast<long long>(u ^ 0x8000000000000000ULL);
+        const long long raw = kind == BQ_DOUBLE ? static_cast<long long>(f64_bits_from_key(k)) : k;
+        if (kind == BQ_INT64 || kind == BQ_DOUBLE) static_cast<long long*>(out)[i] = raw;
+        else if (kind == BQ_STRING) static_cast<unsigned*>(out)[i] = static_cast<unsigned>(raw);
+        else static_cast<int*>(out)[i] = static_cast<int>(raw);
     }
 }
 
@@ -282,15 +304,17 @@ __global__ void __launch_bounds__(kBlock, 3) k_radix_scatter(const unsigned long
 // Stable sort of (keys, vals) by keys ascending; result left in keys/vals (buffers may swap).  One host round trip per
 // sort: which of the eight key bytes vary at all (constant bytes are skipped - an int32-ranged key takes four passes).
 static void radix_sort_pairs(bq_ctx* ctx, unsigned long long*& keys, unsigned*& vals, unsigned long long*& keys_alt,
-                             unsigned*& vals_alt, size_t n) {
+                             unsigned*& vals_alt, size_t n, const int* dev_flag = nullptr, int* host_flag = nullptr) {
     auto* d_diff = static_cast<unsigned long long*>(scratch(ctx, 16));
     BQ_CUDA(cudaMemsetAsync(d_diff, 0, 8, ctx->stream));
     k_diff_bits<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(keys, n, d_diff);
     ctx->launches++;
-    auto* h = static_cast<unsigned long long*>(pinned(ctx, 8));
+    auto* h = static_cast<unsigned long long*>(pinned(ctx, 16));
     BQ_CUDA(cudaMemcpyAsync(h, d_diff, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    if (dev_flag) BQ_CUDA(cudaMemcpyAsync(h + 1, dev_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
     BQ_CUDA(cudaStreamSynchronize(ctx->stream));
     const unsigned long long diff = *h;
+    if (dev_flag && host_flag) *host_flag = static_cast<int>(h[1] & 0xFFFFFFFFull);
     const unsigned n_tiles = static_cast<unsigned>((n + kSortTile - 1) / kSortTile);
     DevBuf hist(ctx, 256 * (size_t)n_tiles * 4), offs(ctx, 256 * (size_t)n_tiles * 8);
     BQ_CUDA(cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSortSmem)));
@@ -346,6 +370,8 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
                 DevBuf permA(ctx, n * 4), permB(ctx, n * 4);
                 auto* perm = static_cast<unsigned*>(permA.p);
                 auto* perm_alt = static_cast<unsigned*>(permB.p);
+                std::unique_ptr<DevBuf> sort_keys_a, sort_keys_b;      // a full sort's key buffers outlive the sort: see k_unmake_keys
+                const unsigned long long* first_key_sorted = nullptr;
                 if (n_keys == 0) {
                     k_iota<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(perm, n);
                     ctx->launches++;
@@ -391,18 +417,25 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
                         cur = next;
                     }
                 } else {
-                    DevBuf keysA(ctx, n * 8), keysB(ctx, n * 8);
-                    auto* keys = static_cast<unsigned long long*>(keysA.p);
-                    auto* keys_alt = static_cast<unsigned long long*>(keysB.p);
+                    sort_keys_a = std::make_unique<DevBuf>(ctx, n * 8);
+                    sort_keys_b = std::make_unique<DevBuf>(ctx, n * 8);
+                    auto* keys = static_cast<unsigned long long*>(sort_keys_a->p);
+                    auto* keys_alt = static_cast<unsigned long long*>(sort_keys_b->p);
                     k_iota<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(perm, n);
                     ctx->launches++;
+                    DevBuf flag_buf(ctx, 16);
+                    int neg_zero = 0;
                     for (int k = n_keys - 1; k >= 0; --k) {      // least-significant sort column first
                         const bq_col* c = rel->cols[key_cols[k]];
-                        k_make_keys<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(c->ptr, c->type, asc[k], perm, n, keys);
+                        if (k == 0) BQ_CUDA(cudaMemsetAsync(flag_buf.p, 0, 4, ctx->stream));
+                        // (the first column sorted reads its rows in place: the permutation is still the identity)
+                        k_make_keys<<<grid_for(ctx, n, 8), kBlock, 0, ctx->stream>>>(c->ptr, c->type, asc[k], k == n_keys - 1 ? nullptr : perm, n, keys,
+                                                                                     k == 0 ? flag_buf.as<int>() : nullptr);
                         ctx->launches++;
                         BQ_CUDA(cudaGetLastError());
-                        radix_sort_pairs(ctx, keys, perm, keys_alt, perm_alt, n);
+                        radix_sort_pairs(ctx, keys, perm, keys_alt, perm_alt, n, k == 0 ? flag_buf.as<int>() : nullptr, &neg_zero);
                     }
+                    if (!neg_zero) first_key_sorted = keys;
                 }
                 // gather the first m rows of every column
                 bq_col ids;
@@ -413,6 +446,14 @@ extern "C" int bq_rel_sort(bq_ctx* ctx, const bq_rel* rel, int n_keys, const int
                 ids.owns = false;
                 for (int c = 0; c < nc; ++c) {
                     bq_col* o = nullptr;
+                    if (first_key_sorted && c == key_cols[0]) {
+                        o = new_col(ctx, rel->cols[c]->type, m);
+                        cols.push_back(o);
+                        k_unmake_keys<<<grid_for(ctx, m, 8), kBlock, 0, ctx->stream>>>(first_key_sorted, rel->cols[c]->type, asc[0], m, o->ptr);
+                        ctx->launches++;
+                        BQ_CUDA(cudaGetLastError());
+                        continue;
+                    }
                     if (bq_gather(ctx, rel->cols[c], &ids, &o)) throw std::runtime_error(bq_last_error());
                     cols.push_back(o);
                 }

@@ -413,11 +413,20 @@ int bqx_plan_run_device(bqx_plan* p, bq_rel** out) {
             throw;
         }
         p->root->close();
-        // an owning relation for the caller: device-to-device copies, so a scan's table columns stay with the table
+        // An owning relation for the caller.  Columns that this result alone holds (the output of an aggregate, a sort, a
+        // gather) are handed over as they are; anything shared - a scan's table columns, a view into one - is copied
+        // device to device, so the table keeps its columns.
+        const bool sole_owner = rel.use_count() == 1;
         std::vector<bq_col*> cols;
         for (auto& c : rel->cols) {
             bq_col* v = nullptr;
-            gpu::check(bq_slice(gpu::context(), c->h, 0, rel->rows, &v));
+            if (sole_owner && c.use_count() == 1 && c->owns && !c->parent && bq_col_owns(c->h) && bq_col_size(c->h) == rel->rows) {
+                v = c->h;
+                c->owns = false;              // the handle leaves with the result
+            } else if (bq_slice(gpu::context(), c->h, 0, rel->rows, &v)) {
+                for (bq_col* done : cols) bq_col_free(gpu::context(), done);      // handed-over and copied columns alike are ours by now
+                gpu::throw_last_error();
+            }
             cols.push_back(v);
         }
         gpu::check(bq_rel_create(gpu::context(), cols.data(), static_cast<int>(cols.size()), out));

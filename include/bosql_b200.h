@@ -69,6 +69,7 @@ void bq_col_free(bq_ctx* ctx, bq_col* col);
 /* non-owning column over device memory the caller manages (e.g. a buffer filled by an NCCL collective) */
 int bq_col_wrap(bq_ctx* ctx, int type, void* device_ptr, size_t n, bq_col** out);
 size_t bq_col_size(const bq_col* col);
+int bq_col_owns(const bq_col* col);                        /* 1: the handle owns its device memory (not a wrap / view) */
 int bq_col_type(const bq_col* col);
 void* bq_col_ptr(const bq_col* col);                       /* raw device pointer */
 /* Catalog statistics (include/catalog/catalog.h:16-21): min/max on the column's integer key

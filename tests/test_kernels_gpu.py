@@ -479,6 +479,26 @@ def test_radix_sort_wide_keys(bq, ctx):
     assert np.array_equal(got[1], f[order]) and np.array_equal(got[0], k[order]) and np.array_equal(got[2], tag[order])
 
 
+def test_full_sort_keeps_negative_zero_bits(bq, ctx):
+    """A full sort writes its first sort column back from the sorted keys - except when the column holds -0.0, whose sign the
+    key does not carry (-0.0 and +0.0 compare equal and must tie): then the column is gathered, and the bits survive."""
+    n = 50_001
+    rng = np.random.default_rng(9)
+    f = rng.integers(-3, 4, size=n).astype(np.float64)
+    f[::5] = -0.0
+    tag = np.arange(n, dtype=np.int64)
+    rel = ctx.rel_create([ctx.upload(DOUBLE, f), ctx.upload(INT64, tag)])
+    for asc in (1, 0):
+        got = ctx.rel_sort(rel, [0], [asc]).to_numpy()
+        order = np.argsort(f if asc else -f, kind="stable")
+        assert np.array_equal(got[0].view(np.int64), f[order].view(np.int64)) and np.array_equal(got[1], tag[order])
+    g = np.where(f == 0.0, 0.0, f)                      # no -0.0 left: the reconstruction path, checked bit for bit as well
+    rel = ctx.rel_create([ctx.upload(DOUBLE, g), ctx.upload(INT64, tag)])
+    got = ctx.rel_sort(rel, [0], [0]).to_numpy()
+    order = np.argsort(-g, kind="stable")
+    assert np.array_equal(got[0].view(np.int64), g[order].view(np.int64)) and np.array_equal(got[1], tag[order])
+
+
 # ---- expression programs -----------------------------------------------------------------------------
 def test_eval_programs(bq, ctx):
     n = 10_007
