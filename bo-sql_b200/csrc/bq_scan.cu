@@ -445,8 +445,13 @@ constexpr int kStageCap = 64;     // staged qualifying rows per warp (flushed 32
 // RSHAPE: 2 bits per slot = how many ranges the slot carries (specialised kernels; the generic kernel reads it at run time)
 constexpr uint32_t rshape_bits(int slot, int n_ranges) { return static_cast<uint32_t>(n_ranges) << (2 * slot); }
 
+// resident CTAs per SM the compiler must leave room for: the fused bitmap probe into a dense table is bound by requests in
+// flight (one random L2 sector per row), so it trades registers for a sixth CTA
+constexpr int scan_min_blocks(uint32_t shape, uint32_t xs, int gmode, bool staged) {
+    return shape == kGenericShape ? 2 : (xs == xshape(BQ_JOIN_BITMAP, 1, BQ_V_MUL, BQ_L_A, BQ_R_B) && gmode == G_DENSE && !staged) ? 6 : 4;
+}
 template <uint32_t SHAPE, uint32_t RSHAPE, uint32_t XSHAPE, int GMODE, bool STAGED>
-__global__ void __launch_bounds__(kBlock, (SHAPE == kGenericShape) ? 2 : 4) k_scan(const __grid_constant__ ScanParams p) {
+__global__ void __launch_bounds__(kBlock, scan_min_blocks(SHAPE, XSHAPE, GMODE, STAGED)) k_scan(const __grid_constant__ ScanParams p) {
     using Sh = Shape<SHAPE>;
     using Xs = XShape<XSHAPE>;
     extern __shared__ double smem_dyn[];
