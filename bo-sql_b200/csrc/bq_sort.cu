@@ -174,7 +174,14 @@ static void launch_tile_topk(bq_ctx* ctx, const TopkCols& cols, int n_keys, cons
 // digit_base[d] + the earlier warps' counts + the running count + rank-in-group is the stable position.
 constexpr int kSortItems = 16;                        // keys per thread
 constexpr int kSortTile = kBlock * kSortItems;        // 4096 keys per CTA
-constexpr size_t kSortSmem = static_cast<size_t>(kSortTile) * 12;      // the tile's keys and row ids in digit order: 48 KB, three CTAs per SM
+constexpr size_t kSortSmem = static_cast<size_t>(kSortTile) * 12;      // the tile's keys and row ids in digit order: 48 KB
+#ifndef BQ_SCAT_THREADS
+#define BQ_SCAT_THREADS 512
+#define BQ_SCAT_BLOCKS 3
+#endif
+constexpr int kScatThreads = BQ_SCAT_THREADS;         // scatter CTA: 512 threads x 8 keys, three CTAs per SM (measured: 0.87 ms per pass; 256 x 16 x 3: 0.99, 1024 x 4 x 2: 0.94)
+constexpr int kScatItems = kSortTile / kScatThreads;
+constexpr int kScatBlocks = BQ_SCAT_BLOCKS;
 
 __global__ void __launch_bounds__(kBlock) k_diff_bits(const unsigned long long* __restrict__ keys, size_t n,
                                                       unsigned long long* __restrict__ out) {
@@ -210,7 +217,7 @@ __global__ void __launch_bounds__(kBlock) k_radix_hist(const unsigned long long*
     hist[threadIdx.x * (size_t)n_tiles + blockIdx.x] = t;
 }
 
-__global__ void __launch_bounds__(kBlock, 3) k_radix_scatter(const unsigned long long* __restrict__ keys_in,
+__global__ void __launch_bounds__(kScatThreads, kScatBlocks) k_radix_scatter(const unsigned long long* __restrict__ keys_in,
                                                              const unsigned* __restrict__ vals_in,
                                                              unsigned long long* __restrict__ keys_out,
                                                              unsigned* __restrict__ vals_out, size_t n, int shift,
@@ -219,20 +226,19 @@ __global__ void __launch_bounds__(kBlock, 3) k_radix_scatter(const unsigned long
     extern __shared__ __align__(16) unsigned char sort_smem[];
     auto* skey = reinterpret_cast<unsigned long long*>(sort_smem);                          // tile in digit order
     auto* sval = reinterpret_cast<unsigned*>(sort_smem + kSortTile * 8);
-    __shared__ unsigned short cnt[kBlock / 32][256];                                        // per warp: keys of digit d seen so far
+    __shared__ unsigned short cnt[kScatThreads / 32][256];                                        // per warp: keys of digit d seen so far
     __shared__ unsigned digit_base[256];
     __shared__ unsigned long long goff[256];                                                // global offset of a digit's run minus its tile-local base
-    __shared__ unsigned warp_tot[kBlock / 32];
+    __shared__ unsigned warp_tot[8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t base = blockIdx.x * (size_t)kSortTile;
     const unsigned tile_n = static_cast<unsigned>((n - base) < (size_t)kSortTile ? (n - base) : (size_t)kSortTile);
-    constexpr unsigned kWarpKeys = kSortItems * 32;                                         // a warp owns 512 consecutive keys of the tile
+    constexpr unsigned kWarpKeys = kScatItems * 32;                                         // a warp owns 512 consecutive keys of the tile
 
+    for (int i = threadIdx.x; i < (kScatThreads / 32) * 256; i += kScatThreads) (&cnt[0][0])[i] = 0;
+    unsigned long long k[kScatItems];
 #pragma unroll
-    for (int w = 0; w < kBlock / 32; ++w) cnt[w][threadIdx.x] = 0;
-    unsigned long long k[kSortItems];
-#pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
+    for (int r = 0; r < kScatItems; ++r) {
         const unsigned x = warp * kWarpKeys + r * 32 + lane;
         k[r] = x < tile_n ? keys_in[base + x] : 0ULL;
     }
@@ -240,28 +246,43 @@ __global__ void __launch_bounds__(kBlock, 3) k_radix_scatter(const unsigned long
     // Ranking.  Input order inside the tile is (warp, round, lane); a warp walks its rounds in order, so the running count
     // of digit d in cnt[warp][d] is touched by one warp only - no block-wide barrier per round.  Lanes holding the same
     // digit find each other with match.any; each of them reads the running count, the first of them adds the group size.
-    unsigned short off_in_warp[kSortItems];
+    unsigned short off_in_warp[kScatItems];
+    unsigned peers[kScatItems];
+    // all sixteen matches first: they do not depend on each other, and match.any has a long latency (ncu: a third of the
+    // kernel's stall samples sat on its consumer when each round waited for its own match)
 #pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
+    for (int r = 0; r < kScatItems; ++r) {
         const bool valid = warp * kWarpKeys + r * 32 + lane < tile_n;
         const unsigned d = static_cast<unsigned>((k[r] >> shift) & 255u);
-        const unsigned peers = __match_any_sync(0xffffffffu, valid ? d : 256u + lane);
-        const unsigned rk = __popc(peers & ((1u << lane) - 1u));
+        peers[r] = __match_any_sync(0xffffffffu, valid ? d : 256u + lane);
+    }
+#pragma unroll
+    for (int r = 0; r < kScatItems; ++r) {
+        const bool valid = warp * kWarpKeys + r * 32 + lane < tile_n;
+        const unsigned d = static_cast<unsigned>((k[r] >> shift) & 255u);
+        const unsigned rk = __popc(peers[r] & ((1u << lane) - 1u));
+        // only the first lane of a group touches the counter (one shared-memory access per distinct digit); the others
+        // get the old value by shuffle
         unsigned before = 0;
-        if (valid) before = cnt[warp][d];
-        __syncwarp();
-        if (valid && rk == 0) cnt[warp][d] = static_cast<unsigned short>(before + __popc(peers));
-        __syncwarp();
+        if (valid && rk == 0) {
+            before = cnt[warp][d];
+            cnt[warp][d] = static_cast<unsigned short>(before + __popc(peers[r]));
+        }
+        before = __shfl_sync(0xffffffffu, before, __ffs(peers[r]) - 1);
+        __syncwarp();          // the next round's leaders read what this round's leaders wrote
         off_in_warp[r] = static_cast<unsigned short>(before + rk);
     }
     __syncthreads();
-    {   // thread d: digit d's counts over the warps -> exclusive offsets per warp; then the digits' bases
+    {   // thread d (the first 256 threads): digit d's counts over the warps -> exclusive offsets per warp; then the digits' bases
+        const bool owner = threadIdx.x < 256;
         unsigned run = 0;
+        if (owner) {
 #pragma unroll
-        for (int w = 0; w < kBlock / 32; ++w) {
-            const unsigned c = cnt[w][threadIdx.x];
-            cnt[w][threadIdx.x] = static_cast<unsigned short>(run);
-            run += c;
+            for (int w = 0; w < kScatThreads / 32; ++w) {
+                const unsigned c = cnt[w][threadIdx.x];
+                cnt[w][threadIdx.x] = static_cast<unsigned short>(run);
+                run += c;
+            }
         }
         unsigned incl = run;
 #pragma unroll
@@ -269,17 +290,19 @@ __global__ void __launch_bounds__(kBlock, 3) k_radix_scatter(const unsigned long
             const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += y;
         }
-        if (lane == 31) warp_tot[warp] = incl;
+        if (owner && lane == 31) warp_tot[warp] = incl;
         __syncthreads();
-        unsigned pre = 0;
-        for (int w = 0; w < warp; ++w) pre += warp_tot[w];
-        const unsigned excl = pre + incl - run;
-        digit_base[threadIdx.x] = excl;
-        goff[threadIdx.x] = offsets[threadIdx.x * (size_t)n_tiles + blockIdx.x] - excl;
+        if (owner) {
+            unsigned pre = 0;
+            for (int w = 0; w < warp; ++w) pre += warp_tot[w];
+            const unsigned excl = pre + incl - run;
+            digit_base[threadIdx.x] = excl;
+            goff[threadIdx.x] = offsets[threadIdx.x * (size_t)n_tiles + blockIdx.x] - excl;
+        }
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
+    for (int r = 0; r < kScatItems; ++r) {
         const unsigned x = warp * kWarpKeys + r * 32 + lane;
         if (x < tile_n) {
             const unsigned d = static_cast<unsigned>((k[r] >> shift) & 255u);
@@ -290,8 +313,8 @@ __global__ void __launch_bounds__(kBlock, 3) k_radix_scatter(const unsigned long
     }
     __syncthreads();
 #pragma unroll
-    for (int r = 0; r < kSortItems; ++r) {
-        const unsigned j = r * kBlock + threadIdx.x;
+    for (int r = 0; r < kScatItems; ++r) {
+        const unsigned j = r * kScatThreads + threadIdx.x;
         if (j < tile_n) {
             const unsigned long long key = skey[j];
             const unsigned long long g = goff[(key >> shift) & 255u] + j;
@@ -331,7 +354,7 @@ static void radix_sort_pairs(bq_ctx* ctx, unsigned long long*& keys, unsigned*& 
         ctx->launches++;
         BQ_CUDA(cudaGetLastError());
         exclusive_scan_u32(ctx, static_cast<unsigned*>(hist.p), 256 * (size_t)n_tiles, static_cast<unsigned long long*>(offs.p), false);
-        k_radix_scatter<<<n_tiles, kBlock, kSortSmem, ctx->stream>>>(keys, vals, keys_alt, vals_alt, n, shift,
+        k_radix_scatter<<<n_tiles, kScatThreads, kSortSmem, ctx->stream>>>(keys, vals, keys_alt, vals_alt, n, shift,
                                                                    static_cast<unsigned long long*>(offs.p), n_tiles);
         ctx->launches++;
         BQ_CUDA(cudaGetLastError());
