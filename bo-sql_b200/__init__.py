@@ -334,6 +334,12 @@ class Join:
         _check(kernel_lib().bq_join_bitmap_popcount(self.ctx.h, self.h, C.byref(out)))
         return int(out.value)
 
+    def verdict(self):
+        """(bits set, rows inserted, flags) of a bitmap built with join_build_bitmap_nosync (after any merge of the words)."""
+        bits, ins, flags = C.c_uint64(0), C.c_uint64(0), C.c_int(0)
+        _check(kernel_lib().bq_join_bitmap_verdict(self.ctx.h, self.h, C.byref(bits), C.byref(ins), C.byref(flags)))
+        return int(bits.value), int(ins.value), int(flags.value)
+
     def probe_bits(self, probe_key, row_begin=0, row_end=None, slice_bytes=48 << 20):
         """Per-row match bits (uint32 column, bit i = row i) computed in key-range passes over an L2-sized bitmap slice."""
         out = C.c_void_p()
@@ -510,6 +516,20 @@ class Context:
         s.key_min, s.key_max = key_min, key_max
         h = C.c_void_p()
         _check(self.L.bq_join_build(self.h, C.byref(s), C.byref(h)))
+        return Join(self, h)
+
+    def join_build_bitmap_nosync(self, key, preds=(), row_begin=0, row_end=None, key_min=0, key_max=-1) -> Join:
+        """The bitmap build ranks use before they merge their bitmaps: nothing is read back; Join.verdict() does that."""
+        s = JoinSpec()
+        s.key = key.h
+        for i, p in enumerate(preds):
+            s.pred[i] = p
+        s.row_begin = row_begin
+        s.row_end = key.n if row_end is None else row_end
+        s.kind = JOIN_BITMAP
+        s.key_min, s.key_max = key_min, key_max
+        h = C.c_void_p()
+        _check(self.L.bq_join_build_bitmap_nosync(self.h, C.byref(s), C.byref(h)))
         return Join(self, h)
 
     def join_probe(self, join, probe_key, rowids=None, row_begin=0, row_end=None):

@@ -99,10 +99,19 @@ def q1_kernel_spec(bq, status_col, date_col, total_col, n, status_id, d_lo, d_hi
 
 
 def run_smoke(bq):
-    from oracle import datagen
+    """One small Q1 on cuda:0, twice: through the kernel layer's C ABI (bq_scan_aggregate + bq_rel_sort) and through the
+    operator layer (bqx_*: parse -> plan -> open / next / close), both checked against the ORACLE - the numpy restatement of
+    the reference's executor (oracle/oracle.py, itself pinned to the compiled reference by tests/test_oracle.py)."""
+    from oracle import datagen, oracle as ORA
     n, seed = 200_000, 7
     tab = datagen.host_table(datagen.orders_schema(n), n, seed)
     cols = {name: arr for name, _t, arr in tab}
+    sql = ("SELECT order_date, SUM(total) AS revenue FROM orders WHERE status = 'COMPLETE' AND order_date >= 20240101 "
+           "AND order_date <= 20240131 GROUP BY order_date ORDER BY order_date")
+    ora = ORA.Oracle()
+    ora.add_table("orders", tab, ora.new_dict(datagen.STATUS_DICT))
+    want = ora.query(sql)
+    assert want.rows > 0
     ctx = bq.Context(0)
     try:
         status = ctx.upload(STRING, cols["status"])
@@ -112,11 +121,11 @@ def run_smoke(bq):
         rel = ctx.scan_aggregate(spec)
         srt = ctx.rel_sort(rel, [0], [1])
         got = srt.to_numpy()
-        # checker: numpy restatement of Selection + HashAggregate + OrderBy for this shape
-        m = (cols["status"] == 0) & (cols["order_date"] >= 20240101) & (cols["order_date"] <= 20240131)
-        keys = np.unique(cols["order_date"][m])
-        sums = np.array([np.sum(cols["total"][m & (cols["order_date"] == k)]) for k in keys])
-        assert np.array_equal(got[0], keys.astype(np.int32)), "smoke: group keys differ"
-        assert_close(got[1], sums, "smoke: SUM(total)")
+        assert_same_rows(got, want.cols, ordered_by=[(0, True)], what="smoke, kernel layer vs oracle")
     finally:
         ctx.close()
+    eng = bq.Engine(0)
+    eng.add_table("orders", tab, eng.new_dict(datagen.STATUS_DICT))
+    res = eng.query(sql)
+    assert res.names == want.names, (res.names, want.names)
+    assert_same_rows(res.cols, want.cols, ordered_by=[(0, True)], what="smoke, operator layer vs oracle")

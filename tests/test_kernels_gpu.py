@@ -438,6 +438,73 @@ def test_join_payload_from_build_side(bq, ctx):
         assert got[0][0] == want_cnt and got[1][0] == want_sum       # dyadic values: exact
 
 
+def test_bitmap_build_without_round_trip(bq, ctx):
+    """bq_join_build_bitmap_nosync + bq_join_bitmap_verdict: the counters packed behind the bitmap words say what was inserted;
+    a repeated key shows as fewer bits than rows, a key outside the catalog's bounds as flag 2 - the two conditions on which
+    ranks that summed their bitmaps fall back to a broadcast join."""
+    n = 100_003
+    rng = np.random.default_rng(21)
+    keys = rng.permutation(np.arange(1, n + 1, dtype=np.int64))
+    status = rng.integers(0, 4, size=n).astype(np.uint32)
+    kc, sc = ctx.upload(INT64, keys), ctx.upload(STRING, status)
+    j = ctx.join_build_bitmap_nosync(kc, preds=[bq.make_slot(sc, [(0, 0, 0)])], key_min=1, key_max=n)
+    bits, ins, flags = j.verdict()
+    want = int((status == 0).sum())
+    assert (bits, ins, flags) == (want, want, 0) and j.build_rows == want
+    p, words = j.bitmap()
+    assert words == (n + 31) // 32
+    # the bits themselves: the same probe answers as the synchronous build
+    j2 = ctx.join_build(kc, preds=[bq.make_slot(sc, [(0, 0, 0)])], unique=True, key_min=1, key_max=n)
+    probe = ctx.upload(INT64, np.arange(1, n + 1, dtype=np.int64))
+    a = j.probe_bits(probe, 0, n, slice_bytes=1 << 30).to_numpy()
+    b = j2.probe_bits(probe, 0, n, slice_bytes=1 << 30).to_numpy()
+    assert np.array_equal(a, b)
+    dup = keys.copy()
+    dup[5] = dup[77]
+    dc = ctx.upload(INT64, dup)
+    bits, ins, flags = ctx.join_build_bitmap_nosync(dc, key_min=1, key_max=n).verdict()
+    assert ins == n and bits == n - 1 and flags == 0
+    far = keys.copy()
+    far[9] = n + 1000
+    fc = ctx.upload(INT64, far)
+    bits, ins, flags = ctx.join_build_bitmap_nosync(fc, key_min=1, key_max=n).verdict()
+    assert flags == 2 and ins == n - 1 == bits
+
+
+@pytest.mark.parametrize("domain", [1, 31, 16384, 16385, 70_001])
+def test_dense_group_by_emit_paths(bq, ctx, domain):
+    """Small dense states finish in one launch (k_finish_small, up to 16384 slots), larger ones through presence bits,
+    compaction and emit: both must give the groups that exist, in key order, with COUNT / SUM / AVG as the reference defines them."""
+    n = 200_003
+    rng = np.random.default_rng(domain)
+    present = np.sort(rng.choice(domain, size=max(1, (domain * 2) // 3), replace=False))
+    k = (present[rng.integers(0, present.size, size=n)] + 1000).astype(np.int64)
+    v = (rng.integers(-500, 500, size=n) / 8.0).astype(np.float64)
+    kc, vc = ctx.upload(INT64, k), ctx.upload(DOUBLE, v)        # (kept alive: a slot holds the handle, not the Column)
+    s = bq.ScanSpec()
+    s.key = bq.make_slot(kc)
+    s.a = bq.make_slot(vc)
+    s.row_begin, s.row_end = 0, n
+    s.n_v = 1
+    s.v[0] = bq.VExpr(op=bq.V_A)
+    s.group_mode = bq.GROUP_DENSE
+    s.key_min, s.key_max = 1000, 1000 + domain - 1
+    s.n_out = 3
+    s.out[0] = bq.AggOut(func=bq.AGG_COUNT)
+    s.out[1] = bq.AggOut(func=bq.AGG_SUM, v=0)
+    s.out[2] = bq.AggOut(func=bq.AGG_AVG, v=0)
+    got = ctx.scan_aggregate(s).to_numpy()
+    keys, inv, counts = np.unique(k, return_inverse=True, return_counts=True)
+    sums = np.bincount(inv, weights=v, minlength=keys.size)
+    assert np.array_equal(got[0], keys) and np.array_equal(got[1], counts)          # key order, exact counts
+    assert np.array_equal(got[2], sums)                                              # multiples of 1/8: sums are exact in any order
+    assert np.array_equal(got[3], sums / counts)
+    s.n_out = 1                                                                      # SUM only: presence rides on the sums (-0.0 marks)
+    s.out[0] = bq.AggOut(func=bq.AGG_SUM, v=0)
+    got = ctx.scan_aggregate(s).to_numpy()
+    assert np.array_equal(got[0], keys) and np.array_equal(got[1], sums)
+
+
 # ---- sort / limit --------------------------------------------------------------------------------
 @pytest.mark.parametrize("n", [0, 1, 2, 500, 4096, 4097, 300_001])
 def test_sort_multi_key(bq, ctx, n):

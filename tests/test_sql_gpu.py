@@ -185,6 +185,12 @@ AGG_QUERIES = [
     "SELECT s, SUM(v) AS total FROM t GROUP BY s ORDER BY total DESC",
     "SELECT s, SUM(v) AS total FROM t GROUP BY s ORDER BY total DESC LIMIT 3",
     "SELECT c_str, SUM(w) AS sw, COUNT(*) AS n FROM t GROUP BY c_str ORDER BY n DESC, c_str LIMIT 10",
+    # ORDER BY on the key of a dense aggregate: ascending reuses the emit order, everything else still sorts
+    "SELECT c_date, SUM(v) AS total FROM t GROUP BY c_date ORDER BY c_date",
+    "SELECT c_date, SUM(v) AS total FROM t GROUP BY c_date ORDER BY c_date DESC",
+    "SELECT c_date, SUM(v) AS total FROM t GROUP BY c_date ORDER BY c_date LIMIT 7",
+    "SELECT c_date, SUM(v) AS total, COUNT(*) AS n FROM t WHERE c_i64 < 500000 GROUP BY c_date ORDER BY c_date ASC",
+    "SELECT c_str, COUNT(*) AS n FROM t GROUP BY c_str ORDER BY c_str, n",
     "SELECT COUNT(*), SUM(v) FROM t WHERE c_i64 < 0",                                 # zero rows -> zero output rows (H5)
     "SELECT s, COUNT(*) FROM t WHERE c_i64 < 0 GROUP BY s",
 ]
