@@ -794,58 +794,100 @@ __global__ void __launch_bounds__(kBlock) k_emit(const __grid_constant__ EmitPar
     }
 }
 
-// Small dense / global states (a date domain, a handful of statuses, a global aggregate): ONE CTA finds the groups that exist,
-// numbers them in slot order and writes the output columns - presence test, ordered compaction and emit in one launch, with
-// the group count and the scan's error word left for one host round trip.  The general path below spends four launches and
-// needs the count on the host BEFORE it can emit; for Q1's 31 groups that was most of the time after the scan.
-constexpr size_t kSmallState = 16384;
-__global__ void __launch_bounds__(1024) k_finish_small(const __grid_constant__ EmitParams p, size_t slots, int presence,
-                                                       unsigned long long* __restrict__ n_groups) {
+// Dense / global states of up to a million slots: CTAs of 1024 threads find the groups that exist in their 16384-slot chunk,
+// number them in slot order and write the output columns - presence test, ordered compaction and emit in one launch (two
+// when there are several chunks: a counting launch first, whose per-chunk totals give every CTA its base), with the group
+// count and the scan's error word left for ONE host round trip.  The general path below spends five launches and needs the
+// count on the host BEFORE it can emit; for Q1's 31 groups that was most of the time after the scan.
+constexpr size_t kFinishChunk = 16384;
+constexpr size_t kFinishMaxSlots = kFinishChunk * 64;
+BQ_D bool slot_present(const EmitParams& p, int presence, size_t g) {
+    return presence == 1 ? (__double_as_longlong(p.sum0[g]) != INT64_MIN) : (p.cnt[g] != 0);
+}
+__global__ void __launch_bounds__(1024) k_finish_count(const __grid_constant__ EmitParams p, size_t slots, int presence,
+                                                       unsigned* __restrict__ chunk_count) {
     __shared__ unsigned warp_tot[32];
-    __shared__ unsigned carry;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) carry = 0;
+    const size_t lo = blockIdx.x * kFinishChunk, hi = lo + kFinishChunk < slots ? lo + kFinishChunk : slots;
+    unsigned c = 0;
+    for (size_t g = lo + threadIdx.x; g < hi; g += 1024) c += slot_present(p, presence, g) ? 1u : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = c;
     __syncthreads();
-    for (size_t base = 0; base < slots; base += 1024) {
-        const size_t g = base + threadIdx.x;
-        bool present = false;
-        if (g < slots) present = presence == 1 ? (__double_as_longlong(p.sum0[g]) != INT64_MIN) : (p.cnt[g] != 0);
-        const unsigned ballot = __ballot_sync(0xffffffffu, present);
-        if (lane == 0) warp_tot[warp] = __popc(ballot);
-        __syncthreads();
-        unsigned pre = carry, total = 0;
-        for (int w = 0; w < 32; ++w) {
-            if (w < warp) pre += warp_tot[w];
-            total += warp_tot[w];
-        }
-        if (present) {
-            const size_t i = pre + __popc(ballot & ((1u << lane) - 1u));
-            if (p.out_key) {
-                const long long k = p.key_min + static_cast<long long>(g);
-                switch (p.key_type) {
-                    case BQ_INT64:
-                    case BQ_DOUBLE: static_cast<long long*>(p.out_key)[i] = k; break;
-                    case BQ_STRING: static_cast<unsigned*>(p.out_key)[i] = static_cast<unsigned>(k); break;
-                    default: static_cast<int*>(p.out_key)[i] = static_cast<int>(k); break;
-                }
-            }
-            const unsigned long long c = p.cnt[g];
-            for (int o = 0; o < p.n_out; ++o) {
-                const double sv = p.v[o] == 0 ? p.sum0[g] : p.sum1[g];
-                if (p.func[o] == BQ_AGG_COUNT) static_cast<long long*>(p.out[o])[i] = static_cast<long long>(c);
-                else if (p.func[o] == BQ_AGG_SUM) {
-                    if (p.as_int[o]) static_cast<long long*>(p.out[o])[i] = static_cast<long long>(sv);      // :1044
-                    else static_cast<double*>(p.out[o])[i] = sv;
-                } else {
-                    static_cast<double*>(p.out[o])[i] = c == 0 ? 0.0 : __ddiv_rn(sv, static_cast<double>(c));   // :1047
-                }
-            }
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) carry += total;
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int w = 0; w < 32; ++w) t += warp_tot[w];
+        chunk_count[blockIdx.x] = t;
     }
-    if (threadIdx.x == 0) *n_groups = carry;
+}
+// chunk_count == nullptr: a single chunk (grid of one).  Slot g of the chunk belongs to (round g / 1024, thread g % 1024), so
+// every load is coalesced; the sixteen rounds' ballots stay in registers, their per-warp counts (16 x 32 values) are scanned
+// ONCE by the first 512 threads, and the rounds are then emitted without another barrier.  (One barrier pair per round cost
+// 2 us each; sixteen consecutive slots per thread made the loads and stores strided: 56 us for Q2's 100 000 skus.)
+__global__ void __launch_bounds__(1024) k_finish_small(const __grid_constant__ EmitParams p, size_t slots, int presence,
+                                                       const unsigned* __restrict__ chunk_count, unsigned long long* __restrict__ n_groups) {
+    constexpr int kRounds = static_cast<int>(kFinishChunk / 1024);
+    __shared__ unsigned cnt[kRounds * 32];          // [round][warp] -> exclusive offsets after the scan
+    __shared__ unsigned round_tot[kRounds];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const size_t lo = blockIdx.x * kFinishChunk, hi = lo + kFinishChunk < slots ? lo + kFinishChunk : slots;
+    unsigned ballots[kRounds];
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        const size_t g = lo + static_cast<size_t>(r) * 1024 + threadIdx.x;
+        ballots[r] = __ballot_sync(0xffffffffu, g < hi && slot_present(p, presence, g));
+        if (lane == 0) cnt[r * 32 + warp] = __popc(ballots[r]);
+    }
+    __syncthreads();
+    unsigned v = 0, incl = 0;
+    if (threadIdx.x < kRounds * 32) {               // warp w of these threads holds round w's 32 warp counts
+        v = cnt[threadIdx.x];
+        incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned y = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += y;
+        }
+        if (lane == 31) round_tot[warp] = incl;
+    }
+    __syncthreads();
+    if (threadIdx.x < kRounds * 32) {
+        unsigned pre = 0;
+        for (int w = 0; w < warp; ++w) pre += round_tot[w];
+        cnt[threadIdx.x] = pre + incl - v;
+    }
+    unsigned before = 0, total = 0;
+    if (chunk_count)
+        for (unsigned q = 0; q < blockIdx.x; ++q) before += chunk_count[q];
+    for (int r = 0; r < kRounds; ++r) total += round_tot[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kRounds; ++r) {
+        if (!((ballots[r] >> lane) & 1u)) continue;
+        const size_t g = lo + static_cast<size_t>(r) * 1024 + threadIdx.x;
+        const size_t i = static_cast<size_t>(before) + cnt[r * 32 + warp] + __popc(ballots[r] & ((1u << lane) - 1u));
+        if (p.out_key) {
+            const long long k = p.key_min + static_cast<long long>(g);
+            switch (p.key_type) {
+                case BQ_INT64:
+                case BQ_DOUBLE: static_cast<long long*>(p.out_key)[i] = k; break;
+                case BQ_STRING: static_cast<unsigned*>(p.out_key)[i] = static_cast<unsigned>(k); break;
+                default: static_cast<int*>(p.out_key)[i] = static_cast<int>(k); break;
+            }
+        }
+        const unsigned long long cg = p.cnt[g];
+        for (int o = 0; o < p.n_out; ++o) {
+            const double sv = p.v[o] == 0 ? p.sum0[g] : p.sum1[g];
+            if (p.func[o] == BQ_AGG_COUNT) static_cast<long long*>(p.out[o])[i] = static_cast<long long>(cg);
+            else if (p.func[o] == BQ_AGG_SUM) {
+                if (p.as_int[o]) static_cast<long long*>(p.out[o])[i] = static_cast<long long>(sv);      // :1044
+                else static_cast<double*>(p.out[o])[i] = sv;
+            } else {
+                static_cast<double*>(p.out[o])[i] = cg == 0 ? 0.0 : __ddiv_rn(sv, static_cast<double>(cg));   // :1047
+            }
+        }
+    }
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1) *n_groups = static_cast<unsigned long long>(before) + total;
 }
 
 __global__ void __launch_bounds__(kBlock) k_fill_keys(long long* __restrict__ keys, size_t n, long long v) {
@@ -1213,8 +1255,8 @@ static bq_rel* emit_state(bq_ctx* ctx, AggState& st, const bq_agg_out* outs, int
         n_out = 3;
     }
     if (n_out < 0 || n_out > BQ_MAX_AGG_OUT) throw std::runtime_error("too many aggregate outputs");
-    if (st.gmode != G_HASH && st.slots <= kSmallState) {
-        // the columns are allocated for every slot (at most 16384 rows) and cut to the group count afterwards
+    if (st.gmode != G_HASH && st.slots <= kFinishMaxSlots) {
+        // the columns are allocated for every slot (at most a million rows) and cut to the group count afterwards
         std::vector<bq_col*> cols;
         try {
             EmitParams e{};
@@ -1241,8 +1283,14 @@ static bq_rel* emit_state(bq_ctx* ctx, AggState& st, const bq_agg_out* outs, int
                 e.as_int[o] = outs[o].as_int;
                 e.out[o] = cols.back()->ptr;
             }
-            auto* d = static_cast<unsigned long long*>(scratch(ctx, 16));
-            k_finish_small<<<1, 1024, 0, ctx->stream>>>(e, st.slots, st.presence, d);
+            const unsigned chunks = static_cast<unsigned>((st.slots + kFinishChunk - 1) / kFinishChunk);
+            auto* d = static_cast<unsigned long long*>(scratch(ctx, 16 + 64 * 4));
+            auto* chunk_count = reinterpret_cast<unsigned*>(d + 2);
+            if (chunks > 1) {
+                k_finish_count<<<chunks, 1024, 0, ctx->stream>>>(e, st.slots, st.presence, chunk_count);
+                ctx->launches++;
+            }
+            k_finish_small<<<chunks, 1024, 0, ctx->stream>>>(e, st.slots, st.presence, chunks > 1 ? chunk_count : nullptr, d);
             ctx->launches++;
             BQ_CUDA(cudaGetLastError());
             auto* h = static_cast<unsigned long long*>(pinned(ctx, 16));

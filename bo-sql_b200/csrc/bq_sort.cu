@@ -133,11 +133,25 @@ __global__ void __launch_bounds__(kTopkThreads) k_tile_topk(const __grid_constan
             __syncthreads();
             for (unsigned t = threadIdx.x; t < span / 2; t += blockDim.x) {
                 const unsigned pos = 2 * t - (t & (stride - 1));
-                const unsigned a = idx[pos], b = idx[pos + stride];
                 const bool up = (pos & size) == 0;
-                if (up ? before(b, a) : before(a, b)) {
-                    idx[pos] = static_cast<unsigned short>(b);
-                    idx[pos + stride] = static_cast<unsigned short>(a);
+                if (NK == 1) {
+                    // one sort column: the key travels with its position, so a step reads two (key, position) pairs at
+                    // regular addresses instead of chasing positions into the key array
+                    const unsigned long long ka = sk[pos], kb = sk[pos + stride];
+                    const unsigned short ia = idx[pos], ib = idx[pos + stride];
+                    const bool b_first = kb < ka || (kb == ka && ib < ia);
+                    if (up ? b_first : !b_first) {
+                        sk[pos] = kb;
+                        sk[pos + stride] = ka;
+                        idx[pos] = ib;
+                        idx[pos + stride] = ia;
+                    }
+                } else {
+                    const unsigned a = idx[pos], b = idx[pos + stride];
+                    if (up ? before(b, a) : before(a, b)) {
+                        idx[pos] = static_cast<unsigned short>(b);
+                        idx[pos + stride] = static_cast<unsigned short>(a);
+                    }
                 }
             }
         }

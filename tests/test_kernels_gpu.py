@@ -471,10 +471,11 @@ def test_bitmap_build_without_round_trip(bq, ctx):
     assert flags == 2 and ins == n - 1 == bits
 
 
-@pytest.mark.parametrize("domain", [1, 31, 16384, 16385, 70_001])
+@pytest.mark.parametrize("domain", [1, 31, 16384, 16385, 70_001, 1_048_576, 1_100_003])
 def test_dense_group_by_emit_paths(bq, ctx, domain):
-    """Small dense states finish in one launch (k_finish_small, up to 16384 slots), larger ones through presence bits,
-    compaction and emit: both must give the groups that exist, in key order, with COUNT / SUM / AVG as the reference defines them."""
+    """Dense states finish in one launch per 16384-slot chunk (k_finish_small; a counting launch first when there are several
+    chunks) up to 2^20 slots, larger ones through presence bits, compaction and emit: every path must give the groups that
+    exist, in key order, with COUNT / SUM / AVG as the reference defines them."""
     n = 200_003
     rng = np.random.default_rng(domain)
     present = np.sort(rng.choice(domain, size=max(1, (domain * 2) // 3), replace=False))
