@@ -103,6 +103,17 @@ QUERIES = [
     ("star", "SELECT d.tag, COUNT(*), SUM(p.v) FROM probe p JOIN dup d ON p.k = d.k WHERE d.w > 4 GROUP BY d.tag"),
     ("star", "SELECT p.k, p.v, d.w, d.tag FROM probe p JOIN dup d ON p.k = d.k"),
     ("star", "SELECT COUNT(*) FROM probe p JOIN dup d ON p.k = d.w"),
+    # round 2: any number of sort keys (operator.cpp:1115-1122), several GROUP BY expressions (:972-982), ORDER BY on the key
+    # of a dense aggregate in both directions, a full ORDER BY over un-aggregated rows, LIMIT above Project / Selection
+    ("sweep", "SELECT s, z, c_str, w, c_date, c_i64 FROM t ORDER BY s, z DESC, c_str, w DESC, c_date, c_i64 DESC"),
+    ("sweep", "SELECT s, z, c_str, w, c_date FROM t WHERE w < 300 ORDER BY c_date DESC, w, c_str DESC, z, s DESC LIMIT 40"),
+    ("sweep", "SELECT z + 1, w - 1, COUNT(*), SUM(v) FROM t WHERE w < 20 GROUP BY z + 1, w - 1"),
+    ("sweep", "SELECT s, z * 2, COUNT(*) FROM t GROUP BY s, z * 2"),
+    ("sweep", "SELECT c_date, SUM(v) AS total, COUNT(*) AS n FROM t GROUP BY c_date ORDER BY c_date"),
+    ("sweep", "SELECT c_date, SUM(v) AS total FROM t GROUP BY c_date ORDER BY c_date DESC LIMIT 9"),
+    ("sweep", "SELECT c_f64, c_i64 FROM t ORDER BY c_f64 DESC, c_i64"),
+    ("sweep", "SELECT c_i64 / 7, v * 2 FROM t WHERE z > 10 LIMIT 12"),
+    ("sweep", "SELECT c_i64 FROM t LIMIT 0"),
 ]
 
 EXPLAIN = [
