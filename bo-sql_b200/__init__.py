@@ -155,6 +155,8 @@ def kernel_lib():
         "bq_agg_state_emit": ([vp, vp, P(AggOut), C.c_int, P(vp)], C.c_int),
         "bq_agg_state_free": ([vp], None),
         "bq_partition": ([vp, vp, P(vp), C.c_int, sz, sz, C.c_int, C.c_int, P(vp), P(vp), P(vp)], C.c_int),
+        "bq_group_tables_plan": ([sz, C.c_int, P(C.c_int), P(C.c_int)], C.c_int),
+        "bq_partition_aggregate": ([vp, vp, P(vp), C.c_int, vp, C.c_int, C.c_int, P(AggOut), C.c_int, P(vp)], C.c_int),
         "bq_partition_count": ([vp, vp, sz, sz, C.c_int, C.c_int, P(i64), P(vp)], C.c_int),
         "bq_partition_count_hot": ([vp, vp, sz, sz, C.c_int, C.c_int, P(i64), C.c_int, P(i64), P(vp)], C.c_int),
         "bq_partition_scatter": ([vp, vp, P(vp), C.c_int, P(vp), P(vp), P(vp)], C.c_int),
@@ -449,6 +451,21 @@ class Context:
         h = C.c_void_p()
         fn = self.L.bq_scan_partial if partial else self.L.bq_scan_aggregate
         _check(fn(self.h, C.byref(spec), C.byref(h)))
+        return Relation(self, h)
+
+    def group_tables_plan(self, ndv_hint, n_args):
+        """(log2_parts, splits) of the shared-memory-table GROUP BY for `ndv_hint` groups, or None when it does not apply."""
+        lp, sp = C.c_int(), C.c_int()
+        if not self.L.bq_group_tables_plan(int(ndv_hint), n_args, C.byref(lp), C.byref(sp)):
+            return None
+        return lp.value, sp.value
+
+    def partition_aggregate(self, key, args, offsets, log2_parts, splits, outs) -> Relation:
+        """GROUP BY over rows ordered by partition(): one shared-memory table per (partition, split)."""
+        a = (C.c_void_p * max(1, len(args)))(*[c.h for c in args])
+        o = (AggOut * max(1, len(outs)))(*outs)
+        h = C.c_void_p()
+        _check(self.L.bq_partition_aggregate(self.h, key.h, a, len(args), offsets.h, log2_parts, splits, o, len(outs), C.byref(h)))
         return Relation(self, h)
 
     def agg_finish(self, parts, has_key, key_type, outs) -> Relation:

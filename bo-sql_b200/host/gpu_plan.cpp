@@ -86,6 +86,8 @@ void resolve_stats(PipeCol& col, bool force_device) {
 // Across GPUs that is a fact about ONE rank's shard, so programs containing such a division exchange their outcome: either
 // every rank continues or every rank throws (none is left alone inside the next collective).  Whether a program divides is
 // a property of the plan, so all ranks agree on whether the exchange happens - also a rank whose shard is empty.
+constexpr bool kGroupTablesDefault = false;
+
 static void run_program(const std::function<void()>& launch, const std::vector<bq_insn>& code) {
     bool divides = false;
     for (const bq_insn& in : code) divides = divides || in.op == BQ_OP_DIV_I;
@@ -334,6 +336,13 @@ struct Domain {
 // Heavy hitters of a (probe-side) join key, agreed by all ranks: every rank counts the keys of a sample of its rows
 // (the fused GROUP BY kernel over the first 2^20 rows, top 16 by count), the candidates are pooled on the host, and a key
 // is hot when its estimated share of all rows exceeds 1 / (8 * world) - enough to overload the rank that would own it.
+// BOSQL_GROUP_TABLES=0|1 overrides the default choice between the shared-memory group tables (bq_partition_aggregate) and
+// the L2-resident table (bq_scan_aggregate) for a high-cardinality GROUP BY over plain column arguments.
+static bool group_tables_enabled() {
+    const char* e = std::getenv("BOSQL_GROUP_TABLES");
+    return e ? *e != '0' : kGroupTablesDefault;
+}
+
 static std::vector<int64_t> find_hot_keys(PipeCol& key, size_t rows) {
     Exchange& xch = exchange();
     bq_ctx* ctx = context();
@@ -916,6 +925,9 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         const bool plain_stream = !p.joined && probe_conj.empty() && !s.mask;      // key / a / b are read as they lie
         size_t cur_rows = p.rows;
         std::vector<DevColPtr> reordered;        // keeps shuffled / partitioned columns alive through the scan
+        bool smem_tables = false;                // shared-memory group tables over the partitioned rows (bq_partition_aggregate)
+        int smem_splits = 1;
+        const bq_col* part_offsets = nullptr;
 
         // Across GPUs, a GROUP BY with more groups than fit a partial-state exchange moves the ROWS instead: hash-partition
         // by key, all-to-all, and every rank aggregates the keys it owns (SURVEY.md 8e, high-cardinality GROUP BY).
@@ -959,6 +971,20 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             static_cast<uint64_t>(s.ndv_hint) * 32 > (96ull << 20)) {
             int log2p = 4;
             while (log2p < 10 && ((static_cast<uint64_t>(s.ndv_hint) * 64) >> log2p) > (32ull << 20)) ++log2p;
+            // Plain column arguments: partition finely enough for one SHARED-MEMORY table per (partition, split) and let
+            // bq_partition_aggregate do accumulate and emit in one launch (csrc/bq_groupby.cuh).
+            bool plain_args = true;
+            for (int k = 0; k < s.n_v; ++k) {
+                if (s.v[k].op != BQ_V_A && s.v[k].op != BQ_V_B) plain_args = false;
+                const int src = s.v[k].op == BQ_V_A ? ps.col_a : ps.col_b;
+                if (src < 0 || p.cols[src].type == TypeId::STRING) plain_args = false;
+            }
+            int tables_log2p = 0, tables_splits = 0;
+            if (group_tables_enabled() && plain_args && bq_group_tables_plan(s.ndv_hint, s.n_v, &tables_log2p, &tables_splits)) {
+                log2p = tables_log2p;
+                smem_tables = true;
+                smem_splits = tables_splits;
+            }
             const bq_col* pay[2];
             int n_pay = 0;
             if (ps.col_a >= 0) pay[n_pay++] = s.a.col;
@@ -969,6 +995,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             ptrace.mark("local L2 partition");
             reordered.push_back(adopt(ok));
             reordered.push_back(adopt(off));
+            part_offsets = off;
             s.key.col = ok;
             int k = 0;
             if (ps.col_a >= 0) { reordered.push_back(adopt(op[k])); s.a.col = op[k++]; }
@@ -977,9 +1004,24 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             s.hash_part_shift = 64 - log2p;
         }
 
+        // One shared-memory table per (partition, split) when the plan above chose it; a table that fills up (statistics too
+        // low, a skewed partition) sends the same partitioned rows through the L2-resident table instead.  Local work only:
+        // across GPUs every rank may decide for itself.
+        auto aggregate_rows = [&](bq_rel** rel) -> int {
+            if (smem_tables) {
+                const bq_col* args[2] = {nullptr, nullptr};
+                for (int k = 0; k < s.n_v; ++k) args[k] = s.v[k].op == BQ_V_A ? s.a.col : s.b.col;
+                const int rc = bq_partition_aggregate(ctx, s.key.col, args, s.n_v, part_offsets, s.hash_part_log2, smem_splits, s.out, s.n_out, rel);
+                if (!rc) return 0;
+                if (!std::strstr(bq_last_error(), "table overflow")) return rc;
+                smem_tables = false;
+            }
+            return bq_scan_aggregate(ctx, &s, rel);
+        };
         // a hash table sized from a stale (too low) ndv overflows: the retry sizes it from the rows themselves and gives up
         // the partition-major layout, whose regions assume an even spread of the keys
         auto widen_table = [&] {
+            smem_tables = false;
             s.ndv_hint = std::max<size_t>(cur_rows, 1);
             s.hash_part_log2 = 0;
             s.hash_part_shift = 0;
@@ -988,14 +1030,14 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
         DeviceRelationPtr r;
         if (!dist) {
             bq_rel* rel = nullptr;
-            int rc = bq_scan_aggregate(ctx, &s, &rel);
+            int rc = aggregate_rows(&rel);
             if (rc && std::strstr(bq_last_error(), "stale statistics")) {
                 choose_group(true);                 // the catalog's min/max were wrong: measure and retry
-                rc = bq_scan_aggregate(ctx, &s, &rel);
+                rc = aggregate_rows(&rel);
             }
             if (rc && std::strstr(bq_last_error(), "table overflow")) {
                 widen_table();                      // the catalog's ndv was too low (or a partition is skewed): size by rows
-                rc = bq_scan_aggregate(ctx, &s, &rel);
+                rc = aggregate_rows(&rel);
             }
             check(rc);
             r = relation_from(rel);
@@ -1003,7 +1045,7 @@ DeviceRelationPtr run_aggregate(Pipeline& p, const AggRequest& req) {
             // every rank owns a disjoint set of keys: aggregate locally, agree on the outcome, then replicate the groups
             auto attempt = [&](std::string& message) {
                 bq_rel* rel = nullptr;
-                int rc = bq_scan_aggregate(ctx, &s, &rel);
+                int rc = aggregate_rows(&rel);
                 if (rc) message = bq_last_error();
                 else r = relation_from(rel);
                 int64_t mine = rc ? (message.find("stale statistics") != std::string::npos ? 2 : message.find("table overflow") != std::string::npos ? 3 : 1) : 0, worst = 0;

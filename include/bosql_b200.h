@@ -306,6 +306,20 @@ int bq_join_probe(bq_ctx* ctx, const bq_join* j, const bq_col* probe_key, const 
  * the per-peer send buffers of the multi-GPU all-to-all (2^log2_parts = number of ranks). */
 int bq_partition(bq_ctx* ctx, const bq_col* key, const bq_col* const* payload, int n_payload, size_t row_begin, size_t row_end,
                  int log2_parts, int hash_shift, bq_col** out_key, bq_col** out_payload, bq_col** out_offsets);
+/* High-cardinality GROUP BY over rows that bq_partition has ordered (HashAggregate's accumulate and emit phases,
+ * src/exec/operator.cpp:984-1062, when tens of millions of groups receive a handful of rows each): one launch, `splits`
+ * CTAs per partition, each keeping the groups of its share of the partition's keys in a SHARED-MEMORY table that is updated
+ * without atomics (slot ownership by tag, see csrc/bq_groupby.cuh) and writing the finished output columns itself - no
+ * table in HBM, no presence / compaction / emit passes.  `args` are the aggregate arguments as plain numeric columns
+ * (outs[i].v indexes them), `offsets` is bq_partition's out_offsets for the same log2_parts with hash_shift = 64 - log2_parts.
+ * Result: [key] then one column per outs[], groups in no particular order.  Fails with "group table
+ * overflow" when a table cannot hold its keys (statistics too low, or a skewed partition): the caller then aggregates the
+ * same partitioned rows with bq_scan_aggregate (hash_part_log2 = log2_parts).
+ * bq_group_tables_plan: the sizing rule - how many partitions and splits make every table's expected load <= 0.55;
+ * returns 0 when more than four splits would be needed (the caller keeps the L2-resident table of bq_scan_aggregate). */
+int bq_group_tables_plan(size_t ndv_hint, int n_args, int* log2_parts, int* splits);
+int bq_partition_aggregate(bq_ctx* ctx, const bq_col* key, const bq_col* const* args, int n_args, const bq_col* offsets,
+                           int log2_parts, int splits, const bq_agg_out* outs, int n_out, bq_rel** out);
 /* The same pass in two halves, for the multi-GPU shuffle: count first (host_counts[2^log2_parts] = rows per partition, one
  * host round trip), then scatter every partition to an address of the caller's choice - dest_key[q] / dest_pay*[q] is
  * where THIS launch's first row of partition q goes.  The addresses may lie in a peer GPU's memory (bq_ipc_open): the

@@ -180,9 +180,12 @@ def test_high_cardinality_group_by(bq, ctx):
     assert np.array_equal(g[0][o], uk) and np.array_equal(g[1][o], np.bincount(inv)) and np.array_equal(g[2][o], np.bincount(inv, weights=vv))
 
 
-def test_sql_high_cardinality_group_by_takes_the_partitioned_path(bq, ctx):
-    """Through the operator layer: catalog NDV says the table will not fit in L2, so the planner partitions first.
+@pytest.mark.parametrize("tables", ["0", "1"])
+def test_sql_high_cardinality_group_by_takes_the_partitioned_path(bq, ctx, monkeypatch, tables):
+    """Through the operator layer: catalog NDV says the table will not fit in L2, so the planner partitions first - then
+    either the partition-major table in L2 (BOSQL_GROUP_TABLES=0) or one shared-memory table per partition (=1).
     The answer must equal the unpartitioned kernel's, bit for bit (dyadic values)."""
+    monkeypatch.setenv("BOSQL_GROUP_TABLES", tables)
     n, ids = 8_000_003, 4_000_000
     k = ctx.alloc(INT64, n).generate(dist=bq.GEN_HASHED, seed=SEED, stream=0, lo=0, hi=ids - 1, modulus=1 << 61)
     v = ctx.alloc(DOUBLE, n).generate(dist=bq.GEN_UNIFORM_DIV, seed=SEED, stream=1, lo=1, hi=6400, div=64.0)
@@ -198,3 +201,26 @@ def test_sql_high_cardinality_group_by_takes_the_partitioned_path(bq, ctx):
     for g, w in zip(r.cols, want):
         assert np.array_equal(g[a], w[b])
     assert int(r.cols[1].sum()) == n
+    # the shared-memory tables finish in ONE launch after the partition pass; the L2-resident table needs seven more
+    launches = bq.wrap_context(bq.exec_lib().bqx_context()).launches - before
+    assert (launches <= 10) == (tables == "1"), launches
+
+
+@pytest.mark.parametrize("tables", ["0", "1"])
+def test_sql_group_by_survives_a_stale_ndv(bq, ctx, monkeypatch, tables):
+    """The catalog claims 3.2 M distinct keys; the rows hold ten million.  The shared-memory tables fill up, the L2-resident
+    table sized from the claim fills up as well, and the third attempt sizes the table from the rows: slower, same answer."""
+    monkeypatch.setenv("BOSQL_GROUP_TABLES", tables)
+    n = 10_000_019
+    k = ctx.alloc(INT64, n).generate(dist=bq.GEN_HASHED, seed=SEED + 9, stream=0, lo=0, hi=(1 << 40) - 1, modulus=1 << 61)
+    v = ctx.alloc(DOUBLE, n).generate(dist=bq.GEN_UNIFORM_DIV, seed=SEED + 9, stream=1, lo=1, hi=6400, div=64.0)
+    ctx.sync()
+    eng = bq.Engine()
+    eng.add_table("t", [("k", INT64, k), ("v", DOUBLE, v)], stats={"k": (0, (1 << 61) - 1, 3_200_000)})
+    r = eng.query("SELECT k, COUNT(*), SUM(v) FROM t GROUP BY k")
+    kk, vv = k.to_numpy(), v.to_numpy()
+    uk, inv = np.unique(kk, return_inverse=True)
+    assert len(uk) > 9_990_000
+    o = np.argsort(r.cols[0])
+    assert np.array_equal(r.cols[0][o], uk) and np.array_equal(r.cols[1][o], np.bincount(inv))
+    assert np.array_equal(r.cols[2][o], np.bincount(inv, weights=vv))

@@ -684,6 +684,90 @@ def test_group_by_over_partitioned_rows(bq, ctx):
     assert np.array_equal(got[3][o], sm / cnt)
 
 
+# ---- shared-memory group tables over partitioned rows (bq_partition_aggregate, csrc/bq_groupby.cuh) -----------------
+def _group_tables_case(bq, ctx, n, ids, log2p, splits, n_args, key_type=INT64, heavy=0.0, seed=0):
+    """Rows -> partition() -> partition_aggregate(); numpy restatement of HashAggregate (src/exec/operator.cpp:984-1062).
+    Values are dyadic, so every order of addition gives the same bits: the comparison is exact."""
+    rng = np.random.default_rng(seed + n + ids)
+    base = rng.integers(0, ids, size=n)
+    if key_type == INT64:
+        k = (base * 7919 - 1_000_000_007 * (base % 3)).astype(np.int64)
+        if n > 2000:
+            k[5::977] = np.iinfo(np.int64).min          # the key that equals the tables' empty marker
+            k[7::1013] = np.iinfo(np.int64).max
+        kd = k
+    else:
+        k = (20200101 + base).astype(np.int32)
+        kd = k.astype(np.int64)
+    if heavy:
+        hot = rng.random(n) < heavy
+        k[hot] = 42
+        kd = k.astype(np.int64)
+    a = rng.integers(-1000, 1001, size=n).astype(np.int64)
+    b = rng.integers(-25600, 25601, size=n).astype(np.float64) / 8.0
+    kc, ac, bc = ctx.upload(key_type, k), ctx.upload(INT64, a), ctx.upload(DOUBLE, b)
+    pay = [bc] if n_args == 1 else ([ac, bc] if n_args == 2 else [])
+    ko, po, off = ctx.partition(kc, pay, log2_parts=log2p)
+    if n_args == 0:
+        outs = [bq.AggOut(func=bq.AGG_COUNT)]
+    elif n_args == 1:
+        outs = [bq.AggOut(func=bq.AGG_COUNT), bq.AggOut(func=bq.AGG_SUM, v=0), bq.AggOut(func=bq.AGG_AVG, v=0)]
+    else:
+        outs = [bq.AggOut(func=bq.AGG_SUM, v=0, as_int=1), bq.AggOut(func=bq.AGG_COUNT), bq.AggOut(func=bq.AGG_SUM, v=1),
+                bq.AggOut(func=bq.AGG_AVG, v=1)]
+    got = ctx.partition_aggregate(ko, po, off, log2p, splits, outs).to_numpy()
+    uk, inv = np.unique(kd, return_inverse=True)
+    cnt = np.bincount(inv, minlength=len(uk))
+    o = np.argsort(got[0].astype(np.int64), kind="stable")
+    assert len(got[0]) == len(uk), f"{len(got[0])} groups, expected {len(uk)}"
+    assert np.array_equal(got[0].astype(np.int64)[o], uk)
+    if n_args == 0:
+        assert np.array_equal(got[1][o], cnt)
+    elif n_args == 1:
+        sb = np.bincount(inv, weights=b, minlength=len(uk))
+        assert np.array_equal(got[1][o], cnt) and np.array_equal(got[2][o], sb) and np.array_equal(got[3][o], sb / cnt)
+    else:
+        sa = np.bincount(inv, weights=a.astype(np.float64), minlength=len(uk))
+        sb = np.bincount(inv, weights=b, minlength=len(uk))
+        assert got[1].dtype == np.int64 and np.array_equal(got[1][o], sa.astype(np.int64))
+        assert np.array_equal(got[2][o], cnt) and np.array_equal(got[3][o], sb) and np.array_equal(got[4][o], sb / cnt)
+
+
+@pytest.mark.parametrize("n,ids,log2p,splits,n_args,key_type,heavy", [
+    (600_011, 40_000, 4, 1, 1, INT64, 0.0),        # 2500 groups per 8192-slot table
+    (600_011, 50_000, 2, 3, 1, INT64, 0.0),        # three splits per partition, load 0.5
+    (400_003, 15_000, 3, 1, 2, INT64, 0.25),       # two sums (4096-slot tables), a quarter of the rows on ONE key
+    (300_007, 9_000, 1, 2, 0, DATE32, 0.02),       # COUNT only, 4-byte keys
+    (4_099, 700, 0, 1, 1, INT64, 0.0),             # one partition, ragged tail
+    (37, 5, 4, 2, 1, INT64, 0.0),                  # mostly empty partitions
+    (1, 1, 0, 1, 1, INT64, 0.0),
+])
+def test_partition_aggregate(bq, ctx, n, ids, log2p, splits, n_args, key_type, heavy):
+    _group_tables_case(bq, ctx, n, ids, log2p, splits, n_args, key_type, heavy)
+
+
+def test_partition_aggregate_sizing_rule_and_overflow(bq, ctx):
+    # the sizing rule: expected load of every table <= 0.55, at most four splits, up to 1024 partitions
+    assert ctx.group_tables_plan(12_500_000, 1) == (10, 3)          # configuration 4 on one GPU
+    assert ctx.group_tables_plan(4_000_000, 1) == (10, 1)
+    assert ctx.group_tables_plan(4_000_000, 2) == (10, 2)
+    assert ctx.group_tables_plan(100_000_000, 1) is None            # would need 22 splits: the L2-resident table stays
+    lp, sp = ctx.group_tables_plan(300_000, 1)
+    _group_tables_case(bq, ctx, 1_200_007, 300_000, lp, sp, 1)
+    # far more keys than the tables hold: a clean error (the operator layer falls back to bq_scan_aggregate), no wrong answer
+    with pytest.raises(RuntimeError, match="table overflow"):
+        _group_tables_case(bq, ctx, 300_000, 60_000, 1, 1, 1)
+    # ... and the context is usable afterwards
+    _group_tables_case(bq, ctx, 50_000, 3_000, 2, 1, 1)
+
+
+def test_partition_aggregate_empty_input(bq, ctx):
+    kc, vc = ctx.upload(INT64, np.zeros(0, np.int64)), ctx.upload(DOUBLE, np.zeros(0))
+    ko, (vo,), off = ctx.partition(kc, [vc], log2_parts=3)
+    got = ctx.partition_aggregate(ko, [vo], off, 3, 2, [bq.AggOut(func=bq.AGG_COUNT), bq.AggOut(func=bq.AGG_SUM, v=0)])
+    assert got.rows == 0 and got.ncols == 3
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("log2p", [1, 4, 9])
 def test_partition_count_then_scatter_to_chosen_destinations(bq, ctx, log2p):
