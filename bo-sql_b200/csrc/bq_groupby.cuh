@@ -24,6 +24,12 @@
 // At the end each CTA numbers its groups (ballot / popc, one atomicAdd on the global cursor per CTA) and writes the
 // finished output columns: no table in HBM, no presence pass, no separate emit.
 //
+// Measured on a B200 (profiles/README.md, "Configuration 4 taken apart"): 250 M rows / 12.5 M groups in 1024 partitions x 3
+// splits take 6.8 ms here against 3.7 ms for the L2-resident table of bq_scan.cu, and the 1024-way partition this kernel needs
+// takes 8.4 ms against 2.1 ms for the 32-way one that table needs.  The kernel is bound by instruction issue (17 warp
+// instructions per row, three quarters of them in the key scan that every split repeats), the partition by half-written
+// sectors.  It is therefore OPT-IN (BOSQL_GROUP_TABLES=1 in the operator layer); the default path is the L2-resident table.
+//
 // The file is plain CUDA C++ without inline PTX on purpose: tests/cpp/emu compiles this very source for the host with a
 // fibre-based CUDA emulation and checks it against std::map on the CPU (-m "not gpu").
 #pragma once
