@@ -14,9 +14,6 @@
 #include "bq_common.cuh"
 #include "bq_internal.cuh"
 
-#include <cuda_pipeline.h>
-#include <cstdlib>
-
 namespace bq {
 
 constexpr int kPartTile = 2048;                 // rows staged per CTA iteration
@@ -26,7 +23,6 @@ constexpr int kHistThreads = 1024;              // histogram CTA (two per SM: on
 constexpr int kHistCells = 2048;                // shared counters per CTA: P partitions x (kHistCells / P) lane-private copies
 constexpr int kMaxPartLog2 = 10;
 constexpr int kMaxHotKeys = 16;
-constexpr bool kPartStageDefault = false;
 
 struct PartParams {
     const void* key;
@@ -47,8 +43,6 @@ struct PartParams {
     // or a peer GPU's buffer mapped through CUDA IPC: the shuffle writes straight over NVLink, no staging copy)
     void* const* dest_key;             // [P]
     void* const* dest_pay[2];          // [P] each
-    int stage_in;                      // 1: the NEXT tile's rows are copied into shared memory (cp.async) while this tile is sorted
-                                       // and written out; 0: a tile's loads are issued where the tile starts
 };
 
 BQ_D unsigned part_of(const PartParams& p, long long k) {
@@ -115,10 +109,6 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_part_scatter(const __grid_c
     unsigned* cnt = reinterpret_cast<unsigned*>(dpay1 + P);
     unsigned* start = cnt + P;
     unsigned short* spart = reinterpret_cast<unsigned short*>(start + P);
-    // stage_in: raw bytes of the next tile, 8 per row and column; thread t reads back exactly the slots it copied
-    unsigned char* in_key = reinterpret_cast<unsigned char*>(spart + kPartTile);
-    unsigned char* in_pay0 = in_key + kPartTile * 8;
-    unsigned char* in_pay1 = in_pay0 + kPartTile * 8;
     __shared__ unsigned warp_tot[kPartThreads / 32];
 
     for (unsigned i = threadIdx.x; i < P; i += blockDim.x) {
@@ -132,66 +122,20 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_part_scatter(const __grid_c
     const size_t hi = lo + p.rows_per_block < p.n ? lo + p.rows_per_block : p.n;
     const int key_w = width_of(p.key_kind);
 
-    // asynchronous copies (global -> shared, no registers) of the rows this thread handles in the tile starting at `from`
-    auto stage = [&](size_t from) {
-        const unsigned n_in = static_cast<unsigned>(hi - from < (size_t)kPartTile ? hi - from : (size_t)kPartTile);
-#pragma unroll
-        for (int j = 0; j < kPartRows; ++j) {
-            const unsigned x = j * kPartThreads + threadIdx.x;
-            if (x < n_in) {
-                const size_t row = p.row_begin + from + x;
-                if (key_w == 8) __pipeline_memcpy_async(in_key + x * 8, static_cast<const char*>(p.key) + row * 8, 8);
-                else __pipeline_memcpy_async(in_key + x * 8, static_cast<const char*>(p.key) + row * 4, 4);
-                if (p.n_pay > 0) {
-                    if (p.pay_w[0] == 8) __pipeline_memcpy_async(in_pay0 + x * 8, static_cast<const char*>(p.pay[0]) + row * 8, 8);
-                    else __pipeline_memcpy_async(in_pay0 + x * 8, static_cast<const char*>(p.pay[0]) + row * 4, 4);
-                }
-                if (p.n_pay > 1) {
-                    if (p.pay_w[1] == 8) __pipeline_memcpy_async(in_pay1 + x * 8, static_cast<const char*>(p.pay[1]) + row * 8, 8);
-                    else __pipeline_memcpy_async(in_pay1 + x * 8, static_cast<const char*>(p.pay[1]) + row * 4, 4);
-                }
-            }
-        }
-        __pipeline_commit();
-    };
-    // a staged 8-byte slot widened like load_raw / load_width
-    auto staged_key = [&](unsigned x) -> long long {
-        if (key_w == 8) return *reinterpret_cast<const long long*>(in_key + x * 8);
-        if (p.key_kind == BQ_STRING) return static_cast<long long>(*reinterpret_cast<const unsigned*>(in_key + x * 8));
-        return static_cast<long long>(*reinterpret_cast<const int*>(in_key + x * 8));
-    };
-    auto staged_pay = [&](const unsigned char* base, int width, unsigned x) -> long long {
-        return width == 8 ? *reinterpret_cast<const long long*>(base + x * 8) : static_cast<long long>(*reinterpret_cast<const int*>(base + x * 8));
-    };
-    if (p.stage_in && lo < hi) stage(lo);
-
     for (size_t tile = lo; tile < hi; tile += kPartTile) {
         const unsigned tn = static_cast<unsigned>(hi - tile < (size_t)kPartTile ? hi - tile : (size_t)kPartTile);
         for (unsigned i = threadIdx.x; i < P; i += blockDim.x) cnt[i] = 0;
         __syncthreads();
         long long k[kPartRows], v0[kPartRows], v1[kPartRows];
         unsigned part[kPartRows], rank[kPartRows];
-        if (p.stage_in) {
-            __pipeline_wait_prior(0);              // this thread's copies of the tile have landed
 #pragma unroll
-            for (int j = 0; j < kPartRows; ++j) {
-                const unsigned x = j * kPartThreads + threadIdx.x;
-                if (x < tn) {
-                    k[j] = staged_key(x);
-                    v0[j] = p.n_pay > 0 ? staged_pay(in_pay0, p.pay_w[0], x) : 0;
-                    v1[j] = p.n_pay > 1 ? staged_pay(in_pay1, p.pay_w[1], x) : 0;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < kPartRows; ++j) {
-                const unsigned x = j * kPartThreads + threadIdx.x;
-                if (x < tn) {
-                    const size_t row = p.row_begin + tile + x;
-                    k[j] = load_raw(p.key, p.key_kind, row);
-                    v0[j] = p.n_pay > 0 ? load_width(p.pay[0], p.pay_w[0], row) : 0;
-                    v1[j] = p.n_pay > 1 ? load_width(p.pay[1], p.pay_w[1], row) : 0;
-                }
+        for (int j = 0; j < kPartRows; ++j) {
+            const unsigned x = j * kPartThreads + threadIdx.x;
+            if (x < tn) {
+                const size_t row = p.row_begin + tile + x;
+                k[j] = load_raw(p.key, p.key_kind, row);
+                v0[j] = p.n_pay > 0 ? load_width(p.pay[0], p.pay_w[0], row) : 0;
+                v1[j] = p.n_pay > 1 ? load_width(p.pay[1], p.pay_w[1], row) : 0;
             }
         }
 #pragma unroll
@@ -203,9 +147,6 @@ __global__ void __launch_bounds__(kPartThreads, 2) k_part_scatter(const __grid_c
             }
         }
         __syncthreads();
-        // The staged rows are in registers (the barrier above orders this thread's shared-memory reads before what follows),
-        // so the slots can take the next tile while this one is ranked, ordered and written out.
-        if (p.stage_in && tile + kPartTile < hi) stage(tile + kPartTile);
         // exclusive scan of cnt[0..P) into start[]: each thread owns P/kPartThreads consecutive entries (P >= kPartThreads) or one
         {
             const unsigned per = P > (unsigned)kPartThreads ? P / kPartThreads : 1;
@@ -355,12 +296,7 @@ static void part_scatter(bq_part_plan* pl, const bq_col* const* payload, int n_p
     p.dest_pay[0] = d_dest_pay0;
     p.dest_pay[1] = d_dest_pay1;
     if (!p.n) return;
-    size_t smem = static_cast<size_t>(kPartTile) * 24 + pl->P * 40 + kPartTile * 2;
-    // Staging the next tile costs 48 KB more per CTA; it pays while two CTAs still fit an SM (P <= 128).
-    // BOSQL_PART_STAGE=0|1 overrides the default.
-    const char* stage_env = std::getenv("BOSQL_PART_STAGE");
-    p.stage_in = ((stage_env ? *stage_env != '0' : kPartStageDefault) && pl->P <= 128) ? 1 : 0;
-    if (p.stage_in) smem += static_cast<size_t>(kPartTile) * 24;
+    const size_t smem = static_cast<size_t>(kPartTile) * 24 + pl->P * 40 + kPartTile * 2;
     BQ_CUDA(cudaFuncSetAttribute(k_part_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     k_part_scatter<<<pl->G, kPartThreads, smem, ctx->stream>>>(p);
     ctx->launches++;
